@@ -1,0 +1,259 @@
+// Flash-style attention for head dim 64 on tcgen05 / TMEM / TMA (sm_100a).
+//
+// One CTA owns 128 query rows of one (image, head) and streams the keys in tiles
+// of 64:  S = Q K^T (UMMA, fp32 in TMEM, double-buffered) -> online softmax with
+// one thread per query row (no shuffles: a TMEM lane is a row) -> P (bf16) into
+// 128-byte-swizzled shared memory -> O_tile = P V (UMMA, V consumed MN-major
+// straight from the [keys, 64] TMA box) -> running O kept in registers.
+// Q/K/V are read in place from the projection GEMM outputs ([B, L, heads*64]
+// rows): the head split/merge permutes of the reference are TMA coordinates.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace edtr {
+
+constexpr int kAttThreads = 192;
+constexpr int kQT = 128;   // query rows per CTA
+constexpr int kKT = 64;    // keys per tile
+constexpr int kD = 64;     // head dim
+constexpr int kAttSmem = kQT * kD * 2 + 2 * (kKT * kD * 2) * 2 + kQT * kKT * 2 + 1024 + 256;
+constexpr int kAttTmemCols = 256;  // S0 [0,64) S1 [64,128) O_tile [128,192)
+
+struct AttParams {
+  void* O;
+  int ldo;
+  int Lq, Lk;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(kAttThreads, 2)
+attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                         // 16 KB
+  uint8_t* sK = sQ + kQT * kD * 2;            // 2 x 8 KB
+  uint8_t* sV = sK + 2 * kKT * kD * 2;        // 2 x 8 KB
+  uint8_t* sP = sV + 2 * kKT * kD * 2;        // 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kQT * kKT * 2);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* s_full = bars + 5;    // [2]
+  uint64_t* p_full = bars + 7;
+  uint64_t* pv_full = bars + 8;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQT;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int nkv = (p.Lk + kKT - 1) / kKT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(pv_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, kAttTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kQT * kD * 2);
+      tma_load_4d(sQ, &tmQ, q_full, 0, q0, head, img);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[s], 2 * kKT * kD * 2);
+        tma_load_4d(sK + s * kKT * kD * 2, &tmK, &kv_full[s], 0, j * kKT, head, img);
+        tma_load_4d(sV + s * kKT * kD * 2, &tmV, &kv_full[s], 0, j * kKT, head, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kQT, kKT, false);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kD, true);
+      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ));
+      const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP));
+      auto issue_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK + s * kKT * kD * 2));
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss(tmem_base + s * kKT, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[s]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        const int s = j & 1;
+        if (j + 1 < nkv) issue_s(j + 1);
+        mbar_wait(p_full, j & 1);
+        tc_fence_after();
+        const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV + s * kKT * kD * 2));
+#pragma unroll
+        for (int k = 0; k < kKT / 16; ++k) {
+          // A: +32 B per 16 keys (K-major P); B: +16 rows * 128 B (MN-major V)
+          umma_ss(tmem_base + 128, pdesc + 2 * k, vdesc + 128 * k, idesc_pv, k != 0);
+        }
+        umma_commit(pv_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    float o[kD];
+#pragma unroll
+    for (int i = 0; i < kD; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    uint8_t* prow = sP + r * 128;
+    for (int j = 0; j < nkv; ++j) {
+      const int s = j & 1;
+      mbar_wait(&s_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      uint32_t sr[2][32];
+      tmem_ld32(trow + s * kKT, sr[0]);
+      tmem_ld32(trow + s * kKT + 32, sr[1]);
+      tmem_ld_wait();
+      const int valid = p.Lk - j * kKT;  // >= 1
+      float mx = -INFINITY;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(sr[h][i]);
+          if (h * 32 + i >= valid) v = -INFINITY;
+          sr[h][i] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f((m - m_new) * p.scale_log2);
+      const float mb = m_new * p.scale_log2;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 B
+        float pv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int idx = c * 8 + i;
+          pv[i] = exp2f(__uint_as_float(sr[idx >> 5][idx & 31]) * p.scale_log2 - mb);
+          sum += pv[i];
+        }
+        uint4 u;
+        u.x = pack_bf16(pv[0], pv[1]);
+        u.y = pack_bf16(pv[2], pv[3]);
+        u.z = pack_bf16(pv[4], pv[5]);
+        u.w = pack_bf16(pv[6], pv[7]);
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = u;
+      }
+      l = l * alpha + sum;
+      m = m_new;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // O_tile = P V_j
+      mbar_wait(pv_full, j & 1);
+      tc_fence_after();
+      uint32_t orr[2][32];
+      tmem_ld32(trow + 128, orr[0]);
+      tmem_ld32(trow + 128 + 32, orr[1]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[h * 32 + i] = o[h * 32 + i] * alpha + __uint_as_float(orr[h][i]);
+    }
+    const int q = q0 + r;
+    if (q < p.Lq) {
+      const float inv = 1.f / l;
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.O) +
+                          (static_cast<size_t>(img) * p.Lq + q) * p.ldo + head * kD;
+      uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 u;
+        u.x = pack_bf16(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
+        u.y = pack_bf16(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
+        u.z = pack_bf16(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
+        u.w = pack_bf16(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+        o4[c] = u;
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kAttTmemCols);
+  }
+}
+
+int prime_attention_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
+    return EDTR_ERR_CUDA;
+  }
+  return EDTR_OK;
+}
+
+static int make_head_tmap(CUtensorMap* tm, const void* base, int ld, int B, int heads, int L, int box_rows) {
+  uint64_t dims[4] = {static_cast<uint64_t>(kD), static_cast<uint64_t>(L), static_cast<uint64_t>(heads),
+                      static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {static_cast<uint64_t>(ld) * 2, static_cast<uint64_t>(kD) * 2,
+                         static_cast<uint64_t>(ld) * 2 * L};
+  uint32_t box[4] = {kD, static_cast<uint32_t>(box_rows), 1, 1};
+  return make_tmap_bf16(tm, base, 4, dims, strides, box);
+}
+
+}  // namespace edtr
+
+using namespace edtr;
+
+extern "C" int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv,
+                                   void* O, int ldo, int B, int heads, int Lq, int Lk, float scale,
+                                   void* stream) {
+  EDTR_REQUIRE(Q && K && V && O, "Q/K/V/O is NULL");
+  EDTR_REQUIRE(B > 0 && heads > 0 && Lq > 0 && Lk > 0, "bad attention shape");
+  EDTR_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0, "row strides must be multiples of 8");
+  EDTR_REQUIRE(ldq >= heads * kD && ldk >= heads * kD && ldv >= heads * kD && ldo >= heads * kD,
+               "row strides must cover heads*64 columns");
+  EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) | reinterpret_cast<uintptr_t>(V) |
+                 reinterpret_cast<uintptr_t>(O)) & 15) == 0, "Q/K/V/O must be 16-byte aligned");
+  EDTR_REQUIRE(heads <= 65535 && B <= 65535, "grid too large");
+  CUtensorMap tmQ, tmK, tmV;
+  int rc = make_head_tmap(&tmQ, Q, ldq, B, heads, Lq, kQT);
+  if (rc) return rc;
+  rc = make_head_tmap(&tmK, K, ldk, B, heads, Lk, kKT);
+  if (rc) return rc;
+  rc = make_head_tmap(&tmV, V, ldv, B, heads, Lk, kKT);
+  if (rc) return rc;
+  AttParams p;
+  p.O = O; p.ldo = ldo; p.Lq = Lq; p.Lk = Lk;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid((Lq + kQT - 1) / kQT, heads, B);
+  attention_kernel<<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  return check_launch("attention_kernel");
+}

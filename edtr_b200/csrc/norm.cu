@@ -1,0 +1,291 @@
+// HBM-bound normalisation kernels: GroupNorm statistics, GroupNorm apply (+SiLU),
+// LayerNorm, row softmax.  All activations are bf16 channels-last; every global
+// access is a 16-byte vector of 8 channels, adjacent threads touch adjacent
+// vectors (coalesced), reductions use warp shuffles + shared memory.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace edtr {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+  u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  return u;
+}
+
+// ------------------------------------------------------------ GroupNorm stats
+// grid (pixel chunks, B, channel slabs); block = vslab * ppar threads where vslab =
+// 16-byte vectors per slab.  Thread (v, q) owns vector v and walks pixels q, q+ppar, ...
+// so its 8 per-channel accumulators stay in registers.
+__global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int C,
+                                       int groups, int rows_per_cta, int vslab, float* __restrict__ stats) {
+  extern __shared__ float sh[];  // [2][vslab*8]
+  const int cslab = vslab * 8;
+  const int ppar = blockDim.x / vslab;
+  const int v = threadIdx.x % vslab;
+  const int q = threadIdx.x / vslab;
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.z * cslab;
+  const int p0 = blockIdx.x * rows_per_cta;
+  const int p1 = min(HW, p0 + rows_per_cta);
+  for (int i = threadIdx.x; i < 2 * cslab; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
+  if (q < ppar && c0 + v * 8 < C) {
+    const __nv_bfloat16* base = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
+    for (int pidx = p0 + q; pidx < p1; pidx += ppar) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pidx) * ldx));
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sh[v * 8 + i], s[i]);
+      atomicAdd(&sh[cslab + v * 8 + i], ss[i]);
+    }
+  }
+  __syncthreads();
+  // fold channels into groups; one thread per (group in slab)
+  const int cpg = C / groups;
+  const int g_first = c0 / cpg;
+  const int g_last = (min(C, c0 + cslab) - 1) / cpg;
+  for (int g = g_first + threadIdx.x; g <= g_last; g += blockDim.x) {
+    const int lo = max(g * cpg, c0), hi = min((g + 1) * cpg, min(C, c0 + cslab));
+    float a = 0.f, a2 = 0.f;
+    for (int c = lo; c < hi; ++c) { a += sh[c - c0]; a2 += sh[cslab + c - c0]; }
+    atomicAdd(&stats[(static_cast<size_t>(b) * groups + g) * 2 + 0], a);
+    atomicAdd(&stats[(static_cast<size_t>(b) * groups + g) * 2 + 1], a2);
+  }
+}
+
+// ------------------------------------------------------------ GroupNorm apply
+__global__ void groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx,
+                                       __nv_bfloat16* __restrict__ Y, int ldy, int HW, int C, int groups,
+                                       int rows_per_cta, const float* __restrict__ stats,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float eps, int silu) {
+  extern __shared__ float sh[];  // scale[C], shift[C]
+  float* sc = sh;
+  float* sf = sh + C;
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  const float inv_n = 1.f / (static_cast<float>(cpg) * static_cast<float>(HW));
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const float mean = stats[(static_cast<size_t>(b) * groups + g) * 2 + 0] * inv_n;
+    const float ex2 = stats[(static_cast<size_t>(b) * groups + g) * 2 + 1] * inv_n;
+    const float var = fmaxf(ex2 - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float a = rstd * __ldg(gamma + c);
+    sc[c] = a;
+    sf[c] = __ldg(beta + c) - mean * a;
+  }
+  __syncthreads();
+  const int vpr = C / 8;
+  const int p0 = blockIdx.x * rows_per_cta;
+  const int nrows = min(HW, p0 + rows_per_cta) - p0;
+  const int total = nrows * vpr;
+  const size_t rowbase = static_cast<size_t>(b) * HW + p0;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int pr = idx / vpr, v = idx - pr * vpr;
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(X + (rowbase + pr) * ldx + v * 8));
+    float f[8];
+    unpack8(u, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = f[i] * sc[v * 8 + i] + sf[v * 8 + i];
+      f[i] = silu ? silu_f(y) : y;
+    }
+    *reinterpret_cast<uint4*>(Y + (rowbase + pr) * ldy + v * 8) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm
+// One warp per row, the row lives in registers (two exact passes).
+template <int MAXV>
+__global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y,
+                                 int ldy, int M, int C, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int vpr = C / 8;
+  float f[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < vpr) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(X + static_cast<size_t>(row) * ldx + v * 8));
+      unpack8(u, f[k]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += f[k][i];
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(C);
+  float s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < vpr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; s2 += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(C) + eps);
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int v = lane + 32 * k;
+    if (v < vpr) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = (f[k][i] - mean) * rstd * gg[i] + bb[i];
+      *reinterpret_cast<uint4*>(Y + static_cast<size_t>(row) * ldy + v * 8) = pack8(o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- row softmax
+// One CTA per row; fp32 logits in, bf16 probabilities out.
+__global__ void softmax_rows_kernel(const float* __restrict__ S, int lds, __nv_bfloat16* __restrict__ P,
+                                    int ldp, int N, float scale_log2) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const float* s = S + static_cast<size_t>(row) * lds;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) mx = fmaxf(mx, s[i]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = lane < nw ? red[lane] : -INFINITY;
+  mx = warp_max(mx);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) sum += exp2f((s[i] - mx) * scale_log2);
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = lane < nw ? red[lane] : 0.f;
+  sum = warp_sum(sum);
+  const float inv = 1.f / sum;
+  __nv_bfloat16* p = P + static_cast<size_t>(row) * ldp;
+  for (int i = threadIdx.x; i < N; i += blockDim.x)
+    p[i] = __float2bfloat16(exp2f((s[i] - mx) * scale_log2) * inv);
+}
+
+static int rows_per_cta_for(int HW) {
+  int r = HW / 64;
+  if (r < 64) r = 64;
+  if (r > 1024) r = 1024;
+  return r;
+}
+
+}  // namespace edtr
+
+using namespace edtr;
+
+static int check_gn_args(const void* X, int ldx, int B, int HW, int C, int groups) {
+  EDTR_REQUIRE(X != nullptr, "X is NULL");
+  EDTR_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0, "bad GroupNorm shape");
+  EDTR_REQUIRE(C % 8 == 0 && C % groups == 0, "C (%d) must be a multiple of 8 and of groups (%d)", C, groups);
+  EDTR_REQUIRE(ldx % 8 == 0 && ldx >= C, "ldx must be >= C and a multiple of 8");
+  EDTR_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0, "X must be 16-byte aligned");
+  EDTR_REQUIRE(B <= 65535, "B too large");
+  return EDTR_OK;
+}
+
+extern "C" int edtr_groupnorm_stats(const void* X, int ldx, int B, int HW, int C, int groups, float* stats,
+                                    void* stream) {
+  int rc = check_gn_args(X, ldx, B, HW, C, groups);
+  if (rc) return rc;
+  EDTR_REQUIRE(stats != nullptr, "stats is NULL");
+  const int vpr = C / 8;
+  // slab = largest divisor of vpr that is <= 256 vectors
+  int vslab = vpr;
+  if (vslab > 256) {
+    vslab = 256;
+    while (vpr % vslab != 0) --vslab;
+  }
+  const int nslab = vpr / vslab;
+  int ppar = 256 / vslab;
+  if (ppar < 1) ppar = 1;
+  const int threads = vslab * ppar;
+  const int rows = rows_per_cta_for(HW);
+  dim3 grid((HW + rows - 1) / rows, B, nslab);
+  const size_t sh = 2 * static_cast<size_t>(vslab) * 8 * sizeof(float);
+  groupnorm_stats_kernel<<<grid, threads, sh, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(X), ldx, HW, C, groups, rows, vslab, stats);
+  return check_launch("groupnorm_stats_kernel");
+}
+
+extern "C" int edtr_groupnorm_apply(const void* X, int ldx, void* Y, int ldy, int B, int HW, int C, int groups,
+                                    const float* stats, const float* gamma, const float* beta, float eps,
+                                    int silu, void* stream) {
+  int rc = check_gn_args(X, ldx, B, HW, C, groups);
+  if (rc) return rc;
+  EDTR_REQUIRE(Y && stats && gamma && beta, "Y/stats/gamma/beta is NULL");
+  EDTR_REQUIRE(ldy % 8 == 0 && ldy >= C && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "bad Y stride/alignment");
+  EDTR_REQUIRE(C <= 5120, "C too large for the shared scale/shift table");
+  const int rows = rows_per_cta_for(HW);
+  dim3 grid((HW + rows - 1) / rows, B, 1);
+  const size_t sh = 2 * static_cast<size_t>(C) * sizeof(float);
+  groupnorm_apply_kernel<<<grid, 256, sh, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
+      rows, stats, gamma, beta, eps, silu);
+  return check_launch("groupnorm_apply_kernel");
+}
+
+extern "C" int edtr_layernorm_bf16(const void* X, int ldx, void* Y, int ldy, int M, int C, const float* gamma,
+                                   const float* beta, float eps, void* stream) {
+  EDTR_REQUIRE(X && Y && gamma && beta, "X/Y/gamma/beta is NULL");
+  EDTR_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "bad LayerNorm shape (C %% 8 == 0 required)");
+  EDTR_REQUIRE(C <= 2048, "LayerNorm supports C <= 2048 (got %d)", C);
+  EDTR_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C, "bad strides");
+  EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) |
+                 reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+               "pointers must be 16-byte aligned");
+  const int warps = 8;
+  dim3 grid((M + warps - 1) / warps);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(X);
+  __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(Y);
+  const int vpr = C / 8;
+  if (vpr <= 64) layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, M, C, gamma, beta, eps);
+  else if (vpr <= 160) layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, M, C, gamma, beta, eps);
+  else layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, M, C, gamma, beta, eps);
+  return check_launch("layernorm_kernel");
+}
+
+extern "C" int edtr_softmax_rows(const float* S, int lds, void* P, int ldp, int M, int N, float scale,
+                                 void* stream) {
+  EDTR_REQUIRE(S && P && M > 0 && N > 0 && lds >= N && ldp >= N, "bad softmax arguments");
+  softmax_rows_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      S, lds, reinterpret_cast<__nv_bfloat16*>(P), ldp, N, scale * 1.4426950408889634f);
+  return check_launch("softmax_rows_kernel");
+}

@@ -1,0 +1,333 @@
+"""Tensor-level wrappers over the C-ABI (``include/edtr_b200.h``).
+
+PyTorch supplies device memory and the current stream only; every function here
+validates its arguments (``ValueError`` for shape / dtype / layout problems, as the
+reference asserts on shapes — model/unet.py:70,107) and then launches the CUDA
+kernels through ctypes.  There is no CPU path: CPU tensors raise ``RuntimeError``.
+
+Activations are bf16 channels-last.  A "rows view" is any tensor whose last dim is
+contiguous and whose leading dims collapse to rows with one uniform stride, e.g. a
+channel slice ``buf[..., :320]`` of a wider concat buffer.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import lib as _lib
+from .lib import EdtrEpilogue
+
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+OUT_BF16, OUT_F32, OUT_NCHW_F32, OUT_NCHW_BF16 = 0, 1, 2, 3
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("edtr_b200 ops need CUDA tensors (no CPU fallback)")
+
+
+def rows_view(t: torch.Tensor, dtype=BF16) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a tensor usable as a row-major matrix with row stride ld."""
+    if t.dtype != dtype:
+        raise ValueError(f"expected dtype {dtype}, got {t.dtype}")
+    if t.dim() < 2:
+        raise ValueError("expected at least 2 dims")
+    if t.stride(-1) != 1:
+        raise ValueError("last dim must be contiguous")
+    ld = t.stride(-2)
+    cols = t.shape[-1]
+    rows = 1
+    expect = ld
+    for d in range(t.dim() - 2, -1, -1):
+        if t.shape[d] != 1 and t.stride(d) != expect:
+            raise ValueError(f"tensor with shape {tuple(t.shape)} strides {t.stride()} is not a uniform rows view")
+        expect *= t.shape[d]
+        rows *= t.shape[d]
+    return rows, cols, ld
+
+
+def _f32(t: Optional[torch.Tensor], n: int, name: str) -> Optional[int]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() < n:
+        raise ValueError(f"{name} must be a contiguous fp32 tensor with >= {n} elements")
+    return t.data_ptr()
+
+
+def _epilogue(M: int, n_out: int, out: torch.Tensor, *, bias, rowvec, rows_per_group, residual, act, out_mode, hw,
+              alpha) -> EdtrEpilogue:
+    ep = EdtrEpilogue()
+    ep.bias = _f32(bias, n_out if act != ACT_GEGLU else 2 * n_out, "bias")
+    if rowvec is not None:
+        if rowvec.dtype != torch.float32 or rowvec.dim() != 2 or rowvec.stride(1) != 1:
+            raise ValueError("rowvec must be a 2-D fp32 tensor with contiguous rows")
+        if rows_per_group <= 0 or M % rows_per_group != 0 or rowvec.shape[0] < M // rows_per_group:
+            raise ValueError("rowvec / rows_per_group do not match the row count")
+        ep.rowvec = rowvec.data_ptr()
+        ep.rowvec_ld = rowvec.stride(0)
+        ep.rows_per_group = rows_per_group
+    if residual is not None:
+        r_rows, r_cols, ldr = rows_view(residual)
+        if r_rows != M or r_cols != n_out:
+            raise ValueError(f"residual shape {tuple(residual.shape)} != ({M}, {n_out})")
+        ep.residual = residual.data_ptr()
+        ep.ldr = ldr
+    ep.out = out.data_ptr()
+    if out_mode == OUT_BF16:
+        o_rows, o_cols, ldc = rows_view(out)
+        if o_rows != M or o_cols != n_out:
+            raise ValueError(f"out shape {tuple(out.shape)} != ({M}, {n_out})")
+        ep.ldc = ldc
+    elif out_mode == OUT_F32:
+        o_rows, o_cols, ldc = rows_view(out, torch.float32)
+        if o_rows != M or o_cols != n_out:
+            raise ValueError(f"out shape {tuple(out.shape)} != ({M}, {n_out})")
+        ep.ldc = ldc
+    else:
+        want = torch.float32 if out_mode == OUT_NCHW_F32 else BF16
+        if out.dtype != want or not out.is_contiguous() or out.numel() != M * n_out:
+            raise ValueError("NCHW output must be a contiguous tensor of M*N elements")
+        ep.ldc = 0
+    ep.act = act
+    ep.out_mode = out_mode
+    ep.hw = hw
+    ep.alpha = alpha
+    return ep
+
+
+def _alloc_out(M: int, n_out: int, out_mode: int, hw: int, device) -> torch.Tensor:
+    if out_mode == OUT_BF16:
+        return torch.empty((M, n_out), dtype=BF16, device=device)
+    if out_mode == OUT_F32:
+        return torch.empty((M, n_out), dtype=torch.float32, device=device)
+    dt = torch.float32 if out_mode == OUT_NCHW_F32 else BF16
+    return torch.empty((M // hw, n_out, hw), dtype=dt, device=device)
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, rows_per_group=0, residual=None,
+         act=ACT_NONE, out=None, out_mode=OUT_BF16, hw=0, alpha=1.0) -> torch.Tensor:
+    """``epilogue(a @ w.T)`` — a [..., K] rows view, w [N, K] (bf16)."""
+    _require_cuda(a, w, bias, rowvec, residual, out)
+    M, K, lda = rows_view(a)
+    N, Kw, ldw = rows_view(w)
+    if Kw != K:
+        raise ValueError(f"K mismatch: a has {K}, w has {Kw}")
+    n_out = N // 2 if act == ACT_GEGLU else N
+    if out is None:
+        out = _alloc_out(M, n_out, out_mode, hw, a.device)
+    ep = _epilogue(M, n_out, out, bias=bias, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual,
+                   act=act, out_mode=out_mode, hw=hw, alpha=alpha)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_gemm_bf16(a.data_ptr(), lda, w.data_ptr(), ldw, M, N, K, ctypes.byref(ep), _stream()),
+               "edtr_gemm_bf16")
+    return out
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, residual=None, act=ACT_NONE, out=None,
+            out_mode=OUT_BF16, alpha=1.0) -> torch.Tensor:
+    """3x3/s1/p1 conv. x [B,H,W,Cin] channels-last rows view, w [Cout, 9*Cin] (tap-major)."""
+    _require_cuda(x, w, bias, rowvec, residual, out)
+    if x.dim() != 4:
+        raise ValueError("x must be [B, H, W, C]")
+    B, H, W, Cin = x.shape
+    M, _, ldx = rows_view(x)
+    Cout, Kw, ldw = rows_view(w)
+    if Kw != 9 * Cin or ldw != Kw:
+        raise ValueError(f"weight must be contiguous [Cout, 9*Cin={9 * Cin}], got {tuple(w.shape)}")
+    hw = H * W
+    if out is None:
+        out = _alloc_out(M, Cout, out_mode, hw, x.device)
+    ep = _epilogue(M, Cout, out, bias=bias, rowvec=rowvec, rows_per_group=hw, residual=residual, act=act,
+                   out_mode=out_mode, hw=hw, alpha=alpha)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_conv3x3_bf16(x.data_ptr(), ldx, B, H, W, Cin, w.data_ptr(), Cout, ctypes.byref(ep), _stream()),
+               "edtr_conv3x3_bf16")
+    return out
+
+
+def conv3x3_supported(H: int, W: int, Cin: int) -> bool:
+    """Geometry the TMA implicit-GEMM path covers (else: im2col + gemm)."""
+    if Cin % 64 != 0:
+        return False
+    if W >= 128:
+        return W % 128 == 0
+    if W < 8 or 128 % W != 0:
+        return False
+    rows = 128 // W
+    return H % rows == 0 if H >= rows else rows % H == 0
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v per head (d=64). q [B,Lq,heads*64], k/v [B,Lk,heads*64] rows views."""
+    _require_cuda(q, k, v, out)
+    for t in (q, k, v):
+        if t.dim() != 3:
+            raise ValueError("q/k/v must be [B, L, heads*64]")
+    B, Lq, C = q.shape
+    Bk, Lk, Ck = k.shape
+    if C != heads * 64 or Ck != C or v.shape != k.shape or Bk != B:
+        raise ValueError("attention shape mismatch")
+    _, _, ldq = rows_view(q)
+    _, _, ldk = rows_view(k)
+    _, _, ldv = rows_view(v)
+    if out is None:
+        out = torch.empty((B, Lq, C), dtype=BF16, device=q.device)
+    _, _, ldo = rows_view(out)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_attention_bf16(q.data_ptr(), ldq, k.data_ptr(), ldk, v.data_ptr(), ldv, out.data_ptr(), ldo,
+                                     B, heads, Lq, Lk, scale, _stream()), "edtr_attention_bf16")
+    return out
+
+
+def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
+              stats: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm (+SiLU) over x [B, HW..., C] channels-last rows view."""
+    _require_cuda(x, gamma, beta, stats, out)
+    B = x.shape[0]
+    M, C, ldx = rows_view(x)
+    HW = M // B
+    if stats is None:
+        stats = torch.zeros((B, groups, 2), dtype=torch.float32, device=x.device)
+    elif stats.dtype != torch.float32 or stats.numel() != B * groups * 2 or not stats.is_contiguous():
+        raise ValueError("stats must be a contiguous fp32 [B, groups, 2] tensor")
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    Mo, Co, ldy = rows_view(out)
+    if Mo != M or Co != C:
+        raise ValueError("out shape mismatch")
+    g = _f32(gamma, C, "gamma")
+    b = _f32(beta, C, "beta")
+    L = _lib.device_lib()
+    st = _stream()
+    _lib.check(L.edtr_groupnorm_stats(x.data_ptr(), ldx, B, HW, C, groups, stats.data_ptr(), st),
+               "edtr_groupnorm_stats")
+    _lib.check(L.edtr_groupnorm_apply(x.data_ptr(), ldx, out.data_ptr(), ldy, B, HW, C, groups, stats.data_ptr(),
+                                      g, b, eps, 1 if silu else 0, st), "edtr_groupnorm_apply")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, gamma, beta, out)
+    M, C, ldx = rows_view(x)
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    _, _, ldy = rows_view(out)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_layernorm_bf16(x.data_ptr(), ldx, out.data_ptr(), ldy, M, C, _f32(gamma, C, "gamma"),
+                                     _f32(beta, C, "beta"), eps, _stream()), "edtr_layernorm_bf16")
+    return out
+
+
+def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(s, out)
+    M, N, lds = rows_view(s, torch.float32)
+    if out is None:
+        out = torch.empty(s.shape, dtype=BF16, device=s.device)
+    _, _, ldp = rows_view(out)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_softmax_rows(s.data_ptr(), lds, out.data_ptr(), ldp, M, N, scale, _stream()),
+               "edtr_softmax_rows")
+    return out
+
+
+def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, out)
+    B, H, W, C = x.shape
+    _, _, ldx = rows_view(x)
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, C), dtype=BF16, device=x.device)
+    _, _, ldy = rows_view(out)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_upsample2x_bf16(x.data_ptr(), ldx, out.data_ptr(), ldy, B, H, W, C, _stream()),
+               "edtr_upsample2x_bf16")
+    return out
+
+
+def im2col(x: torch.Tensor, kh: int, kw: int, stride: int, pad_top: int, pad_left: int, Ho: int, Wo: int) -> torch.Tensor:
+    _require_cuda(x)
+    B, H, W, C = x.shape
+    _, _, ldx = rows_view(x)
+    out = torch.empty((B * Ho * Wo, kh * kw * C), dtype=BF16, device=x.device)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_im2col_bf16(x.data_ptr(), ldx, out.data_ptr(), B, H, W, C, kh, kw, stride, pad_top, pad_left,
+                                  Ho, Wo, _stream()), "edtr_im2col_bf16")
+    return out
+
+
+def nchw_to_nhwc(x: torch.Tensor, out: torch.Tensor, coff: int = 0) -> torch.Tensor:
+    """x [B,C,H,W] fp32 contiguous -> out[..., coff:coff+C] (bf16 channels-last rows view)."""
+    _require_cuda(x, out)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 4:
+        raise ValueError("x must be a contiguous fp32 NCHW tensor")
+    B, C, H, W = x.shape
+    M, Co, ldy = rows_view(out)
+    if M != B * H * W or coff + C > Co:
+        raise ValueError("out does not match x")
+    L = _lib.device_lib()
+    _lib.check(L.edtr_nchw_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), ldy, coff, B, C, H * W, _stream()),
+               "edtr_nchw_f32_to_nhwc_bf16")
+    return out
+
+
+def nhwc_to_nchw(x: torch.Tensor, B: int, out_f32: bool = True) -> torch.Tensor:
+    """x [B*HW, C] rows view (bf16) -> [B, C, HW] contiguous."""
+    _require_cuda(x)
+    M, C, ldx = rows_view(x)
+    HW = M // B
+    out = torch.empty((B, C, HW), dtype=torch.float32 if out_f32 else BF16, device=x.device)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_nhwc_bf16_to_nchw(x.data_ptr(), ldx, out.data_ptr(), B, C, HW, 1 if out_f32 else 0, _stream()),
+               "edtr_nhwc_bf16_to_nchw")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _require_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous():
+        raise ValueError("x must be contiguous fp32")
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "edtr_cast_f32_to_bf16")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
+    _require_cuda(t)
+    if t.dtype != torch.int64 or t.dim() != 1 or not t.is_contiguous():
+        raise ValueError("timesteps must be a contiguous int64 vector")
+    out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)
+    L = _lib.device_lib()
+    _lib.check(L.edtr_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], dim, max_period, _stream()),
+               "edtr_timestep_embedding")
+    return out
+
+
+def sampler_update(x, eps, noise, index, tables, want_pred_x0: bool = True):
+    """Fused p_sample arithmetic; tables = (sqrt_recip, sqrt_recipm1, coef1, coef2, var) fp32 device vectors."""
+    _require_cuda(x, eps, noise, index, *tables)
+    for t in (x, eps, noise):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.shape != x.shape:
+            raise ValueError("x / eps / noise must be contiguous fp32 tensors of one shape")
+    if index.dtype != torch.int64 or index.numel() != x.shape[0]:
+        raise ValueError("index must be int64 [B]")
+    B = x.shape[0]
+    n = x.numel() // B
+    x_prev = torch.empty_like(x)
+    pred = torch.empty_like(x) if want_pred_x0 else None
+    L = _lib.device_lib()
+    _lib.check(L.edtr_sampler_update(x.data_ptr(), eps.data_ptr(), noise.data_ptr(), index.data_ptr(),
+                                     *[t.data_ptr() for t in tables], x_prev.data_ptr(),
+                                     pred.data_ptr() if pred is not None else None, B, n, _stream()),
+               "edtr_sampler_update")
+    return x_prev, pred

@@ -1,0 +1,181 @@
+/*
+ * edtr_b200 — C-ABI of the B200 (sm_100a) kernels behind the EDTR ControlLDM
+ * restore path (SpacedSampler loop -> ControlNet + SD-2.1 UNet -> VAE decoder).
+ *
+ * The reference (JaehaKim97/EDTR) has no FFI layer: its hot path is a tree of
+ * torch.nn modules calling ATen/cuDNN/cuBLAS.  Each entry point below replaces
+ * one family of those library call sites; the citation after "replaces:" is the
+ * reference file:line whose arithmetic the kernel reproduces.
+ *
+ * Conventions (all entry points):
+ *   - raw device pointers + sizes only, no torch types; activations are bf16
+ *     channels-last ("NHWC": a [rows, channels] matrix with a row stride `ld`
+ *     given in ELEMENTS), parameters of norms / biases are fp32;
+ *   - stream-ordered on `stream` (a cudaStream_t passed as void*), no allocation,
+ *     no synchronisation, CUDA-Graph capturable;
+ *   - return 0 on success or a negative EDTR_ERR_* code; edtr_last_error() gives
+ *     a thread-local human readable message.
+ */
+#ifndef EDTR_B200_H_
+#define EDTR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDTR_OK 0
+#define EDTR_ERR_INVALID (-1) /* bad argument (shape / alignment / mode) */
+#define EDTR_ERR_CUDA (-2)    /* CUDA runtime / driver error */
+#define EDTR_ERR_DEVICE (-3)  /* not a compute-capability 10.x device */
+
+/* Epilogue activation of edtr_gemm_bf16 / edtr_conv3x3_bf16. */
+#define EDTR_ACT_NONE 0
+#define EDTR_ACT_SILU 1  /* x * sigmoid(x)            replaces: model/unet.py:166-172 (emb SiLU) */
+#define EDTR_ACT_GEGLU 2 /* x * gelu_erf(gate)         replaces: model/attention.py:20-27 */
+
+/* Output addressing of the GEMM epilogue. */
+#define EDTR_OUT_BF16 0      /* out[row*ldc + col], bf16                         */
+#define EDTR_OUT_F32 1       /* out[row*ldc + col], fp32                         */
+#define EDTR_OUT_NCHW_F32 2  /* out[((row/hw)*N + col)*hw + row%hw], fp32 (NCHW) */
+#define EDTR_OUT_NCHW_BF16 3 /* same addressing, bf16                            */
+
+/*
+ * Fused epilogue applied to the fp32 accumulator acc[row, col]:
+ *   v = alpha*acc + bias[col] + rowvec[(row / rows_per_group)*rowvec_ld + col]
+ *         + residual[row*ldr + col];   v = act(v);   store(v)
+ * Any of bias / rowvec / residual may be NULL.  For EDTR_ACT_GEGLU the weight
+ * rows must be pre-interleaved per N-tile (first half of every tile = value
+ * columns, second half = gate columns; see edtr_gemm_tile_n) and the stored
+ * matrix has N/2 columns.
+ *   rowvec  replaces: h + emb_out[:, :, None, None]        model/unet.py:221
+ *   residual replaces: skip_connection(x) + h               model/unet.py:223,
+ *            attn(x) + x / ff(x) + x                        model/attention.py:231-233,
+ *            x + x_in                                       model/attention.py:302,
+ *            hs.pop() + control.pop(), h += control.pop()   model/controlnet.py:31,37
+ */
+typedef struct EdtrEpilogue {
+  const float* bias;
+  const float* rowvec;
+  int32_t rowvec_ld;
+  int32_t rows_per_group;
+  const void* residual; /* bf16 */
+  int32_t ldr;
+  void* out;
+  int32_t ldc;
+  int32_t act;
+  int32_t out_mode;
+  int32_t hw; /* rows per image, for the NCHW output modes */
+  float alpha;
+} EdtrEpilogue;
+
+/* ---- library ------------------------------------------------------------ */
+const char* edtr_last_error(void);
+int edtr_version(void);
+/* Makes `device` current for this library's runtime instance (one process per
+ * GPU: call once with the rank's device before edtr_init). */
+int edtr_set_device(int device);
+/* Verifies the current device is sm_100-class and primes kernel attributes. */
+int edtr_init(void);
+/* N-tile width the GEMM will use for an N-column problem (for GEGLU weight
+ * interleaving at plan time). */
+int edtr_gemm_tile_n(int M, int N, int K, int act);
+
+/* ---- tensor-core kernels (tcgen05 / TMEM / TMA) ------------------------- */
+/* out = epilogue(A[M,K] * Wt[N,K]^T).  A, Wt bf16, K-contiguous, lda/ldw in
+ * elements (multiples of 8), K a multiple of 64.
+ * replaces: nn.Linear / 1x1 nn.Conv2d call sites — model/attention.py:23,43,
+ * 170-174,266,280; model/unet.py:168-171,189,476-480; model/controlnet.py:129-133,
+ * 260-261; model/vae.py:97-101,265-284,689-690. */
+int edtr_gemm_bf16(const void* A, int lda, const void* Wt, int ldw, int M, int N, int K,
+                   const EdtrEpilogue* ep, void* stream);
+
+/* 3x3 / stride 1 / zero-pad 1 convolution as an implicit GEMM.  X is bf16
+ * channels-last [B, H, W, Cin] with pixel stride ldx; Wt is bf16 [Cout, 3, 3, Cin]
+ * (tap-major, channel-minor).  Cin % 64 == 0; W in {8,16,32,64} or W % 128 == 0.
+ * Output rows are pixels in (b, y, x) order.
+ * replaces: conv_nd(dims=2, ..., 3, padding=1) — model/unet.py:152,178,76-78,
+ * 675-679; model/controlnet.py:137; model/vae.py:74-88,36-38,477-481,523-527. */
+int edtr_conv3x3_bf16(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wt,
+                      int Cout, const EdtrEpilogue* ep, void* stream);
+
+/* Flash-style softmax(Q K^T * scale) V, head dim 64, no mask.
+ * Q [B, Lq, heads*64] (row stride ldq), K/V [B, Lk, heads*64] (strides ldk/ldv),
+ * O [B, Lq, heads*64] (stride ldo); all bf16; head h occupies columns
+ * [64h, 64h+64).  Lk is arbitrary (tail keys are masked).
+ * replaces: F.scaled_dot_product_attention + the head split/merge permutes —
+ * model/attention.py:176-203. */
+int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ldk, const void* V, int ldv,
+                        void* O, int ldo, int B, int heads, int Lq, int Lk, float scale,
+                        void* stream);
+
+/* ---- memory-bound kernels ------------------------------------------------ */
+/* GroupNorm statistics: accumulates per-(image, group) sum and sum of squares of
+ * X (bf16 [B, HW, C], row stride ldx) into stats[B, groups, 2] (fp32, must be
+ * zero on entry).  replaces: first half of GroupNorm32 — model/util.py:161-163,
+ * model/attention.py:50-51, model/vae.py:22-23. */
+int edtr_groupnorm_stats(const void* X, int ldx, int B, int HW, int C, int groups, float* stats,
+                         void* stream);
+/* Y = (X - mean) * rstd * gamma + beta, optionally followed by SiLU; biased
+ * variance, eps inside the sqrt.  Y bf16 [B, HW, C] with row stride ldy.
+ * replaces: GroupNorm32 + nn.SiLU — model/unet.py:149-151,173-175,675-677;
+ * model/vae.py:103-113,553-554 (nonlinearity). */
+int edtr_groupnorm_apply(const void* X, int ldx, void* Y, int ldy, int B, int HW, int C,
+                         int groups, const float* stats, const float* gamma, const float* beta,
+                         float eps, int silu, void* stream);
+/* Row-wise LayerNorm over C (biased variance, eps 1e-5 typical), bf16 in/out.
+ * replaces: nn.LayerNorm — model/attention.py:222-224. */
+int edtr_layernorm_bf16(const void* X, int ldx, void* Y, int ldy, int M, int C,
+                        const float* gamma, const float* beta, float eps, void* stream);
+/* Row softmax of fp32 S[M, N] (stride lds) scaled by `scale`, bf16 output P.
+ * replaces: the softmax inside SDPA for the single-head d=512 VAE attention —
+ * model/vae.py:298. */
+int edtr_softmax_rows(const float* S, int lds, void* P, int ldp, int M, int N, float scale,
+                      void* stream);
+
+/* Y[b, 2y+dy, 2x+dx, :] = X[b, y, x, :]  (nearest, x2), bf16 channels-last.
+ * replaces: F.interpolate(scale_factor=2, mode="nearest") — model/unet.py:76,
+ * model/vae.py:36. */
+int edtr_upsample2x_bf16(const void* X, int ldx, void* Y, int ldy, int B, int H, int W, int C,
+                         void* stream);
+/* Generic im2col for the convolutions the TMA path does not cover (stride 2,
+ * asymmetric padding, odd sizes): Y[(b,oy,ox), (ky,kx,c)] = X[b, oy*s+ky-pt, ox*s+kx-pl, c]
+ * (zero outside).  replaces: the patch gather inside nn.Conv2d(stride=2) —
+ * model/unet.py:99-101, model/vae.py:54-58. */
+int edtr_im2col_bf16(const void* X, int ldx, void* Y, int B, int H, int W, int C, int KH, int KW,
+                     int stride, int pad_top, int pad_left, int Ho, int Wo, void* stream);
+
+/* NCHW fp32 -> channels-last bf16: Y[(b, p), coff + c] = X[b, c, p].
+ * replaces: x.type(self.dtype) + torch.cat((x, hint), 1) — model/controlnet.py:266-269. */
+int edtr_nchw_f32_to_nhwc_bf16(const float* X, void* Y, int ldy, int coff, int B, int C, int HW,
+                               void* stream);
+/* channels-last bf16 -> NCHW (fp32 if out_f32 else bf16): Y[b, c, p] = X[(b,p), c]. */
+int edtr_nhwc_bf16_to_nchw(const void* X, int ldx, void* Y, int B, int C, int HW, int out_f32,
+                           void* stream);
+/* fp32 -> bf16 element cast (n elements). */
+int edtr_cast_f32_to_bf16(const float* X, void* Y, size_t n, void* stream);
+
+/* Sinusoidal timestep embedding [B, dim] = [cos(t f_k) | sin(t f_k)],
+ * f_k = exp(-ln(max_period) k / (dim/2)), computed in fp32, stored bf16.
+ * replaces: timestep_embedding — model/util.py:98-118. */
+int edtr_timestep_embedding(const int64_t* t, void* Y, int B, int dim, float max_period,
+                            void* stream);
+
+/* One spaced-DDPM update for every element of x [n_per_image * B]:
+ *   pred_x0 = sqrt_recip[idx]*x - sqrt_recipm1[idx]*eps
+ *   mean    = coef1[idx]*pred_x0 + coef2[idx]*x
+ *   x_prev  = mean + (idx != 0) * sqrt(var[idx]) * noise
+ * idx is the per-image coefficient index (int64 [B]); tables are fp32 device
+ * arrays.  pred_x0 may be NULL.
+ * replaces: SpacedSampler.p_sample arithmetic — utils/sampler.py:150-164,195-203. */
+int edtr_sampler_update(const float* x, const float* eps, const float* noise,
+                        const int64_t* index, const float* sqrt_recip, const float* sqrt_recipm1,
+                        const float* coef1, const float* coef2, const float* var, float* x_prev,
+                        float* pred_x0, int B, int n_per_image, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDTR_B200_H_ */

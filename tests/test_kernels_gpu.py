@@ -1,0 +1,250 @@
+"""GPU unit tests: every C-ABI kernel against a plain PyTorch fp32 evaluation of the same op
+(inputs rounded to bf16 first, so only accumulation order and the final bf16 store differ)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+def relerr(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, generator=g, device="cuda") * scale).to(BF)
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from edtr_b200 import ops as o
+
+    return o
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (300, 320, 320), (8, 1280, 320),
+                                    (512, 1280, 1280), (1024, 960, 320), (200, 64, 128), (4096, 320, 1280)])
+def test_gemm_plain(ops, M, N, K):
+    a = rnd(M, K, seed=1)
+    w = rnd(N, K, scale=K ** -0.5, seed=2)
+    out = ops.gemm(a, w)
+    ref = a.float() @ w.float().t()
+    assert relerr(out, ref) < 1e-2
+
+
+def test_gemm_epilogue_bias_residual_rowvec_silu(ops):
+    M, N, K = 512, 320, 640
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    res = rnd(M, N, seed=3)
+    rowvec = torch.randn(4, N, device="cuda")
+    out = ops.gemm(a, w, bias=bias, residual=res, rowvec=rowvec, rows_per_group=128)
+    ref = a.float() @ w.float().t() + bias + res.float() + rowvec.repeat_interleave(128, 0)
+    assert relerr(out, ref) < 1e-2
+    out = ops.gemm(a, w, bias=bias, act=ops.ACT_SILU)
+    assert relerr(out, F.silu(a.float() @ w.float().t() + bias)) < 1e-2
+
+
+def test_gemm_strided_views_and_inplace_residual(ops):
+    M, N, K = 256, 320, 320
+    abuf = rnd(M, 960, seed=1)
+    a = abuf[:, 320:640]
+    w = rnd(N, K, scale=K ** -0.5, seed=2)
+    cat = rnd(M, 640, seed=3)
+    before = cat.clone()
+    ops.gemm(a, w, residual=cat[:, 320:], out=cat[:, 320:])
+    ref = a.float() @ w.float().t() + before[:, 320:].float()
+    assert relerr(cat[:, 320:], ref) < 1e-2
+    assert torch.equal(cat[:, :320], before[:, :320])
+
+
+def test_gemm_geglu(ops):
+    from edtr_b200 import lib
+
+    M, C = 384, 320
+    a = rnd(M, C, seed=1)
+    w = rnd(8 * C, C, scale=C ** -0.5, seed=2)
+    bias = torch.randn(8 * C, device="cuda") * 0.1
+    bn = lib.device_lib().edtr_gemm_tile_n(M, 8 * C, C, ops.ACT_GEGLU)
+    half = bn // 2
+    n_half = 4 * C
+    assert n_half % half == 0
+    idx = torch.arange(n_half, device="cuda").view(-1, half)
+    perm = torch.cat([idx, idx + n_half], dim=1).reshape(-1)
+    out = ops.gemm(a, w[perm].contiguous(), bias=bias[perm].contiguous(), act=ops.ACT_GEGLU)
+    y = a.float() @ w.float().t() + bias
+    x, gate = y.chunk(2, dim=-1)
+    assert relerr(out, x * F.gelu(gate)) < 1e-2
+
+
+def test_gemm_out_modes(ops):
+    M, N, K, hw = 512, 4, 320, 256
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    ref = a.float() @ w.float().t() + bias
+    o32 = ops.gemm(a, w, bias=bias, out_mode=ops.OUT_F32)
+    assert relerr(o32, ref) < 1e-3
+    on = ops.gemm(a, w, bias=bias, out_mode=ops.OUT_NCHW_F32, hw=hw)
+    assert relerr(on, ref.view(M // hw, hw, N).permute(0, 2, 1)) < 1e-3
+    w2 = rnd(192, K, scale=K ** -0.5, seed=4)
+    ob = ops.gemm(a, w2, out_mode=ops.OUT_NCHW_BF16, hw=hw)
+    assert relerr(ob, (a.float() @ w2.float().t()).view(M // hw, hw, 192).permute(0, 2, 1)) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 64, 128), (1, 8, 8, 128, 64), (3, 8, 8, 64, 64),
+                                             (2, 16, 16, 320, 320), (1, 32, 32, 640, 320), (1, 128, 128, 64, 64),
+                                             (1, 256, 256, 128, 3), (8, 8, 8, 1280, 1280), (1, 64, 64, 64, 4)])
+def test_conv3x3(ops, B, H, W, Cin, Cout):
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = torch.randn(Cout, device="cuda")
+    emb = torch.randn(B, Cout, device="cuda")
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    if Cout % 8 == 0:
+        res = rnd(B, H, W, Cout, seed=3)
+        out = ops.conv3x3(x, wp, bias=bias, rowvec=emb, residual=res.view(-1, Cout))
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + emb[:, :, None, None]
+        ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout) + res.view(-1, Cout).float()
+        assert relerr(out, ref) < 1e-2
+    else:
+        out = ops.conv3x3(x, wp, bias=bias, out_mode=ops.OUT_NCHW_F32)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
+        assert relerr(out.view(B, Cout, H, W), ref) < 1e-2
+
+
+def test_conv3x3_channel_slice_input(ops):
+    B, H, W = 2, 16, 16
+    buf = rnd(B, H, W, 192, seed=1)
+    x = buf[..., 64:192]
+    w = rnd(64, 128, 3, 3, scale=(9 * 128) ** -0.5, seed=2)
+    wp = w.permute(0, 2, 3, 1).reshape(64, -1).contiguous()
+    out = ops.conv3x3(x, wp)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, 64)
+    assert relerr(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,heads,Lq,Lk", [(2, 5, 256, 256), (1, 2, 4096, 4096), (2, 3, 128, 77), (1, 20, 64, 64),
+                                            (1, 1, 200, 130), (2, 2, 1024, 77)])
+def test_attention(ops, B, heads, Lq, Lk):
+    C = heads * 64
+    qkv = rnd(B, Lq, 3 * C, seed=1)
+    if Lk == Lq:
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    else:
+        q = qkv[..., :C]
+        kv = rnd(B, Lk, 2 * C, seed=2)
+        k, v = kv[..., :C], kv[..., C:]
+    out = ops.attention(q, k, v, heads, 0.125)
+
+    def split(t):
+        return t.float().view(B, -1, heads, 64).permute(0, 2, 1, 3)
+
+    ref = F.scaled_dot_product_attention(split(q), split(k), split(v)).permute(0, 2, 1, 3).reshape(B, Lq, C)
+    assert relerr(out, ref) < 2e-2
+
+
+@pytest.mark.parametrize("B,HW,C,silu,eps", [(2, 4096, 320, True, 1e-5), (2, 64, 2560, True, 1e-5),
+                                              (1, 1024, 1920, False, 1e-6), (3, 256, 960, True, 1e-5),
+                                              (1, 65536, 128, True, 1e-6), (2, 4096, 512, True, 1e-6)])
+def test_groupnorm(ops, B, HW, C, silu, eps):
+    x = (rnd(B, HW, C, seed=1).float() * 1.5 + 0.7).to(BF)
+    gamma = torch.randn(C, device="cuda")
+    beta = torch.randn(C, device="cuda")
+    out = ops.groupnorm(x, gamma, beta, 32, eps, silu)
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    assert relerr(out, ref.permute(0, 2, 1)) < 1e-2
+
+
+def test_groupnorm_on_channel_slice(ops):
+    B, HW = 2, 256
+    buf = rnd(B, HW, 640, seed=1)
+    x = buf[..., :320]
+    gamma, beta = torch.randn(320, device="cuda"), torch.randn(320, device="cuda")
+    out = ops.groupnorm(x, gamma, beta, 32, 1e-5, False)
+    ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1)
+    assert relerr(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,C", [(1000, 320), (512, 640), (300, 1280)])
+def test_layernorm(ops, M, C):
+    x = (rnd(M, C, seed=1).float() * 2 + 0.3).to(BF)
+    gamma, beta = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    out = ops.layernorm(x, gamma, beta, 1e-5)
+    assert relerr(out, F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)) < 1e-2
+
+
+def test_softmax_rows(ops):
+    s = torch.randn(300, 4096, device="cuda") * 20
+    out = ops.softmax_rows(s, 0.044)
+    assert relerr(out, torch.softmax(s * 0.044, -1)) < 1e-2
+
+
+def test_upsample_im2col_layout(ops):
+    x = rnd(2, 8, 16, 64, seed=1)
+    up = ops.upsample2x(x)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    # stride-2 pad-1 3x3 gather == unfold
+    col = ops.im2col(x, 3, 3, 2, 1, 1, 4, 8)
+    unf = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)  # [B, C*9, L]
+    unf = unf.view(2, 64, 9, -1).permute(0, 3, 2, 1).reshape(2 * 32, 9 * 64)
+    assert torch.equal(col.float(), unf)
+    # asymmetric pad (0,1,0,1), stride 2, no top/left pad (VAE encoder downsample)
+    col = ops.im2col(x, 3, 3, 2, 0, 0, 4, 8)
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    unf = F.unfold(xp, 3, stride=2).view(2, 64, 9, -1).permute(0, 3, 2, 1).reshape(2 * 32, 9 * 64)
+    assert torch.equal(col.float(), unf)
+    # NCHW fp32 -> channels-last bf16 at a channel offset, and back
+    src = torch.randn(2, 4, 8, 8, device="cuda")
+    dst = torch.zeros(2, 8, 8, 64, dtype=BF, device="cuda")
+    ops.nchw_to_nhwc(src, dst, coff=4)
+    assert torch.equal(dst[..., 4:8].float(), src.to(BF).float().permute(0, 2, 3, 1))
+    assert dst[..., :4].abs().max() == 0 and dst[..., 8:].abs().max() == 0
+    back = ops.nhwc_to_nchw(dst.view(-1, 64)[:, 4:8], 2)
+    assert torch.equal(back.view(2, 4, 8, 8), src.to(BF).float())
+    t16 = ops.nhwc_to_nchw(x.view(2, 128, 64), 2, out_f32=False)
+    assert torch.equal(t16, x.view(2, 128, 64).permute(0, 2, 1))
+    assert torch.equal(ops.cast_bf16(src), src.to(BF))
+
+
+def test_timestep_embedding(ops):
+    t = torch.tensor([200, 150, 100, 50, 0, 999], device="cuda")
+    out = ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device="cuda") / half)
+    args = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert (out.float() - ref).abs().max() < 1e-2
+
+
+def test_sampler_update(ops):
+    B = 3
+    x, eps, noise = (torch.randn(B, 4, 64, 64, device="cuda") for _ in range(3))
+    idx = torch.tensor([3, 0, 1], device="cuda")
+    tabs = [torch.rand(4, device="cuda") + 0.1 for _ in range(5)]
+    xp, x0 = ops.sampler_update(x, eps, noise, idx, tabs)
+    e = lambda t: t[idx].view(B, 1, 1, 1)
+    rx0 = e(tabs[0]) * x - e(tabs[1]) * eps
+    mean = e(tabs[2]) * rx0 + e(tabs[3]) * x
+    ref = mean + (idx != 0).float().view(B, 1, 1, 1) * torch.sqrt(e(tabs[4])) * noise
+    assert torch.allclose(x0, rx0, atol=1e-6) and torch.allclose(xp, ref, atol=1e-6)
+
+
+def test_validation_errors(ops):
+    a = rnd(128, 100, seed=1)
+    w = rnd(64, 100, seed=2)
+    with pytest.raises(ValueError):
+        ops.gemm(a, w)  # K not a multiple of 64
+    with pytest.raises(ValueError):
+        ops.gemm(rnd(128, 64).float(), rnd(64, 64))
+    with pytest.raises(RuntimeError):
+        ops.gemm(torch.zeros(128, 64, dtype=BF), torch.zeros(64, 64, dtype=BF))
