@@ -1,0 +1,156 @@
+"""Generates the golden fixtures in this directory by running the UNMODIFIED reference.
+
+Run in the build container only (needs /root/reference):
+    python tests/golden/make_golden.py [--full]
+
+The reference (JaehaKim97/EDTR) is imported from its tree with three import stubs for
+packages missing here (omegaconf / ftfy / timm — none is on the hot path).
+The synthetic weights of ``oracle.cldm_oracle`` are loaded into the reference modules with
+``load_state_dict`` (strict for UNet / ControlNet, which also pins the oracle's key/shape
+enumeration), then the reference's own public API is executed on CPU in fp32:
+``SpacedSampler.manual_sample_with_timesteps`` -> ``ControlLDM.forward`` and
+``ControlLDM.vae_decode``.  ``torch.randn_like`` is patched during the sampler call so the
+four per-step noise draws are the seeded tensors the oracle receives explicitly.
+
+Outputs:  golden_tiny.npz  (TINY config, B=2, 16x16 latent; everything in fp32)
+          golden_s4.npz    (s4 config, B=1, 64x64 latent; --full; image stored as fp16)
+"""
+import argparse
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("EDTR_REFERENCE", "/root/reference")
+sys.path.insert(0, ROOT)
+sys.path.insert(0, REF)
+
+
+def _stub_missing_packages():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    try:
+        import omegaconf  # noqa: F401
+    except ImportError:
+        mod("omegaconf")
+        mod("omegaconf.listconfig", ListConfig=type("ListConfig", (list,), {}))
+    try:
+        import ftfy  # noqa: F401
+    except ImportError:
+        mod("ftfy", fix_text=lambda s: s)
+    try:
+        import timm  # noqa: F401
+    except ImportError:
+        import torch.nn as nn
+
+        mod("timm")
+        mod("timm.models")
+        mod("timm.models.layers", DropPath=nn.Identity, to_2tuple=lambda x: (x, x),
+            trunc_normal_=lambda t, std=1.0, **kw: torch.nn.init.trunc_normal_(t, std=std))
+
+
+def build_reference(cfg, weights):
+    """ControlLDM shell without CLIP (its ctor would build a 1 GB text tower unrelated to the path)."""
+    _stub_missing_packages()
+    from model.cldm import ControlLDM
+    from model.controlnet import ControlledUnetModel, ControlNet
+    from model.vae import AutoencoderKL
+
+    def common(c):
+        return dict(image_size=32, in_channels=c["in_channels"], model_channels=c["model_channels"],
+                    attention_resolutions=list(c["attention_resolutions"]), num_res_blocks=c["num_res_blocks"],
+                    channel_mult=list(c["channel_mult"]), num_head_channels=c["num_head_channels"],
+                    use_spatial_transformer=True, use_linear_in_transformer=True, transformer_depth=1,
+                    context_dim=c["context_dim"], legacy=False, use_checkpoint=True)
+
+    m = ControlLDM.__new__(ControlLDM)
+    torch.nn.Module.__init__(m)
+    m.unet = ControlledUnetModel(out_channels=cfg["unet"]["out_channels"], **common(cfg["unet"]))
+    m.controlnet = ControlNet(hint_channels=cfg["controlnet"]["hint_channels"], **common(cfg["controlnet"]))
+    v = cfg["vae"]
+    m.vae = AutoencoderKL(ddconfig=dict(double_z=True, z_channels=v["z_channels"], resolution=256,
+                                        in_channels=v["in_channels"], out_ch=v["out_ch"], ch=v["ch"],
+                                        ch_mult=list(v["ch_mult"]), num_res_blocks=v["num_res_blocks"],
+                                        attn_resolutions=[], dropout=0.0), embed_dim=v["embed_dim"])
+    m.scale_factor = cfg["latent_scale_factor"]
+    m.control_scales = [1.0] * (len(m.controlnet.zero_convs) + 1)
+    m.unet.load_state_dict(weights["unet"], strict=True)
+    m.controlnet.load_state_dict(weights["controlnet"], strict=True)
+    res = m.vae.load_state_dict(weights["vae"], strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith(("encoder.", "quant_conv.")) for k in res.missing_keys), res.missing_keys
+    return m.eval()
+
+
+def run_reference(cfg, batch, latent_hw):
+    from oracle import cldm_oracle as O
+
+    weights = O.make_cldm_weights(cfg, seed=0)
+    x_T, cond, noise = O.make_inputs(cfg, batch, latent_hw, seed=1)
+    model = build_reference(cfg, weights)
+    from utils.sampler import SpacedSampler
+
+    sampler = SpacedSampler(O.make_betas(**cfg["diffusion"]))
+    used = list(cfg["used_timesteps"])
+    draws = list(noise)
+    real_randn_like = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: draws.pop(0)
+    try:
+        with torch.no_grad():
+            # per-step x_prev through the public p_sample, exactly as the loop of
+            # manual_sample_with_timesteps does (utils/sampler.py:304-314)
+            sampler.make_schedule(len(used), used)
+            ts = np.flip(sampler.timesteps)
+            x = x_T
+            xs, x0s, eps0 = [], [], None
+            for i, step in enumerate(ts):
+                t = torch.full((batch,), int(step), dtype=torch.long)
+                index = torch.full_like(t, len(ts) - i - 1)
+                if i == 0:
+                    eps0 = model(x, t, cond)
+                x, x0 = sampler.p_sample(model, x, t, index, cond, None, 1.0)
+                xs.append(x)
+                x0s.append(x0)
+            # and the whole public loop once more, to pin the loop itself
+            draws[:] = list(noise)
+            z = sampler.manual_sample_with_timesteps(model, "cpu", x_T, len(used), used, batch, cond, None, 1.0,
+                                                     progress=False)
+            assert torch.equal(z, xs[-1])
+            img = model.vae_decode(z)
+    finally:
+        torch.randn_like = real_randn_like
+    sched = {k: getattr(sampler, k).numpy() for k in
+             ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+              "posterior_mean_coef1", "posterior_mean_coef2")}
+    return dict(eps0=eps0, xs=torch.stack(xs), x0s=torch.stack(x0s), img=img, sched=sched)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--full", action="store_true", help="also generate the s4 (full-size) fixture; ~2 min")
+    args = ap.parse_args()
+    from oracle import cldm_oracle as O
+
+    torch.set_num_threads(os.cpu_count())
+    r = run_reference(O.TINY, batch=2, latent_hw=16)
+    np.savez_compressed(os.path.join(HERE, "golden_tiny.npz"), eps0=r["eps0"].numpy(), xs=r["xs"].numpy(),
+                        x0s=r["x0s"].numpy(), img=r["img"].numpy(), **{"sched_" + k: v for k, v in r["sched"].items()})
+    print("tiny:", {k: tuple(v.shape) for k, v in r.items() if hasattr(v, "shape")})
+    if args.full:
+        r = run_reference(O.S4, batch=1, latent_hw=64)
+        np.savez_compressed(os.path.join(HERE, "golden_s4.npz"), eps0=r["eps0"].numpy(), xs=r["xs"].numpy(),
+                            x0s=r["x0s"].numpy(), img=r["img"].numpy().astype(np.float16),
+                            **{"sched_" + k: v for k, v in r["sched"].items()})
+        print("s4:", {k: tuple(v.shape) for k, v in r.items() if hasattr(v, "shape")})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,68 @@
+"""CPU tests: the oracle restatement against fixtures recorded from the live reference
+(tests/golden/make_golden.py), plus the host-side schedule arithmetic."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cldm_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    w = O.make_cldm_weights(O.TINY, seed=0)
+    x_T, cond, noise = O.make_inputs(O.TINY, 2, 16, seed=1)
+    return w, x_T, cond, noise, np.load(os.path.join(GOLD, "golden_tiny.npz"))
+
+
+def test_oracle_matches_reference_tiny(tiny):
+    w, x_T, cond, noise, g = tiny
+    with torch.no_grad():
+        t = torch.full((2,), 200, dtype=torch.long)
+        eps0 = O.cldm_forward(w, O.TINY, x_T, t, cond)
+        z, xs, x0s = O.sample(w, O.TINY, x_T, cond, noise)
+        img = O.vae_decode(w["vae"], O.TINY["vae"], z, O.TINY["latent_scale_factor"])
+    assert np.abs(g["eps0"]).max() > 0.05  # the fixture is not the all-zero trap of zero_module
+    assert O.max_rel_err(eps0, torch.from_numpy(g["eps0"])) < 1e-5
+    for i in range(4):
+        assert O.max_rel_err(xs[i], torch.from_numpy(g["xs"][i])) < 1e-5
+        assert O.max_rel_err(x0s[i], torch.from_numpy(g["x0s"][i])) < 1e-5
+    assert O.max_rel_err(img, torch.from_numpy(g["img"])) < 1e-5
+
+
+def test_schedule_matches_reference(tiny):
+    g = tiny[-1]
+    s = O.make_schedule(O.make_betas(**O.TINY["diffusion"]), 4, O.TINY["used_timesteps"])
+    for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_variance",
+              "posterior_mean_coef1", "posterior_mean_coef2"):
+        assert np.array_equal(s[k], g["sched_" + k]), k
+    assert list(s["timesteps"]) == [50, 100, 150, 200]
+    # SURVEY.md §3.2 measured values
+    assert np.allclose(s["posterior_mean_coef1"], [1.0, 0.5558, 0.4079, 0.3307], atol=1e-4)
+    assert np.allclose(s["posterior_variance"], [0, 0.02759, 0.04562, 0.06259], atol=1e-5)
+
+
+def test_space_timesteps():
+    assert O.space_timesteps(1000, "4") == {0, 333, 666, 999}
+    assert O.space_timesteps(300, [10, 15, 20]) is not None
+    assert len(O.space_timesteps(1000, "ddim50")) == 50
+    with pytest.raises(ValueError):
+        O.space_timesteps(10, "20")
+
+
+def test_param_enumeration_counts():
+    n = lambda shapes: sum(int(np.prod(s)) for _, s in shapes)
+    # SURVEY.md / BASELINE.md §2: UNet 865.9 M, ControlNet 363.2 M, VAE decoder 49.5 M parameters
+    assert abs(n(O.unet_param_shapes(O.S4["unet"])) / 1e6 - 865.9) < 0.1
+    assert abs(n(O.unet_param_shapes(O.S4["controlnet"], True)) / 1e6 - 363.2) < 0.5
+    assert abs(n(O.vae_decoder_param_shapes(O.S4["vae"])) / 1e6 - 49.5) < 0.1
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLD, "golden_s4.npz")), reason="full-size fixture absent")
+def test_s4_fixture_is_sane():
+    g = np.load(os.path.join(GOLD, "golden_s4.npz"))
+    assert g["xs"].shape == (4, 1, 4, 64, 64) and g["img"].shape == (1, 3, 512, 512)
+    assert np.isfinite(g["xs"]).all() and np.abs(g["eps0"]).max() > 0.05
