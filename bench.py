@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the EDTR ControlLDM restore path (BASELINE.json metric: 512x512 restored images/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+One *step* = the restoration of one batch of synthetic 512x512 images: 4-step spaced-DDPM sampling of the
+ControlLDM (ControlNet + SD-2.1 UNet per step, timesteps [200,150,100,50]) on 64x64x4 latents, then the VAE
+decode to [B,3,512,512] — BASELINE.json configs[1] (batch 8 per GPU, bf16 tensor-core math, random-init
+weights of the s4 architecture, seeded synthetic inputs).  With N GPUs every rank restores its own batch
+(image-parallel, no per-step collective) and the restored images are all-gathered over NCCL at the end of
+each step (configs[2]); time is the max over ranks.
+
+Reported on ONE JSON line: `value` (inputs resident in HBM, graph replay), `e2e` (through the drop-in public
+API with pinned-host inputs copied H2D and the restored images read back D2H inside the timed region),
+`roofline` (tensor-core kernels vs the measured bf16 peak), `cpu_baseline` (the oracle port of the reference
+on the host cores, bounded sample), `clocks`, `gpu_launches`.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "512x512 restored images/sec (4-step ControlLDM + VAE decode)"
+UNIT = "images/s"
+GF_PER_IMAGE = 6808.0          # 4 x 1073.38 (ControlNet+UNet step) + 2514.52 (VAE decode)
+GF_GEMM_PER_IMAGE = 4 * (530.4 + 366.5) + 2514.52  # conv + linear per step, x4, + VAE decode (its attention runs as GEMMs)
+GF_ATTN_PER_IMAGE = 4 * 176.5
+
+S4_NET = dict(image_size=32, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
+              num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_head_channels=64, use_spatial_transformer=True,
+              use_linear_in_transformer=True, transformer_depth=1, context_dim=1024, legacy=False,
+              use_checkpoint=True)
+S4_VAE = dict(embed_dim=4, ddconfig=dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                                         ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0))
+USED_TIMESTEPS = [50, 100, 150, 200]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tf_sustained=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], hbm=d["hbm_gbs"], source="measured")
+    return dict(tf_sustained=1400.0, tf_burst=1590.0, hbm=6650.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                    power_w_max=max(power) if power else None)
+
+
+# --------------------------------------------------------------------------- reference arm / CPU baseline
+def cpu_restore_once(O, w, cfg, seed):
+    import torch
+
+    x_T, cond, noise = O.make_inputs(cfg, 1, 64, seed=seed)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        img, _ = O.restore(w, cfg, x_T, cond, noise)
+    return time.perf_counter() - t0, img
+
+
+def run_reference(args):
+    """The reference's algorithm (oracle port, fp32, PyTorch CPU ops exactly as the reference issues them) on all
+    host cores; one step = one 512x512 image restored (B=1, BASELINE configs[0])."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from oracle import cldm_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.S4
+    w = O.make_cldm_weights(cfg, seed=0)
+    budget = float(os.environ.get("EDTR_REF_BUDGET_S", "240"))
+    t_start = time.perf_counter()
+    for i in range(args.warmup):
+        cpu_restore_once(O, w, cfg, 100 + i)
+        if time.perf_counter() - t_start > budget / 3:
+            break
+    times = []
+    for i in range(args.steps):
+        dt, _ = cpu_restore_once(O, w, cfg, 1 + i)
+        times.append(dt)
+        if time.perf_counter() - t_start > budget:
+            break
+    total = sum(times)
+    val = len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "4-step ControlLDM (s4) restore + VAE decode of 512x512 images, batch 1 per step, "
+                               "random-init weights, fp32 on host CPU", "steps_requested": args.steps},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} x (1 image: 4 ControlLDM steps + VAE decode), oracle/cldm_oracle.py "
+                                   f"with torch CPU ops on {cores} threads"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample():
+    """Bounded sample for the `cpu_baseline` object of our own line: one image, 4 steps + decode."""
+    import torch
+
+    from oracle import cldm_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = O.make_cldm_weights(O.S4, seed=0)
+    dt, _ = cpu_restore_once(O, w, O.S4, 1)
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 image (4 ControlLDM steps + VAE decode, fp32) in {dt:.1f} s, oracle/cldm_oracle.py on "
+                      f"{cores} torch CPU threads, no warm-up"}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def build_model(device):
+    """Random-init weights of the s4 architecture through the drop-in classes (zero modules re-randomised)."""
+    import torch
+
+    from edtr_b200.cldm import ControlLDM
+
+    torch.manual_seed(0)
+    cn = dict(S4_NET)
+    cn.pop("out_channels")
+    cn["hint_channels"] = 4
+    model = ControlLDM(S4_NET, S4_VAE, None, cn, 0.18215)
+    g = torch.Generator().manual_seed(123)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2 and float(p.abs().max()) == 0.0:
+                fan = p[0].numel()
+                p.uniform_(-fan ** -0.5, fan ** -0.5, generator=g)
+    return model.to(device).eval()
+
+
+class TensorCoreTimer:
+    """Brackets every tensor-core launch (gemm / conv3x3 / attention) of one eager pass with CUDA events on the
+    launching stream; used after the timed region to attribute time to the dominant kernel family."""
+
+    def __init__(self, ops):
+        import torch
+
+        self.ops, self.torch = ops, torch
+        self.events = {"gemm": [], "conv3x3": [], "attention": []}
+        self.orig = {}
+
+    def __enter__(self):
+        for name in self.events:
+            fn = getattr(self.ops, name)
+            self.orig[name] = fn
+
+            def wrapped(*a, _fn=fn, _name=name, **k):
+                s, e = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+                s.record()
+                r = _fn(*a, **k)
+                e.record()
+                self.events[_name].append((s, e))
+                return r
+
+            setattr(self.ops, name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        for name, fn in self.orig.items():
+            setattr(self.ops, name, fn)
+
+    def totals(self):
+        self.torch.cuda.synchronize()
+        return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in self.events.items()}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: edtr_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from edtr_b200 import lib as elib
+    from edtr_b200 import ops
+    from edtr_b200.sampler import SpacedSampler
+
+    B = args.batch
+    model = build_model(dev)
+    eng = model.engine()
+    vae_eng = model.vae._decoder_engine()
+    betas = (torch.linspace(0.00085 ** 0.5, 0.0120 ** 0.5, 1000, dtype=torch.float64) ** 2).numpy()
+    sampler = SpacedSampler(betas)
+    sampler.make_schedule(4, USED_TIMESTEPS)
+    sampler.to(dev)
+
+    # synthetic inputs: pinned host copies (for e2e) and device-resident copies (for `value`)
+    g = torch.Generator().manual_seed(1 + rank)
+    c_img_h = (0.8 * torch.randn(B, 4, 64, 64, generator=g)).pin_memory()
+    c_txt_h = torch.randn(B, 77, 1024, generator=g).pin_memory()
+    x_T_h = (0.9 * c_img_h + 0.45 * torch.randn(B, 4, 64, 64, generator=g)).pin_memory()
+    img_h = torch.empty(B, 3, 512, 512, dtype=torch.float32).pin_memory()
+    c_img, c_txt, x_T = c_img_h.to(dev), c_txt_h.to(dev), x_T_h.to(dev)
+    tables = {k: getattr(sampler, k) for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                                               "posterior_mean_coef1", "posterior_mean_coef2", "posterior_variance")}
+    ts = [200, 150, 100, 50]
+    gather = [torch.empty(B, 3, 512, 512, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_resident():
+        noise = [torch.randn_like(x_T) for _ in range(4)]
+        z = eng.sample(x_T, ts, tables, c_img, c_txt, noise, control_scales=model.control_scales)
+        img = vae_eng.decode(z, model.scale_factor)
+        if gather is not None:
+            dist.all_gather(gather, img)
+        return img
+
+    def step_e2e():
+        cond = {"c_txt": c_txt_h.to(dev, non_blocking=True), "c_img": c_img_h.to(dev, non_blocking=True)}
+        x = x_T_h.to(dev, non_blocking=True)
+        z = sampler.manual_sample_with_timesteps(model, dev, x, 4, USED_TIMESTEPS, B, cond, None, 1.0, progress=False)
+        img = model.vae_decode(z)
+        if gather is not None:
+            dist.all_gather(gather, img)
+        img_h.copy_(img, non_blocking=True)
+        return img
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        clk = ClockSampler(local) if sample_clocks else None
+        if clk:
+            clk.start()
+        n0 = elib.LAUNCHES[0]
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sample_clocks and os.environ.get("EDTR_NCU"):
+            torch.cuda.profiler.start()  # ncu --profile-from-start off: profile exactly the timed steps
+        s.record()
+        for _ in range(steps):
+            fn()
+        e.record()
+        barrier()
+        if sample_clocks and os.environ.get("EDTR_NCU"):
+            torch.cuda.profiler.stop()
+        clocks = clk.stop() if clk else None
+        ms = s.elapsed_time(e)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, elib.LAUNCHES[0] - n0, clocks
+
+    W = max(args.warmup, 3)
+    ms, launches, clocks = timed(step_resident, args.steps, W, sample_clocks=True)
+    value = world * B * args.steps / (ms / 1e3)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, W)
+    e2e = world * B * args.steps / (ms_e2e / 1e3)
+
+    # secondary metric of BASELINE.json: one ControlLDM evaluation (ControlNet + UNet) at batch B
+    t200 = torch.full((B,), 200, dtype=torch.long, device=dev)
+    ms_fwd, _, _ = timed(lambda: eng.forward(x_T, t200, c_img, c_txt), 5, 3)
+    unet_step_ms = ms_fwd / 5
+
+    # dominant kernel family, measured live: one eager (non-graph) restore with every tensor-core launch bracketed
+    pk = peaks()
+    with TensorCoreTimer(ops) as tc:
+        noise = [torch.randn_like(x_T) for _ in range(4)]
+        z = eng.sample(x_T, ts, tables, c_img, c_txt, noise, use_graph=False)
+        vae_eng.decode(z, model.scale_factor, use_graph=False)
+    tot = tc.totals()
+    gemm_ms = tot["gemm"][1] + tot["conv3x3"][1]
+    gemm_n = tot["gemm"][0] + tot["conv3x3"][0]
+    achieved = GF_GEMM_PER_IMAGE * B / gemm_ms  # GF / ms = TFLOP/s
+    roofline = {
+        "bound": "tensor", "kernel": "edtr::gemm_conv_kernel (tcgen05 implicit-GEMM: all conv3x3 / 1x1 / Linear launches)",
+        "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
+        "traffic": None, "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
+        "launches_per_step": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
+        "algorithmic_gflop_per_step": GF_GEMM_PER_IMAGE * B,
+        "attention": {"launches_per_step": tot["attention"][0], "ms_per_step": tot["attention"][1],
+                      "achieved": GF_ATTN_PER_IMAGE * B / max(tot["attention"][1], 1e-9)},
+        "whole_step": {"achieved": value / world * GF_PER_IMAGE / 1e3, "frac": value / world * GF_PER_IMAGE / 1e3 / pk["tf_sustained"]},
+    }
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_baseline_sample()
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"4-step ControlLDM (SD-2.1 UNet + ControlNet, s4) + VAE decode, batch {B} per GPU, "
+                                   f"512x512 (64x64x4 latent), random-init weights", "batch_per_gpu": B,
+                       "global_batch": B * world, "parallelism": f"image-parallel x{world}",
+                       "l2": "per-step working set (2.5 GB weights + activations) exceeds the 126 MB L2; no flush needed",
+                       "unet_step_ms": None},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(c_img_h.numel() * 4 + c_txt_h.numel() * 4 + x_T_h.numel() * 4),
+                    "d2h_bytes_per_step": int(img_h.numel() * 4),
+                    "api": "edtr_b200.SpacedSampler.manual_sample_with_timesteps + ControlLDM.vae_decode"},
+            "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        line["config"]["unet_step_ms"] = unet_step_ms
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

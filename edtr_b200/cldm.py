@@ -1,0 +1,142 @@
+"""Drop-in ``ControlLDM`` (model/cldm.py:17-194): same constructor, attributes, weight loaders and
+call signatures; ``forward`` / ``vae_decode`` execute on the sm_100a kernels through ``engine.py``.
+
+Select it from a reference config by changing ``target: model.cldm.ControlLDM`` to
+``target: edtr_b200.cldm.ControlLDM`` (the reference instantiates models by dotted path,
+utils/common.py:23-34), or build it from an existing reference instance with
+``ControlLDM.from_reference(ref_model)``.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Set, Tuple
+
+import torch
+from torch import nn
+
+from .nets import AutoencoderKL, ControlledUnetModel, ControlNet, state_version
+
+
+def disabled_train(self: nn.Module) -> nn.Module:
+    return self
+
+
+class ControlLDM(nn.Module):
+
+    def __init__(self, unet_cfg, vae_cfg, clip_cfg, controlnet_cfg, latent_scale_factor, tail_block=False,
+                 clip: Optional[nn.Module] = None):
+        super().__init__()
+        if tail_block:
+            raise NotImplementedError("tail_block / woSD is not used by any EDTR config or script (SURVEY §8 a4)")
+        self.unet = ControlledUnetModel(**unet_cfg)
+        self.vae = AutoencoderKL(**vae_cfg)
+        # The OpenCLIP text tower produces an INPUT of the path (c_txt for the constant "" prompt,
+        # model/clip.py:41-63); it is not re-implemented here.  Pass a ready embedder (e.g. the
+        # reference's FrozenOpenCLIPEmbedder) as `clip`, or supply cond["c_txt"] directly.
+        self.clip = clip
+        self.clip_cfg = clip_cfg
+        self.controlnet = ControlNet(**controlnet_cfg)
+        self.scale_factor = latent_scale_factor
+        self.control_scales = [1.0] * 13
+        self._engine = None
+        self._engine_version = None
+
+    # ----------------------------------------------------------------- construction helpers
+    @classmethod
+    def from_reference(cls, ref: nn.Module, unet_cfg: Dict, vae_cfg: Dict, controlnet_cfg: Dict) -> "ControlLDM":
+        """Adopt the weights (and CLIP embedder) of a reference ``model.cldm.ControlLDM`` instance."""
+        m = cls(unet_cfg, vae_cfg, None, controlnet_cfg, ref.scale_factor, clip=getattr(ref, "clip", None))
+        m.unet.load_state_dict(ref.unet.state_dict(), strict=True)
+        m.controlnet.load_state_dict(ref.controlnet.state_dict(), strict=True)
+        m.vae.load_state_dict(ref.vae.state_dict(), strict=True)
+        m.control_scales = list(ref.control_scales)
+        return m
+
+    # ----------------------------------------------------------------- reference weight loaders
+    @torch.no_grad()
+    def load_pretrained_sd(self, sd: Dict[str, torch.Tensor], is_turbo: bool = False) -> Set[str]:
+        """model/cldm.py:46-77: SD-2.1 checkpoint keys -> unet / vae (/ clip when an embedder is attached)."""
+        module_map = {"unet": "model.diffusion_model", "vae": "first_stage_model",
+                      "clip": "conditioner.embedders.0" if is_turbo else "cond_stage_model"}
+        modules = [("unet", self.unet), ("vae", self.vae)]
+        if self.clip is not None:
+            modules.append(("clip", self.clip))
+        used = set()
+        for name, module in modules:
+            init_sd = {}
+            for key in module.state_dict():
+                target_key = ".".join([module_map[name], key])
+                init_sd[key] = sd[target_key].clone()
+                used.add(target_key)
+            module.load_state_dict(init_sd, strict=True)
+        for module in [m for m in (self.clip, self.unet) if m is not None]:
+            module.eval()
+            module.train = disabled_train
+            for p in module.parameters():
+                p.requires_grad = False
+        return set(sd.keys()) - used
+
+    @torch.no_grad()
+    def load_controlnet_from_ckpt(self, sd: Dict[str, torch.Tensor]) -> None:
+        self.controlnet.load_state_dict(sd, strict=True)
+
+    @torch.no_grad()
+    def load_controlnet_from_unet(self) -> Tuple[Set[str], Set[str]]:
+        """model/cldm.py:83-105: copy the UNet encoder into the ControlNet, zero-padding the first conv."""
+        unet_sd = self.unet.state_dict()
+        scratch_sd = self.controlnet.state_dict()
+        init_sd, with_new_zero, with_scratch = {}, set(), set()
+        for key, this in scratch_sd.items():
+            if key in unet_sd:
+                target = unet_sd[key]
+                if this.size() == target.size():
+                    init_sd[key] = target.clone()
+                else:
+                    oc, _, h, w = this.size()
+                    pad = torch.zeros((oc, this.size(1) - target.size(1), h, w), dtype=target.dtype,
+                                      device=target.device)
+                    init_sd[key] = torch.cat((target, pad), dim=1)
+                    with_new_zero.add(key)
+            else:
+                init_sd[key] = this.clone()
+                with_scratch.add(key)
+        self.controlnet.load_state_dict(init_sd, strict=True)
+        return with_new_zero, with_scratch
+
+    # ----------------------------------------------------------------- engine plumbing
+    def engine(self):
+        from .engine import CldmEngine
+
+        dev = next(self.unet.parameters()).device
+        ver = (state_version(self.unet), state_version(self.controlnet), dev)
+        if self._engine is None or self._engine_version != ver:
+            if dev.type != "cuda":
+                raise RuntimeError("edtr_b200 has no CPU path: move the model to a CUDA device first")
+            self._engine = CldmEngine(self.unet.cfg, self.controlnet.cfg, self.unet.state_dict(),
+                                      self.controlnet.state_dict(), dev)
+            self._engine_version = ver
+        return self._engine
+
+    # ----------------------------------------------------------------- reference API
+    def vae_encode(self, image, sample=True, tiled=False, tile_size=-1):
+        raise NotImplementedError("vae_encode precedes the accelerated path (SURVEY §8f rank 1); run the "
+                                  "reference encoder and pass c_img")
+
+    @torch.no_grad()
+    def vae_decode(self, z: torch.Tensor, tiled: bool = False, tile_size: int = -1) -> torch.Tensor:
+        """model/cldm.py:136-156 (untiled).  Returns fp32 NCHW in [-1, 1]."""
+        if tiled:
+            raise NotImplementedError("tiled VAE decode (VAEHook) is not implemented in this round")
+        return self.vae._decoder_engine().decode(z.float().contiguous(), float(self.scale_factor))
+
+    def prepare_condition(self, clean: torch.Tensor, prompt: List[str]) -> Dict[str, torch.Tensor]:
+        raise NotImplementedError("prepare_condition = CLIP text tower + VAE encoder, both inputs of the path")
+
+    @torch.no_grad()
+    def forward(self, x_noisy, t, cond, woSD=False):
+        """model/cldm.py:166-194."""
+        if woSD:
+            raise NotImplementedError("woSD=True (tail_block) is not on the EDTR path")
+        c_txt, c_img = cond["c_txt"], cond["c_img"]
+        eps = self.engine().forward(x_noisy.float().contiguous(), t.long().contiguous(), c_img.float().contiguous(),
+                                    c_txt.float().contiguous(), control_scales=self.control_scales)
+        return eps.to(x_noisy.dtype)

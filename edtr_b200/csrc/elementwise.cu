@@ -17,6 +17,25 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ X, __nv_bfloat16* 
   for (int c = 0; c < C; ++c) y[c] = __float2bfloat16(__ldg(x + static_cast<size_t>(c) * HW));
 }
 
+// Y[(b,p), coff+co] = bias[co] + sum_ci W[co,ci] * (scale * X[b,ci,p]); tiny channel counts, fp32 math.
+__global__ void pointwise_nchw_kernel(const float* __restrict__ X, const float* __restrict__ Wm,
+                                      const float* __restrict__ bias, float scale,
+                                      __nv_bfloat16* __restrict__ Y, int ldy, int coff, int Cin, int Cout, int HW,
+                                      size_t total_pix) {
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total_pix) return;
+  const size_t b = i / HW, pix = i - b * HW;
+  const float* x = X + b * Cin * HW + pix;
+  float xin[16];
+  for (int c = 0; c < Cin; ++c) xin[c] = scale * __ldg(x + static_cast<size_t>(c) * HW);
+  __nv_bfloat16* y = Y + i * ldy + coff;
+  for (int co = 0; co < Cout; ++co) {
+    float acc = bias != nullptr ? __ldg(bias + co) : 0.f;
+    for (int c = 0; c < Cin; ++c) acc += __ldg(Wm + co * Cin + c) * xin[c];
+    y[co] = __float2bfloat16(acc);
+  }
+}
+
 // Tiled transpose [B, HW, C] (bf16, stride ldx) -> [B, C, HW] (fp32 or bf16).
 template <typename OutT>
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ X, int ldx, OutT* __restrict__ Y, int C,
@@ -131,6 +150,18 @@ extern "C" int edtr_nchw_f32_to_nhwc_bf16(const float* X, void* Y, int ldy, int 
   nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       X, reinterpret_cast<__nv_bfloat16*>(Y), ldy, coff, C, HW, total);
   return check_launch("nchw_to_nhwc_kernel");
+}
+
+extern "C" int edtr_pointwise_nchw_f32_to_nhwc_bf16(const float* X, const float* Wm, const float* bias, float scale,
+                                                    void* Y, int ldy, int coff, int B, int Cin, int Cout, int HW,
+                                                    void* stream) {
+  EDTR_REQUIRE(X && Wm && Y && B > 0 && HW > 0 && coff >= 0, "bad pointwise-conv arguments");
+  EDTR_REQUIRE(Cin > 0 && Cin <= 16 && Cout > 0 && Cout <= 16, "pointwise conv supports 1..16 channels");
+  EDTR_REQUIRE(ldy >= coff + Cout, "ldy too small");
+  const size_t total = static_cast<size_t>(B) * HW;
+  pointwise_nchw_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      X, Wm, bias, scale, reinterpret_cast<__nv_bfloat16*>(Y), ldy, coff, Cin, Cout, HW, total);
+  return check_launch("pointwise_nchw_kernel");
 }
 
 extern "C" int edtr_nhwc_bf16_to_nchw(const void* X, int ldx, void* Y, int B, int C, int HW, int out_f32,

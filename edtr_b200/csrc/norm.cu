@@ -29,12 +29,17 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ------------------------------------------------------------ GroupNorm stats
-// grid (pixel chunks, B, channel slabs); block = vslab * ppar threads where vslab =
-// 16-byte vectors per slab.  Thread (v, q) owns vector v and walks pixels q, q+ppar, ...
-// so its 8 per-channel accumulators stay in registers.
-__global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int C,
-                                       int groups, int rows_per_cta, int vslab, float* __restrict__ stats) {
-  extern __shared__ float sh[];  // [2][vslab*8]
+// Deterministic two-level reduction, no atomics.  grid (pixel chunks, B, channel slabs);
+// block = vslab * ppar threads (vslab = 16-byte vectors per slab).  Thread (v, q) owns vector v
+// and walks pixels q, q+ppar, ... four at a time (four independent 16-byte loads in flight),
+// keeping its 8 per-channel sums in registers.  The CTA folds the ppar partial rows through
+// shared memory in a fixed order and writes per-(chunk, channel-group) partial sums to
+// partial[b][chunk][group][2]; slabs that split a group write their share into separate
+// slab slots: partial[b][chunk][slab][group][2].
+__global__ void __launch_bounds__(256)
+groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int C, int groups,
+                       int rows_per_cta, int vslab, float* __restrict__ partial) {
+  extern __shared__ float sh[];  // [ppar][2][cslab]
   const int cslab = vslab * 8;
   const int ppar = blockDim.x / vslab;
   const int v = threadIdx.x % vslab;
@@ -43,79 +48,138 @@ __global__ void groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int 
   const int c0 = blockIdx.z * cslab;
   const int p0 = blockIdx.x * rows_per_cta;
   const int p1 = min(HW, p0 + rows_per_cta);
-  for (int i = threadIdx.x; i < 2 * cslab; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
   float s[8], ss[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
-  if (q < ppar && c0 + v * 8 < C) {
+  if (q < ppar) {
     const __nv_bfloat16* base = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
-    for (int pidx = p0 + q; pidx < p1; pidx += ppar) {
+    int pidx = p0 + q;
+    for (; pidx + 3 * ppar < p1; pidx += 4 * ppar) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        u[k] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pidx + k * ppar) * ldx));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8(u[k], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+      }
+    }
+    for (; pidx < p1; pidx += ppar) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pidx) * ldx));
       float f[8];
       unpack8(u, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
     }
+    float* row = sh + static_cast<size_t>(q) * 2 * cslab;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sh[v * 8 + i], s[i]);
-      atomicAdd(&sh[cslab + v * 8 + i], ss[i]);
-    }
+    for (int i = 0; i < 8; ++i) { row[v * 8 + i] = s[i]; row[cslab + v * 8 + i] = ss[i]; }
   }
   __syncthreads();
-  // fold channels into groups; one thread per (group in slab)
+  // fold rows then channels into groups; one thread per group that intersects this slab
   const int cpg = C / groups;
   const int g_first = c0 / cpg;
   const int g_last = (min(C, c0 + cslab) - 1) / cpg;
   for (int g = g_first + threadIdx.x; g <= g_last; g += blockDim.x) {
-    const int lo = max(g * cpg, c0), hi = min((g + 1) * cpg, min(C, c0 + cslab));
+    const int lo = max(g * cpg, c0) - c0, hi = min((g + 1) * cpg, min(C, c0 + cslab)) - c0;
     float a = 0.f, a2 = 0.f;
-    for (int c = lo; c < hi; ++c) { a += sh[c - c0]; a2 += sh[cslab + c - c0]; }
-    atomicAdd(&stats[(static_cast<size_t>(b) * groups + g) * 2 + 0], a);
-    atomicAdd(&stats[(static_cast<size_t>(b) * groups + g) * 2 + 1], a2);
+    for (int r = 0; r < ppar; ++r) {
+      const float* row = sh + static_cast<size_t>(r) * 2 * cslab;
+      for (int c = lo; c < hi; ++c) { a += row[c]; a2 += row[cslab + c]; }
+    }
+    float* dst = partial + ((((static_cast<size_t>(b) * gridDim.x + blockIdx.x) * gridDim.z + blockIdx.z) * groups + g) * 2);
+    dst[0] = a;
+    dst[1] = a2;
   }
 }
 
 // ------------------------------------------------------------ GroupNorm apply
-__global__ void groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx,
-                                       __nv_bfloat16* __restrict__ Y, int ldy, int HW, int C, int groups,
-                                       int rows_per_cta, const float* __restrict__ stats,
-                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                       float eps, int silu) {
-  extern __shared__ float sh[];  // scale[C], shift[C]
-  float* sc = sh;
-  float* sf = sh + C;
+// Same thread <-> channel-vector mapping, so the 8 scale/shift pairs of a thread live in
+// registers.  Every CTA first re-reduces the (tiny) partial-sum table in a fixed order.
+__global__ void __launch_bounds__(256)
+groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y, int ldy,
+                       int HW, int C, int groups, int rows_per_cta, int vslab, int nchunks_stats, int nslab_stats,
+                       int cslab_stats, const float* __restrict__ partial, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float eps, int silu) {
+  __shared__ float g_mean[64], g_rstd[64];  // groups intersecting this slab (<= 64)
+  const int cslab = vslab * 8;
+  const int ppar = blockDim.x / vslab;
+  const int v = threadIdx.x % vslab;
+  const int q = threadIdx.x / vslab;
   const int b = blockIdx.y;
+  const int c0 = blockIdx.z * cslab;
   const int cpg = C / groups;
+  const int g_first = c0 / cpg;
+  const int g_last = (min(C, c0 + cslab) - 1) / cpg;
   const float inv_n = 1.f / (static_cast<float>(cpg) * static_cast<float>(HW));
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float mean = stats[(static_cast<size_t>(b) * groups + g) * 2 + 0] * inv_n;
-    const float ex2 = stats[(static_cast<size_t>(b) * groups + g) * 2 + 1] * inv_n;
-    const float var = fmaxf(ex2 - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float a = rstd * __ldg(gamma + c);
-    sc[c] = a;
-    sf[c] = __ldg(beta + c) - mean * a;
+  for (int g = g_first + threadIdx.x; g <= g_last; g += blockDim.x) {
+    // stats slabs that contain channels of group g
+    const int s_lo = (g * cpg) / cslab_stats, s_hi = ((g + 1) * cpg - 1) / cslab_stats;
+    float a = 0.f, a2 = 0.f;
+    for (int ch = 0; ch < nchunks_stats; ++ch)
+      for (int sl = s_lo; sl <= s_hi; ++sl) {
+        const float* src = partial + ((((static_cast<size_t>(b) * nchunks_stats + ch) * nslab_stats + sl) * groups + g) * 2);
+        a += src[0];
+        a2 += src[1];
+      }
+    const float mean = a * inv_n;
+    const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
+    g_mean[g - g_first] = mean;
+    g_rstd[g - g_first] = rsqrtf(var + eps);
   }
   __syncthreads();
-  const int vpr = C / 8;
+  if (q >= ppar) return;
+  float sc[8], sf[8];
+  {
+    const int cbase = c0 + v * 8;
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + cbase));
+    const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + cbase + 4));
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + cbase));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + cbase + 4));
+    const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (cbase + i) / cpg - g_first;
+      sc[i] = g_rstd[g] * gg[i];
+      sf[i] = bt[i] - g_mean[g] * sc[i];
+    }
+  }
   const int p0 = blockIdx.x * rows_per_cta;
-  const int nrows = min(HW, p0 + rows_per_cta) - p0;
-  const int total = nrows * vpr;
-  const size_t rowbase = static_cast<size_t>(b) * HW + p0;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int pr = idx / vpr, v = idx - pr * vpr;
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(X + (rowbase + pr) * ldx + v * 8));
+  const int p1 = min(HW, p0 + rows_per_cta);
+  const __nv_bfloat16* xb = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
+  __nv_bfloat16* yb = Y + (static_cast<size_t>(b) * HW) * ldy + c0 + v * 8;
+  int pidx = p0 + q;
+  for (; pidx + 3 * ppar < p1; pidx += 4 * ppar) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(u[k], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float y = f[i] * sc[i] + sf[i];
+        f[i] = silu ? silu_f(y) : y;
+      }
+      *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
+    }
+  }
+  for (; pidx < p1; pidx += ppar) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx) * ldx));
     float f[8];
     unpack8(u, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float y = f[i] * sc[v * 8 + i] + sf[v * 8 + i];
+      const float y = f[i] * sc[i] + sf[i];
       f[i] = silu ? silu_f(y) : y;
     }
-    *reinterpret_cast<uint4*>(Y + (rowbase + pr) * ldy + v * 8) = pack8(f);
+    *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx) * ldy) = pack8(f);
   }
 }
 
@@ -199,11 +263,33 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, int lds, __nv_b
     p[i] = __float2bfloat16(exp2f((s[i] - mx) * scale_log2) * inv);
 }
 
-static int rows_per_cta_for(int HW) {
-  int r = HW / 64;
-  if (r < 64) r = 64;
-  if (r > 1024) r = 1024;
-  return r;
+struct GnGeom {
+  int vslab, nslab, ppar, threads, rows, nchunks;
+};
+
+// Launch geometry shared by the stats and apply kernels (and by edtr_groupnorm_partial_size).
+static GnGeom gn_geom(int B, int HW, int C) {
+  GnGeom g;
+  const int vpr = C / 8;
+  g.vslab = vpr;
+  if (g.vslab > 256) {
+    g.vslab = 256;
+    while (vpr % g.vslab != 0) --g.vslab;
+  }
+  g.nslab = vpr / g.vslab;
+  g.ppar = 256 / g.vslab;
+  if (g.ppar < 1) g.ppar = 1;
+  g.threads = g.vslab * g.ppar;
+  // aim for >= 2 CTAs per SM over the whole launch, at least 4 rows per thread-row
+  const int want_ctas = 2 * 148;
+  int chunks = (want_ctas + B * g.nslab - 1) / (B * g.nslab);
+  int rows = (HW + chunks - 1) / chunks;
+  const int min_rows = 4 * g.ppar;
+  if (rows < min_rows) rows = min_rows;
+  if (rows > HW) rows = HW;
+  g.rows = rows;
+  g.nchunks = (HW + rows - 1) / rows;
+  return g;
 }
 
 }  // namespace edtr
@@ -220,27 +306,23 @@ static int check_gn_args(const void* X, int ldx, int B, int HW, int C, int group
   return EDTR_OK;
 }
 
+extern "C" size_t edtr_groupnorm_partial_size(int B, int HW, int C, int groups) {
+  if (B <= 0 || HW <= 0 || C <= 0 || groups <= 0 || C % 8 != 0) return 0;
+  const GnGeom g = gn_geom(B, HW, C);
+  return static_cast<size_t>(B) * g.nchunks * g.nslab * groups * 2;
+}
+
 extern "C" int edtr_groupnorm_stats(const void* X, int ldx, int B, int HW, int C, int groups, float* stats,
                                     void* stream) {
   int rc = check_gn_args(X, ldx, B, HW, C, groups);
   if (rc) return rc;
   EDTR_REQUIRE(stats != nullptr, "stats is NULL");
-  const int vpr = C / 8;
-  // slab = largest divisor of vpr that is <= 256 vectors
-  int vslab = vpr;
-  if (vslab > 256) {
-    vslab = 256;
-    while (vpr % vslab != 0) --vslab;
-  }
-  const int nslab = vpr / vslab;
-  int ppar = 256 / vslab;
-  if (ppar < 1) ppar = 1;
-  const int threads = vslab * ppar;
-  const int rows = rows_per_cta_for(HW);
-  dim3 grid((HW + rows - 1) / rows, B, nslab);
-  const size_t sh = 2 * static_cast<size_t>(vslab) * 8 * sizeof(float);
-  groupnorm_stats_kernel<<<grid, threads, sh, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(X), ldx, HW, C, groups, rows, vslab, stats);
+  const GnGeom g = gn_geom(B, HW, C);
+  dim3 grid(g.nchunks, B, g.nslab);
+  const size_t sh = static_cast<size_t>(g.ppar) * 2 * g.vslab * 8 * sizeof(float);
+  EDTR_REQUIRE(sh <= 48 * 1024, "GroupNorm stats shared memory too large");
+  groupnorm_stats_kernel<<<grid, g.threads, sh, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(X), ldx, HW, C, groups, g.rows, g.vslab, stats);
   return check_launch("groupnorm_stats_kernel");
 }
 
@@ -251,13 +333,14 @@ extern "C" int edtr_groupnorm_apply(const void* X, int ldx, void* Y, int ldy, in
   if (rc) return rc;
   EDTR_REQUIRE(Y && stats && gamma && beta, "Y/stats/gamma/beta is NULL");
   EDTR_REQUIRE(ldy % 8 == 0 && ldy >= C && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "bad Y stride/alignment");
-  EDTR_REQUIRE(C <= 5120, "C too large for the shared scale/shift table");
-  const int rows = rows_per_cta_for(HW);
-  dim3 grid((HW + rows - 1) / rows, B, 1);
-  const size_t sh = 2 * static_cast<size_t>(C) * sizeof(float);
-  groupnorm_apply_kernel<<<grid, 256, sh, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+               "gamma/beta must be 16-byte aligned");
+  const GnGeom g = gn_geom(B, HW, C);
+  EDTR_REQUIRE(g.vslab * 8 / (C / groups) + 2 <= 64, "too many groups per channel slab");
+  dim3 grid(g.nchunks, B, g.nslab);
+  groupnorm_apply_kernel<<<grid, g.threads, 0, static_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
-      rows, stats, gamma, beta, eps, silu);
+      g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, stats, gamma, beta, eps, silu);
   return check_launch("groupnorm_apply_kernel");
 }
 

@@ -1,0 +1,729 @@
+"""Execution engine of the ControlLDM restore path on the C-ABI kernels.
+
+Walks the block topology of the reference networks and launches, per block, the
+kernels of ``include/edtr_b200.h`` on channels-last bf16 activations:
+
+* ``ControlLDM.forward`` (model/cldm.py:166-194) = ``CldmEngine.forward``: UNet
+  encoder -> UNet middle -> ControlNet (its 13 zero-conv GEMMs accumulate straight
+  into the UNet skip tensors / middle output in their epilogue, replacing
+  ``hs.pop() + control.pop()`` and ``h += control.pop()``, model/controlnet.py:31,37)
+  -> UNet decoder.  The reorder is legal because the UNet encoder does not read
+  ``control`` (model/controlnet.py:25-28).
+* skip concatenations (``torch.cat([h, skip], 1)``, model/controlnet.py:35-37) never
+  happen: producers write at channel offsets of one pre-allocated buffer per
+  decoder block.
+* ``SpacedSampler`` loop (utils/sampler.py:267-323) = ``CldmEngine.sample``, and
+  ``ControlLDM.vae_decode`` (model/cldm.py:136-156) = ``VaeDecoderEngine.decode``.
+
+All buffers are static per (batch, H, W), so a whole 4-step sample or a decode is
+captured once into a CUDA graph and replayed.
+
+The kernels are reached through ``self.ops`` (default ``edtr_b200.ops``); there is no
+other execution path in the product.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import topology as T
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _ceil(a: int, b: int) -> int:
+    return (a + b - 1) // b * b
+
+
+# --------------------------------------------------------------------------- packing
+def pack_conv3x3(w: torch.Tensor, device) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> bf16 [Cout, 9 * Cin_pad] tap-major / channel-minor (Cin padded to 64)."""
+    cout, cin = w.shape[:2]
+    cp = _ceil(cin, 64)
+    wp = torch.zeros((cout, 3, 3, cp), dtype=F32)
+    wp[..., :cin] = w.detach().float().cpu().permute(0, 2, 3, 1)
+    return wp.reshape(cout, 9 * cp).to(BF16).contiguous().to(device)
+
+
+def pack_matrix(w: torch.Tensor, device) -> torch.Tensor:
+    """Linear [N, K] or 1x1 conv [N, K, 1, 1] -> bf16 [N, K]."""
+    w = w.detach()
+    return w.reshape(w.shape[0], -1).to(BF16).contiguous().to(device)
+
+
+def vec(v: torch.Tensor, device) -> torch.Tensor:
+    return v.detach().float().contiguous().to(device)
+
+
+def geglu_permutation(n_half: int, tile_n: int) -> torch.Tensor:
+    """Row order that puts, inside every N-tile of the GEGLU projection, the value columns in the
+    first half and the matching gate columns in the second half (see EDTR_ACT_GEGLU)."""
+    half = tile_n // 2
+    if n_half % half != 0:
+        raise ValueError(f"GEGLU width {n_half} is not a multiple of {half}")
+    idx = torch.arange(n_half).view(-1, half)
+    return torch.cat([idx, idx + n_half], dim=1).reshape(-1)
+
+
+class Workspace:
+    """Named, lazily grown device buffers: a name is one live tensor at a time."""
+
+    def __init__(self, device):
+        self.device = device
+        self._bufs: Dict[Tuple[str, torch.dtype], torch.Tensor] = {}
+
+    def get(self, name: str, shape: Sequence[int], dtype=BF16) -> torch.Tensor:
+        n = int(math.prod(shape))
+        key = (name, dtype)
+        t = self._bufs.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(n, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t[:n].view(*shape)
+
+    def zeros(self, name: str, shape: Sequence[int], dtype=BF16) -> torch.Tensor:
+        """A buffer that is allocated zero-filled once and keeps its identity (padding channels)."""
+        key = (name, dtype)
+        t = self._bufs.get(key)
+        n = int(math.prod(shape))
+        if t is None or t.numel() != n:
+            t = torch.zeros(n, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t.view(*shape)
+
+    def gn_scratch(self, ops, x: torch.Tensor, groups: int = 32) -> torch.Tensor:
+        """Partial-sum scratch of the two-pass GroupNorm (written by pass 1, read by pass 2)."""
+        B, C = x.shape[0], x.shape[-1]
+        hw = x.numel() // (B * C)
+        return self.get("gn_partial", (ops.groupnorm_partial_size(B, hw, C, groups),), F32)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self._bufs.values())
+
+
+# ------------------------------------------------------------------ UNet / ControlNet
+class _PackedNet:
+    """bf16/fp32 device copies of one UNet-family state-dict, laid out for the kernels."""
+
+    def __init__(self, cfg: Dict, sd: Dict[str, torch.Tensor], controlnet: bool, device, ops):
+        self.cfg = cfg
+        self.controlnet = controlnet
+        self.inputs, self.middle, self.outputs = T.unet_blocks(cfg, controlnet)
+        self.mc = cfg["model_channels"]
+        self.ctx_dim = cfg["context_dim"]
+        self.w: Dict[str, torch.Tensor] = {}
+        want = dict(T.unet_param_shapes(cfg, controlnet))
+        for k, shp in want.items():
+            if k not in sd:
+                raise KeyError(f"state-dict is missing {k}")
+            if tuple(sd[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(sd[k].shape)}")
+        w = self.w
+        dev = device
+        geglu_tile = ops.geglu_tile_n()
+        emb_w, emb_b, ctx_w = [], [], []
+        self.emb_off: Dict[str, Tuple[int, int]] = {}
+        self.ctx_off: Dict[str, Tuple[int, int]] = {}
+        eo = co = 0
+
+        def add_layer(p: str, layer):
+            nonlocal eo, co
+            kind = layer[0]
+            if kind in ("conv_in", "down", "up"):
+                q = p if kind == "conv_in" else p + ("op." if kind == "down" else "conv.")
+                w[q + "weight"] = pack_conv3x3(sd[q + "weight"], dev)
+                w[q + "bias"] = vec(sd[q + "bias"], dev)
+            elif kind == "res":
+                cout = layer[2]
+                for n in ("in_layers.0.", "out_layers.0."):
+                    w[p + n + "weight"] = vec(sd[p + n + "weight"], dev)
+                    w[p + n + "bias"] = vec(sd[p + n + "bias"], dev)
+                for n in ("in_layers.2.", "out_layers.3."):
+                    w[p + n + "weight"] = pack_conv3x3(sd[p + n + "weight"], dev)
+                    w[p + n + "bias"] = vec(sd[p + n + "bias"], dev)
+                if (p + "skip_connection.weight") in sd:
+                    w[p + "skip_connection.weight"] = pack_matrix(sd[p + "skip_connection.weight"], dev)
+                    w[p + "skip_connection.bias"] = vec(sd[p + "skip_connection.bias"], dev)
+                emb_w.append(sd[p + "emb_layers.1.weight"].detach().float().cpu())
+                emb_b.append(sd[p + "emb_layers.1.bias"].detach().float().cpu())
+                self.emb_off[p] = (eo, cout)
+                eo += cout
+            elif kind == "st":
+                ch = layer[1]
+                t = p + "transformer_blocks.0."
+                for n in (p + "norm.", t + "norm1.", t + "norm2.", t + "norm3."):
+                    w[n + "weight"] = vec(sd[n + "weight"], dev)
+                    w[n + "bias"] = vec(sd[n + "bias"], dev)
+                for n in (p + "proj_in.", p + "proj_out.", t + "attn1.to_out.0.", t + "attn2.to_out.0.", t + "ff.net.2."):
+                    w[n + "weight"] = pack_matrix(sd[n + "weight"], dev)
+                    w[n + "bias"] = vec(sd[n + "bias"], dev)
+                w[t + "attn1.qkv"] = pack_matrix(
+                    torch.cat([sd[t + "attn1.to_q.weight"], sd[t + "attn1.to_k.weight"], sd[t + "attn1.to_v.weight"]], 0), dev)
+                w[t + "attn2.to_q.weight"] = pack_matrix(sd[t + "attn2.to_q.weight"], dev)
+                ctx_w.append(torch.cat([sd[t + "attn2.to_k.weight"], sd[t + "attn2.to_v.weight"]], 0).detach().float().cpu())
+                self.ctx_off[p] = (co, ch)
+                co += 2 * ch
+                perm = geglu_permutation(4 * ch, geglu_tile)
+                w[t + "ff.net.0.proj.weight"] = pack_matrix(sd[t + "ff.net.0.proj.weight"].detach().cpu()[perm], dev)
+                w[t + "ff.net.0.proj.bias"] = vec(sd[t + "ff.net.0.proj.bias"].detach().cpu()[perm], dev)
+
+        for j, block in enumerate(self.inputs):
+            for k, layer in enumerate(block):
+                add_layer(f"input_blocks.{j}.{k}.", layer)
+        for k, layer in enumerate(self.middle):
+            add_layer(f"middle_block.{k}.", layer)
+        for j, block in enumerate(self.outputs):
+            for k, layer in enumerate(block):
+                add_layer(f"output_blocks.{j}.{k}.", layer)
+        for n in ("time_embed.0.", "time_embed.2."):
+            w[n + "weight"] = pack_matrix(sd[n + "weight"], dev)
+            w[n + "bias"] = vec(sd[n + "bias"], dev)
+        w["emb_cat.weight"] = pack_matrix(torch.cat(emb_w, 0), dev)
+        w["emb_cat.bias"] = vec(torch.cat(emb_b, 0), dev)
+        w["ctx_cat.weight"] = pack_matrix(torch.cat(ctx_w, 0), dev)
+        self.emb_total, self.ctx_total = eo, co
+        if controlnet:
+            for j in range(len(self.inputs)):
+                q = f"zero_convs.{j}.0."
+                w[q + "weight"] = pack_matrix(sd[q + "weight"], dev)
+                w[q + "bias"] = vec(sd[q + "bias"], dev)
+            w["middle_block_out.0.weight"] = pack_matrix(sd["middle_block_out.0.weight"], dev)
+            w["middle_block_out.0.bias"] = vec(sd["middle_block_out.0.bias"], dev)
+        else:
+            w["out.0.weight"] = vec(sd["out.0.weight"], dev)
+            w["out.0.bias"] = vec(sd["out.0.bias"], dev)
+            w["out.2.weight"] = pack_conv3x3(sd["out.2.weight"], dev)
+            w["out.2.bias"] = vec(sd["out.2.bias"], dev)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.w.values())
+
+
+class _NetRunner:
+    """Launch sequences of the reference leaf blocks on one packed net."""
+
+    def __init__(self, net: _PackedNet, ws: Workspace, ops, tag: str):
+        self.net, self.ws, self.ops, self.tag = net, ws, ops, tag
+        self.emb: Optional[torch.Tensor] = None   # [B, emb_total] fp32: Linear(SiLU(emb)) of every ResBlock
+        self.ctx: Optional[torch.Tensor] = None   # [B, 77, ctx_total] bf16: cross-attention K|V of every block
+
+    # -- embeddings (model/util.py:98-118; model/unet.py:475-480,166-172,212) ---------------
+    def time_embedding(self, t: torch.Tensor) -> None:
+        net, ops, ws, w = self.net, self.ops, self.ws, self.net.w
+        B = t.shape[0]
+        te = ops.timestep_embedding(t, net.mc, out=ws.get(self.tag + "te", (B, net.mc)))
+        e1 = ops.gemm(te, w["time_embed.0.weight"], bias=w["time_embed.0.bias"], act=ops.ACT_SILU,
+                      out=ws.get(self.tag + "e1", (B, 4 * net.mc)))
+        # emb is consumed only through nn.SiLU() -> Linear (emb_layers), so SiLU rides in this epilogue
+        e2 = ops.gemm(e1, w["time_embed.2.weight"], bias=w["time_embed.2.bias"], act=ops.ACT_SILU,
+                      out=ws.get(self.tag + "e2", (B, 4 * net.mc)))
+        self.emb = ops.gemm(e2, w["emb_cat.weight"], bias=w["emb_cat.bias"], out_mode=ops.OUT_F32,
+                            out=ws.get(self.tag + "emb", (B, net.emb_total), F32))
+
+    # -- cross-attention K/V of all blocks in one GEMM (model/attention.py:178-180) ---------
+    def context(self, c_txt_bf16: torch.Tensor) -> None:
+        B, L, D = c_txt_bf16.shape
+        out = self.ws.get(self.tag + "ctx", (B, L, self.net.ctx_total))
+        self.ops.gemm(c_txt_bf16, self.net.w["ctx_cat.weight"], out=out)
+        self.ctx = out
+
+    # -- ResBlock._forward (model/unet.py:203-223) ---------------------------------------
+    def res(self, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
+        ops, ws, w = self.ops, self.ws, self.net.w
+        B, H, W, cin = x.shape
+        cout = out.shape[-1]
+        y = ops.groupnorm(x, w[p + "in_layers.0.weight"], w[p + "in_layers.0.bias"], 32, 1e-5, True,
+                          stats=ws.gn_scratch(ops, x), out=ws.get("gn", (B, H, W, cin)))
+        eo, _ = self.net.emb_off[p]
+        h = ops.conv3x3(y, w[p + "in_layers.2.weight"], bias=w[p + "in_layers.2.bias"],
+                        rowvec=self.emb[:, eo:eo + cout], out=ws.get("res_h", (B, H, W, cout)))
+        y2 = ops.groupnorm(h, w[p + "out_layers.0.weight"], w[p + "out_layers.0.bias"], 32, 1e-5, True,
+                           stats=ws.gn_scratch(ops, h), out=ws.get("gn", (B, H, W, cout)))
+        if (p + "skip_connection.weight") in w:
+            skip = ops.gemm(x, w[p + "skip_connection.weight"], bias=w[p + "skip_connection.bias"],
+                            out=ws.get("res_skip", (B, H, W, cout)))
+        else:
+            skip = x
+        ops.conv3x3(y2, w[p + "out_layers.3.weight"], bias=w[p + "out_layers.3.bias"], residual=skip, out=out)
+
+    # -- SpatialTransformer.forward + BasicTransformerBlock (model/attention.py:283-302,230-234)
+    def st(self, p: str, x: torch.Tensor, out: torch.Tensor, heads: int) -> None:
+        ops, ws, w = self.ops, self.ws, self.net.w
+        B, H, W, C = x.shape
+        L = H * W
+        t = p + "transformer_blocks.0."
+        y = ops.groupnorm(x, w[p + "norm.weight"], w[p + "norm.bias"], 32, 1e-6, False,
+                          stats=ws.gn_scratch(ops, x), out=ws.get("gn", (B, L, C)))
+        t0 = ops.gemm(y, w[p + "proj_in.weight"], bias=w[p + "proj_in.bias"], out=ws.get("st_t0", (B, L, C)))
+        # self-attention
+        n = ops.layernorm(t0, w[t + "norm1.weight"], w[t + "norm1.bias"], 1e-5, out=ws.get("st_ln", (B, L, C)))
+        qkv = ops.gemm(n, w[t + "attn1.qkv"], out=ws.get("st_qkv", (B, L, 3 * C)))
+        a = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, 0.125,
+                          out=ws.get("st_att", (B, L, C)))
+        t1 = ops.gemm(a, w[t + "attn1.to_out.0.weight"], bias=w[t + "attn1.to_out.0.bias"], residual=t0,
+                      out=ws.get("st_t1", (B, L, C)))
+        # cross-attention against the hoisted K/V
+        n = ops.layernorm(t1, w[t + "norm2.weight"], w[t + "norm2.bias"], 1e-5, out=ws.get("st_ln", (B, L, C)))
+        q = ops.gemm(n, w[t + "attn2.to_q.weight"], out=ws.get("st_q", (B, L, C)))
+        co, _ = self.net.ctx_off[p]
+        a = ops.attention(q, self.ctx[..., co:co + C], self.ctx[..., co + C:co + 2 * C], heads, 0.125,
+                          out=ws.get("st_att", (B, L, C)))
+        t2 = ops.gemm(a, w[t + "attn2.to_out.0.weight"], bias=w[t + "attn2.to_out.0.bias"], residual=t1,
+                      out=ws.get("st_t0", (B, L, C)))
+        # GEGLU feed-forward
+        n = ops.layernorm(t2, w[t + "norm3.weight"], w[t + "norm3.bias"], 1e-5, out=ws.get("st_ln", (B, L, C)))
+        g = ops.gemm(n, w[t + "ff.net.0.proj.weight"], bias=w[t + "ff.net.0.proj.bias"], act=ops.ACT_GEGLU,
+                     out=ws.get("st_ff", (B, L, 4 * C)))
+        t3 = ops.gemm(g, w[t + "ff.net.2.weight"], bias=w[t + "ff.net.2.bias"], residual=t2,
+                      out=ws.get("st_t1", (B, L, C)))
+        ops.gemm(t3, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out)
+
+    def conv(self, q: str, x: torch.Tensor, out: torch.Tensor, **kw) -> None:
+        self.ops.conv3x3(x, self.net.w[q + "weight"], bias=self.net.w[q + "bias"], out=out, **kw)
+
+    # -- Downsample (model/unet.py:99-108): 3x3 stride 2 pad 1 ----------------------------
+    def down(self, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
+        ops, ws, w = self.ops, self.ws, self.net.w
+        B, H, W, C = x.shape
+        Ho, Wo = (H + 1) // 2, (W + 1) // 2
+        col = ops.im2col(x, 3, 3, 2, 1, 1, Ho, Wo, out=ws.get("col", (B * Ho * Wo, 9 * C)))
+        ops.gemm(col, w[p + "op.weight"], bias=w[p + "op.bias"], out=out)
+
+    # -- Upsample (model/unet.py:69-79): nearest x2 then 3x3 ------------------------------
+    def up(self, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
+        B, H, W, C = x.shape
+        u = self.ops.upsample2x(x, out=self.ws.get("up", (B, 2 * H, 2 * W, C)))
+        self.conv(p + "conv.", u, out)
+
+    def block(self, prefix: str, layers, x: torch.Tensor, out: torch.Tensor) -> None:
+        """TimestepEmbedSequential.forward (model/unet.py:40-48); the last layer writes `out`."""
+        ws = self.ws
+        n = len(layers)
+        for k, layer in enumerate(layers):
+            p = f"{prefix}{k}."
+            kind = layer[0]
+            B, H, W, _ = x.shape
+            if kind == "up":
+                H, W = 2 * H, 2 * W
+            elif kind == "down":
+                H, W = (H + 1) // 2, (W + 1) // 2
+            cout = layer[2] if kind in ("conv_in", "res") else layer[1]
+            dst = out if k == n - 1 else ws.get(f"blk{k % 2}", (B, H, W, cout))
+            if kind == "conv_in":
+                self.conv(p, x, dst)
+            elif kind == "res":
+                self.res(p, x, dst)
+            elif kind == "st":
+                self.st(p, x, dst, layer[2])
+            elif kind == "down":
+                self.down(p, x, dst)
+            elif kind == "up":
+                self.up(p, x, dst)
+            x = dst
+
+
+class CldmEngine:
+    """ControlNet + ControlledUnetModel evaluation and the spaced sampler loop."""
+
+    def __init__(self, unet_cfg: Dict, controlnet_cfg: Dict, unet_sd, controlnet_sd, device, ops=None):
+        if ops is None:
+            from . import ops as _ops
+            ops = _ops
+        self.ops = ops
+        self.device = torch.device(device)
+        for cfg in (unet_cfg, controlnet_cfg):
+            if cfg["num_head_channels"] != 64:
+                raise NotImplementedError("attention kernel supports head dim 64 (num_head_channels=64)")
+            if cfg["model_channels"] % 64 != 0:
+                raise NotImplementedError("model_channels must be a multiple of 64")
+        self.unet = _PackedNet(unet_cfg, unet_sd, False, self.device, ops)
+        self.cnet = _PackedNet(controlnet_cfg, controlnet_sd, True, self.device, ops)
+        if len(self.unet.inputs) != len(self.cnet.inputs):
+            raise ValueError("UNet and ControlNet encoders differ")
+        self.zc = unet_cfg["in_channels"]
+        self.hint_c = controlnet_cfg.get("hint_channels", 0)
+        self.out_c = unet_cfg["out_channels"]
+        self._ws: Dict[Tuple[int, int, int], Workspace] = {}
+        self._graphs: Dict[Tuple, "_Graph"] = {}
+        # channel / resolution bookkeeping of the skip structure
+        ins = self.unet.inputs
+        self.in_ch = [T.block_out_channels(b) for b in ins]
+        ds, cur = [], 1
+        for b in ins:
+            if b[0][0] == "down":
+                cur *= 2
+            ds.append(cur)
+        self.in_ds = ds
+        self.mid_ch = self.unet.middle[-1][2]
+        n_in = len(ins)
+        self.cat_geom = []  # per output block: (ds, c_prev, c_skip)
+        cprev = self.mid_ch
+        for j, blk in enumerate(self.unet.outputs):
+            s = n_in - 1 - j
+            self.cat_geom.append((self.in_ds[s], cprev, self.in_ch[s]))
+            cprev = blk[0][2]
+        self.final_ch = cprev
+
+    # ------------------------------------------------------------------ workspace
+    def workspace(self, B: int, H: int, W: int) -> Workspace:
+        key = (B, H, W)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = Workspace(self.device)
+            self._ws[key] = ws
+        return ws
+
+    def _check_hw(self, H: int, W: int) -> None:
+        top = max(self.in_ds)
+        if H % top or W % top:
+            raise ValueError(f"latent size {H}x{W} must be a multiple of {top}")
+
+    # ------------------------------------------------------------------ one evaluation
+    def _forward(self, ws: Workspace, x: torch.Tensor, t: torch.Tensor, c_img: torch.Tensor,
+                 eps_out: torch.Tensor, control_scales: Sequence[float], ctx_ready: bool = False,
+                 c_txt: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x, c_img: fp32 NCHW; t int64 [B]; eps_out fp32 [B, out_c, H, W] (written)."""
+        ops = self.ops
+        B, _, H, W = x.shape
+        un = _NetRunner(self.unet, ws, ops, "u_")
+        cn = _NetRunner(self.cnet, ws, ops, "c_")
+        if ctx_ready:
+            un.ctx = ws.get("u_ctx", (B, c_txt.shape[1], self.unet.ctx_total))
+            cn.ctx = ws.get("c_ctx", (B, c_txt.shape[1], self.cnet.ctx_total))
+        else:
+            self._context(ws, un, cn, c_txt)
+        un.time_embedding(t)
+        cn.time_embedding(t)
+
+        n_in = len(self.unet.inputs)
+        cats = [ws.get(f"cat{j}", (B, H // d, W // d, cp + cs)) for j, (d, cp, cs) in enumerate(self.cat_geom)]
+
+        def hs_view(s: int) -> torch.Tensor:
+            j = n_in - 1 - s
+            return cats[j][..., self.cat_geom[j][1]:]
+
+        # inputs -> channels-last bf16, channel-padded to 64 for the first conv
+        xu = ws.zeros("u_xin", (B, H, W, 64))
+        ops.nchw_to_nhwc(x, xu, 0)
+        xc = ws.zeros("c_xin", (B, H, W, 64))
+        ops.nchw_to_nhwc(x, xc, 0)
+        ops.nchw_to_nhwc(c_img, xc, self.zc)
+
+        # UNet encoder + middle (model/controlnet.py:25-28)
+        h = xu
+        for s, blk in enumerate(self.unet.inputs):
+            un.block(f"input_blocks.{s}.", blk, h, hs_view(s))
+            h = hs_view(s)
+        mid = cats[0][..., :self.cat_geom[0][1]]
+        un.block("middle_block.", self.unet.middle, h, mid)
+
+        # ControlNet; zero-conv epilogues accumulate into the UNet tensors (model/controlnet.py:263-277,31,37)
+        w = self.cnet.w
+        h = xc
+        for s, blk in enumerate(self.cnet.inputs):
+            d = self.in_ds[s]
+            dst = ws.get(f"c_h{s % 2}", (B, H // d, W // d, self.in_ch[s]))
+            cn.block(f"input_blocks.{s}.", blk, h, dst)
+            h = dst
+            self._zero_conv(w, f"zero_convs.{s}.0.", h, hs_view(s), control_scales[s])
+        d = self.in_ds[-1]
+        dst = ws.get("c_mid", (B, H // d, W // d, self.mid_ch))
+        cn.block("middle_block.", self.cnet.middle, h, dst)
+        self._zero_conv(w, "middle_block_out.0.", dst, mid, control_scales[n_in])
+
+        # UNet decoder (model/controlnet.py:33-38)
+        n_out = len(self.unet.outputs)
+        for j, blk in enumerate(self.unet.outputs):
+            if j + 1 < n_out:
+                out = cats[j + 1][..., :self.cat_geom[j + 1][1]]
+            else:
+                out = ws.get("u_final", (B, H, W, self.final_ch))
+            un.block(f"output_blocks.{j}.", blk, cats[j], out)
+        # out: GroupNorm32 -> SiLU -> conv3x3 (model/unet.py:675-679), stored NCHW fp32
+        uw = self.unet.w
+        y = ops.groupnorm(out, uw["out.0.weight"], uw["out.0.bias"], 32, 1e-5, True, stats=ws.gn_scratch(ops, out),
+                          out=ws.get("gn", (B, H, W, self.final_ch)))
+        ops.conv3x3(y, uw["out.2.weight"], bias=uw["out.2.bias"], out=eps_out.view(B, self.out_c, H * W),
+                    out_mode=ops.OUT_NCHW_F32)
+        return eps_out
+
+    def _zero_conv(self, w, q: str, h: torch.Tensor, dst: torch.Tensor, scale: float) -> None:
+        bias = w[q + "bias"]
+        if scale != 1.0:
+            bias = bias * scale
+        self.ops.gemm(h, w[q + "weight"], bias=bias, residual=dst, out=dst, alpha=float(scale))
+
+    def _context(self, ws: Workspace, un: _NetRunner, cn: _NetRunner, c_txt: torch.Tensor) -> None:
+        if c_txt.shape[-1] != self.unet.ctx_dim:
+            raise ValueError(f"c_txt last dim {c_txt.shape[-1]} != context_dim {self.unet.ctx_dim}")
+        c = self.ops.cast_bf16(c_txt, out=ws.get("ctxt_bf16", tuple(c_txt.shape)))
+        un.context(c)
+        cn.context(c)
+
+    # ------------------------------------------------------------------ public API
+    def _check_inputs(self, x, t, c_img, c_txt):
+        if x.dim() != 4 or x.shape[1] != self.zc:
+            raise ValueError(f"x_noisy must be [B, {self.zc}, H, W], got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        self._check_hw(H, W)
+        if tuple(c_img.shape) != (B, self.hint_c, H, W):
+            raise ValueError(f"c_img must be {(B, self.hint_c, H, W)}, got {tuple(c_img.shape)}")
+        if c_txt.dim() != 3 or c_txt.shape[0] != B:
+            raise ValueError(f"c_txt must be [B, L, {self.unet.ctx_dim}], got {tuple(c_txt.shape)}")
+        if t is not None and (t.dim() != 1 or t.shape[0] != B):
+            raise ValueError("t must be an int64 vector of length B")
+        if getattr(self.ops, "REQUIRES_CUDA", True):
+            for a in (x, c_img, c_txt):
+                if not a.is_cuda:
+                    raise RuntimeError("edtr_b200 has no CPU path: inputs must be CUDA tensors")
+
+    def forward(self, x_noisy, t, c_img, c_txt, control_scales=None, use_graph: bool = True) -> torch.Tensor:
+        """eps = ControlLDM.forward(x_noisy, t, {c_txt, c_img}) (model/cldm.py:166-194)."""
+        self._check_inputs(x_noisy, t, c_img, c_txt)
+        B, _, H, W = x_noisy.shape
+        scales = tuple(float(s) for s in (control_scales or [1.0] * (len(self.unet.inputs) + 1)))
+        ws = self.workspace(B, H, W)
+        sx = ws.get("in_x", tuple(x_noisy.shape), F32)
+        st = ws.get("in_t", (B,), torch.int64)
+        si = ws.get("in_cimg", tuple(c_img.shape), F32)
+        sc = ws.get("in_ctxt", tuple(c_txt.shape), F32)
+        eps = ws.get("out_eps", (B, self.out_c, H, W), F32)
+        sx.copy_(x_noisy)
+        st.copy_(t)
+        si.copy_(c_img)
+        sc.copy_(c_txt)
+        run = lambda: self._forward(ws, sx, st, si, eps, scales, c_txt=sc)
+        if use_graph:
+            self._graph(("fwd", B, H, W, c_txt.shape[1], scales), run).replay()
+        else:
+            run()
+        return eps.clone()
+
+    def sample(self, x_T, timesteps: Sequence[int], tables: Dict[str, torch.Tensor], c_img, c_txt,
+               noise: Sequence[torch.Tensor], control_scales=None, use_graph: bool = True,
+               return_intermediates: bool = False):
+        """The loop of SpacedSampler.sample / manual_sample_with_timesteps (utils/sampler.py:304-323) with
+        cfg_scale == 1: `timesteps` descending model timesteps, `tables` the five fp32 coefficient
+        vectors of make_schedule, `noise[i]` the i-th torch.randn_like draw."""
+        self._check_inputs(x_T, None, c_img, c_txt)
+        B, _, H, W = x_T.shape
+        n = len(timesteps)
+        if len(noise) != n:
+            raise ValueError("one noise tensor per step is required")
+        scales = tuple(float(s) for s in (control_scales or [1.0] * (len(self.unet.inputs) + 1)))
+        ws = self.workspace(B, H, W)
+        sx = ws.get("in_x", tuple(x_T.shape), F32)
+        si = ws.get("in_cimg", tuple(c_img.shape), F32)
+        sc = ws.get("in_ctxt", tuple(c_txt.shape), F32)
+        sn = ws.get("in_noise", (n,) + tuple(x_T.shape), F32)
+        tabs = ws.get("in_tabs", (5, n), F32)
+        ts = ws.get("in_ts", (n, B), torch.int64)
+        idx = ws.get("in_idx", (n, B), torch.int64)
+        xs = ws.get("out_xs", (n,) + tuple(x_T.shape), F32)
+        x0s = ws.get("out_x0s", (n,) + tuple(x_T.shape), F32)
+        eps = ws.get("out_eps", (B, self.out_c, H, W), F32)
+        sx.copy_(x_T)
+        si.copy_(c_img)
+        sc.copy_(c_txt)
+        for i in range(n):
+            sn[i].copy_(noise[i])
+        names = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                 "posterior_mean_coef2", "posterior_variance")
+        for r, k in enumerate(names):
+            tabs[r].copy_(tables[k])
+        ts.copy_(torch.tensor([[int(s)] * B for s in timesteps], dtype=torch.int64))
+        idx.copy_(torch.tensor([[n - i - 1] * B for i in range(n)], dtype=torch.int64))
+
+        def run():
+            un = _NetRunner(self.unet, ws, self.ops, "u_")
+            cn = _NetRunner(self.cnet, ws, self.ops, "c_")
+            self._context(ws, un, cn, sc)  # c_txt is step-invariant: project K/V once
+            cur = sx
+            for i in range(n):
+                self._forward(ws, cur, ts[i], si, eps, scales, ctx_ready=True, c_txt=sc)
+                self.ops.sampler_update(cur, eps, sn[i], idx[i], [tabs[r] for r in range(5)],
+                                        x_prev=xs[i], pred_x0=x0s[i])
+                cur = xs[i]
+
+        if use_graph:
+            self._graph(("sample", B, H, W, c_txt.shape[1], n, scales), run).replay()
+        else:
+            run()
+        if return_intermediates:
+            return xs[n - 1].clone(), [x0s[i].clone() for i in range(n)], [xs[i].clone() for i in range(n)]
+        return xs[n - 1].clone()
+
+    def _graph(self, key, fn) -> "_Graph":
+        g = self._graphs.get(key)
+        if g is None:
+            g = _Graph(fn)
+            self._graphs[key] = g
+        return g
+
+
+class _Graph:
+    """Warm up twice eagerly (sizes every workspace buffer), then capture into a CUDA graph."""
+
+    def __init__(self, fn):
+        from . import lib as _lib
+
+        fn()
+        fn()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.LAUNCHES[0]
+        with torch.cuda.graph(self.graph):
+            fn()
+        self.launches = _lib.LAUNCHES[0] - n0  # kernels per replay
+
+    def replay(self) -> None:
+        from . import lib as _lib
+
+        self.graph.replay()
+        _lib.LAUNCHES[0] += self.launches
+
+
+# ------------------------------------------------------------------------ VAE decoder
+class VaeDecoderEngine:
+    """ControlLDM.vae_decode (untiled): z / scale -> post_quant_conv -> Decoder.forward
+    (model/cldm.py:136-156, model/vae.py:731-734, :527-560)."""
+
+    def __init__(self, ddconfig: Dict, embed_dim: int, sd: Dict[str, torch.Tensor], device, ops=None):
+        if ops is None:
+            from . import ops as _ops
+            ops = _ops
+        self.ops = ops
+        self.device = torch.device(device)
+        self.dd = ddconfig
+        self.z = ddconfig["z_channels"]
+        self.embed_dim = embed_dim
+        if ddconfig.get("attn_resolutions"):
+            raise NotImplementedError("per-level VAE attention (attn_resolutions) is not used by EDTR configs")
+        if ddconfig["ch"] % 64 != 0:
+            raise NotImplementedError("VAE base width must be a multiple of 64")
+        self.levels, self.last = T.vae_decoder_levels(ddconfig)
+        self.top = ddconfig["ch"] * tuple(ddconfig["ch_mult"])[-1]
+        w: Dict[str, torch.Tensor] = {}
+        dev = self.device
+        for k, shp in T.vae_decoder_param_shapes(ddconfig, embed_dim):
+            if k not in sd:
+                raise KeyError(f"state-dict is missing {k}")
+            if tuple(sd[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(sd[k].shape)}")
+            v = sd[k]
+            if k == "post_quant_conv.weight":
+                w[k] = v.detach().float().reshape(v.shape[0], -1).contiguous().to(dev)
+            elif v.dim() == 4 and v.shape[-1] == 3:
+                w[k] = pack_conv3x3(v, dev)
+            elif v.dim() == 4:
+                w[k] = pack_matrix(v, dev)
+            else:
+                w[k] = vec(v, dev)
+        a = "decoder.mid.attn_1."
+        w[a + "qk.weight"] = torch.cat([w[a + "q.weight"], w[a + "k.weight"]], 0).contiguous()
+        w[a + "qk.bias"] = torch.cat([w[a + "q.bias"], w[a + "k.bias"]], 0).contiguous()
+        self.w = w
+        self._ws: Dict[Tuple[int, int, int], Workspace] = {}
+        self._graphs: Dict[Tuple, _Graph] = {}
+
+    def _res(self, ws: Workspace, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
+        """ResnetBlock.forward, temb=None (model/vae.py:103-124)."""
+        ops, w = self.ops, self.w
+        B, H, W, cin = x.shape
+        cout = out.shape[-1]
+        y = ops.groupnorm(x, w[p + "norm1.weight"], w[p + "norm1.bias"], 32, 1e-6, True, stats=ws.gn_scratch(ops, x),
+                          out=ws.get("gn", (B, H, W, cin)))
+        h = ops.conv3x3(y, w[p + "conv1.weight"], bias=w[p + "conv1.bias"], out=ws.get("res_h", (B, H, W, cout)))
+        y2 = ops.groupnorm(h, w[p + "norm2.weight"], w[p + "norm2.bias"], 32, 1e-6, True, stats=ws.gn_scratch(ops, h),
+                           out=ws.get("gn", (B, H, W, cout)))
+        if (p + "nin_shortcut.weight") in w:
+            skip = ops.gemm(x, w[p + "nin_shortcut.weight"], bias=w[p + "nin_shortcut.bias"],
+                            out=ws.get("res_skip", (B, H, W, cout)))
+        else:
+            skip = x
+        ops.conv3x3(y2, w[p + "conv2.weight"], bias=w[p + "conv2.bias"], residual=skip, out=out)
+
+    def _attn(self, ws: Workspace, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
+        """SDPAttnBlock.forward: one head of width C (model/vae.py:279-308)."""
+        ops, w = self.ops, self.w
+        B, H, W, C = x.shape
+        L = H * W
+        y = ops.groupnorm(x, w[p + "norm.weight"], w[p + "norm.bias"], 32, 1e-6, False, stats=ws.gn_scratch(ops, x),
+                          out=ws.get("gn", (B, L, C)))
+        qk = ops.gemm(y, w[p + "qk.weight"], bias=w[p + "qk.bias"], out=ws.get("va_qk", (B, L, 2 * C)))
+        # V^T per image ([C, L], keys contiguous) is the K-major B operand of P @ V
+        vt = ops.gemm(y, w[p + "v.weight"], bias=w[p + "v.bias"], out_mode=ops.OUT_NCHW_BF16, hw=L,
+                      out=ws.get("va_vt", (B, C, L)))
+        o = ws.get("va_o", (B, L, C))
+        s = ws.get("va_s", (L, L), F32)
+        pm = ws.get("va_p", (L, L))
+        for b in range(B):
+            ops.gemm(qk[b, :, :C], qk[b, :, C:], out_mode=ops.OUT_F32, out=s)
+            ops.softmax_rows(s, float(C) ** -0.5, out=pm)
+            ops.gemm(pm, vt[b], out=o[b])
+        ops.gemm(o, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out)
+
+    def _decode(self, ws: Workspace, z: torch.Tensor, scale_factor: float, img_out: torch.Tensor) -> None:
+        ops, w = self.ops, self.w
+        B, _, H, W = z.shape
+        zin = ws.zeros("v_zin", (B, H, W, 64))
+        ops.pointwise_nchw_to_nhwc(z, w["post_quant_conv.weight"], w["post_quant_conv.bias"], 1.0 / scale_factor, zin, 0)
+        ping = lambda i, shape: ws.get(f"v_h{i % 2}", shape)
+        n = 0
+        h = ping(n, (B, H, W, self.top))
+        ops.conv3x3(zin, w["decoder.conv_in.weight"], bias=w["decoder.conv_in.bias"], out=h)
+        for name in ("block_1", "attn_1", "block_2"):
+            n += 1
+            o = ping(n, (B, H, W, self.top))
+            if name == "attn_1":
+                self._attn(ws, "decoder.mid.attn_1.", h, o)
+            else:
+                self._res(ws, f"decoder.mid.{name}.", h, o)
+            h = o
+        for level, blocks, has_up in self.levels:
+            for i, (cin, cout) in enumerate(blocks):
+                n += 1
+                o = ping(n, (B, H, W, cout))
+                self._res(ws, f"decoder.up.{level}.block.{i}.", h, o)
+                h = o
+            if has_up:  # Upsample: nearest x2 then conv (model/vae.py:36-38)
+                c = h.shape[-1]
+                u = ops.upsample2x(h, out=ws.get("up", (B, 2 * H, 2 * W, c)))
+                H, W = 2 * H, 2 * W
+                n += 1
+                o = ping(n, (B, H, W, c))
+                ops.conv3x3(u, w[f"decoder.up.{level}.upsample.conv.weight"],
+                            bias=w[f"decoder.up.{level}.upsample.conv.bias"], out=o)
+                h = o
+        y = ops.groupnorm(h, w["decoder.norm_out.weight"], w["decoder.norm_out.bias"], 32, 1e-6, True,
+                          stats=ws.gn_scratch(ops, h), out=ws.get("gn", (B, H, W, self.last)))
+        ops.conv3x3(y, w["decoder.conv_out.weight"], bias=w["decoder.conv_out.bias"],
+                    out=img_out.view(B, self.dd["out_ch"], H * W), out_mode=ops.OUT_NCHW_F32)
+
+    def decode(self, z: torch.Tensor, scale_factor: float, use_graph: bool = True) -> torch.Tensor:
+        if z.dim() != 4 or z.shape[1] != self.embed_dim:
+            raise ValueError(f"z must be [B, {self.embed_dim}, H, W], got {tuple(z.shape)}")
+        if getattr(self.ops, "REQUIRES_CUDA", True) and not z.is_cuda:
+            raise RuntimeError("edtr_b200 has no CPU path: z must be a CUDA tensor")
+        B, _, H, W = z.shape
+        up = 2 ** (len(self.levels) - 1)
+        key = (B, H, W)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = self._ws[key] = Workspace(self.device)
+        sz = ws.get("in_z", tuple(z.shape), F32)
+        img = ws.get("out_img", (B, self.dd["out_ch"], H * up, W * up), F32)
+        sz.copy_(z)
+        run = lambda: self._decode(ws, sz, float(scale_factor), img)
+        if use_graph:
+            gk = (B, H, W, float(scale_factor))
+            g = self._graphs.get(gk)
+            if g is None:
+                g = self._graphs[gk] = _Graph(run)
+            g.replay()
+        else:
+            run()
+        return img.clone()

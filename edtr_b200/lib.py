@@ -29,9 +29,9 @@ NVCC_FLAGS = [
 # every symbol include/edtr_b200.h declares
 EXPORTED = [
     "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_gemm_tile_n", "edtr_gemm_bf16",
-    "edtr_conv3x3_bf16", "edtr_attention_bf16", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
+    "edtr_conv3x3_bf16", "edtr_attention_bf16", "edtr_groupnorm_partial_size", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
     "edtr_layernorm_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
-    "edtr_nchw_f32_to_nhwc_bf16", "edtr_nhwc_bf16_to_nchw", "edtr_cast_f32_to_bf16",
+    "edtr_nchw_f32_to_nhwc_bf16", "edtr_pointwise_nchw_f32_to_nhwc_bf16", "edtr_nhwc_bf16_to_nchw", "edtr_cast_f32_to_bf16",
     "edtr_timestep_embedding", "edtr_sampler_update",
 ]
 
@@ -109,6 +109,8 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_conv3x3_bf16.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, ep, vp]
     lib.edtr_attention_bf16.restype = ci
     lib.edtr_attention_bf16.argtypes = [vp, ci, vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, c_float, vp]
+    lib.edtr_groupnorm_partial_size.restype = c_size_t
+    lib.edtr_groupnorm_partial_size.argtypes = [ci, ci, ci, ci]
     lib.edtr_groupnorm_stats.restype = ci
     lib.edtr_groupnorm_stats.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp]
     lib.edtr_groupnorm_apply.restype = ci
@@ -123,6 +125,8 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_im2col_bf16.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, ci, vp]
     lib.edtr_nchw_f32_to_nhwc_bf16.restype = ci
     lib.edtr_nchw_f32_to_nhwc_bf16.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp]
+    lib.edtr_pointwise_nchw_f32_to_nhwc_bf16.restype = ci
+    lib.edtr_pointwise_nchw_f32_to_nhwc_bf16.argtypes = [vp, vp, vp, c_float, vp, ci, ci, ci, ci, ci, ci, vp]
     lib.edtr_nhwc_bf16_to_nchw.restype = ci
     lib.edtr_nhwc_bf16_to_nchw.argtypes = [vp, ci, vp, ci, ci, ci, ci, vp]
     lib.edtr_cast_f32_to_bf16.restype = ci
@@ -152,8 +156,12 @@ def last_error() -> str:
     return load().edtr_last_error().decode("utf-8", "replace")
 
 
+LAUNCHES = [0]  # successful kernel launches through the C-ABI
+
+
 def check(rc: int, what: str) -> None:
     if rc == 0:
+        LAUNCHES[0] += 1
         return
     msg = f"{what}: {last_error()} (code {rc})"
     if rc == -1:

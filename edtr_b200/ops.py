@@ -23,6 +23,12 @@ ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 OUT_BF16, OUT_F32, OUT_NCHW_F32, OUT_NCHW_BF16 = 0, 1, 2, 3
 
 BF16 = torch.bfloat16
+REQUIRES_CUDA = True  # there is no CPU implementation of any op
+
+
+def geglu_tile_n() -> int:
+    """N-tile width of the GEGLU GEMM (plan-time weight interleaving); no device needed."""
+    return int(_lib.load().edtr_gemm_tile_n(128, 1024, 64, ACT_GEGLU))
 
 
 def _stream() -> ctypes.c_void_p:
@@ -189,17 +195,26 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     return out
 
 
+def groupnorm_partial_size(B: int, HW: int, C: int, groups: int) -> int:
+    """fp32 elements of the partial-sum scratch edtr_groupnorm_stats writes (no device needed)."""
+    return int(_lib.load().edtr_groupnorm_partial_size(B, HW, C, groups))
+
+
 def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int, eps: float, silu: bool,
               stats: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm (+SiLU) over x [B, HW..., C] channels-last rows view."""
+    """GroupNorm (+SiLU) over x [B, HW..., C] channels-last rows view. `stats` = optional fp32 scratch of
+    at least groupnorm_partial_size(...) elements (contents are overwritten)."""
     _require_cuda(x, gamma, beta, stats, out)
     B = x.shape[0]
     M, C, ldx = rows_view(x)
     HW = M // B
+    if C % 8 != 0 or C % groups != 0:
+        raise ValueError(f"C ({C}) must be a multiple of 8 and of groups ({groups})")
+    need = groupnorm_partial_size(B, HW, C, groups)
     if stats is None:
-        stats = torch.zeros((B, groups, 2), dtype=torch.float32, device=x.device)
-    elif stats.dtype != torch.float32 or stats.numel() != B * groups * 2 or not stats.is_contiguous():
-        raise ValueError("stats must be a contiguous fp32 [B, groups, 2] tensor")
+        stats = torch.empty((need,), dtype=torch.float32, device=x.device)
+    elif stats.dtype != torch.float32 or stats.numel() < need or not stats.is_contiguous():
+        raise ValueError(f"stats must be a contiguous fp32 scratch tensor with >= {need} elements")
     if out is None:
         out = torch.empty(x.shape, dtype=BF16, device=x.device)
     Mo, Co, ldy = rows_view(out)
@@ -234,7 +249,9 @@ def softmax_rows(s: torch.Tensor, scale: float, out: Optional[torch.Tensor] = No
     M, N, lds = rows_view(s, torch.float32)
     if out is None:
         out = torch.empty(s.shape, dtype=BF16, device=s.device)
-    _, _, ldp = rows_view(out)
+    Mo, No, ldp = rows_view(out)
+    if (Mo, No) != (M, N):
+        raise ValueError("softmax out shape mismatch")
     L = _lib.device_lib()
     _lib.check(L.edtr_softmax_rows(s.data_ptr(), lds, out.data_ptr(), ldp, M, N, scale, _stream()),
                "edtr_softmax_rows")
@@ -254,11 +271,15 @@ def upsample2x(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Ten
     return out
 
 
-def im2col(x: torch.Tensor, kh: int, kw: int, stride: int, pad_top: int, pad_left: int, Ho: int, Wo: int) -> torch.Tensor:
-    _require_cuda(x)
+def im2col(x: torch.Tensor, kh: int, kw: int, stride: int, pad_top: int, pad_left: int, Ho: int, Wo: int,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, out)
     B, H, W, C = x.shape
     _, _, ldx = rows_view(x)
-    out = torch.empty((B * Ho * Wo, kh * kw * C), dtype=BF16, device=x.device)
+    if out is None:
+        out = torch.empty((B * Ho * Wo, kh * kw * C), dtype=BF16, device=x.device)
+    elif out.dtype != BF16 or not out.is_contiguous() or out.numel() != B * Ho * Wo * kh * kw * C:
+        raise ValueError("im2col out must be a contiguous bf16 [B*Ho*Wo, kh*kw*C] tensor")
     L = _lib.device_lib()
     _lib.check(L.edtr_im2col_bf16(x.data_ptr(), ldx, out.data_ptr(), B, H, W, C, kh, kw, stride, pad_top, pad_left,
                                   Ho, Wo, _stream()), "edtr_im2col_bf16")
@@ -280,6 +301,26 @@ def nchw_to_nhwc(x: torch.Tensor, out: torch.Tensor, coff: int = 0) -> torch.Ten
     return out
 
 
+def pointwise_nchw_to_nhwc(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], scale: float,
+                           out: torch.Tensor, coff: int = 0) -> torch.Tensor:
+    """out[..., coff:coff+Cout] = bias + w @ (scale * x) per pixel; x [B,Cin,H,W] fp32, w [Cout,Cin] fp32."""
+    _require_cuda(x, w, bias, out)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 4:
+        raise ValueError("x must be a contiguous fp32 NCHW tensor")
+    B, Cin, H, W = x.shape
+    if w.dtype != torch.float32 or not w.is_contiguous() or w.dim() != 2 or w.shape[1] != Cin:
+        raise ValueError("w must be a contiguous fp32 [Cout, Cin] matrix")
+    Cout = w.shape[0]
+    M, Co, ldy = rows_view(out)
+    if M != B * H * W or coff + Cout > Co:
+        raise ValueError("out does not match x")
+    L = _lib.device_lib()
+    _lib.check(L.edtr_pointwise_nchw_f32_to_nhwc_bf16(x.data_ptr(), w.data_ptr(), _f32(bias, Cout, "bias"), scale,
+                                                      out.data_ptr(), ldy, coff, B, Cin, Cout, H * W, _stream()),
+               "edtr_pointwise_nchw_f32_to_nhwc_bf16")
+    return out
+
+
 def nhwc_to_nchw(x: torch.Tensor, B: int, out_f32: bool = True) -> torch.Tensor:
     """x [B*HW, C] rows view (bf16) -> [B, C, HW] contiguous."""
     _require_cuda(x)
@@ -292,39 +333,50 @@ def nhwc_to_nchw(x: torch.Tensor, B: int, out_f32: bool = True) -> torch.Tensor:
     return out
 
 
-def cast_bf16(x: torch.Tensor) -> torch.Tensor:
-    _require_cuda(x)
+def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(x, out)
     if x.dtype != torch.float32 or not x.is_contiguous():
         raise ValueError("x must be contiguous fp32")
-    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    elif out.dtype != BF16 or not out.is_contiguous() or out.numel() != x.numel():
+        raise ValueError("cast out must be a contiguous bf16 tensor of the same size")
     L = _lib.device_lib()
     _lib.check(L.edtr_cast_f32_to_bf16(x.data_ptr(), out.data_ptr(), x.numel(), _stream()), "edtr_cast_f32_to_bf16")
     return out
 
 
-def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0) -> torch.Tensor:
-    _require_cuda(t)
+def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0,
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda(t, out)
     if t.dtype != torch.int64 or t.dim() != 1 or not t.is_contiguous():
         raise ValueError("timesteps must be a contiguous int64 vector")
-    out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)
+    if out is None:
+        out = torch.empty((t.shape[0], dim), dtype=BF16, device=t.device)
+    elif out.dtype != BF16 or not out.is_contiguous() or tuple(out.shape) != (t.shape[0], dim):
+        raise ValueError("timestep embedding out must be a contiguous bf16 [B, dim] tensor")
     L = _lib.device_lib()
     _lib.check(L.edtr_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], dim, max_period, _stream()),
                "edtr_timestep_embedding")
     return out
 
 
-def sampler_update(x, eps, noise, index, tables, want_pred_x0: bool = True):
+def sampler_update(x, eps, noise, index, tables, want_pred_x0: bool = True, x_prev=None, pred_x0=None):
     """Fused p_sample arithmetic; tables = (sqrt_recip, sqrt_recipm1, coef1, coef2, var) fp32 device vectors."""
     _require_cuda(x, eps, noise, index, *tables)
-    for t in (x, eps, noise):
-        if t.dtype != torch.float32 or not t.is_contiguous() or t.shape != x.shape:
-            raise ValueError("x / eps / noise must be contiguous fp32 tensors of one shape")
-    if index.dtype != torch.int64 or index.numel() != x.shape[0]:
-        raise ValueError("index must be int64 [B]")
+    for t in (x, eps, noise, x_prev, pred_x0):
+        if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.shape != x.shape):
+            raise ValueError("x / eps / noise / outputs must be contiguous fp32 tensors of one shape")
+    if index.dtype != torch.int64 or index.numel() != x.shape[0] or not index.is_contiguous():
+        raise ValueError("index must be contiguous int64 [B]")
+    for t in tables:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("coefficient tables must be contiguous fp32 vectors")
     B = x.shape[0]
     n = x.numel() // B
-    x_prev = torch.empty_like(x)
-    pred = torch.empty_like(x) if want_pred_x0 else None
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    pred = pred_x0 if pred_x0 is not None else (torch.empty_like(x) if want_pred_x0 else None)
     L = _lib.device_lib()
     _lib.check(L.edtr_sampler_update(x.data_ptr(), eps.data_ptr(), noise.data_ptr(), index.data_ptr(),
                                      *[t.data_ptr() for t in tables], x_prev.data_ptr(),

@@ -1,0 +1,40 @@
+"""Image-parallel sharding of the restore path: one process per GPU, every rank restores a
+contiguous slice of the batch with replicated weights and no per-step traffic; restored images and metric
+scalars are all-gathered once at the end of a batch (the reference's ``accelerator.gather_for_metrics``,
+main/det/test_edtr.py:163, main/cls/test_edtr.py:134-138)."""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of `total` images for `rank`; the first total % world ranks take one extra."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def sliced_noise(shape, seed: int, steps: int, lo: int, hi: int, device) -> List[torch.Tensor]:
+    """Per-step noise of the full batch drawn with one seed on every rank, then sliced, so an N-GPU run
+    reproduces the 1-GPU result image by image (RNG note)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return [torch.randn(shape, generator=g)[lo:hi].to(device) for _ in range(steps)]
+
+
+def gather_images(local: torch.Tensor, counts: List[int]) -> torch.Tensor:
+    """All-gather variable-size image shards [b_r, C, H, W] into the full batch on every rank."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    mx = max(counts)
+    pad = local
+    if local.shape[0] < mx:
+        pad = torch.cat([local, local.new_zeros((mx - local.shape[0],) + tuple(local.shape[1:]))], 0)
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad.contiguous())
+    return torch.cat([b[:n] for b, n in zip(bufs, counts)], 0)

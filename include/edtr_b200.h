@@ -112,13 +112,16 @@ int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ldk, const vo
                         void* stream);
 
 /* ---- memory-bound kernels ------------------------------------------------ */
-/* GroupNorm statistics: accumulates per-(image, group) sum and sum of squares of
- * X (bf16 [B, HW, C], row stride ldx) into stats[B, groups, 2] (fp32, must be
- * zero on entry).  replaces: first half of GroupNorm32 — model/util.py:161-163,
+/* GroupNorm statistics, pass 1: per-(image, pixel chunk, channel slab, group) partial sum and
+ * sum of squares of X (bf16 [B, HW, C], row stride ldx) written to `stats` (fp32,
+ * edtr_groupnorm_partial_size(B, HW, C, groups) elements; no zero-fill needed, no atomics, so the
+ * result is bit-reproducible).  replaces: first half of GroupNorm32 — model/util.py:161-163,
  * model/attention.py:50-51, model/vae.py:22-23. */
+size_t edtr_groupnorm_partial_size(int B, int HW, int C, int groups);
 int edtr_groupnorm_stats(const void* X, int ldx, int B, int HW, int C, int groups, float* stats,
                          void* stream);
-/* Y = (X - mean) * rstd * gamma + beta, optionally followed by SiLU; biased
+/* Pass 2: folds the partial sums of edtr_groupnorm_stats (same B, HW, C, groups) and writes
+ * Y = (X - mean) * rstd * gamma + beta, optionally followed by SiLU; biased
  * variance, eps inside the sqrt.  Y bf16 [B, HW, C] with row stride ldy.
  * replaces: GroupNorm32 + nn.SiLU — model/unet.py:149-151,173-175,675-677;
  * model/vae.py:103-113,553-554 (nonlinearity). */
@@ -151,6 +154,13 @@ int edtr_im2col_bf16(const void* X, int ldx, void* Y, int B, int H, int W, int C
  * replaces: x.type(self.dtype) + torch.cat((x, hint), 1) — model/controlnet.py:266-269. */
 int edtr_nchw_f32_to_nhwc_bf16(const float* X, void* Y, int ldy, int coff, int B, int C, int HW,
                                void* stream);
+/* 1x1 convolution over a few channels fused with the layout change:
+ * Y[(b, p), coff + co] = bias[co] + sum_ci W[co, ci] * (scale * X[b, ci, p]), Cin, Cout <= 16,
+ * X NCHW fp32, Y channels-last bf16, fp32 math.
+ * replaces: z / self.scale_factor (model/cldm.py:156) + post_quant_conv (model/vae.py:732). */
+int edtr_pointwise_nchw_f32_to_nhwc_bf16(const float* X, const float* W, const float* bias, float scale,
+                                         void* Y, int ldy, int coff, int B, int Cin, int Cout, int HW,
+                                         void* stream);
 /* channels-last bf16 -> NCHW (fp32 if out_f32 else bf16): Y[b, c, p] = X[(b,p), c]. */
 int edtr_nhwc_bf16_to_nchw(const void* X, int ldx, void* Y, int B, int C, int HW, int out_f32,
                            void* stream);

@@ -265,7 +265,7 @@ def make_inputs(cfg: dict, batch: int, latent_hw: int = 64, seed: int = 1):
 def timestep_embedding(t: Tensor, dim: int, max_period: float = 10000.0) -> Tensor:
     """model/util.py:98-118 (repeat_only=False)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:

@@ -1,0 +1,211 @@
+"""TEST INFRASTRUCTURE ONLY — a torch/CPU stand-in for ``edtr_b200.ops``.
+
+Mirrors the semantics of every C-ABI kernel (include/edtr_b200.h) with plain fp32 torch
+ops so that the host-side engine logic (block walk, buffer aliasing, channel-offset
+writes, in-place zero-conv accumulation, weight packing, GEGLU interleave, hoisted
+cross-attention K/V) can be checked against the oracle without a GPU.  Outputs are
+written into the ``out`` views the engine passes, in the dtype of those views (bf16
+storage rounding included).  Never imported by the product.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+OUT_BF16, OUT_F32, OUT_NCHW_F32, OUT_NCHW_BF16 = 0, 1, 2, 3
+REQUIRES_CUDA = False
+GEGLU_TILE = 128
+LAUNCHES = [0]
+
+
+def geglu_tile_n():
+    return GEGLU_TILE
+
+
+def groupnorm_partial_size(B, HW, C, groups):
+    return 64
+
+
+def _rows(t):
+    return t.reshape(-1, t.shape[-1]).float()
+
+
+def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, out_mode, hw, alpha, geglu_bias=None):
+    LAUNCHES[0] += 1
+    v = v * alpha
+    if act == ACT_GEGLU:
+        if bias is not None:
+            v = v + bias.float()
+        half = GEGLU_TILE // 2
+        v = v.view(M, -1, 2, half)
+        v = (v[:, :, 0] * F.gelu(v[:, :, 1])).reshape(M, n_out)
+    elif bias is not None:
+        v = v + bias.float()
+    if rowvec is not None:
+        v = v + rowvec.float().repeat_interleave(rows_per_group, 0)[:M]
+    if residual is not None:
+        v = v + _rows(residual)
+    if act == ACT_SILU:
+        v = F.silu(v)
+    if out_mode in (OUT_BF16, OUT_F32):
+        want = torch.bfloat16 if out_mode == OUT_BF16 else torch.float32
+        if out is None:
+            out = torch.empty((M, n_out), dtype=want)
+        assert out.dtype == want and out.numel() == M * n_out, (out.dtype, out.shape, M, n_out)
+        out.copy_(v.view(out.shape))
+    else:
+        want = torch.float32 if out_mode == OUT_NCHW_F32 else torch.bfloat16
+        if out is None:
+            out = torch.empty((M // hw, n_out, hw), dtype=want)
+        assert out.dtype == want and out.is_contiguous() and out.numel() == M * n_out
+        out.view(M // hw, n_out, hw).copy_(v.view(M // hw, hw, n_out).permute(0, 2, 1))
+    return out
+
+
+def gemm(a, w, *, bias=None, rowvec=None, rows_per_group=0, residual=None, act=ACT_NONE, out=None,
+         out_mode=OUT_BF16, hw=0, alpha=1.0):
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    A = _rows(a)
+    M, K = A.shape
+    N, Kw = w.shape
+    assert K == Kw and K % 64 == 0, (K, Kw)
+    n_out = N // 2 if act == ACT_GEGLU else N
+    return _finish(A @ w.float().t(), M, n_out, bias=bias, rowvec=rowvec, rows_per_group=rows_per_group,
+                   residual=residual, act=act, out=out, out_mode=out_mode, hw=hw, alpha=alpha)
+
+
+def conv3x3(x, w, *, bias=None, rowvec=None, residual=None, act=ACT_NONE, out=None, out_mode=OUT_BF16, alpha=1.0):
+    assert x.dtype == torch.bfloat16 and x.dim() == 4
+    B, H, W, Cin = x.shape
+    assert Cin % 64 == 0
+    Cout = w.shape[0]
+    assert w.shape[1] == 9 * Cin
+    wt = w.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    return _finish(y, B * H * W, Cout, bias=bias, rowvec=rowvec, rows_per_group=H * W, residual=residual, act=act,
+                   out=out, out_mode=out_mode, hw=H * W, alpha=alpha)
+
+
+def attention(q, k, v, heads, scale, out=None):
+    LAUNCHES[0] += 1
+    B, Lq, C = q.shape
+    split = lambda t: t.float().view(B, t.shape[1], heads, 64).permute(0, 2, 1, 3)
+    w = torch.softmax(split(q) @ split(k).transpose(-1, -2) * scale, dim=-1)
+    o = (w @ split(v)).permute(0, 2, 1, 3).reshape(B, Lq, C)
+    if out is None:
+        out = torch.empty((B, Lq, C), dtype=torch.bfloat16)
+    out.copy_(o)
+    return out
+
+
+def groupnorm(x, gamma, beta, groups, eps, silu, stats=None, out=None):
+    LAUNCHES[0] += 2
+    B, C = x.shape[0], x.shape[-1]
+    if stats is not None:
+        assert stats.dtype == torch.float32 and stats.numel() >= 1
+    xf = x.float().reshape(B, -1, C).permute(0, 2, 1)
+    y = F.group_norm(xf, groups, gamma, beta, eps)
+    if silu:
+        y = F.silu(y)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16)
+    out.copy_(y.permute(0, 2, 1).reshape(out.shape))
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out=None):
+    LAUNCHES[0] += 1
+    y = F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16)
+    out.copy_(y.view(out.shape))
+    return out
+
+
+def softmax_rows(s, scale, out=None):
+    LAUNCHES[0] += 1
+    p = torch.softmax(s.float() * scale, dim=-1)
+    if out is None:
+        out = torch.empty(s.shape, dtype=torch.bfloat16)
+    out.copy_(p)
+    return out
+
+
+def upsample2x(x, out=None):
+    LAUNCHES[0] += 1
+    B, H, W, C = x.shape
+    y = x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.bfloat16)
+    out.copy_(y)
+    return out
+
+
+def im2col(x, kh, kw, stride, pad_top, pad_left, Ho, Wo, out=None):
+    LAUNCHES[0] += 1
+    B, H, W, C = x.shape
+    pb = max(0, (Ho - 1) * stride + kh - pad_top - H)
+    pr = max(0, (Wo - 1) * stride + kw - pad_left - W)
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (pad_left, pr, pad_top, pb))
+    unf = F.unfold(xp, (kh, kw), stride=stride)  # [B, C*kh*kw, L]
+    L = unf.shape[-1]
+    assert L == Ho * Wo
+    col = unf.view(B, C, kh * kw, L).permute(0, 3, 2, 1).reshape(B * L, kh * kw * C)
+    if out is None:
+        out = torch.empty(col.shape, dtype=torch.bfloat16)
+    out.copy_(col)
+    return out
+
+
+def nchw_to_nhwc(x, out, coff=0):
+    LAUNCHES[0] += 1
+    C = x.shape[1]
+    out[..., coff:coff + C].copy_(x.permute(0, 2, 3, 1))
+    return out
+
+
+def pointwise_nchw_to_nhwc(x, w, bias, scale, out, coff=0):
+    LAUNCHES[0] += 1
+    y = torch.einsum("oc,bchw->bhwo", w.float(), x.float() * scale)
+    if bias is not None:
+        y = y + bias.float()
+    out[..., coff:coff + w.shape[0]].copy_(y)
+    return out
+
+
+def cast_bf16(x, out=None):
+    LAUNCHES[0] += 1
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16)
+    out.copy_(x)
+    return out
+
+
+def timestep_embedding(t, dim, max_period=10000.0, out=None):
+    LAUNCHES[0] += 1
+    half = dim // 2
+    freqs = torch.exp(-math.log(max_period) * torch.arange(half, dtype=torch.float32) / half)
+    args = t[:, None].float() * freqs[None]
+    e = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
+    if out is None:
+        out = torch.empty((t.shape[0], dim), dtype=torch.bfloat16)
+    out.copy_(e)
+    return out
+
+
+def sampler_update(x, eps, noise, index, tables, want_pred_x0=True, x_prev=None, pred_x0=None):
+    LAUNCHES[0] += 1
+    B = x.shape[0]
+    e = lambda t: t[index].view(B, *([1] * (x.dim() - 1)))
+    x0 = e(tables[0]) * x - e(tables[1]) * eps
+    mean = e(tables[2]) * x0 + e(tables[3]) * x
+    xp = mean + (index != 0).float().view(B, *([1] * (x.dim() - 1))) * torch.sqrt(e(tables[4])) * noise
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    x_prev.copy_(xp)
+    if pred_x0 is None and want_pred_x0:
+        pred_x0 = torch.empty_like(x)
+    if pred_x0 is not None:
+        pred_x0.copy_(x0)
+    return x_prev, pred_x0

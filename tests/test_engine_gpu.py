@@ -1,0 +1,149 @@
+"""GPU parity of the whole path: CUDA engine (through the C-ABI) vs the fixtures recorded from the
+live reference (tests/golden/) and vs the oracle evaluated on the same seeded inputs.
+
+Tolerances are BASELINE.json's: per-step latent max-rel error <= 2e-2 (bf16), final image PSNR >= 40 dB.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cldm_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+STEP_TOL = 2e-2
+PSNR_MIN = 40.0
+
+
+def _dd(v):
+    return dict(z_channels=v["z_channels"], ch=v["ch"], ch_mult=v["ch_mult"], num_res_blocks=v["num_res_blocks"],
+                out_ch=v["out_ch"], in_channels=v["in_channels"], attn_resolutions=[])
+
+
+def _tables(cfg):
+    s = O.make_schedule(O.make_betas(**cfg["diffusion"]), len(cfg["used_timesteps"]), cfg["used_timesteps"])
+    return {k: torch.from_numpy(v).cuda() for k, v in s.items() if k != "timesteps"}, list(s["timesteps"][::-1])
+
+
+def _engines(cfg, w):
+    from edtr_b200.engine import CldmEngine, VaeDecoderEngine
+
+    eng = CldmEngine(cfg["unet"], cfg["controlnet"], w["unet"], w["controlnet"], "cuda")
+    vd = VaeDecoderEngine(_dd(cfg["vae"]), cfg["vae"]["embed_dim"], w["vae"], "cuda")
+    return eng, vd
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    w = O.make_cldm_weights(O.TINY, seed=0)
+    x_T, cond, noise = O.make_inputs(O.TINY, 2, 16, seed=1)
+    return w, x_T, cond, noise, np.load(os.path.join(GOLD, "golden_tiny.npz")), _engines(O.TINY, w)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_tiny_against_reference_fixture(tiny, use_graph):
+    w, x_T, cond, noise, g, (eng, vd) = tiny
+    tabs, ts = _tables(O.TINY)
+    t = torch.full((2,), 200, dtype=torch.long, device="cuda")
+    eps = eng.forward(x_T.cuda(), t, cond["c_img"].cuda(), cond["c_txt"].cuda(), use_graph=use_graph)
+    assert O.max_rel_err(eps.cpu(), torch.from_numpy(g["eps0"])) < 3e-2
+    z, x0s, xs = eng.sample(x_T.cuda(), ts, tabs, cond["c_img"].cuda(), cond["c_txt"].cuda(),
+                            [n.cuda() for n in noise], use_graph=use_graph, return_intermediates=True)
+    for i in range(4):
+        assert O.max_rel_err(xs[i].cpu(), torch.from_numpy(g["xs"][i])) < STEP_TOL, i
+        assert O.max_rel_err(x0s[i].cpu(), torch.from_numpy(g["x0s"][i])) < STEP_TOL, i
+    img = vd.decode(z, O.TINY["latent_scale_factor"], use_graph=use_graph)
+    ref = torch.from_numpy(g["img"])
+    assert O.psnr((img.cpu() + 1) / 2, (ref + 1) / 2) >= PSNR_MIN
+    # replay determinism: the captured graph must give the same bits on a second call
+    z2 = eng.sample(x_T.cuda(), ts, tabs, cond["c_img"].cuda(), cond["c_txt"].cuda(), [n.cuda() for n in noise],
+                    use_graph=use_graph)
+    assert torch.equal(z, z2)
+
+
+def test_tiny_odd_batch_and_rectangular_latent(tiny):
+    """Ragged cases: batch 3 (tiles straddle images at the 8x8 level) and a 16x32 latent."""
+    w, _, _, _, _, (eng, vd) = tiny
+    for B, H, W in ((3, 16, 16), (1, 16, 32)):
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(B, 4, H, W, generator=g)
+        cond = dict(c_img=0.8 * torch.randn(B, 4, H, W, generator=g), c_txt=torch.randn(B, 77, 128, generator=g))
+        t = torch.tensor([200, 50, 150][:B])
+        with torch.no_grad():
+            ref = O.cldm_forward(w, O.TINY, x, t, cond)
+        eps = eng.forward(x.cuda(), t.cuda(), cond["c_img"].cuda(), cond["c_txt"].cuda(), use_graph=False)
+        assert O.max_rel_err(eps.cpu(), ref) < 3e-2, (B, H, W)
+        z = 0.5 * torch.randn(B, 4, H, W, generator=g)
+        with torch.no_grad():
+            iref = O.vae_decode(w["vae"], O.TINY["vae"], z, 0.18215)
+        img = vd.decode(z.cuda(), 0.18215, use_graph=False)
+        assert O.psnr((img.cpu() + 1) / 2, (iref + 1) / 2) >= PSNR_MIN, (B, H, W)
+
+
+@pytest.fixture(scope="module")
+def s4():
+    w = O.make_cldm_weights(O.S4, seed=0)
+    return w, _engines(O.S4, w)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLD, "golden_s4.npz")), reason="full-size fixture absent")
+def test_s4_against_reference_fixture(s4):
+    """BASELINE config C1 inputs (B=1, 64x64 latent, s4 widths) against the reference's fp32 CPU output."""
+    w, (eng, vd) = s4
+    g = np.load(os.path.join(GOLD, "golden_s4.npz"))
+    x_T, cond, noise = O.make_inputs(O.S4, 1, 64, seed=1)
+    tabs, ts = _tables(O.S4)
+    t = torch.full((1,), 200, dtype=torch.long, device="cuda")
+    eps = eng.forward(x_T.cuda(), t, cond["c_img"].cuda(), cond["c_txt"].cuda())
+    print("eps0 rel", O.max_rel_err(eps.cpu(), torch.from_numpy(g["eps0"])))
+    z, x0s, xs = eng.sample(x_T.cuda(), ts, tabs, cond["c_img"].cuda(), cond["c_txt"].cuda(),
+                            [n.cuda() for n in noise], return_intermediates=True)
+    errs = [O.max_rel_err(xs[i].cpu(), torch.from_numpy(g["xs"][i])) for i in range(4)]
+    print("per-step latent max-rel", errs)
+    assert max(errs) < STEP_TOL
+    img = vd.decode(z, O.S4["latent_scale_factor"])
+    ref = torch.from_numpy(g["img"].astype(np.float32))
+    p = O.psnr((img.cpu() + 1) / 2, (ref + 1) / 2)
+    print("psnr", p)
+    assert p >= PSNR_MIN
+
+
+def test_s4_batch8_against_oracle_on_device(s4):
+    """BASELINE config C2 (B=8): the oracle restatement evaluated in fp32 on the GPU (TF32 off) is the checker."""
+    w, (eng, vd) = s4
+    B = 8
+    x_T, cond, noise = O.make_inputs(O.S4, B, 64, seed=3)
+    tabs, ts = _tables(O.S4)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    wd = {k: {n: v.cuda() for n, v in sd.items()} for k, sd in w.items()}
+    condd = {k: v.cuda() for k, v in cond.items()}
+    z, x0s, xs = eng.sample(x_T.cuda(), ts, tabs, condd["c_img"], condd["c_txt"], [n.cuda() for n in noise],
+                            return_intermediates=True)
+    img = vd.decode(z, O.S4["latent_scale_factor"])
+    with torch.no_grad():
+        # image by image keeps the fp32 checker's memory small
+        for b in range(0, B, 2):
+            sl = slice(b, b + 2)
+            zr, xr, _ = _oracle_sample_cuda(wd, x_T[sl].cuda(), {k: v[sl] for k, v in condd.items()},
+                                            [n[sl].cuda() for n in noise])
+            for i in range(4):
+                assert O.max_rel_err(xs[i][sl], xr[i]) < STEP_TOL, (b, i)
+            ir = O.vae_decode(wd["vae"], O.S4["vae"], zr, O.S4["latent_scale_factor"])
+            assert O.psnr((img[sl] + 1) / 2, (ir + 1) / 2) >= PSNR_MIN, b
+    del wd
+    torch.cuda.empty_cache()
+
+
+def _oracle_sample_cuda(wd, x_T, cond, noise):
+    sched = O.make_schedule(O.make_betas(**O.S4["diffusion"]), 4, O.S4["used_timesteps"])
+    ts = sched["timesteps"][::-1]
+    x, xs = x_T, []
+    for i, step in enumerate(ts):
+        t = torch.full((x.shape[0],), int(step), dtype=torch.long, device=x.device)
+        eps = O.cldm_forward(wd, O.S4, x, t, cond)
+        x, _ = O.p_sample_update(sched, x, eps, len(ts) - i - 1, noise[i])
+        xs.append(x)
+    return x, xs, None
