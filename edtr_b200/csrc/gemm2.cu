@@ -1,0 +1,444 @@
+// Persistent CTA-pair (cta_group::2) tcgen05 implicit-GEMM for sm_100a — the main dense kernel.
+//
+// A cluster of two CTAs (one TPC) owns 256 output rows x `bn` output columns per tile:
+//   * each CTA TMA-loads its own 128 rows of A (a 2-D box for GEMMs, a shifted 4-D box per
+//     filter tap for 3x3 convolutions; out-of-image pixels are zero-filled = the padding) and
+//     its own half (bn/2 rows) of the weight tile; all loads signal the leader CTA's barrier;
+//   * the leader issues tcgen05.mma.cta_group::2 (M=256, N=bn, K=16) reading both CTAs'
+//     shared memory; accumulators (128 lanes x bn fp32 columns per CTA) are double-buffered
+//     in TMEM so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * four epilogue warps per CTA drain TMEM in 64-column chunks: optional residual chunk is
+//     TMA-loaded into a swizzled staging buffer, bias / time-embedding row vector / residual /
+//     SiLU / GEGLU are applied in fp32, the bf16 result is written back to the staging buffer
+//     and TMA-stored (fully coalesced, clipped at the matrix edge).
+// Tiles are scheduled round-robin over the persistent clusters (grid = 2 x min(tiles, 74)).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace edtr {
+
+constexpr int k2BM = 128;   // rows per CTA (pair = 256)
+constexpr int k2BK = 64;
+constexpr int k2Threads = 192;
+constexpr int k2MaxStages = 10;
+constexpr int k2MaxBN = 256;
+constexpr int k2ABytes = k2BM * k2BK * 2;            // 16 KB
+constexpr int k2PipeBytes = 6 * (k2ABytes + (k2MaxBN / 2) * k2BK * 2);  // 192 KB ring: 6 stages at bn=256 ... 9 at bn=64
+constexpr int k2StagingBufs = 2;
+constexpr int k2StagingBytes = k2BM * 64 * 2;        // 128 rows x 64 bf16 = 16 KB
+constexpr int k2SmemBytes = k2PipeBytes + k2StagingBufs * k2StagingBytes + 1024 + 512;
+
+struct Gemm2Params {
+  int M, N;                // accumulator matrix: rows, columns (= weight rows)
+  int num_kblocks;
+  int mode;                // 0 gemm, 1 conv3x3
+  int H, W, cblocks;
+  int tiles_m, tiles_n;    // 256-row pair tiles, column tiles
+  int bn_base;             // width of every column tile but the last (multiple of 64, <= 256)
+  int b_box_rows;          // rows of the weight TMA box (= bn_base / 2)
+  int stages;              // pipeline depth: k2PipeBytes / stage_bytes, <= k2MaxStages
+  int stage_bytes;         // 16 KB of A + b_box_rows * 128 B of B
+  int geglu;
+  int has_residual;
+  int act;
+  float alpha;
+  const float* bias;
+  const float* rowvec;
+  int rowvec_ld;
+  int rows_per_group;
+};
+
+__device__ __forceinline__ float gelu_fast(float x) {
+  // x * Phi(x) with erf from Abramowitz-Stegun 7.1.26 (|abs err| < 1.5e-7, far below bf16 resolution)
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.f - poly * t * __expf(-z * z);   // erf(|x|/sqrt2)
+  const float erfv = copysignf(e, x);
+  return 0.5f * x * (1.f + erfv);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
+             const Gemm2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sPipe = smem;                             // stage s: A at s*stage_bytes, B right after it
+  uint8_t* sC = sPipe + k2PipeBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + k2StagingBufs * k2StagingBytes);
+  uint64_t* full_bar = bars;                         // [stages]  (leader's copy is the live one)
+  uint64_t* empty_bar = bars + k2MaxStages;          // [stages]
+  uint64_t* tfull_bar = bars + 2 * k2MaxStages;      // [2] accumulator ready (multicast to both CTAs)
+  uint64_t* tempty_bar = bars + 2 * k2MaxStages + 2; // [2] accumulator drained (leader's copy, 8 arrivals)
+  uint64_t* res_bar = bars + 2 * k2MaxStages + 4;    // [2] residual chunk landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * k2MaxStages + 8);
+  const int nstages = p.stages;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    if (p.has_residual) tma_prefetch_desc(&tmC);
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_bar[s], 2);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);
+    }
+    for (int b = 0; b < k2StagingBufs; ++b) mbar_init(&res_bar[b], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_holder, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        const int m0 = tm * (2 * k2BM) + static_cast<int>(rank) * k2BM;
+        const int n_tile0 = tn * p.bn_base;
+        const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
+        const int nrow0 = n_tile0 + static_cast<int>(rank) * (bn >> 1);
+        int cx = 0, cy = 0, cn = 0;
+        if (p.mode == 1) {
+          cx = (p.W >= k2BM) ? (m0 % p.W) : 0;
+          cy = (m0 / p.W) % p.H;
+          cn = m0 / (p.W * p.H);
+        }
+        for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+          const int s = it % nstages;
+          const uint32_t ph = (it / nstages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+          mbar_arrive_expect_tx_cluster(fb, p.stage_bytes);
+          uint8_t* sa = sPipe + s * p.stage_bytes;
+          if (p.mode == 0) {
+            tma_load_2d_pair(sa, &tmA, fb, kb * k2BK, m0);
+          } else {
+            const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma_load_4d_pair(sa, &tmA, fb, cb * k2BK, cx + dx, cy + dy, cn);
+          }
+          tma_load_2d_pair(sa + k2ABytes, &tmB, fb, kb * k2BK, nrow0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------- UMMA issuer (leader only)
+    if (lane == 0 && leader) {
+      uint32_t it = 0, ti = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
+        const int tn = tile % p.tiles_n;
+        const int n_tile0 = tn * p.bn_base;
+        const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
+        const uint32_t idesc = umma_idesc_bf16(2 * k2BM, bn);
+        const uint32_t a = ti & 1, aph = (ti >> 1) & 1;
+        mbar_wait(&tempty_bar[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * k2MaxBN;
+        for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+          const int s = it % nstages;
+          const uint32_t ph = (it / nstages) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(sPipe + s * p.stage_bytes);
+          const uint64_t adesc = umma_smem_desc_sw128(sa);
+          const uint64_t bdesc = umma_smem_desc_sw128(sa + k2ABytes);
+#pragma unroll
+          for (int k = 0; k < k2BK / 16; ++k)
+            umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit_pair(&empty_bar[s], 0x3);
+        }
+        umma_commit_pair(&tfull_bar[a], 0x3);
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue (both CTAs)
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;               // row inside this CTA's 128-row half == TMEM lane
+    const bool e0 = (warp == 2 && lane == 0);   // issues the residual loads and the output stores
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    uint8_t* my_row = nullptr;
+    uint32_t ti = 0;
+    uint32_t res_uses[k2StagingBufs] = {0, 0};
+    const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int m0 = tm * (2 * k2BM) + static_cast<int>(rank) * k2BM;
+      const int row = m0 + r;
+      const int n_tile0 = tn * p.bn_base;
+      const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
+      const uint32_t a = ti & 1, aph = (ti >> 1) & 1;
+      const int out_cols_tile = p.geglu ? (bn >> 1) : bn;
+      const int nchunks = out_cols_tile >> 6;
+      const int out_col_tile0 = p.geglu ? (n_tile0 >> 1) : n_tile0;
+      const int n_out = p.geglu ? (p.N >> 1) : p.N;
+      // all stores of the previous tile must have finished reading the staging buffers
+      if (e0) {
+        bulk_wait_group_read<0>();
+        if (p.has_residual) {
+          mbar_arrive_expect_tx(&res_bar[0], k2StagingBytes);
+          tma_load_2d(sC, &tmC, &res_bar[0], out_col_tile0, m0);
+        }
+      }
+      named_bar_sync(1, 128);
+      mbar_wait(&tfull_bar[a], aph);
+      tc_fence_after();
+      const uint32_t tacc = trow + a * k2MaxBN;
+      for (int c = 0; c < nchunks; ++c) {
+        const int out_col0 = out_col_tile0 + c * 64;
+        if (out_col0 >= n_out) break;            // uniform over the CTA
+        const int buf = c & 1;
+        uint8_t* stage = sC + buf * k2StagingBytes;
+        my_row = stage + r * 128;
+        // the other staging buffer was last stored from at chunk c-1: once that store has read it,
+        // prefetch the next residual chunk into it (and it is free for chunk c+1's output)
+        if (e0 && c > 0) bulk_wait_group_read<0>();
+        if (e0 && p.has_residual && c + 1 < nchunks && out_col0 + 64 < n_out) {
+          mbar_arrive_expect_tx(&res_bar[buf ^ 1], k2StagingBytes);
+          tma_load_2d(sC + (buf ^ 1) * k2StagingBytes, &tmC, &res_bar[buf ^ 1], out_col0 + 64, m0);
+        }
+        float v[64];
+        {
+          uint32_t r0[32], r1[32];
+          if (!p.geglu) {
+            tmem_ld32(tacc + c * 64, r0);
+            tmem_ld32(tacc + c * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              v[j] = __uint_as_float(r0[j]) * p.alpha;
+              v[32 + j] = __uint_as_float(r1[j]) * p.alpha;
+            }
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_tile0 + c * 64);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 b = __ldg(b4 + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+          } else {
+            const int half = bn >> 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tmem_ld32(tacc + c * 64 + h * 32, r0);          // value columns
+              tmem_ld32(tacc + half + c * 64 + h * 32, r1);   // gate columns
+              tmem_ld_wait();
+              float xb[32], gb[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { xb[j] = 0.f; gb[j] = 0.f; }
+              if (p.bias != nullptr) {
+                const float4* bx = reinterpret_cast<const float4*>(p.bias + n_tile0 + c * 64 + h * 32);
+                const float4* bg = reinterpret_cast<const float4*>(p.bias + n_tile0 + half + c * 64 + h * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 x4 = __ldg(bx + j), g4 = __ldg(bg + j);
+                  xb[4 * j] = x4.x; xb[4 * j + 1] = x4.y; xb[4 * j + 2] = x4.z; xb[4 * j + 3] = x4.w;
+                  gb[4 * j] = g4.x; gb[4 * j + 1] = g4.y; gb[4 * j + 2] = g4.z; gb[4 * j + 3] = g4.w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = fmaf(__uint_as_float(r0[j]), p.alpha, xb[j]);
+                const float g = fmaf(__uint_as_float(r1[j]), p.alpha, gb[j]);
+                v[h * 32 + j] = x * gelu_fast(g);
+              }
+            }
+          }
+        }
+        if (p.rowvec != nullptr && row < p.M) {
+          const float4* r4 = reinterpret_cast<const float4*>(
+              p.rowvec + static_cast<size_t>(row / p.rows_per_group) * p.rowvec_ld + out_col0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 b = __ldg(r4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+          }
+        }
+        if (p.has_residual) {
+          mbar_wait(&res_bar[buf], res_uses[buf] & 1);
+          res_uses[buf]++;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ (r & 7)) << 4));
+            const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+            v[8 * j] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
+            v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
+          }
+        }
+        if (p.act == EDTR_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = silu_f(v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 u;
+          u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+          u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+          u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+          u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+          *reinterpret_cast<uint4*>(my_row + ((j ^ (r & 7)) << 4)) = u;
+        }
+        if (c == nchunks - 1 || out_col0 + 64 >= n_out) {
+          // last TMEM read of this tile: hand the accumulator stage back to the MMA issuer
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (e0) {
+          tma_store_2d(&tmD, stage, out_col0, m0);
+          bulk_commit_group();
+        }
+      }
+    }
+    if (e0) bulk_wait_group<0>();
+  }
+  __syncwarp();  // role branches diverge inside a warp; the cluster barrier below is .aligned
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+int prime_gemm2_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(gemm2): %s", cudaGetErrorString(e));
+    return EDTR_ERR_CUDA;
+  }
+  return EDTR_OK;
+}
+
+// Column tiling.  Every tile but the last is `bn_base` wide (a multiple of 64, <= 256).  The width is
+// chosen with a small cost model: waves over the 74 CTA pairs x time per k-block, where a k-block of a
+// bn-wide pair tile costs max(2*bn, 280) cycles (narrow tiles are bound by operand fetch, not by the
+// tensor pipe).  GEGLU is pinned to 256 because its weight interleave is done at pack time.
+static void split_n(int M, int N, int geglu, int* tiles_n, int* bn_base) {
+  if (geglu) {
+    *tiles_n = N / k2MaxBN;
+    *bn_base = k2MaxBN;
+    return;
+  }
+  const int tiles_m = (M + 2 * k2BM - 1) / (2 * k2BM);
+  long best_cost = -1;
+  int best_t = 1, best_b = 64;
+  for (int cap = k2MaxBN; cap >= 64; cap -= 64) {
+    const int t = (N + cap - 1) / cap;
+    int base = ((N + t - 1) / t + 63) & ~63;
+    if (base > cap) base = cap;
+    const int tn = (N + base - 1) / base;
+    const long waves = (static_cast<long>(tiles_m) * tn + 73) / 74;
+    const long per_kb = 2 * base > 300 ? 2 * base : 300;
+    const long cost = waves * per_kb;
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best_t = tn;
+      best_b = base;
+    }
+  }
+  *tiles_n = best_t;
+  *bn_base = best_b;
+}
+
+bool gemm2_disabled();
+
+bool gemm2_eligible(int M, int N, const EdtrEpilogue* ep) {
+  if (gemm2_disabled()) return false;
+  if (ep->out_mode != EDTR_OUT_BF16) return false;
+  const int n_out = ep->act == EDTR_ACT_GEGLU ? N / 2 : N;
+  if (ep->act == EDTR_ACT_GEGLU) return N % k2MaxBN == 0;  // any M: the weight interleave is tied to this kernel
+  if (M < 256) return false;
+  if (n_out % 8 != 0 || N % 64 != 0) return false;
+  if (ep->rowvec != nullptr && ((ep->rowvec_ld & 3) != 0 || (reinterpret_cast<uintptr_t>(ep->rowvec) & 15) != 0))
+    return false;
+  return true;
+}
+
+int gemm2_tile_n(int N, int geglu) {
+  int t, b;
+  split_n(1 << 20, N, geglu, &t, &b);
+  return b;
+}
+
+bool gemm2_disabled() {
+  const char* e = getenv("EDTR_GEMM_V1");  // debugging switch: force the single-CTA kernel
+  return e != nullptr && e[0] == '1';
+}
+
+// A/B tensor maps are built by the caller (gemm or conv geometry); C/D maps are built here.
+int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, int N, int mode, int H, int W,
+                 int cblocks, const EdtrEpilogue* ep, cudaStream_t stream) {
+  Gemm2Params p{};
+  p.M = M; p.N = N; p.num_kblocks = K / k2BK; p.mode = mode; p.H = H; p.W = W; p.cblocks = cblocks;
+  p.geglu = ep->act == EDTR_ACT_GEGLU;
+  split_n(M, N, p.geglu, &p.tiles_n, &p.bn_base);
+  p.tiles_m = (M + 2 * k2BM - 1) / (2 * k2BM);
+  p.b_box_rows = p.bn_base / 2;
+  p.stage_bytes = k2ABytes + p.b_box_rows * k2BK * 2;
+  p.stages = k2PipeBytes / p.stage_bytes;
+  if (p.stages > k2MaxStages) p.stages = k2MaxStages;
+  p.has_residual = ep->residual != nullptr;
+  p.act = ep->act; p.alpha = ep->alpha; p.bias = ep->bias; p.rowvec = ep->rowvec; p.rowvec_ld = ep->rowvec_ld;
+  p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+  const int n_out = p.geglu ? N / 2 : N;
+  CUtensorMap tmB, tmC, tmD;
+  int rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {k2BK, static_cast<uint32_t>(p.b_box_rows)};
+    rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ep->ldc) * 2};
+    uint32_t box[2] = {64, k2BM};
+    rc = make_tmap_bf16(&tmD, ep->out, 2, dims, strides, box);
+    if (rc) return rc;
+  }
+  if (p.has_residual) {
+    uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ep->ldr) * 2};
+    uint32_t box[2] = {64, k2BM};
+    rc = make_tmap_bf16(&tmC, ep->residual, 2, dims, strides, box);
+    if (rc) return rc;
+  } else {
+    tmC = tmD;
+  }
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int clusters = tiles < 74 ? tiles : 74;
+  gemm2_kernel<<<2 * clusters, k2Threads, k2SmemBytes, stream>>>(tmA, tmB, tmC, tmD, p);
+  return check_launch("gemm2_kernel");
+}
+
+}  // namespace edtr

@@ -335,6 +335,12 @@ int prime_gemm_attributes() {
   return EDTR_OK;
 }
 
+bool gemm2_eligible(int M, int N, const EdtrEpilogue* ep);
+int gemm2_tile_n(int N, int geglu);
+bool gemm2_disabled();
+int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, int N, int mode, int H, int W,
+                 int cblocks, const EdtrEpilogue* ep, cudaStream_t stream);
+
 static int check_epilogue(const EdtrEpilogue* ep, int M, int N) {
   EDTR_REQUIRE(ep != nullptr && ep->out != nullptr, "epilogue/out is NULL");
   EDTR_REQUIRE(ep->act >= 0 && ep->act <= 2, "bad act %d", ep->act);
@@ -356,7 +362,11 @@ static int check_epilogue(const EdtrEpilogue* ep, int M, int N) {
     EDTR_REQUIRE(ep->rows_per_group > 0 && ep->rowvec_ld >= n_out, "bad rowvec geometry");
   if (ep->bias != nullptr)
     EDTR_REQUIRE((reinterpret_cast<uintptr_t>(ep->bias) & 15) == 0, "bias must be 16-byte aligned");
-  if (ep->act == EDTR_ACT_GEGLU) EDTR_REQUIRE(N % 128 == 0, "GEGLU needs N %% 128 == 0 (N %d)", N);
+  if (ep->act == EDTR_ACT_GEGLU) {
+    EDTR_REQUIRE(N % 128 == 0, "GEGLU needs N %% 128 == 0 (N %d)", N);
+    EDTR_REQUIRE(ep->out_mode == EDTR_OUT_BF16 || N % 256 != 0 || gemm2_disabled(),
+                 "GEGLU with N %% 256 == 0 runs on the CTA-pair kernel, which stores bf16 only");
+  }
   return EDTR_OK;
 }
 
@@ -366,6 +376,7 @@ using namespace edtr;
 
 extern "C" int edtr_gemm_tile_n(int M, int N, int K, int act) {
   (void)K;
+  if (act == EDTR_ACT_GEGLU && N % 256 == 0 && !gemm2_disabled()) return gemm2_tile_n(N, 1);
   return pick_bn(M, N, act);
 }
 
@@ -387,6 +398,8 @@ extern "C" int edtr_gemm_bf16(const void* A, int lda, const void* Wt, int ldw, i
     rc = make_tmap_bf16(&tmA, A, 2, dims, strides, box);
     if (rc) return rc;
   }
+  if (gemm2_eligible(M, N, ep))
+    return launch_gemm2(tmA, Wt, ldw, K, M, N, 0, 0, 0, 0, ep, static_cast<cudaStream_t>(stream));
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
     uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
@@ -440,6 +453,8 @@ extern "C" int edtr_conv3x3_bf16(const void* X, int ldx, int B, int H, int W, in
     if (rc) return rc;
   }
   const int K = 9 * Cin;
+  if (gemm2_eligible(M, Cout, ep))
+    return launch_gemm2(tmA, Wt, K, K, M, Cout, 1, H, W, Cin / kBK, ep, static_cast<cudaStream_t>(stream));
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(Cout)};
     uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};

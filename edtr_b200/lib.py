@@ -18,7 +18,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libedtr_b200.so")
-SOURCES = ["api.cu", "gemm_conv.cu", "attention.cu", "norm.cu", "elementwise.cu"]
+SOURCES = ["api.cu", "gemm_conv.cu", "gemm2.cu", "attention.cu", "norm.cu", "elementwise.cu"]
 HEADER = os.path.join(_REPO_DIR, "include", "edtr_b200.h")
 
 NVCC_FLAGS = [

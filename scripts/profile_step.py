@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--out", default="gpurun_out/profile_step.txt")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--shapes", action="store_true", help="eager per-shape timing of the tensor-core launches")
     a = ap.parse_args()
     B = a.batch
     cn_cfg = dict(S4_NET, hint_channels=4)
@@ -93,6 +94,59 @@ def main():
     ws = eng.workspace(B, 64, 64)
     lines.append(f"weights {eng.unet.nbytes() / 1e9:.2f}+{eng.cnet.nbytes() / 1e9:.2f} GB, workspace {ws.nbytes() / 1e9:.2f} GB, "
                  f"mem allocated {torch.cuda.memory_allocated() / 1e9:.2f} GB")
+    if a.shapes:
+        # eager pass with every tensor-core launch bracketed by events, aggregated by op and shape
+        from edtr_b200 import ops
+
+        recs = []
+        orig = {n: getattr(ops, n) for n in ("gemm", "conv3x3", "attention", "groupnorm", "layernorm")}
+
+        def wrap(name, fn):
+            def w(*args, **kw):
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record()
+                r = fn(*args, **kw)
+                e_.record()
+                if name == "gemm":
+                    A, Wt = args[0], args[1]
+                    M = A.numel() // A.shape[-1]
+                    key = (name, M, Wt.shape[0], Wt.shape[1], "geglu" if kw.get("act") == 2 else "res" if kw.get("residual") is not None else "")
+                    fl = 2.0 * M * Wt.shape[0] * Wt.shape[1]
+                elif name == "conv3x3":
+                    X, Wt = args[0], args[1]
+                    M = X.numel() // X.shape[-1]
+                    key = (name, M, Wt.shape[0], Wt.shape[1], "res" if kw.get("residual") is not None else "")
+                    fl = 2.0 * M * Wt.shape[0] * Wt.shape[1]
+                elif name == "attention":
+                    q, k_ = args[0], args[1]
+                    key = (name, q.shape[0] * q.shape[1], k_.shape[1], q.shape[2], "")
+                    fl = 4.0 * q.shape[0] * q.shape[1] * k_.shape[1] * q.shape[2]
+                else:
+                    x = args[0]
+                    key = (name, x.numel() // x.shape[-1], x.shape[-1], 0, "")
+                    fl = 4.0 * x.numel()  # bytes (bf16 in + out)
+                recs.append((key, fl, s_, e_))
+                return r
+            return w
+
+        for n, fn in orig.items():
+            setattr(ops, n, wrap(n, fn))
+        try:
+            z2 = eng.sample(x_T, ts, tabs, c_img, c_txt, noise, use_graph=False)
+            vd.decode(z2, 0.18215, use_graph=False)
+        finally:
+            for n, fn in orig.items():
+                setattr(ops, n, fn)
+        torch.cuda.synchronize()
+        agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+        for key, fl, s_, e_ in recs:
+            agg[key][0] += 1
+            agg[key][1] += s_.elapsed_time(e_)
+            agg[key][2] += fl
+        tot = sum(v[1] for v in agg.values())
+        lines.append(f"--- eager per-shape breakdown: {tot:.2f} ms bracketed (op, M, N, K / L, flag): count, ms, TFLOP/s (or GB/s)")
+        for key, (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+            lines.append(f"{ms:8.3f} ms {100 * ms / tot:5.1f}% x{n:<4d} {fl / ms / 1e9:8.1f}  {key}")
     if not a.no_profile:
         from torch.profiler import ProfilerActivity, profile
 

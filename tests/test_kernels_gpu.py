@@ -84,6 +84,53 @@ def test_gemm_geglu(ops):
     assert relerr(out, x * F.gelu(gate)) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(20000, 320, 320), (32768, 960, 320), (8192, 640, 2560), (2048, 1280, 1280),
+                                    (512, 1280, 5120), (33000, 128, 1152), (4096, 1920, 640)])
+def test_gemm_persistent_pair_kernel(ops, M, N, K):
+    """Shapes with several tiles per CTA pair (persistence, TMEM double buffering, ragged last column tile)."""
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    res = rnd(M, N, seed=3)
+    out = ops.gemm(a, w, bias=bias, residual=res)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    assert relerr(out, ref) < 1e-2
+    out = ops.gemm(a, w)
+    assert relerr(out, a.float() @ w.float().t()) < 1e-2
+
+
+def test_gemm_geglu_large(ops):
+    from edtr_b200 import lib
+
+    M, C = 8192, 320
+    a = rnd(M, C, seed=1)
+    w = rnd(8 * C, C, scale=C ** -0.5, seed=2)
+    bias = torch.randn(8 * C, device="cuda") * 0.1
+    bn = lib.device_lib().edtr_gemm_tile_n(M, 8 * C, C, ops.ACT_GEGLU)
+    half, n_half = bn // 2, 4 * C
+    idx = torch.arange(n_half, device="cuda").view(-1, half)
+    perm = torch.cat([idx, idx + n_half], dim=1).reshape(-1)
+    out = ops.gemm(a, w[perm].contiguous(), bias=bias[perm].contiguous(), act=ops.ACT_GEGLU)
+    y = a.float() @ w.float().t() + bias
+    x, gate = y.chunk(2, dim=-1)
+    assert relerr(out, x * F.gelu(gate)) < 1e-2
+
+
+def test_conv3x3_large_batch(ops):
+    B, H, W, Cin, Cout = 8, 64, 64, 320, 320
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = torch.randn(Cout, device="cuda")
+    emb = torch.randn(B, Cout, device="cuda")
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    cat = rnd(B, H, W, 640, seed=3)
+    before = cat.clone()
+    ops.conv3x3(x, wp, bias=bias, rowvec=emb, residual=cat[..., 320:], out=cat[..., 320:])
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + emb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1) + before[..., 320:].float()
+    assert relerr(cat[..., 320:], ref) < 1e-2
+    assert torch.equal(cat[..., :320], before[..., :320])
+
+
 def test_gemm_out_modes(ops):
     M, N, K, hw = 512, 4, 320, 256
     a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
