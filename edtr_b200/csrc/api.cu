@@ -86,6 +86,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int prime_gemm_attributes();
 int prime_attention_attributes();
 int prime_gemm2_attributes();
+void set_gemm_workspace(void* ptr, size_t bytes);
 
 }  // namespace edtr
 
@@ -99,6 +100,15 @@ extern "C" int edtr_set_device(int device) {
     edtr::set_error("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
     return EDTR_ERR_CUDA;
   }
+  return EDTR_OK;
+}
+
+extern "C" int edtr_set_workspace(void* ptr, size_t bytes) {
+  if ((reinterpret_cast<uintptr_t>(ptr) & 255) != 0) {
+    edtr::set_error("workspace must be 256-byte aligned");
+    return EDTR_ERR_INVALID;
+  }
+  edtr::set_gemm_workspace(ptr, ptr == nullptr ? 0 : bytes);
   return EDTR_OK;
 }
 

@@ -1,12 +1,15 @@
 // Flash-style attention for head dim 64 on tcgen05 / TMEM / TMA (sm_100a).
 //
-// One CTA owns 128 query rows of one (image, head) and streams the keys in tiles
-// of 64:  S = Q K^T (UMMA, fp32 in TMEM, double-buffered) -> online softmax with
-// one thread per query row (no shuffles: a TMEM lane is a row) -> P (bf16) into
-// 128-byte-swizzled shared memory -> O_tile = P V (UMMA, V consumed MN-major
-// straight from the [keys, 64] TMA box) -> running O kept in registers.
-// Q/K/V are read in place from the projection GEMM outputs ([B, L, heads*64]
-// rows): the head split/merge permutes of the reference are TMA coordinates.
+// One CTA owns 128 query rows of one (image, head) and streams the keys in tiles of 64 through a
+// 3-stage TMA ring:  S = Q K^T (UMMA, fp32 in TMEM, double-buffered) -> softmax numerators with one
+// thread per query row (a TMEM lane is a row: no shuffles) -> P (bf16) into one of two 128-byte-
+// swizzled shared buffers -> O += P V (UMMA accumulating in TMEM, V consumed MN-major straight from
+// the [keys, 64] TMA box).  O never leaves TMEM inside the loop: the running maximum used for the
+// exponent is only raised when the tile maximum exceeds it by more than 2^8 (lazy rescaling), and
+// only then are the 64 O columns of the affected rows rescaled in place (tcgen05.ld / st).  So the
+// softmax warps of tile j+1 overlap the PV MMA of tile j, and the loop is bound by the exp2 rate.
+// Q/K/V are read in place from the projection GEMM outputs ([B, L, heads*64] rows): the head
+// split/merge permutes of the reference are TMA coordinates.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -16,8 +19,11 @@ constexpr int kAttThreads = 192;
 constexpr int kQT = 128;   // query rows per CTA
 constexpr int kKT = 64;    // keys per tile
 constexpr int kD = 64;     // head dim
-constexpr int kAttSmem = kQT * kD * 2 + 2 * (kKT * kD * 2) * 2 + kQT * kKT * 2 + 1024 + 256;
-constexpr int kAttTmemCols = 256;  // S0 [0,64) S1 [64,128) O_tile [128,192)
+constexpr int kKvStages = 3;
+constexpr int kTileBytes = kKT * kD * 2;   // 8 KB
+constexpr int kAttSmem = kQT * kD * 2 + kKvStages * 2 * kTileBytes + 2 * kQT * kKT * 2 + 1024 + 256;
+constexpr int kAttTmemCols = 256;  // S0 [0,64) S1 [64,128) O [128,192)
+constexpr float kRescaleThreshold = 8.f;   // log2 units
 
 struct AttParams {
   void* O;
@@ -31,18 +37,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                         // 16 KB
-  uint8_t* sK = sQ + kQT * kD * 2;            // 2 x 8 KB
-  uint8_t* sV = sK + 2 * kKT * kD * 2;        // 2 x 8 KB
-  uint8_t* sP = sV + 2 * kKT * kD * 2;        // 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kQT * kKT * 2);
+  uint8_t* sQ = smem;                              // 16 KB
+  uint8_t* sK = sQ + kQT * kD * 2;                 // stages x 8 KB
+  uint8_t* sV = sK + kKvStages * kTileBytes;       // stages x 8 KB
+  uint8_t* sP = sV + kKvStages * kTileBytes;       // 2 x 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kQT * kKT * 2);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* s_full = bars + 5;    // [2]
-  uint64_t* p_full = bars + 7;
-  uint64_t* pv_full = bars + 8;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_full = bars + 1;                    // [stages]
+  uint64_t* kv_empty = kv_full + kKvStages;        // [stages]
+  uint64_t* s_full = kv_empty + kKvStages;         // [2]
+  uint64_t* p_full = s_full + 2;                   // 128 arrivals per tile
+  uint64_t* pv_done = p_full + 1;                  // [2] PV of the tile that used P buffer b has retired
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -56,13 +62,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kKvStages; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
+      mbar_init(&pv_done[i], 1);
     }
     mbar_init(p_full, 128);
-    mbar_init(pv_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -79,12 +87,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_arrive_expect_tx(q_full, kQT * kD * 2);
       tma_load_4d(sQ, &tmQ, q_full, 0, q0, head, img);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * kKT * kD * 2);
-        tma_load_4d(sK + s * kKT * kD * 2, &tmK, &kv_full[s], 0, j * kKT, head, img);
-        tma_load_4d(sV + s * kKT * kD * 2, &tmV, &kv_full[s], 0, j * kKT, head, img);
+        const int st = j % kKvStages;
+        const uint32_t ph = (j / kKvStages) & 1;
+        mbar_wait(&kv_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * kTileBytes);
+        tma_load_4d(sK + st * kTileBytes, &tmK, &kv_full[st], 0, j * kKT, head, img);
+        tma_load_4d(sV + st * kTileBytes, &tmV, &kv_full[st], 0, j * kKT, head, img);
       }
     }
   } else if (warp == 1) {
@@ -92,65 +100,92 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       constexpr uint32_t idesc_s = umma_idesc_bf16(kQT, kKT, false);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kD, true);
       const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ));
-      const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP));
       auto issue_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        const int st = j % kKvStages;
+        mbar_wait(&kv_full[st], (j / kKvStages) & 1);
         tc_fence_after();
-        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK + s * kKT * kD * 2));
+        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK + st * kTileBytes));
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k)
-          umma_ss(tmem_base + s * kKT, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[s]);
+          umma_ss(tmem_base + (j & 1) * kKT, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit(&s_full[j & 1]);
       };
       mbar_wait(q_full, 0);
       issue_s(0);
       for (int j = 0; j < nkv; ++j) {
-        const int s = j & 1;
+        const int st = j % kKvStages;
         if (j + 1 < nkv) issue_s(j + 1);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV + s * kKT * kD * 2));
+        const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP + (j & 1) * kQT * kKT * 2));
+        const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV + st * kTileBytes));
 #pragma unroll
         for (int k = 0; k < kKT / 16; ++k) {
           // A: +32 B per 16 keys (K-major P); B: +16 rows * 128 B (MN-major V)
-          umma_ss(tmem_base + 128, pdesc + 2 * k, vdesc + 128 * k, idesc_pv, k != 0);
+          umma_ss(tmem_base + 128, pdesc + 2 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
         }
-        umma_commit(pv_full);
-        umma_commit(&kv_empty[s]);
+        umma_commit(&pv_done[j & 1]);
+        umma_commit(&kv_empty[st]);
       }
     }
   } else {
     const int lg = warp & 3;
     const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    float o[kD];
-#pragma unroll
-    for (int i = 0; i < kD; ++i) o[i] = 0.f;
-    float m = -INFINITY, l = 0.f;
-    uint8_t* prow = sP + r * 128;
+    float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < nkv; ++j) {
-      const int s = j & 1;
-      mbar_wait(&s_full[s], (j >> 1) & 1);
+      const int b = j & 1;
+      mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
       uint32_t sr[2][32];
-      tmem_ld32(trow + s * kKT, sr[0]);
-      tmem_ld32(trow + s * kKT + 32, sr[1]);
+      tmem_ld32(trow + b * kKT, sr[0]);
+      tmem_ld32(trow + b * kKT + 32, sr[1]);
       tmem_ld_wait();
       const int valid = p.Lk - j * kKT;  // >= 1
       float mx = -INFINITY;
+      if (valid >= kKT) {
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(sr[h][i]);
-          if (h * 32 + i >= valid) v = -INFINITY;
-          sr[h][i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[h][i]));
+      } else {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = __uint_as_float(sr[h][i]);
+            if (h * 32 + i >= valid) v = -INFINITY;
+            sr[h][i] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+          }
+      }
+      if (j == 0) {
+        m_used = mx;
+      } else {
+        const bool need = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // O must be quiescent: the PV MMA of tile j-1 is the last one issued
+          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          tc_fence_after();
+          const float f = need ? exp2f((m_used - mx) * p.scale_log2) : 1.f;
+          if (need) m_used = mx;
+          l *= f;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t o[32];
+            tmem_ld32(trow + 128 + h * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st32(trow + 128 + h * 32, o);
+          }
+          tmem_st_wait();
         }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f((m - m_new) * p.scale_log2);
-      const float mb = m_new * p.scale_log2;
+      }
+      // P buffer b was last read by the PV MMA of tile j-2
+      if (j >= 2) mbar_wait(&pv_done[b], ((j - 2) >> 1) & 1);
+      const float mb = m_used * p.scale_log2;
+      uint8_t* prow = sP + b * (kQT * kKT * 2) + r * 128;
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 B
@@ -158,7 +193,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int idx = c * 8 + i;
-          pv[i] = exp2f(__uint_as_float(sr[idx >> 5][idx & 31]) * p.scale_log2 - mb);
+          pv[i] = exp2f(fmaf(__uint_as_float(sr[idx >> 5][idx & 31]), p.scale_log2, -mb));
           sum += pv[i];
         }
         uint4 u;
@@ -168,23 +203,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         u.w = pack_bf16(pv[6], pv[7]);
         *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = u;
       }
-      l = l * alpha + sum;
-      m = m_new;
+      l += sum;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);
-      // O_tile = P V_j
-      mbar_wait(pv_full, j & 1);
-      tc_fence_after();
-      uint32_t orr[2][32];
-      tmem_ld32(trow + 128, orr[0]);
-      tmem_ld32(trow + 128 + 32, orr[1]);
-      tmem_ld_wait();
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[h * 32 + i] = o[h * 32 + i] * alpha + __uint_as_float(orr[h][i]);
     }
+    // last PV retired -> O complete
+    mbar_wait(&pv_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
+    tc_fence_after();
+    uint32_t o0[32], o1[32];
+    tmem_ld32(trow + 128, o0);
+    tmem_ld32(trow + 128 + 32, o1);
+    tmem_ld_wait();
     const int q = q0 + r;
     if (q < p.Lq) {
       const float inv = 1.f / l;
@@ -192,13 +222,22 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                           (static_cast<size_t>(img) * p.Lq + q) * p.ldo + head * kD;
       uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint4 u;
-        u.x = pack_bf16(o[8 * c + 0] * inv, o[8 * c + 1] * inv);
-        u.y = pack_bf16(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
-        u.z = pack_bf16(o[8 * c + 4] * inv, o[8 * c + 5] * inv);
-        u.w = pack_bf16(o[8 * c + 6] * inv, o[8 * c + 7] * inv);
+        u.x = pack_bf16(__uint_as_float(o0[8 * c + 0]) * inv, __uint_as_float(o0[8 * c + 1]) * inv);
+        u.y = pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv);
+        u.z = pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv);
+        u.w = pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv);
         o4[c] = u;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 u;
+        u.x = pack_bf16(__uint_as_float(o1[8 * c + 0]) * inv, __uint_as_float(o1[8 * c + 1]) * inv);
+        u.y = pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv);
+        u.z = pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv);
+        u.w = pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv);
+        o4[4 + c] = u;
       }
     }
     tc_fence_before();

@@ -38,6 +38,9 @@ struct Gemm2Params {
   int tiles_m, tiles_n;    // 256-row pair tiles, column tiles
   int bn_base;             // width of every column tile but the last (multiple of 64, <= 256)
   int b_box_rows;          // rows of the weight TMA box (= bn_base / 2)
+  int splits;              // split-K factor (1 = none); partial tiles go to `ws` as fp32 [splits][M][N]
+  int kb_per_split;
+  float* ws;
   int stages;              // pipeline depth: k2PipeBytes / stage_bytes, <= k2MaxStages
   int stage_bytes;         // 16 KB of A + b_box_rows * 128 B of B
   int geglu;
@@ -86,7 +89,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int num_work = p.tiles_m * p.tiles_n * p.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -117,7 +120,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int w = cluster_id; w < num_work; w += num_clusters) {
+        const int tile = w / p.splits, ks = w - tile * p.splits;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
         const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
         const int m0 = tm * (2 * k2BM) + static_cast<int>(rank) * k2BM;
         const int n_tile0 = tn * p.bn_base;
@@ -129,7 +134,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           cy = (m0 / p.W) % p.H;
           cn = m0 / (p.W * p.H);
         }
-        for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % nstages;
           const uint32_t ph = (it / nstages) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
@@ -151,7 +156,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------- UMMA issuer (leader only)
     if (lane == 0 && leader) {
       uint32_t it = 0, ti = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
+      for (int w = cluster_id; w < num_work; w += num_clusters, ++ti) {
+        const int tile = w / p.splits, ks = w - tile * p.splits;
+        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
         const int tn = tile % p.tiles_n;
         const int n_tile0 = tn * p.bn_base;
         const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
@@ -160,7 +167,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&tempty_bar[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * k2MaxBN;
-        for (int kb = 0; kb < p.num_kblocks; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % nstages;
           const uint32_t ph = (it / nstages) & 1;
           mbar_wait(&full_bar[s], ph);
@@ -170,7 +177,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const uint64_t bdesc = umma_smem_desc_sw128(sa + k2ABytes);
 #pragma unroll
           for (int k = 0; k < k2BK / 16; ++k)
-            umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0) || (k != 0));
           umma_commit_pair(&empty_bar[s], 0x3);
         }
         umma_commit_pair(&tfull_bar[a], 0x3);
@@ -186,7 +193,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t ti = 0;
     uint32_t res_uses[k2StagingBufs] = {0, 0};
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++ti) {
+    for (int w = cluster_id; w < num_work; w += num_clusters, ++ti) {
+      const int tile = w / p.splits, ks = w - tile * p.splits;
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int m0 = tm * (2 * k2BM) + static_cast<int>(rank) * k2BM;
       const int row = m0 + r;
@@ -197,6 +205,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int nchunks = out_cols_tile >> 6;
       const int out_col_tile0 = p.geglu ? (n_tile0 >> 1) : n_tile0;
       const int n_out = p.geglu ? (p.N >> 1) : p.N;
+      if (p.splits > 1) {
+        // split-K: raw fp32 partial sums to the workspace; edtr::splitk_reduce_kernel finishes the epilogue
+        mbar_wait(&tfull_bar[a], aph);
+        tc_fence_after();
+        const uint32_t tacc = trow + a * k2MaxBN;
+        float* wrow = p.ws + (static_cast<size_t>(ks) * p.M + row) * p.N + n_tile0;
+        for (int c = 0; c < (bn >> 5); ++c) {
+          uint32_t r0[32];
+          tmem_ld32(tacc + c * 32, r0);
+          tmem_ld_wait();
+          if (row < p.M) {
+            float4* dst = reinterpret_cast<float4*>(wrow + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(__uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]),
+                                   __uint_as_float(r0[4 * j + 2]), __uint_as_float(r0[4 * j + 3]));
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
+        continue;
+      }
       // all stores of the previous tile must have finished reading the staging buffers
       if (e0) {
         bulk_wait_group_read<0>();
@@ -329,6 +360,62 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
+// Sums the split-K partial tiles in a fixed order and applies the fused epilogue (bias / row vector /
+// residual / SiLU), 8 columns per thread.
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, float alpha,
+                     const float* __restrict__ bias, const float* __restrict__ rowvec, int rowvec_ld,
+                     int rows_per_group, const __nv_bfloat16* residual, int ldr, __nv_bfloat16* out, int ldc,
+                     int act) {
+  const int vpr = N >> 3;
+  const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<size_t>(M) * vpr) return;
+  const int row = static_cast<int>(idx / vpr), col = static_cast<int>(idx - static_cast<size_t>(row) * vpr) << 3;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  const size_t plane = static_cast<size_t>(M) * N;
+  const float* src = ws + static_cast<size_t>(row) * N + col;
+  for (int s = 0; s < splits; ++s) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src + s * plane));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(src + s * plane + 4));
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] *= alpha;
+  if (bias != nullptr) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + col));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  }
+  if (rowvec != nullptr) {
+    const float* rv = rowvec + static_cast<size_t>(row / rows_per_group) * rowvec_ld + col;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(rv));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(rv + 4));
+    v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+  }
+  if (residual != nullptr) {
+    const uint4 u = *reinterpret_cast<const uint4*>(residual + static_cast<size_t>(row) * ldr + col);
+    const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+    v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y; v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+  }
+  if (act == EDTR_ACT_SILU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+  }
+  uint4 o;
+  o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ldc + col) = o;
+}
+
+static float* g_ws = nullptr;      // split-K workspace registered by the host (edtr_set_workspace)
+static size_t g_ws_bytes = 0;
+
+void set_gemm_workspace(void* ptr, size_t bytes) {
+  g_ws = static_cast<float*>(ptr);
+  g_ws_bytes = bytes;
+}
+
 int prime_gemm2_attributes() {
   cudaError_t e = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
   if (e != cudaSuccess) {
@@ -338,11 +425,14 @@ int prime_gemm2_attributes() {
   return EDTR_OK;
 }
 
-// Column tiling.  Every tile but the last is `bn_base` wide (a multiple of 64, <= 256).  The width is
-// chosen with a small cost model: waves over the 74 CTA pairs x time per k-block, where a k-block of a
-// bn-wide pair tile costs max(2*bn, 280) cycles (narrow tiles are bound by operand fetch, not by the
-// tensor pipe).  GEGLU is pinned to 256 because its weight interleave is done at pack time.
-static void split_n(int M, int N, int geglu, int* tiles_n, int* bn_base) {
+// Column tiling and split-K.  Every column tile but the last is `bn_base` wide (a multiple of 64,
+// <= 256).  Width and split factor are chosen with a small cost model: waves over the 74 CTA pairs x
+// (k-blocks per work item x cycles per k-block + a fixed fill/drain cost), where a k-block of a bn-wide
+// pair tile costs max(2*bn, 300) cycles (narrow tiles are bound by operand fetch, not by the tensor
+// pipe) and splitting pays for the fp32 round trip + reduce launch.  GEGLU is pinned to 256 columns,
+// unsplit, because its weight interleave is done at pack time.
+static void plan_tiles(int M, int N, int nkb, int geglu, size_t ws_bytes, int* tiles_n, int* bn_base, int* splits) {
+  *splits = 1;
   if (geglu) {
     *tiles_n = N / k2MaxBN;
     *bn_base = k2MaxBN;
@@ -350,23 +440,31 @@ static void split_n(int M, int N, int geglu, int* tiles_n, int* bn_base) {
   }
   const int tiles_m = (M + 2 * k2BM - 1) / (2 * k2BM);
   long best_cost = -1;
-  int best_t = 1, best_b = 64;
+  int best_t = 1, best_b = 64, best_s = 1;
+  const int max_split_ws = static_cast<int>(ws_bytes / (static_cast<size_t>(M) * N * sizeof(float)));
   for (int cap = k2MaxBN; cap >= 64; cap -= 64) {
     const int t = (N + cap - 1) / cap;
     int base = ((N + t - 1) / t + 63) & ~63;
     if (base > cap) base = cap;
     const int tn = (N + base - 1) / base;
-    const long waves = (static_cast<long>(tiles_m) * tn + 73) / 74;
     const long per_kb = 2 * base > 300 ? 2 * base : 300;
-    const long cost = waves * per_kb;
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best_t = tn;
-      best_b = base;
+    for (int sp = 1; sp <= 16; ++sp) {
+      if (sp > 1 && (sp > max_split_ws || nkb / sp < 8)) break;
+      const int kbs = (nkb + sp - 1) / sp;
+      if (sp > 1 && kbs * (sp - 1) >= nkb) continue;  // an empty split
+      const long waves = (static_cast<long>(tiles_m) * tn * sp + 73) / 74;
+      const long cost = waves * (kbs * per_kb + 3000) + (sp > 1 ? 10000 : 0);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best_t = tn;
+        best_b = base;
+        best_s = sp;
+      }
     }
   }
   *tiles_n = best_t;
   *bn_base = best_b;
+  *splits = best_s;
 }
 
 bool gemm2_disabled();
@@ -384,8 +482,8 @@ bool gemm2_eligible(int M, int N, const EdtrEpilogue* ep) {
 }
 
 int gemm2_tile_n(int N, int geglu) {
-  int t, b;
-  split_n(1 << 20, N, geglu, &t, &b);
+  int t, b, sp;
+  plan_tiles(1 << 20, N, 64, geglu, 0, &t, &b, &sp);
   return b;
 }
 
@@ -400,7 +498,9 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   Gemm2Params p{};
   p.M = M; p.N = N; p.num_kblocks = K / k2BK; p.mode = mode; p.H = H; p.W = W; p.cblocks = cblocks;
   p.geglu = ep->act == EDTR_ACT_GEGLU;
-  split_n(M, N, p.geglu, &p.tiles_n, &p.bn_base);
+  plan_tiles(M, N, p.num_kblocks, p.geglu, g_ws_bytes, &p.tiles_n, &p.bn_base, &p.splits);
+  p.kb_per_split = (p.num_kblocks + p.splits - 1) / p.splits;
+  p.ws = g_ws;
   p.tiles_m = (M + 2 * k2BM - 1) / (2 * k2BM);
   p.b_box_rows = p.bn_base / 2;
   p.stage_bytes = k2ABytes + p.b_box_rows * k2BK * 2;
@@ -435,10 +535,18 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   } else {
     tmC = tmD;
   }
-  const int tiles = p.tiles_m * p.tiles_n;
-  const int clusters = tiles < 74 ? tiles : 74;
+  const int work = p.tiles_m * p.tiles_n * p.splits;
+  const int clusters = work < 74 ? work : 74;
+  if (p.splits > 1) p.has_residual = 0;  // the reduce kernel adds it
   gemm2_kernel<<<2 * clusters, k2Threads, k2SmemBytes, stream>>>(tmA, tmB, tmC, tmD, p);
-  return check_launch("gemm2_kernel");
+  rc = check_launch("gemm2_kernel");
+  if (rc || p.splits == 1) return rc;
+  const size_t nvec = static_cast<size_t>(M) * (N / 8);
+  splitk_reduce_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0, stream>>>(
+      p.ws, p.splits, M, N, ep->alpha, ep->bias, ep->rowvec, ep->rowvec_ld, p.rows_per_group,
+      reinterpret_cast<const __nv_bfloat16*>(ep->residual), ep->ldr, reinterpret_cast<__nv_bfloat16*>(ep->out),
+      ep->ldc, ep->act);
+  return check_launch("splitk_reduce_kernel");
 }
 
 }  // namespace edtr

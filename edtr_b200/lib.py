@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 
 # every symbol include/edtr_b200.h declares
 EXPORTED = [
-    "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_gemm_tile_n", "edtr_gemm_bf16",
+    "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_set_workspace", "edtr_gemm_tile_n", "edtr_gemm_bf16",
     "edtr_conv3x3_bf16", "edtr_attention_bf16", "edtr_groupnorm_partial_size", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
     "edtr_layernorm_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
     "edtr_nchw_f32_to_nhwc_bf16", "edtr_pointwise_nchw_f32_to_nhwc_bf16", "edtr_nhwc_bf16_to_nchw", "edtr_cast_f32_to_bf16",
@@ -86,6 +86,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 _lock = threading.Lock()
+WORKSPACE_BYTES = 64 << 20
+_workspace = None
 _lib = None
 _initialised = False
 
@@ -100,6 +102,8 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_set_device.restype = ci
     lib.edtr_set_device.argtypes = [ci]
     lib.edtr_init.restype = ci
+    lib.edtr_set_workspace.restype = ci
+    lib.edtr_set_workspace.argtypes = [vp, c_size_t]
     lib.edtr_init.argtypes = []
     lib.edtr_gemm_tile_n.restype = ci
     lib.edtr_gemm_tile_n.argtypes = [ci, ci, ci, ci]
@@ -180,5 +184,9 @@ def device_lib() -> ctypes.CDLL:
             raise RuntimeError("edtr_b200 has no CPU fallback: a CUDA (sm_100a) device is required")
         check(lib.edtr_set_device(torch.cuda.current_device()), "edtr_set_device")
         check(lib.edtr_init(), "edtr_init")
+        # split-K scratch (stream-ordered use on the current stream; kept alive for the process lifetime)
+        global _workspace
+        _workspace = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device="cuda")
+        check(lib.edtr_set_workspace(_workspace.data_ptr(), WORKSPACE_BYTES), "edtr_set_workspace")
         _initialised = True
     return lib

@@ -79,6 +79,11 @@ int edtr_version(void);
 int edtr_set_device(int device);
 /* Verifies the current device is sm_100-class and primes kernel attributes. */
 int edtr_init(void);
+/* Registers a device scratch buffer (256-byte aligned, owned by the caller, must outlive every later
+ * call) that the GEMM / convolution entry points may use for split-K partial sums when a problem has
+ * too few output tiles to fill the GPU (the 8x8 level of the UNet).  All calls that use it are ordered
+ * on one stream.  ptr == NULL disables split-K.  The library never allocates. */
+int edtr_set_workspace(void* ptr, size_t bytes);
 /* N-tile width the GEMM will use for an N-column problem (for GEGLU weight
  * interleaving at plan time). */
 int edtr_gemm_tile_n(int M, int N, int K, int act);

@@ -53,8 +53,33 @@ def run(kind, a, iters=20):
     return ms, fl / ms / 1e9
 
 
+def bench_attention():
+    print(f"{'attention B,heads,Lq,Lk':40s} {'ms':>9s} {'TF/s':>9s}")
+    for B, h, Lq, Lk in ((8, 5, 4096, 4096), (8, 10, 1024, 1024), (8, 20, 256, 256), (8, 5, 4096, 77), (8, 20, 64, 64)):
+        g = torch.Generator(device="cuda").manual_seed(0)
+        C = h * 64
+        q = torch.randn(B, Lq, C, generator=g, device="cuda").to(BF)
+        k = torch.randn(B, Lk, C, generator=g, device="cuda").to(BF)
+        v = torch.randn(B, Lk, C, generator=g, device="cuda").to(BF)
+        out = torch.empty(B, Lq, C, dtype=BF, device="cuda")
+        fn = lambda: ops.attention(q, k, v, h, 0.125, out=out)
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 10
+        print(f"{str((B, h, Lq, Lk)):40s} {ms:9.3f} {4.0 * B * h * Lq * Lk * 64 / ms / 1e9:9.1f}", flush=True)
+
+
 def main():
     only = sys.argv[1:]
+    if not only or "attention" in only:
+        bench_attention()
     print(f"{'shape':40s} {'v2 ms':>9s} {'v2 TF/s':>9s} {'v1 ms':>9s} {'v1 TF/s':>9s}")
     for kind, a in SHAPES:
         if only and kind not in only:

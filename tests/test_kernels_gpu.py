@@ -197,6 +197,24 @@ def test_attention(ops, B, heads, Lq, Lk):
     assert relerr(out, ref) < 2e-2
 
 
+@pytest.mark.parametrize("Lq,Lk", [(256, 1024), (384, 200), (128, 4096)])
+def test_attention_growing_scores_exercise_lazy_rescale(ops, Lq, Lk):
+    """Scores that keep growing along the key axis force the in-TMEM rescale of O many times per row."""
+    B, heads = 2, 2
+    C = heads * 64
+    q = rnd(B, Lq, C, seed=1, scale=2.0)
+    ramp = torch.linspace(0.5, 4.0, Lk, device="cuda").view(1, Lk, 1)
+    k = (rnd(B, Lk, C, seed=2).float() * ramp).to(BF)
+    v = rnd(B, Lk, C, seed=3)
+    out = ops.attention(q, k, v, heads, 0.125)
+
+    def split(t):
+        return t.float().view(B, -1, heads, 64).permute(0, 2, 1, 3)
+
+    ref = F.scaled_dot_product_attention(split(q), split(k), split(v)).permute(0, 2, 1, 3).reshape(B, Lq, C)
+    assert relerr(out, ref) < 2e-2
+
+
 @pytest.mark.parametrize("B,HW,C,silu,eps", [(2, 4096, 320, True, 1e-5), (2, 64, 2560, True, 1e-5),
                                               (1, 1024, 1920, False, 1e-6), (3, 256, 960, True, 1e-5),
                                               (1, 65536, 128, True, 1e-6), (2, 4096, 512, True, 1e-6)])
