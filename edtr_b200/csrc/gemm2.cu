@@ -25,10 +25,10 @@ constexpr int k2Threads = 192;
 constexpr int k2MaxStages = 10;
 constexpr int k2MaxBN = 256;
 constexpr int k2ABytes = k2BM * k2BK * 2;            // 16 KB
-constexpr int k2PipeBytes = 6 * (k2ABytes + (k2MaxBN / 2) * k2BK * 2);  // 192 KB ring: 6 stages at bn=256 ... 9 at bn=64
-constexpr int k2StagingBufs = 2;
-constexpr int k2StagingBytes = k2BM * 64 * 2;        // 128 rows x 64 bf16 = 16 KB
-constexpr int k2SmemBytes = k2PipeBytes + k2StagingBufs * k2StagingBytes + 1024 + 512;
+constexpr int k2DataBytes = 224 * 1024;              // operand ring + epilogue staging
+constexpr int k2WarpStageBytes = 32 * 64 * 2;        // one epilogue warp's staging buffer: 32 rows x 64 bf16 = 4 KB
+constexpr int k2MaxRing = 4;                         // staging buffers per epilogue warp (2 or 4)
+constexpr int k2SmemBytes = k2DataBytes + 1024 + 1024;
 
 struct Gemm2Params {
   int M, N;                // accumulator matrix: rows, columns (= weight rows)
@@ -41,7 +41,8 @@ struct Gemm2Params {
   int splits;              // split-K factor (1 = none); partial tiles go to `ws` as fp32 [splits][M][N]
   int kb_per_split;
   float* ws;
-  int stages;              // pipeline depth: k2PipeBytes / stage_bytes, <= k2MaxStages
+  int ring;                // epilogue staging buffers per warp: 4 when the epilogue is the bottleneck (short K), else 2
+  int stages;              // pipeline depth: (k2DataBytes - staging) / stage_bytes, <= k2MaxStages
   int stage_bytes;         // 16 KB of A + b_box_rows * 128 B of B
   int geglu;
   int has_residual;
@@ -73,14 +74,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sPipe = smem;                             // stage s: A at s*stage_bytes, B right after it
-  uint8_t* sC = sPipe + k2PipeBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sC + k2StagingBufs * k2StagingBytes);
+  uint8_t* sC = sPipe + (k2DataBytes - 4 * p.ring * k2WarpStageBytes);   // [4 warps][ring] x 4 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2DataBytes);
   uint64_t* full_bar = bars;                         // [stages]  (leader's copy is the live one)
   uint64_t* empty_bar = bars + k2MaxStages;          // [stages]
   uint64_t* tfull_bar = bars + 2 * k2MaxStages;      // [2] accumulator ready (multicast to both CTAs)
   uint64_t* tempty_bar = bars + 2 * k2MaxStages + 2; // [2] accumulator drained (leader's copy, 8 arrivals)
-  uint64_t* res_bar = bars + 2 * k2MaxStages + 4;    // [2] residual chunk landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * k2MaxStages + 8);
+  uint64_t* res_bar = bars + 2 * k2MaxStages + 4;    // [4 warps][k2MaxRing] residual chunk landed
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * k2MaxStages + 4 + 4 * k2MaxRing);
   const int nstages = p.stages;
 
   const int warp = threadIdx.x >> 5;
@@ -104,7 +105,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 8);
     }
-    for (int b = 0; b < k2StagingBufs; ++b) mbar_init(&res_bar[b], 1);
+    for (int b = 0; b < 4 * k2MaxRing; ++b) mbar_init(&res_bar[b], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -185,32 +186,71 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else {
     // -------------------------------------------------------------------- epilogue (both CTAs)
+    // Every epilogue warp is independent: it owns TMEM lanes / output rows [lg*32, lg*32+32), a ring
+    // of `ring` 4 KB staging buffers and its own TMA traffic (lane 0 issues), so there is no CTA-wide
+    // barrier in the epilogue.  Chunks (64 output columns) are numbered globally across tiles (g);
+    // the residual chunk g+D is requested while chunk g is processed (D = ring/2 chunks of lead).
     const int lg = warp & 3;
-    const int r = lg * 32 + lane;               // row inside this CTA's 128-row half == TMEM lane
-    const bool e0 = (warp == 2 && lane == 0);   // issues the residual loads and the output stores
+    const int rl = lane;                         // row inside this warp's 32-row slab
+    const int ew = warp - 2;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    uint8_t* my_row = nullptr;
-    uint32_t ti = 0;
-    uint32_t res_uses[k2StagingBufs] = {0, 0};
+    const int R = p.ring, D = R >> 1, Pend = R - 1 - D;
+    uint8_t* wstage = sC + ew * R * k2WarpStageBytes;
+    uint64_t* wres = res_bar + ew * k2MaxRing;
     const uint32_t tempty_leader = mapa_u32(smem_u32(&tempty_bar[0]), 0);
+    const int n_out = p.geglu ? (p.N >> 1) : p.N;
+    const int row_off = static_cast<int>(rank) * k2BM + lg * 32;
+
+    // (work item, chunk) -> coordinates; shared by the processing loop and the residual look-ahead
+    auto tile_m0 = [&](int w) { return ((w / p.splits) / p.tiles_n) * (2 * k2BM) + row_off; };
+    auto tile_n0 = [&](int w) { return ((w / p.splits) % p.tiles_n) * p.bn_base; };
+    auto tile_bn = [&](int w) { return min(p.bn_base, ((p.N - tile_n0(w)) + 63) & ~63); };
+    auto tile_chunks = [&](int w) { return (p.geglu ? (tile_bn(w) >> 1) : tile_bn(w)) >> 6; };
+    auto tile_outcol0 = [&](int w) { return p.geglu ? (tile_n0(w) >> 1) : tile_n0(w); };
+
+    // look-ahead cursor (lane 0 only): tile coordinates are recomputed once per tile, not per chunk
+    int lw = cluster_id, lc = 0, l_m0 = 0, l_col0 = 0, l_chunks = 0;
+    uint32_t lgc = 0;              // global index of the chunk the cursor points at
+    auto cursor_load_tile = [&]() {
+      if (lw < num_work) {
+        l_m0 = tile_m0(lw);
+        l_col0 = tile_outcol0(lw);
+        l_chunks = tile_chunks(lw);
+      }
+    };
+    auto issue_residual = [&]() {  // request chunk (lw, lc) into its ring slot and advance the cursor
+      if (lw < num_work) {
+        const int slot = lgc % R;
+        mbar_arrive_expect_tx(&wres[slot], k2WarpStageBytes);
+        tma_load_2d(wstage + slot * k2WarpStageBytes, &tmC, &wres[slot], l_col0 + lc * 64, l_m0);
+        ++lgc;
+        if (++lc >= l_chunks) {
+          lc = 0;
+          lw += num_clusters;
+          cursor_load_tile();
+        }
+      }
+    };
+    if (p.has_residual && lane == 0 && p.splits == 1) {
+      cursor_load_tile();
+      for (int i = 0; i < D; ++i) issue_residual();
+    }
+
+    uint32_t ti = 0, g = 0;
     for (int w = cluster_id; w < num_work; w += num_clusters, ++ti) {
-      const int tile = w / p.splits, ks = w - tile * p.splits;
-      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-      const int m0 = tm * (2 * k2BM) + static_cast<int>(rank) * k2BM;
-      const int row = m0 + r;
-      const int n_tile0 = tn * p.bn_base;
-      const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
+      const int ks = w % p.splits;
+      const int m0 = tile_m0(w);
+      const int row = m0 + rl;
+      const int n_tile0 = tile_n0(w);
+      const int bn = tile_bn(w);
       const uint32_t a = ti & 1, aph = (ti >> 1) & 1;
-      const int out_cols_tile = p.geglu ? (bn >> 1) : bn;
-      const int nchunks = out_cols_tile >> 6;
-      const int out_col_tile0 = p.geglu ? (n_tile0 >> 1) : n_tile0;
-      const int n_out = p.geglu ? (p.N >> 1) : p.N;
+      const uint32_t tacc = trow + a * k2MaxBN;
+      mbar_wait(&tfull_bar[a], aph);
+      tc_fence_after();
       if (p.splits > 1) {
         // split-K: raw fp32 partial sums to the workspace; edtr::splitk_reduce_kernel finishes the epilogue
-        mbar_wait(&tfull_bar[a], aph);
-        tc_fence_after();
-        const uint32_t tacc = trow + a * k2MaxBN;
         float* wrow = p.ws + (static_cast<size_t>(ks) * p.M + row) * p.N + n_tile0;
+#pragma unroll 1
         for (int c = 0; c < (bn >> 5); ++c) {
           uint32_t r0[32];
           tmem_ld32(tacc + c * 32, r0);
@@ -228,128 +268,109 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
         continue;
       }
-      // all stores of the previous tile must have finished reading the staging buffers
-      if (e0) {
-        bulk_wait_group_read<0>();
-        if (p.has_residual) {
-          mbar_arrive_expect_tx(&res_bar[0], k2StagingBytes);
-          tma_load_2d(sC, &tmC, &res_bar[0], out_col_tile0, m0);
-        }
-      }
-      named_bar_sync(1, 128);
-      mbar_wait(&tfull_bar[a], aph);
-      tc_fence_after();
-      const uint32_t tacc = trow + a * k2MaxBN;
-      for (int c = 0; c < nchunks; ++c) {
+      const int nchunks = tile_chunks(w);
+      const int out_col_tile0 = tile_outcol0(w);
+      const int half = bn >> 1;
+      const float* rowvec_row = (p.rowvec != nullptr && row < p.M)
+                                    ? p.rowvec + static_cast<size_t>(row / p.rows_per_group) * p.rowvec_ld
+                                    : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c, ++g) {
         const int out_col0 = out_col_tile0 + c * 64;
-        if (out_col0 >= n_out) break;            // uniform over the CTA
-        const int buf = c & 1;
-        uint8_t* stage = sC + buf * k2StagingBytes;
-        my_row = stage + r * 128;
-        // the other staging buffer was last stored from at chunk c-1: once that store has read it,
-        // prefetch the next residual chunk into it (and it is free for chunk c+1's output)
-        if (e0 && c > 0) bulk_wait_group_read<0>();
-        if (e0 && p.has_residual && c + 1 < nchunks && out_col0 + 64 < n_out) {
-          mbar_arrive_expect_tx(&res_bar[buf ^ 1], k2StagingBytes);
-          tma_load_2d(sC + (buf ^ 1) * k2StagingBytes, &tmC, &res_bar[buf ^ 1], out_col0 + 64, m0);
+        const int slot = g % R;
+        uint8_t* my_row = wstage + slot * k2WarpStageBytes + rl * 128;
+        if (lane == 0) {
+          // stores up to chunk g-1-Pend have released their buffers: slot of chunk g+D (and of g) is free
+          if (Pend == 0) bulk_wait_group_read<0>(); else bulk_wait_group_read<1>();
+          if (p.has_residual) issue_residual();
         }
-        float v[64];
-        {
-          uint32_t r0[32], r1[32];
-          if (!p.geglu) {
-            tmem_ld32(tacc + c * 64, r0);
-            tmem_ld32(tacc + c * 64 + 32, r1);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              v[j] = __uint_as_float(r0[j]) * p.alpha;
-              v[32 + j] = __uint_as_float(r1[j]) * p.alpha;
-            }
-            if (p.bias != nullptr) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_tile0 + c * 64);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float4 b = __ldg(b4 + j);
-                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-              }
-            }
-          } else {
-            const int half = bn >> 1;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              tmem_ld32(tacc + c * 64 + h * 32, r0);          // value columns
-              tmem_ld32(tacc + half + c * 64 + h * 32, r1);   // gate columns
+        __syncwarp();
+        if (p.has_residual) mbar_wait(&wres[slot], (g / R) & 1);
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {            // 32 columns per TMEM load; rolled to keep the code in the I-cache
+          float v[32];
+          const int cb = c * 64 + h * 32;        // accumulator / bias column inside the tile
+          {
+            uint32_t rv[32];
+            tmem_ld32(tacc + cb, rv);
+            if (!p.geglu) {
               tmem_ld_wait();
-              float xb[32], gb[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { xb[j] = 0.f; gb[j] = 0.f; }
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rv[j]) * p.alpha;
               if (p.bias != nullptr) {
-                const float4* bx = reinterpret_cast<const float4*>(p.bias + n_tile0 + c * 64 + h * 32);
-                const float4* bg = reinterpret_cast<const float4*>(p.bias + n_tile0 + half + c * 64 + h * 32);
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_tile0 + cb);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  const float4 x4 = __ldg(bx + j), g4 = __ldg(bg + j);
-                  xb[4 * j] = x4.x; xb[4 * j + 1] = x4.y; xb[4 * j + 2] = x4.z; xb[4 * j + 3] = x4.w;
-                  gb[4 * j] = g4.x; gb[4 * j + 1] = g4.y; gb[4 * j + 2] = g4.z; gb[4 * j + 3] = g4.w;
+                  const float4 b = __ldg(b4 + j);
+                  v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
                 }
               }
+            } else {
+              uint32_t rg[32];
+              tmem_ld32(tacc + half + cb, rg);   // gate columns
+              tmem_ld_wait();
+              const float4* bx = reinterpret_cast<const float4*>(p.bias + n_tile0 + cb);
+              const float4* bg = reinterpret_cast<const float4*>(p.bias + n_tile0 + half + cb);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float x = fmaf(__uint_as_float(r0[j]), p.alpha, xb[j]);
-                const float g = fmaf(__uint_as_float(r1[j]), p.alpha, gb[j]);
-                v[h * 32 + j] = x * gelu_fast(g);
+              for (int j = 0; j < 8; ++j) {
+                float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = x4;
+                if (p.bias != nullptr) { x4 = __ldg(bx + j); g4 = __ldg(bg + j); }
+                v[4 * j] = fmaf(__uint_as_float(rv[4 * j]), p.alpha, x4.x) *
+                           gelu_fast(fmaf(__uint_as_float(rg[4 * j]), p.alpha, g4.x));
+                v[4 * j + 1] = fmaf(__uint_as_float(rv[4 * j + 1]), p.alpha, x4.y) *
+                               gelu_fast(fmaf(__uint_as_float(rg[4 * j + 1]), p.alpha, g4.y));
+                v[4 * j + 2] = fmaf(__uint_as_float(rv[4 * j + 2]), p.alpha, x4.z) *
+                               gelu_fast(fmaf(__uint_as_float(rg[4 * j + 2]), p.alpha, g4.z));
+                v[4 * j + 3] = fmaf(__uint_as_float(rv[4 * j + 3]), p.alpha, x4.w) *
+                               gelu_fast(fmaf(__uint_as_float(rg[4 * j + 3]), p.alpha, g4.w));
               }
             }
           }
-        }
-        if (p.rowvec != nullptr && row < p.M) {
-          const float4* r4 = reinterpret_cast<const float4*>(
-              p.rowvec + static_cast<size_t>(row / p.rows_per_group) * p.rowvec_ld + out_col0);
+          if (rowvec_row != nullptr) {
+            const float4* r4 = reinterpret_cast<const float4*>(rowvec_row + out_col0 + h * 32);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 b = __ldg(r4 + j);
-            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(r4 + j);
+              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (p.has_residual) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = *reinterpret_cast<const uint4*>(my_row + (((h * 4 + q) ^ (rl & 7)) << 4));
+              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+              v[8 * q] += f0.x; v[8 * q + 1] += f0.y; v[8 * q + 2] += f1.x; v[8 * q + 3] += f1.y;
+              v[8 * q + 4] += f2.x; v[8 * q + 5] += f2.y; v[8 * q + 6] += f3.x; v[8 * q + 7] += f3.y;
+            }
+          }
+          if (p.act == EDTR_ACT_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16(v[8 * q], v[8 * q + 1]); o.y = pack_bf16(v[8 * q + 2], v[8 * q + 3]);
+            o.z = pack_bf16(v[8 * q + 4], v[8 * q + 5]); o.w = pack_bf16(v[8 * q + 6], v[8 * q + 7]);
+            *reinterpret_cast<uint4*>(my_row + (((h * 4 + q) ^ (rl & 7)) << 4)) = o;
           }
         }
-        if (p.has_residual) {
-          mbar_wait(&res_bar[buf], res_uses[buf] & 1);
-          res_uses[buf]++;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((j ^ (r & 7)) << 4));
-            const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
-            v[8 * j] += f0.x; v[8 * j + 1] += f0.y; v[8 * j + 2] += f1.x; v[8 * j + 3] += f1.y;
-            v[8 * j + 4] += f2.x; v[8 * j + 5] += f2.y; v[8 * j + 6] += f3.x; v[8 * j + 7] += f3.y;
-          }
-        }
-        if (p.act == EDTR_ACT_SILU) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) v[j] = silu_f(v[j]);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 u;
-          u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
-          u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-          u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-          u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
-          *reinterpret_cast<uint4*>(my_row + ((j ^ (r & 7)) << 4)) = u;
-        }
-        if (c == nchunks - 1 || out_col0 + 64 >= n_out) {
+        if (c == nchunks - 1) {
           // last TMEM read of this tile: hand the accumulator stage back to the MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
         }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
-        if (e0) {
-          tma_store_2d(&tmD, stage, out_col0, m0);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmD, wstage + slot * k2WarpStageBytes, out_col0, m0);
           bulk_commit_group();
         }
       }
     }
-    if (e0) bulk_wait_group<0>();
+    if (lane == 0) bulk_wait_group<0>();
+    (void)n_out;
   }
   __syncwarp();  // role branches diverge inside a warp; the cluster barrier below is .aligned
   tc_fence_before();
@@ -501,11 +522,13 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   plan_tiles(M, N, p.num_kblocks, p.geglu, g_ws_bytes, &p.tiles_n, &p.bn_base, &p.splits);
   p.kb_per_split = (p.num_kblocks + p.splits - 1) / p.splits;
   p.ws = g_ws;
-  p.tiles_m = (M + 2 * k2BM - 1) / (2 * k2BM);
   p.b_box_rows = p.bn_base / 2;
   p.stage_bytes = k2ABytes + p.b_box_rows * k2BK * 2;
-  p.stages = k2PipeBytes / p.stage_bytes;
+  // short main loops are epilogue-bound: give the epilogue a deeper staging ring, the operands fewer stages
+  p.ring = (p.kb_per_split <= 24 && p.splits == 1) ? 4 : 2;
+  p.stages = (k2DataBytes - 4 * p.ring * k2WarpStageBytes) / p.stage_bytes;
   if (p.stages > k2MaxStages) p.stages = k2MaxStages;
+  p.tiles_m = (M + 2 * k2BM - 1) / (2 * k2BM);
   p.has_residual = ep->residual != nullptr;
   p.act = ep->act; p.alpha = ep->alpha; p.bias = ep->bias; p.rowvec = ep->rowvec; p.rowvec_ld = ep->rowvec_ld;
   p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
@@ -522,14 +545,14 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   {
     uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
     uint64_t strides[1] = {static_cast<uint64_t>(ep->ldc) * 2};
-    uint32_t box[2] = {64, k2BM};
+    uint32_t box[2] = {64, 32};
     rc = make_tmap_bf16(&tmD, ep->out, 2, dims, strides, box);
     if (rc) return rc;
   }
   if (p.has_residual) {
     uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
     uint64_t strides[1] = {static_cast<uint64_t>(ep->ldr) * 2};
-    uint32_t box[2] = {64, k2BM};
+    uint32_t box[2] = {64, 32};
     rc = make_tmap_bf16(&tmC, ep->residual, 2, dims, strides, box);
     if (rc) return rc;
   } else {

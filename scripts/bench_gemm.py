@@ -18,6 +18,8 @@ SHAPES = [
     ("gemm", (8192, 640, 640)), ("gemm", (8192, 5120, 640)), ("gemm", (8192, 640, 2560)),
     ("gemm", (2048, 1280, 1280)), ("gemm", (2048, 10240, 1280)), ("gemm", (2048, 1280, 5120)),
     ("gemm", (512, 1280, 1280)), ("gemm", (512, 10240, 1280)),
+    ("gemm_nores", (32768, 320, 320)), ("gemm_nores", (32768, 960, 320)), ("gemm_nores", (8192, 640, 640)),
+    ("geglu", (32768, 2560, 320)), ("geglu", (8192, 5120, 640)), ("geglu", (2048, 10240, 1280)),
 ]
 
 
@@ -31,6 +33,21 @@ def run(kind, a, iters=20):
         out = torch.empty(B, H, W, Co, dtype=BF, device="cuda")
         fn = lambda: ops.conv3x3(x, w, bias=bias, out=out)
         fl = 2.0 * B * H * W * Co * 9 * Ci
+    elif kind == "geglu":
+        M, N, K = a
+        x = torch.randn(M, K, generator=g, device="cuda").to(BF)
+        w = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(BF)
+        bias = torch.randn(N, device="cuda")
+        out = torch.empty(M, N // 2, dtype=BF, device="cuda")
+        fn = lambda: ops.gemm(x, w, bias=bias, act=ops.ACT_GEGLU, out=out)
+        fl = 2.0 * M * N * K
+    elif kind == "gemm_nores":
+        M, N, K = a
+        x = torch.randn(M, K, generator=g, device="cuda").to(BF)
+        w = (torch.randn(N, K, generator=g, device="cuda") * K ** -0.5).to(BF)
+        out = torch.empty(M, N, dtype=BF, device="cuda")
+        fn = lambda: ops.gemm(x, w, out=out)
+        fl = 2.0 * M * N * K
     else:
         M, N, K = a
         x = torch.randn(M, K, generator=g, device="cuda").to(BF)

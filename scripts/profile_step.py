@@ -95,22 +95,24 @@ def main():
     lines.append(f"weights {eng.unet.nbytes() / 1e9:.2f}+{eng.cnet.nbytes() / 1e9:.2f} GB, workspace {ws.nbytes() / 1e9:.2f} GB, "
                  f"mem allocated {torch.cuda.memory_allocated() / 1e9:.2f} GB")
     if a.shapes:
-        # eager pass with every tensor-core launch bracketed by events, aggregated by op and shape
+        # 1) eager pass: record the op sequence with shapes; 2) profile one graph replay and attribute the
+        # kernel durations (CUPTI) to the ops by launch order.
+        from torch.profiler import ProfilerActivity, profile
+
         from edtr_b200 import ops
 
-        recs = []
-        orig = {n: getattr(ops, n) for n in ("gemm", "conv3x3", "attention", "groupnorm", "layernorm")}
+        seq = []
+        names = ("gemm", "conv3x3", "attention", "groupnorm", "layernorm", "softmax_rows", "upsample2x", "im2col",
+                 "nchw_to_nhwc", "pointwise_nchw_to_nhwc", "cast_bf16", "timestep_embedding", "sampler_update")
+        orig = {n: getattr(ops, n) for n in names}
 
         def wrap(name, fn):
             def w(*args, **kw):
-                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s_.record()
-                r = fn(*args, **kw)
-                e_.record()
                 if name == "gemm":
                     A, Wt = args[0], args[1]
                     M = A.numel() // A.shape[-1]
-                    key = (name, M, Wt.shape[0], Wt.shape[1], "geglu" if kw.get("act") == 2 else "res" if kw.get("residual") is not None else "")
+                    flag = "geglu" if kw.get("act") == 2 else "res" if kw.get("residual") is not None else ""
+                    key = (name, M, Wt.shape[0], Wt.shape[1], flag)
                     fl = 2.0 * M * Wt.shape[0] * Wt.shape[1]
                 elif name == "conv3x3":
                     X, Wt = args[0], args[1]
@@ -121,32 +123,69 @@ def main():
                     q, k_ = args[0], args[1]
                     key = (name, q.shape[0] * q.shape[1], k_.shape[1], q.shape[2], "")
                     fl = 4.0 * q.shape[0] * q.shape[1] * k_.shape[1] * q.shape[2]
-                else:
+                elif name in ("groupnorm", "layernorm"):
                     x = args[0]
                     key = (name, x.numel() // x.shape[-1], x.shape[-1], 0, "")
-                    fl = 4.0 * x.numel()  # bytes (bf16 in + out)
-                recs.append((key, fl, s_, e_))
-                return r
+                    fl = 4.0 * x.numel()
+                else:
+                    key = (name, 0, 0, 0, "")
+                    fl = 0.0
+                seq.append((key, fl))
+                return fn(*args, **kw)
             return w
 
-        for n, fn in orig.items():
-            setattr(ops, n, wrap(n, fn))
-        try:
-            z2 = eng.sample(x_T, ts, tabs, c_img, c_txt, noise, use_graph=False)
-            vd.decode(z2, 0.18215, use_graph=False)
-        finally:
+        KCLASS = {"gemm2_kernel": ("gemm", "conv3x3"), "gemm_conv_kernel": ("gemm", "conv3x3"),
+                  "attention_kernel": ("attention",), "groupnorm_stats_kernel": ("groupnorm",),
+                  "layernorm_kernel": ("layernorm",), "softmax_rows_kernel": ("softmax_rows",),
+                  "upsample2x_kernel": ("upsample2x",), "im2col_kernel": ("im2col",),
+                  "nchw_to_nhwc_kernel": ("nchw_to_nhwc",), "pointwise_nchw_kernel": ("pointwise_nchw_to_nhwc",),
+                  "cast_f32_bf16_kernel": ("cast_bf16",), "timestep_embedding_kernel": ("timestep_embedding",),
+                  "sampler_update_kernel": ("sampler_update",)}
+        for phase, eager, replay in (
+                ("sample", lambda: eng.sample(x_T, ts, tabs, c_img, c_txt, noise, use_graph=False),
+                 lambda: eng.sample(x_T, ts, tabs, c_img, c_txt, noise)),
+                ("decode", lambda: vd.decode(z, 0.18215, use_graph=False), lambda: vd.decode(z, 0.18215))):
+            seq.clear()
             for n, fn in orig.items():
-                setattr(ops, n, fn)
-        torch.cuda.synchronize()
-        agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
-        for key, fl, s_, e_ in recs:
-            agg[key][0] += 1
-            agg[key][1] += s_.elapsed_time(e_)
-            agg[key][2] += fl
-        tot = sum(v[1] for v in agg.values())
-        lines.append(f"--- eager per-shape breakdown: {tot:.2f} ms bracketed (op, M, N, K / L, flag): count, ms, TFLOP/s (or GB/s)")
-        for key, (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
-            lines.append(f"{ms:8.3f} ms {100 * ms / tot:5.1f}% x{n:<4d} {fl / ms / 1e9:8.1f}  {key}")
+                setattr(ops, n, wrap(n, fn))
+            try:
+                eager()
+            finally:
+                for n, fn in orig.items():
+                    setattr(ops, n, fn)
+            torch.cuda.synchronize()
+            replay()
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                replay()
+                torch.cuda.synchronize()
+            evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "edtr::" in e.name]
+            evs.sort(key=lambda e: e.time_range.start)
+            agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+            i = 0
+            bad = 0
+            for e in evs:
+                kname = next((k for k in KCLASS if k in e.name), None)
+                us = e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
+                if kname is None:   # splitk_reduce / groupnorm_apply: belongs to the previous op
+                    if i > 0:
+                        agg[seq[i - 1][0]][1] += us
+                    continue
+                while i < len(seq) and seq[i][0][0] not in KCLASS[kname]:
+                    i += 1
+                    bad += 1
+                if i >= len(seq):
+                    break
+                key, fl = seq[i]
+                agg[key][0] += 1
+                agg[key][1] += us
+                agg[key][2] += fl
+                i += 1
+            tot = sum(v[1] for v in agg.values())
+            lines.append(f"--- {phase}: graph-replay kernel time by op/shape: {tot / 1e3:.2f} ms, {len(evs)} kernels, "
+                         f"{len(seq)} ops, {bad} skipped  (op, M, N, K|Lk, flag): count, ms, TFLOP/s (norms: GB/s)")
+            for key, (n, us, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+                lines.append(f"{us / 1e3:8.3f} ms {100 * us / tot:5.1f}% x{n:<4d} avg {us / max(n, 1):7.1f} us {fl / max(us, 1e-9) / 1e6:8.1f}  {key}")
     if not a.no_profile:
         from torch.profiler import ProfilerActivity, profile
 
