@@ -1,6 +1,7 @@
 // Library plumbing of the C-ABI: error string, device check, TMA descriptor
 // encoding through the driver entry point (no link-time libcuda dependency).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -14,6 +15,13 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  // Measured on B200 (profiles/r01c): inside a CUDA graph the launch gaps are already ~0 and the programmatic
+  // edges cost ~1.5 us per kernel, so PDL is opt-in (EDTR_PDL=1).
+  const char* e = getenv("EDTR_PDL");
+  return e != nullptr && e[0] == '1';
 }
 
 int check_launch(const char* what) {

@@ -35,6 +35,7 @@ struct AttParams {
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                              // 16 KB
@@ -81,6 +82,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();  // PDL: everything above overlapped the previous kernel; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -293,6 +295,6 @@ extern "C" int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ld
   p.O = O; p.ldo = ldo; p.Lq = Lq; p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Lq + kQT - 1) / kQT, heads, B);
-  attention_kernel<<<grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream)>>>(tmQ, tmK, tmV, p);
+  EDTR_LAUNCH(attention_kernel, grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream), tmQ, tmK, tmV, p);
   return check_launch("attention_kernel");
 }

@@ -20,6 +20,31 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 
 int check_launch(const char* what);
 
+// Programmatic dependent launch: every kernel is launched with the stream-serialization attribute so its
+// prologue (barrier init, TMEM allocation, descriptor prefetch, index math) overlaps the tail of the previous
+// kernel; on the device every kernel calls pdl_launch_dependents() first and pdl_wait() before it touches
+// global memory.  Opt-in with EDTR_PDL=1 (without the attribute the device calls are no-ops).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#define EDTR_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  (void)edtr::launch_kernel(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__)
+
 #define EDTR_REQUIRE(cond, ...)      \
   do {                               \
     if (!(cond)) {                   \

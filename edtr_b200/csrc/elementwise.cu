@@ -9,6 +9,8 @@ namespace edtr {
 // Y[(b,p), coff+c] = X[b,c,p]; one thread per pixel, coalesced reads per channel plane.
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ Y, int ldy,
                                     int coff, int C, int HW, size_t total_pix) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total_pix) return;
   const size_t b = i / HW, pix = i - b * HW;
@@ -22,6 +24,8 @@ __global__ void pointwise_nchw_kernel(const float* __restrict__ X, const float* 
                                       const float* __restrict__ bias, float scale,
                                       __nv_bfloat16* __restrict__ Y, int ldy, int coff, int Cin, int Cout, int HW,
                                       size_t total_pix) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total_pix) return;
   const size_t b = i / HW, pix = i - b * HW;
@@ -40,6 +44,8 @@ __global__ void pointwise_nchw_kernel(const float* __restrict__ X, const float* 
 template <typename OutT>
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ X, int ldx, OutT* __restrict__ Y, int C,
                                     int HW) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -61,6 +67,8 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ X, int ldx
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ Y, size_t n) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) Y[i] = __float2bfloat16(X[i]);
 }
@@ -68,6 +76,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ X, __nv_bfloat16*
 // One thread per (output pixel, 16-byte channel vector).
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y,
                                   int ldy, int H, int W, int vpr, size_t total) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int v = static_cast<int>(i % vpr);
@@ -85,6 +95,8 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ X, int ldx, 
 __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y,
                               int H, int W, int vpr, int KH, int KW, int stride, int pad_top, int pad_left,
                               int Ho, int Wo, size_t total) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int v = static_cast<int>(i % vpr);
@@ -105,6 +117,8 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv
 
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ Y, int dim,
                                           float log_max_period) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   const int b = blockIdx.x;
   const int half = dim / 2;
   const float tv = static_cast<float>(t[b]);
@@ -123,6 +137,8 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
                                       const float* __restrict__ coef1, const float* __restrict__ coef2,
                                       const float* __restrict__ var, float* __restrict__ x_prev,
                                       float* __restrict__ pred_x0, int n_per_image, size_t total) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int64_t idx = index[i / n_per_image];
@@ -147,7 +163,7 @@ extern "C" int edtr_nchw_f32_to_nhwc_bf16(const float* X, void* Y, int ldy, int 
                                           void* stream) {
   EDTR_REQUIRE(X && Y && B > 0 && C > 0 && HW > 0 && coff >= 0 && ldy >= coff + C, "bad layout-convert arguments");
   const size_t total = static_cast<size_t>(B) * HW;
-  nchw_to_nhwc_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(nchw_to_nhwc_kernel, blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       X, reinterpret_cast<__nv_bfloat16*>(Y), ldy, coff, C, HW, total);
   return check_launch("nchw_to_nhwc_kernel");
 }
@@ -159,7 +175,7 @@ extern "C" int edtr_pointwise_nchw_f32_to_nhwc_bf16(const float* X, const float*
   EDTR_REQUIRE(Cin > 0 && Cin <= 16 && Cout > 0 && Cout <= 16, "pointwise conv supports 1..16 channels");
   EDTR_REQUIRE(ldy >= coff + Cout, "ldy too small");
   const size_t total = static_cast<size_t>(B) * HW;
-  pointwise_nchw_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(pointwise_nchw_kernel, blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       X, Wm, bias, scale, reinterpret_cast<__nv_bfloat16*>(Y), ldy, coff, Cin, Cout, HW, total);
   return check_launch("pointwise_nchw_kernel");
 }
@@ -171,10 +187,10 @@ extern "C" int edtr_nhwc_bf16_to_nchw(const void* X, int ldx, void* Y, int B, in
   dim3 grid((HW + 31) / 32, (C + 31) / 32, B), block(32, 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (out_f32)
-    nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(X), ldx,
+    EDTR_LAUNCH((nhwc_to_nchw_kernel<float>), grid, block, 0, st, reinterpret_cast<const __nv_bfloat16*>(X), ldx,
                                                        reinterpret_cast<float*>(Y), C, HW);
   else
-    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(X), ldx,
+    EDTR_LAUNCH((nhwc_to_nchw_kernel<__nv_bfloat16>), grid, block, 0, st, reinterpret_cast<const __nv_bfloat16*>(X), ldx,
                                                                reinterpret_cast<__nv_bfloat16*>(Y), C, HW);
   return check_launch("nhwc_to_nchw_kernel");
 }
@@ -182,7 +198,7 @@ extern "C" int edtr_nhwc_bf16_to_nchw(const void* X, int ldx, void* Y, int B, in
 extern "C" int edtr_cast_f32_to_bf16(const float* X, void* Y, size_t n, void* stream) {
   EDTR_REQUIRE(X && Y, "X/Y is NULL");
   if (n == 0) return EDTR_OK;
-  cast_f32_bf16_kernel<<<blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(cast_f32_bf16_kernel, blocks_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       X, reinterpret_cast<__nv_bfloat16*>(Y), n);
   return check_launch("cast_f32_bf16_kernel");
 }
@@ -194,7 +210,7 @@ extern "C" int edtr_upsample2x_bf16(const void* X, int ldx, void* Y, int ldy, in
   EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0, "16-byte alignment");
   const int vpr = C / 8;
   const size_t total = static_cast<size_t>(B) * 4 * H * W * vpr;
-  upsample2x_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(upsample2x_kernel, blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, H, W, vpr, total);
   return check_launch("upsample2x_kernel");
 }
@@ -207,7 +223,7 @@ extern "C" int edtr_im2col_bf16(const void* X, int ldx, void* Y, int B, int H, i
   EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) & 15) == 0, "16-byte alignment");
   const int vpr = C / 8;
   const size_t total = static_cast<size_t>(B) * Ho * Wo * KH * KW * vpr;
-  im2col_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(im2col_kernel, blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), H, W, vpr, KH, KW,
       stride, pad_top, pad_left, Ho, Wo, total);
   return check_launch("im2col_kernel");
@@ -216,7 +232,7 @@ extern "C" int edtr_im2col_bf16(const void* X, int ldx, void* Y, int B, int H, i
 extern "C" int edtr_timestep_embedding(const int64_t* t, void* Y, int B, int dim, float max_period,
                                        void* stream) {
   EDTR_REQUIRE(t && Y && B > 0 && dim >= 2, "bad timestep-embedding arguments");
-  timestep_embedding_kernel<<<B, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(timestep_embedding_kernel, B, 128, 0, static_cast<cudaStream_t>(stream), 
       t, reinterpret_cast<__nv_bfloat16*>(Y), dim, logf(max_period));
   return check_launch("timestep_embedding_kernel");
 }
@@ -229,7 +245,7 @@ extern "C" int edtr_sampler_update(const float* x, const float* eps, const float
                "NULL argument");
   EDTR_REQUIRE(B > 0 && n_per_image > 0, "bad sampler-update shape");
   const size_t total = static_cast<size_t>(B) * n_per_image;
-  sampler_update_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(sampler_update_kernel, blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       x, eps, noise, index, sqrt_recip, sqrt_recipm1, coef1, coef2, var, x_prev, pred_x0, n_per_image, total);
   return check_launch("sampler_update_kernel");
 }

@@ -71,6 +71,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
              const Gemm2Params p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sPipe = smem;                             // stage s: A at s*stage_bytes, B right after it
@@ -116,6 +117,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();  // PDL: everything above overlapped the previous kernel; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -388,6 +390,8 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, flo
                      const float* __restrict__ bias, const float* __restrict__ rowvec, int rowvec_ld,
                      int rows_per_group, const __nv_bfloat16* residual, int ldr, __nv_bfloat16* out, int ldc,
                      int act) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   const int vpr = N >> 3;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<size_t>(M) * vpr) return;
@@ -561,11 +565,11 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   const int work = p.tiles_m * p.tiles_n * p.splits;
   const int clusters = work < 74 ? work : 74;
   if (p.splits > 1) p.has_residual = 0;  // the reduce kernel adds it
-  gemm2_kernel<<<2 * clusters, k2Threads, k2SmemBytes, stream>>>(tmA, tmB, tmC, tmD, p);
+  EDTR_LAUNCH(gemm2_kernel, 2 * clusters, k2Threads, k2SmemBytes, stream, tmA, tmB, tmC, tmD, p);
   rc = check_launch("gemm2_kernel");
   if (rc || p.splits == 1) return rc;
   const size_t nvec = static_cast<size_t>(M) * (N / 8);
-  splitk_reduce_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0, stream>>>(
+  EDTR_LAUNCH(splitk_reduce_kernel, static_cast<unsigned>((nvec + 255) / 256), 256, 0, stream, 
       p.ws, p.splits, M, N, ep->alpha, ep->bias, ep->rowvec, ep->rowvec_ld, p.rows_per_group,
       reinterpret_cast<const __nv_bfloat16*>(ep->residual), ep->ldr, reinterpret_cast<__nv_bfloat16*>(ep->out),
       ep->ldc, ep->act);

@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(kGemmThreads, (BN <= 160) ? 2 : 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -170,6 +171,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();  // PDL: everything above overlapped the previous kernel; global memory is touched only below
 
   if (warp == 0) {
     // ------------------------------------------------------ TMA producer
@@ -309,7 +311,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     attr_set = true;
   }
   dim3 grid((p.N + BN - 1) / BN, (p.M + kBM - 1) / kBM, 1);
-  gemm_conv_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, p);
+  EDTR_LAUNCH((gemm_conv_kernel<BN>), grid, kGemmThreads, Cfg::kSmemBytes, stream, tmA, tmB, p);
   return check_launch("gemm_conv_kernel");
 }
 

@@ -39,6 +39,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int C, int groups,
                        int rows_per_cta, int vslab, float* __restrict__ partial) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   extern __shared__ float sh[];  // [ppar][2][cslab]
   const int cslab = vslab * 8;
   const int ppar = blockDim.x / vslab;
@@ -53,12 +55,14 @@ groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int
   for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
   if (q < ppar) {
     const __nv_bfloat16* base = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
-    int pidx = p0 + q;
-    for (; pidx + 3 * ppar < p1; pidx += 4 * ppar) {
+    for (int pidx = p0 + q; pidx < p1; pidx += 4 * ppar) {
       uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        u[k] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pidx + k * ppar) * ldx));
+      for (int k = 0; k < 4; ++k) {
+        u[k] = make_uint4(0u, 0u, 0u, 0u);   // bf16 zeros add nothing to either sum
+        if (pidx + k * ppar < p1)
+          u[k] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pidx + k * ppar) * ldx));
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         float f[8];
@@ -66,13 +70,6 @@ groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int
 #pragma unroll
         for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
       }
-    }
-    for (; pidx < p1; pidx += ppar) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pidx) * ldx));
-      float f[8];
-      unpack8(u, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
     }
     float* row = sh + static_cast<size_t>(q) * 2 * cslab;
 #pragma unroll
@@ -104,6 +101,8 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
                        int HW, int C, int groups, int rows_per_cta, int vslab, int nchunks_stats, int nslab_stats,
                        int cslab_stats, const float* __restrict__ partial, const float* __restrict__ gamma,
                        const float* __restrict__ beta, float eps, int silu) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   __shared__ float g_mean[64], g_rstd[64];  // groups intersecting this slab (<= 64)
   const int cslab = vslab * 8;
   const int ppar = blockDim.x / vslab;
@@ -115,20 +114,30 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
   const int g_first = c0 / cpg;
   const int g_last = (min(C, c0 + cslab) - 1) / cpg;
   const float inv_n = 1.f / (static_cast<float>(cpg) * static_cast<float>(HW));
-  for (int g = g_first + threadIdx.x; g <= g_last; g += blockDim.x) {
-    // stats slabs that contain channels of group g
-    const int s_lo = (g * cpg) / cslab_stats, s_hi = ((g + 1) * cpg - 1) / cslab_stats;
-    float a = 0.f, a2 = 0.f;
-    for (int ch = 0; ch < nchunks_stats; ++ch)
-      for (int sl = s_lo; sl <= s_hi; ++sl) {
-        const float* src = partial + ((((static_cast<size_t>(b) * nchunks_stats + ch) * nslab_stats + sl) * groups + g) * 2);
-        a += src[0];
-        a2 += src[1];
+  {
+    // one warp per group: lanes stride over the (chunk, slab) partial sums, then a fixed shuffle tree
+    // (only full warps take part: the block size need not be a multiple of 32)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int g = g_first + warp; warp < nwarps && g <= g_last; g += nwarps) {
+      const int s_lo = (g * cpg) / cslab_stats, s_hi = ((g + 1) * cpg - 1) / cslab_stats;
+      const int ns = s_hi - s_lo + 1;
+      float a = 0.f, a2 = 0.f;
+      for (int i = lane; i < nchunks_stats * ns; i += 32) {
+        const int ch = i / ns, sl = s_lo + (i - ch * ns);
+        const float2 pr = __ldg(reinterpret_cast<const float2*>(
+            partial + ((((static_cast<size_t>(b) * nchunks_stats + ch) * nslab_stats + sl) * groups + g) * 2)));
+        a += pr.x;
+        a2 += pr.y;
       }
-    const float mean = a * inv_n;
-    const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
-    g_mean[g - g_first] = mean;
-    g_rstd[g - g_first] = rsqrtf(var + eps);
+      a = warp_sum(a);
+      a2 = warp_sum(a2);
+      if (lane == 0) {
+        const float mean = a * inv_n;
+        const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
+        g_mean[g - g_first] = mean;
+        g_rstd[g - g_first] = rsqrtf(var + eps);
+      }
+    }
   }
   __syncthreads();
   if (q >= ppar) return;
@@ -152,34 +161,25 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
   const int p1 = min(HW, p0 + rows_per_cta);
   const __nv_bfloat16* xb = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
   __nv_bfloat16* yb = Y + (static_cast<size_t>(b) * HW) * ldy + c0 + v * 8;
-  int pidx = p0 + q;
-  for (; pidx + 3 * ppar < p1; pidx += 4 * ppar) {
+  for (int pidx = p0 + q; pidx < p1; pidx += 4 * ppar) {
     uint4 u[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+      if (pidx + k * ppar < p1)
+        u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float f[8];
-      unpack8(u[k], f);
+      if (pidx + k * ppar < p1) {
+        float f[8];
+        unpack8(u[k], f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float y = f[i] * sc[i] + sf[i];
-        f[i] = silu ? silu_f(y) : y;
+        for (int i = 0; i < 8; ++i) {
+          const float y = f[i] * sc[i] + sf[i];
+          f[i] = silu ? silu_f(y) : y;
+        }
+        *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
       }
-      *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
     }
-  }
-  for (; pidx < p1; pidx += ppar) {
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx) * ldx));
-    float f[8];
-    unpack8(u, f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float y = f[i] * sc[i] + sf[i];
-      f[i] = silu ? silu_f(y) : y;
-    }
-    *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx) * ldy) = pack8(f);
   }
 }
 
@@ -189,6 +189,8 @@ template <int MAXV>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y,
                                  int ldy, int M, int C, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -238,6 +240,8 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, _
 // One CTA per row; fp32 logits in, bf16 probabilities out.
 __global__ void softmax_rows_kernel(const float* __restrict__ S, int lds, __nv_bfloat16* __restrict__ P,
                                     int ldp, int N, float scale_log2) {
+  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
+  pdl_wait();                // ... and wait for the previous kernel's results
   __shared__ float red[32];
   const int row = blockIdx.x;
   const float* s = S + static_cast<size_t>(row) * lds;
@@ -321,7 +325,7 @@ extern "C" int edtr_groupnorm_stats(const void* X, int ldx, int B, int HW, int C
   dim3 grid(g.nchunks, B, g.nslab);
   const size_t sh = static_cast<size_t>(g.ppar) * 2 * g.vslab * 8 * sizeof(float);
   EDTR_REQUIRE(sh <= 48 * 1024, "GroupNorm stats shared memory too large");
-  groupnorm_stats_kernel<<<grid, g.threads, sh, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(groupnorm_stats_kernel, grid, g.threads, sh, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(X), ldx, HW, C, groups, g.rows, g.vslab, stats);
   return check_launch("groupnorm_stats_kernel");
 }
@@ -338,7 +342,7 @@ extern "C" int edtr_groupnorm_apply(const void* X, int ldx, void* Y, int ldy, in
   const GnGeom g = gn_geom(B, HW, C);
   EDTR_REQUIRE(g.vslab * 8 / (C / groups) + 2 <= 64, "too many groups per channel slab");
   dim3 grid(g.nchunks, B, g.nslab);
-  groupnorm_apply_kernel<<<grid, g.threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(groupnorm_apply_kernel, grid, g.threads, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
       g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, stats, gamma, beta, eps, silu);
   return check_launch("groupnorm_apply_kernel");
@@ -359,16 +363,16 @@ extern "C" int edtr_layernorm_bf16(const void* X, int ldx, void* Y, int ldy, int
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(X);
   __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(Y);
   const int vpr = C / 8;
-  if (vpr <= 64) layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, M, C, gamma, beta, eps);
-  else if (vpr <= 160) layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, M, C, gamma, beta, eps);
-  else layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, ldx, y, ldy, M, C, gamma, beta, eps);
+  if (vpr <= 64) EDTR_LAUNCH((layernorm_kernel<2>), grid, warps * 32, 0, st, x, ldx, y, ldy, M, C, gamma, beta, eps);
+  else if (vpr <= 160) EDTR_LAUNCH((layernorm_kernel<5>), grid, warps * 32, 0, st, x, ldx, y, ldy, M, C, gamma, beta, eps);
+  else EDTR_LAUNCH((layernorm_kernel<8>), grid, warps * 32, 0, st, x, ldx, y, ldy, M, C, gamma, beta, eps);
   return check_launch("layernorm_kernel");
 }
 
 extern "C" int edtr_softmax_rows(const float* S, int lds, void* P, int ldp, int M, int N, float scale,
                                  void* stream) {
   EDTR_REQUIRE(S && P && M > 0 && N > 0 && lds >= N && ldp >= N, "bad softmax arguments");
-  softmax_rows_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  EDTR_LAUNCH(softmax_rows_kernel, M, 256, 0, static_cast<cudaStream_t>(stream), 
       S, lds, reinterpret_cast<__nv_bfloat16*>(P), ldp, N, scale * 1.4426950408889634f);
   return check_launch("softmax_rows_kernel");
 }
