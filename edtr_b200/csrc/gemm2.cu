@@ -21,7 +21,8 @@ namespace edtr {
 
 constexpr int k2BM = 128;   // rows per CTA (pair = 256)
 constexpr int k2BK = 64;
-constexpr int k2Threads = 192;
+constexpr int k2EpiWarps = 8;                         // two warps per TMEM lane group: even / odd 64-column chunks
+constexpr int k2Threads = 64 + 32 * k2EpiWarps;
 constexpr int k2MaxStages = 10;
 constexpr int k2MaxBN = 256;
 constexpr int k2ABytes = k2BM * k2BK * 2;            // 16 KB
@@ -75,14 +76,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sPipe = smem;                             // stage s: A at s*stage_bytes, B right after it
-  uint8_t* sC = sPipe + (k2DataBytes - 4 * p.ring * k2WarpStageBytes);   // [4 warps][ring] x 4 KB
+  uint8_t* sC = sPipe + (k2DataBytes - k2EpiWarps * p.ring * k2WarpStageBytes);   // [warps][ring] x 4 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + k2DataBytes);
   uint64_t* full_bar = bars;                         // [stages]  (leader's copy is the live one)
   uint64_t* empty_bar = bars + k2MaxStages;          // [stages]
   uint64_t* tfull_bar = bars + 2 * k2MaxStages;      // [2] accumulator ready (multicast to both CTAs)
   uint64_t* tempty_bar = bars + 2 * k2MaxStages + 2; // [2] accumulator drained (leader's copy, 8 arrivals)
   uint64_t* res_bar = bars + 2 * k2MaxStages + 4;    // [4 warps][k2MaxRing] residual chunk landed
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * k2MaxStages + 4 + 4 * k2MaxRing);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * k2MaxStages + 4 + k2EpiWarps * k2MaxRing);
   const int nstages = p.stages;
 
   const int warp = threadIdx.x >> 5;
@@ -104,9 +105,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);
+      mbar_init(&tempty_bar[a], 2 * k2EpiWarps);
     }
-    for (int b = 0; b < 4 * k2MaxRing; ++b) mbar_init(&res_bar[b], 1);
+    for (int b = 0; b < k2EpiWarps * k2MaxRing; ++b) mbar_init(&res_bar[b], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -195,6 +196,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int lg = warp & 3;
     const int rl = lane;                         // row inside this warp's 32-row slab
     const int ew = warp - 2;
+    const int grp = ew >> 2;                     // this warp handles chunks c with (c & 1) == grp
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
     const int R = p.ring, D = R >> 1, Pend = R - 1 - D;
     uint8_t* wstage = sC + ew * R * k2WarpStageBytes;
@@ -211,13 +213,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     auto tile_outcol0 = [&](int w) { return p.geglu ? (tile_n0(w) >> 1) : tile_n0(w); };
 
     // look-ahead cursor (lane 0 only): tile coordinates are recomputed once per tile, not per chunk
-    int lw = cluster_id, lc = 0, l_m0 = 0, l_col0 = 0, l_chunks = 0;
+    int lw = cluster_id, lc = grp, l_m0 = 0, l_col0 = 0, l_chunks = 0;
     uint32_t lgc = 0;              // global index of the chunk the cursor points at
-    auto cursor_load_tile = [&]() {
+    auto cursor_load_tile = [&]() {   // skips tiles in which this warp owns no chunk
+      while (lw < num_work) {
+        l_chunks = tile_chunks(lw);
+        if (lc < l_chunks) break;
+        lw += num_clusters;
+      }
       if (lw < num_work) {
         l_m0 = tile_m0(lw);
         l_col0 = tile_outcol0(lw);
-        l_chunks = tile_chunks(lw);
       }
     };
     auto issue_residual = [&]() {  // request chunk (lw, lc) into its ring slot and advance the cursor
@@ -226,8 +232,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_arrive_expect_tx(&wres[slot], k2WarpStageBytes);
         tma_load_2d(wstage + slot * k2WarpStageBytes, &tmC, &wres[slot], l_col0 + lc * 64, l_m0);
         ++lgc;
-        if (++lc >= l_chunks) {
-          lc = 0;
+        lc += 2;
+        if (lc >= l_chunks) {
+          lc = grp;
           lw += num_clusters;
           cursor_load_tile();
         }
@@ -253,7 +260,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // split-K: raw fp32 partial sums to the workspace; edtr::splitk_reduce_kernel finishes the epilogue
         float* wrow = p.ws + (static_cast<size_t>(ks) * p.M + row) * p.N + n_tile0;
 #pragma unroll 1
-        for (int c = 0; c < (bn >> 5); ++c) {
+        for (int c = grp; c < (bn >> 5); c += 2) {
           uint32_t r0[32];
           tmem_ld32(tacc + c * 32, r0);
           tmem_ld_wait();
@@ -271,13 +278,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         continue;
       }
       const int nchunks = tile_chunks(w);
+      if (grp >= nchunks) {   // no chunk of this tile belongs to this warp: release the accumulator at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
+        continue;
+      }
       const int out_col_tile0 = tile_outcol0(w);
       const int half = bn >> 1;
       const float* rowvec_row = (p.rowvec != nullptr && row < p.M)
                                     ? p.rowvec + static_cast<size_t>(row / p.rows_per_group) * p.rowvec_ld
                                     : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c, ++g) {
+      for (int c = grp; c < nchunks; c += 2, ++g) {
         const int out_col0 = out_col_tile0 + c * 64;
         const int slot = g % R;
         uint8_t* my_row = wstage + slot * k2WarpStageBytes + rl * 128;
@@ -357,8 +370,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             *reinterpret_cast<uint4*>(my_row + (((h * 4 + q) ^ (rl & 7)) << 4)) = o;
           }
         }
-        if (c == nchunks - 1) {
-          // last TMEM read of this tile: hand the accumulator stage back to the MMA issuer
+        if (c + 2 >= nchunks) {
+          // last TMEM read of this tile by this warp: hand the accumulator stage back to the MMA issuer
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
@@ -529,8 +542,8 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   p.b_box_rows = p.bn_base / 2;
   p.stage_bytes = k2ABytes + p.b_box_rows * k2BK * 2;
   // short main loops are epilogue-bound: give the epilogue a deeper staging ring, the operands fewer stages
-  p.ring = (p.kb_per_split <= 24 && p.splits == 1) ? 4 : 2;
-  p.stages = (k2DataBytes - 4 * p.ring * k2WarpStageBytes) / p.stage_bytes;
+  p.ring = 2;
+  p.stages = (k2DataBytes - k2EpiWarps * p.ring * k2WarpStageBytes) / p.stage_bytes;
   if (p.stages > k2MaxStages) p.stages = k2MaxStages;
   p.tiles_m = (M + 2 * k2BM - 1) / (2 * k2BM);
   p.has_residual = ep->residual != nullptr;
