@@ -34,8 +34,11 @@ constexpr int k2SmemBytes = k2DataBytes + 1024 + 1024;
 struct Gemm2Params {
   int M, N;                // accumulator matrix: rows, columns (= weight rows)
   int num_kblocks;
-  int mode;                // 0 gemm, 1 conv3x3
+  int mode;                // 0 gemm, 1 convolution (taps_x x taps_y filter taps starting at offset (tap_dy0, tap_dx0))
   int H, W, cblocks;
+  int taps_x, tap_dy0, tap_dx0;
+  int up2x;                // 1: rows are low-resolution pixels of one 2x-upsample phase; D is a 4-D map over the
+                           //    phase's output pixels (x and y strides of two pixels)
   int tiles_m, tiles_n;    // 256-row pair tiles, column tiles
   int bn_base;             // width of every column tile but the last (multiple of 64, <= 256)
   int b_box_rows;          // rows of the weight TMA box (= bn_base / 2)
@@ -149,7 +152,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_load_2d_pair(sa, &tmA, fb, kb * k2BK, m0);
           } else {
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const int dy = tap / p.taps_x + p.tap_dy0, dx = tap % p.taps_x + p.tap_dx0;
             tma_load_4d_pair(sa, &tmA, fb, cb * k2BK, cx + dx, cy + dy, cn);
           }
           tma_load_2d_pair(sa + k2ABytes, &tmB, fb, kb * k2BK, nrow0);
@@ -379,7 +382,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&tmD, wstage + slot * k2WarpStageBytes, out_col0, m0);
+          if (!p.up2x) {
+            tma_store_2d(&tmD, wstage + slot * k2WarpStageBytes, out_col0, m0);
+          } else {  // 32 consecutive low-resolution pixels -> (x, y, image) of the phase's output grid
+            const int ox = (p.W >= 32) ? (m0 % p.W) : 0;
+            tma_store_4d(&tmD, wstage + slot * k2WarpStageBytes, out_col0, ox, (m0 / p.W) % p.H, m0 / (p.W * p.H));
+          }
           bulk_commit_group();
         }
       }
@@ -532,11 +540,13 @@ bool gemm2_disabled() {
 
 // A/B tensor maps are built by the caller (gemm or conv geometry); C/D maps are built here.
 int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, int N, int mode, int H, int W,
-                 int cblocks, const EdtrEpilogue* ep, cudaStream_t stream) {
+                 int cblocks, const EdtrEpilogue* ep, cudaStream_t stream, int taps_x, int tap_dy0, int tap_dx0,
+                 const CUtensorMap* tmD_up) {
   Gemm2Params p{};
   p.M = M; p.N = N; p.num_kblocks = K / k2BK; p.mode = mode; p.H = H; p.W = W; p.cblocks = cblocks;
+  p.taps_x = taps_x; p.tap_dy0 = tap_dy0; p.tap_dx0 = tap_dx0; p.up2x = tmD_up != nullptr;
   p.geglu = ep->act == EDTR_ACT_GEGLU;
-  plan_tiles(M, N, p.num_kblocks, p.geglu, g_ws_bytes, &p.tiles_n, &p.bn_base, &p.splits);
+  plan_tiles(M, N, p.num_kblocks, p.geglu, p.up2x ? 0 : g_ws_bytes, &p.tiles_n, &p.bn_base, &p.splits);
   p.kb_per_split = (p.num_kblocks + p.splits - 1) / p.splits;
   p.ws = g_ws;
   p.b_box_rows = p.bn_base / 2;
@@ -559,7 +569,9 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
     rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
     if (rc) return rc;
   }
-  {
+  if (tmD_up != nullptr) {
+    tmD = *tmD_up;
+  } else {
     uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
     uint64_t strides[1] = {static_cast<uint64_t>(ep->ldc) * 2};
     uint32_t box[2] = {64, 32};
@@ -578,6 +590,10 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   const int work = p.tiles_m * p.tiles_n * p.splits;
   const int clusters = work < 74 ? work : 74;
   if (p.splits > 1) p.has_residual = 0;  // the reduce kernel adds it
+  if (p.up2x && p.splits > 1) {
+    set_error("internal: split-K is not available for the up-sampling convolution");
+    return EDTR_ERR_INVALID;
+  }
   EDTR_LAUNCH(gemm2_kernel, 2 * clusters, k2Threads, k2SmemBytes, stream, tmA, tmB, tmC, tmD, p);
   rc = check_launch("gemm2_kernel");
   if (rc || p.splits == 1) return rc;

@@ -48,6 +48,25 @@ def pack_conv3x3(w: torch.Tensor, device) -> torch.Tensor:
     return wp.reshape(cout, 9 * cp).to(BF16).contiguous().to(device)
 
 
+def pack_conv3x3_up2x(w: torch.Tensor, device) -> torch.Tensor:
+    """Phase filters of `nearest-2x then conv3x3/p1`: [Cout, Cin, 3, 3] -> bf16 [4 (py,px), Cout, 4 (dy,dx) * Cin_pad].
+    Output pixel (2y+py, 2x+px) reads source rows {y-1, y} (py=0) or {y, y+1} (py=1); the 3x3 taps that land on
+    the same source pixel are summed (in fp32) — same for columns."""
+    cout, cin = w.shape[:2]
+    cp = _ceil(cin, 64)
+    wf = w.detach().float().cpu()
+    rows = {0: [wf[:, :, 0, :], wf[:, :, 1, :] + wf[:, :, 2, :]], 1: [wf[:, :, 0, :] + wf[:, :, 1, :], wf[:, :, 2, :]]}
+    out = torch.zeros((2, 2, cout, 2, 2, cp), dtype=F32)
+    for py in (0, 1):
+        for dy in (0, 1):
+            r = rows[py][dy]                      # [Cout, Cin, 3 (kx)]
+            cols = {0: [r[:, :, 0], r[:, :, 1] + r[:, :, 2]], 1: [r[:, :, 0] + r[:, :, 1], r[:, :, 2]]}
+            for px in (0, 1):
+                for dx in (0, 1):
+                    out[py, px, :, dy, dx, :cin] = cols[px][dx]
+    return out.reshape(4, cout, 4 * cp).to(BF16).contiguous().to(device)
+
+
 def pack_matrix(w: torch.Tensor, device) -> torch.Tensor:
     """Linear [N, K] or 1x1 conv [N, K, 1, 1] -> bf16 [N, K]."""
     w = w.detach()
@@ -136,6 +155,8 @@ class _PackedNet:
                 q = p if kind == "conv_in" else p + ("op." if kind == "down" else "conv.")
                 w[q + "weight"] = pack_conv3x3(sd[q + "weight"], dev)
                 w[q + "bias"] = vec(sd[q + "bias"], dev)
+                if kind == "up":
+                    w[q + "weight_up2x"] = pack_conv3x3_up2x(sd[q + "weight"], dev)
             elif kind == "res":
                 cout = layer[2]
                 for n in ("in_layers.0.", "out_layers.0."):
@@ -295,6 +316,10 @@ class _NetRunner:
     # -- Upsample (model/unet.py:69-79): nearest x2 then 3x3 ------------------------------
     def up(self, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
         B, H, W, C = x.shape
+        w = self.net.w
+        if self.ops.conv3x3_up2x_supported(B, H, W, C, out.shape[-1]):
+            self.ops.conv3x3_up2x(x, w[p + "conv.weight_up2x"], bias=w[p + "conv.bias"], out=out)
+            return
         u = self.ops.upsample2x(x, out=self.ws.get("up", (B, 2 * H, 2 * W, C)))
         self.conv(p + "conv.", u, out)
 
@@ -618,6 +643,8 @@ class VaeDecoderEngine:
                 w[k] = v.detach().float().reshape(v.shape[0], -1).contiguous().to(dev)
             elif v.dim() == 4 and v.shape[-1] == 3:
                 w[k] = pack_conv3x3(v, dev)
+                if ".upsample.conv." in k:
+                    w[k + "_up2x"] = pack_conv3x3_up2x(v, dev)
             elif v.dim() == 4:
                 w[k] = pack_matrix(v, dev)
             else:
@@ -691,12 +718,15 @@ class VaeDecoderEngine:
                 h = o
             if has_up:  # Upsample: nearest x2 then conv (model/vae.py:36-38)
                 c = h.shape[-1]
-                u = ops.upsample2x(h, out=ws.get("up", (B, 2 * H, 2 * W, c)))
-                H, W = 2 * H, 2 * W
+                q = f"decoder.up.{level}.upsample.conv."
                 n += 1
-                o = ping(n, (B, H, W, c))
-                ops.conv3x3(u, w[f"decoder.up.{level}.upsample.conv.weight"],
-                            bias=w[f"decoder.up.{level}.upsample.conv.bias"], out=o)
+                o = ping(n, (B, 2 * H, 2 * W, c))
+                if ops.conv3x3_up2x_supported(B, H, W, c, c):
+                    ops.conv3x3_up2x(h, w[q + "weight_up2x"], bias=w[q + "bias"], out=o)
+                else:
+                    u = ops.upsample2x(h, out=ws.get("up", (B, 2 * H, 2 * W, c)))
+                    ops.conv3x3(u, w[q + "weight"], bias=w[q + "bias"], out=o)
+                H, W = 2 * H, 2 * W
                 h = o
         y = ops.groupnorm(h, w["decoder.norm_out.weight"], w["decoder.norm_out.bias"], 32, 1e-6, True,
                           stats=ws.gn_scratch(ops, h), out=ws.get("gn", (B, H, W, self.last)))

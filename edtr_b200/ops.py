@@ -160,6 +160,41 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, residua
     return out
 
 
+def conv3x3_up2x_supported(B: int, H: int, W: int, Cin: int, Cout: int) -> bool:
+    """Geometry the phase-decomposed (sub-pixel) up-sampling convolution covers."""
+    if Cin % 64 or Cout % 64 or B * H * W < 256 or W < 8 or (W & (W - 1)):
+        return False
+    rows = max(1, 128 // W)
+    return H % rows == 0 if H >= rows else rows % H == 0
+
+
+def conv3x3_up2x(x: torch.Tensor, w4: torch.Tensor, *, bias=None, act=ACT_NONE, out=None) -> torch.Tensor:
+    """nearest-2x + 3x3/p1 conv as four 2x2-tap convs. x [B,H,W,Cin]; w4 [4, Cout, 4*Cin] phase filters
+    (engine.pack_conv3x3_up2x); out [B,2H,2W,Cout] rows view."""
+    _require_cuda(x, w4, bias, out)
+    if x.dim() != 4:
+        raise ValueError("x must be [B, H, W, C]")
+    B, H, W, Cin = x.shape
+    _, _, ldx = rows_view(x)
+    if w4.dtype != BF16 or w4.dim() != 3 or w4.shape[0] != 4 or w4.shape[2] != 4 * Cin or not w4.is_contiguous():
+        raise ValueError(f"w4 must be a contiguous bf16 [4, Cout, 4*Cin={4 * Cin}] tensor, got {tuple(w4.shape)}")
+    Cout = w4.shape[1]
+    if not conv3x3_up2x_supported(B, H, W, Cin, Cout):
+        raise ValueError(f"unsupported up-conv geometry B={B} H={H} W={W} Cin={Cin} Cout={Cout}")
+    if act == ACT_GEGLU:
+        raise ValueError("GEGLU is not defined for convolutions")
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, Cout), dtype=BF16, device=x.device)
+    ep = _epilogue(4 * B * H * W, Cout, out, bias=bias, rowvec=None, rows_per_group=0, residual=None, act=act,
+                   out_mode=OUT_BF16, hw=0, alpha=1.0)
+    if tuple(out.shape) != (B, 2 * H, 2 * W, Cout):
+        raise ValueError(f"out must be [B, 2H, 2W, Cout], got {tuple(out.shape)}")
+    L = _lib.device_lib()
+    _lib.check(L.edtr_conv3x3_up2x_bf16(x.data_ptr(), ldx, B, H, W, Cin, w4.data_ptr(), Cout, ctypes.byref(ep),
+                                        _stream()), "edtr_conv3x3_up2x_bf16")
+    return out
+
+
 def conv3x3_supported(H: int, W: int, Cin: int) -> bool:
     """Geometry the TMA implicit-GEMM path covers (else: im2col + gemm)."""
     if Cin % 64 != 0:

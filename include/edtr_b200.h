@@ -106,6 +106,15 @@ int edtr_gemm_bf16(const void* A, int lda, const void* Wt, int ldw, int M, int N
 int edtr_conv3x3_bf16(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wt,
                       int Cout, const EdtrEpilogue* ep, void* stream);
 
+/* Nearest 2x up-sampling followed by a 3x3 / pad-1 convolution, without materialising the up-sampled tensor:
+ * four 2x2-tap implicit GEMMs on the low-resolution input, one per output phase (py, px).  X is bf16
+ * channels-last [B, H, W, Cin]; Wt4 is bf16 [2(py), 2(px), Cout, 2(dy), 2(dx), Cin] holding the phase filters
+ * (sums of the 3x3 taps that fall on the same source pixel); the output is bf16 [B, 2H, 2W, Cout] with pixel
+ * stride ep->ldc.  Epilogue: bias and optional SiLU only.  W a power of two >= 8, B*H*W >= 256.
+ * replaces: Upsample.forward = F.interpolate(nearest, x2) + conv — model/unet.py:69-79, model/vae.py:36-38. */
+int edtr_conv3x3_up2x_bf16(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wt4, int Cout,
+                           const EdtrEpilogue* ep, void* stream);
+
 /* Flash-style softmax(Q K^T * scale) V, head dim 64, no mask.
  * Q [B, Lq, heads*64] (row stride ldq), K/V [B, Lk, heads*64] (strides ldk/ldv),
  * O [B, Lq, heads*64] (stride ldo); all bf16; head h occupies columns

@@ -87,6 +87,41 @@ def conv3x3(x, w, *, bias=None, rowvec=None, residual=None, act=ACT_NONE, out=No
                    out=out, out_mode=out_mode, hw=H * W, alpha=alpha)
 
 
+def conv3x3_up2x_supported(B, H, W, Cin, Cout):
+    if Cin % 64 or Cout % 64 or B * H * W < 256 or W < 8 or (W & (W - 1)):
+        return False
+    rows = max(1, 128 // W)
+    return H % rows == 0 if H >= rows else rows % H == 0
+
+
+def conv3x3_up2x(x, w4, *, bias=None, act=ACT_NONE, out=None):
+    """Four 2x2-tap phase convolutions, evaluated literally from the packed phase filters."""
+    LAUNCHES[0] += 4
+    B, H, W, Cin = x.shape
+    Cout = w4.shape[1]
+    assert w4.shape == (4, Cout, 4 * Cin)
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))   # [B, C, H+2, W+2], source pixel (y, x) at (y+1, x+1)
+    y = torch.zeros((B, 2 * H, 2 * W, Cout), dtype=torch.float32)
+    for py in (0, 1):
+        for px in (0, 1):
+            wp = w4[py * 2 + px].float().view(Cout, 2, 2, Cin)
+            acc = torch.zeros((B, Cout, H, W), dtype=torch.float32)
+            for dy in (0, 1):
+                for dx in (0, 1):
+                    oy, ox = dy + py - 1, dx + px - 1          # source offset
+                    patch = xp[:, :, 1 + oy:1 + oy + H, 1 + ox:1 + ox + W]
+                    acc += torch.einsum("oc,bchw->bohw", wp[:, dy, dx, :], patch)
+            y[:, py::2, px::2, :] = acc.permute(0, 2, 3, 1)
+    if bias is not None:
+        y = y + bias.float()
+    if act == ACT_SILU:
+        y = F.silu(y)
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W, Cout), dtype=torch.bfloat16)
+    out.copy_(y)
+    return out
+
+
 def attention(q, k, v, heads, scale, out=None):
     LAUNCHES[0] += 1
     B, Lq, C = q.shape

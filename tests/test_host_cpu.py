@@ -71,6 +71,24 @@ def test_engine_control_scales_and_input_validation(tiny):
         eng.forward(x_T, t, cond["c_img"], cond["c_txt"][..., :64], use_graph=False)
 
 
+def test_up2x_phase_filters_equal_upsample_then_conv():
+    """pack_conv3x3_up2x: four 2x2-tap phase convolutions == nearest-2x followed by the 3x3/p1 convolution."""
+    import torch.nn.functional as F
+
+    from edtr_b200.engine import pack_conv3x3_up2x
+
+    g = torch.Generator().manual_seed(0)
+    B, H, W, Cin, Cout = 4, 8, 8, 64, 64
+    x = torch.randn(B, H, W, Cin, generator=g).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, 3, 3, generator=g) * (9 * Cin) ** -0.5
+    bias = torch.randn(Cout, generator=g)
+    out = fake_ops.conv3x3_up2x(x, pack_conv3x3_up2x(w, "cpu"), bias=bias)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w, bias, padding=1).permute(0, 2, 3, 1)
+    assert O.max_rel_err(out.float(), ref) < 1e-2
+    assert fake_ops.conv3x3_up2x_supported(8, 8, 8, 1280, 1280) and not fake_ops.conv3x3_up2x_supported(1, 8, 8, 1280, 1280)
+
+
 def test_product_requires_cuda():
     """No CPU fallback: the real ops refuse CPU tensors and the drop-in model refuses to run on CPU."""
     from edtr_b200 import ops
@@ -206,7 +224,7 @@ def test_library_exports_every_header_symbol():
     for sym in declared:
         assert hasattr(handle, sym), sym
     assert handle.edtr_version() >= 100
-    assert handle.edtr_gemm_tile_n(128, 2560, 320, 2) == 128
+    assert handle.edtr_gemm_tile_n(128, 2560, 320, 2) == 256  # GEGLU tile of the CTA-pair kernel
     assert handle.edtr_groupnorm_partial_size(8, 4096, 320, 32) > 0
 
 

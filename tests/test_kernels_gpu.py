@@ -166,6 +166,25 @@ def test_conv3x3(ops, B, H, W, Cin, Cout):
         assert relerr(out.view(B, Cout, H, W), ref) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(8, 8, 8, 128, 128), (2, 16, 16, 320, 256), (1, 32, 32, 64, 64),
+                                             (1, 64, 64, 128, 64), (1, 128, 128, 64, 64), (3, 16, 32, 64, 128)])
+def test_conv3x3_up2x(ops, B, H, W, Cin, Cout):
+    """Phase-decomposed nearest-2x + conv3x3 vs F.interpolate + F.conv2d."""
+    from edtr_b200.engine import pack_conv3x3_up2x
+
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = torch.randn(Cout, device="cuda")
+    w4 = pack_conv3x3_up2x(w.float(), "cuda")
+    cat = rnd(B, 2 * H, 2 * W, Cout + 64, seed=3)
+    before = cat.clone()
+    ops.conv3x3_up2x(x, w4, bias=bias, out=cat[..., :Cout])
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert relerr(cat[..., :Cout], ref) < 1.5e-2
+    assert torch.equal(cat[..., Cout:], before[..., Cout:])
+
+
 def test_conv3x3_channel_slice_input(ops):
     B, H, W = 2, 16, 16
     buf = rnd(B, H, W, 192, seed=1)
