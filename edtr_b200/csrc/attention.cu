@@ -25,6 +25,13 @@ constexpr int kAttSmem = kQT * kD * 2 + kKvStages * 2 * kTileBytes + 2 * kQT * k
 constexpr int kAttTmemCols = 256;  // S0 [0,64) S1 [64,128) O [128,192)
 constexpr float kRescaleThreshold = 8.f;   // log2 units
 
+// ex2.approx: one MUFU op (exp2f() without -use_fast_math adds range handling around it)
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttParams {
   void* O;
   int ldo;
@@ -146,10 +153,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int valid = p.Lk - j * kKT;  // >= 1
       float mx = -INFINITY;
       if (valid >= kKT) {
+        // four independent chains instead of one 64-deep dependent chain
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sr[h][i]));
+        for (int i = 0; i < 32; i += 2) {
+          m0 = fmaxf(m0, __uint_as_float(sr[0][i]));
+          m1 = fmaxf(m1, __uint_as_float(sr[0][i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(sr[1][i]));
+          m3 = fmaxf(m3, __uint_as_float(sr[1][i + 1]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       } else {
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -188,16 +201,17 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (j >= 2) mbar_wait(&pv_done[b], ((j - 2) >> 1) & 1);
       const float mb = m_used * p.scale_log2;
       uint8_t* prow = sP + b * (kQT * kKT * 2) + r * 128;
-      float sum = 0.f;
+      float sum = 0.f, sum1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 B
         float pv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int idx = c * 8 + i;
-          pv[i] = exp2f(fmaf(__uint_as_float(sr[idx >> 5][idx & 31]), p.scale_log2, -mb));
-          sum += pv[i];
+          pv[i] = fast_exp2(fmaf(__uint_as_float(sr[idx >> 5][idx & 31]), p.scale_log2, -mb));
         }
+        sum += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+        sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
         uint4 u;
         u.x = pack_bf16(pv[0], pv[1]);
         u.y = pack_bf16(pv[2], pv[3]);
@@ -205,7 +219,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         u.w = pack_bf16(pv[6], pv[7]);
         *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = u;
       }
-      l += sum;
+      l += sum + sum1;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_full);

@@ -64,7 +64,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > 40000000000LL) {  // ~20 s at 2 GHz (instrumented profiler replays are slow)
       printf("edtr: mbarrier timeout block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
       __trap();
