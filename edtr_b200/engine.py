@@ -122,6 +122,27 @@ class Workspace:
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self._bufs.values())
 
+    def scoped(self, prefix: str) -> "_ScopedWorkspace":
+        """A view whose buffer names are prefixed: scratch of kernels that may run concurrently on two streams
+        (UNet encoder and ControlNet) must not alias."""
+        return _ScopedWorkspace(self, prefix)
+
+
+class _ScopedWorkspace:
+    def __init__(self, base: Workspace, prefix: str):
+        self.base, self.prefix, self.device = base, prefix, base.device
+
+    def get(self, name, shape, dtype=BF16):
+        return self.base.get(self.prefix + name, shape, dtype)
+
+    def zeros(self, name, shape, dtype=BF16):
+        return self.base.zeros(self.prefix + name, shape, dtype)
+
+    def gn_scratch(self, ops, x, groups: int = 32):
+        B, C = x.shape[0], x.shape[-1]
+        hw = x.numel() // (B * C)
+        return self.base.get(self.prefix + "gn_partial", (ops.groupnorm_partial_size(B, hw, C, groups),), F32)
+
 
 # ------------------------------------------------------------------ UNet / ControlNet
 class _PackedNet:
@@ -227,7 +248,7 @@ class _NetRunner:
     """Launch sequences of the reference leaf blocks on one packed net."""
 
     def __init__(self, net: _PackedNet, ws: Workspace, ops, tag: str):
-        self.net, self.ws, self.ops, self.tag = net, ws, ops, tag
+        self.net, self.ws, self.ops, self.tag = net, ws.scoped(tag), ops, ""
         self.emb: Optional[torch.Tensor] = None   # [B, emb_total] fp32: Linear(SiLU(emb)) of every ResBlock
         self.ctx: Optional[torch.Tensor] = None   # [B, 77, ctx_total] bf16: cross-attention K|V of every block
 
@@ -373,6 +394,8 @@ class CldmEngine:
         self.out_c = unet_cfg["out_channels"]
         self._ws: Dict[Tuple[int, int, int], Workspace] = {}
         self._graphs: Dict[Tuple, "_Graph"] = {}
+        self.overlap = True      # run the ControlNet concurrently with the UNet encoder on a second stream
+        self._side = None
         # channel / resolution bookkeeping of the skip structure
         ins = self.unet.inputs
         self.in_ch = [T.block_out_channels(b) for b in ins]
@@ -391,6 +414,11 @@ class CldmEngine:
             self.cat_geom.append((self.in_ds[s], cprev, self.in_ch[s]))
             cprev = blk[0][2]
         self.final_ch = cprev
+
+    def _side_stream(self):
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
 
     # ------------------------------------------------------------------ workspace
     def workspace(self, B: int, H: int, W: int) -> Workspace:
@@ -416,8 +444,8 @@ class CldmEngine:
         un = _NetRunner(self.unet, ws, ops, "u_")
         cn = _NetRunner(self.cnet, ws, ops, "c_")
         if ctx_ready:
-            un.ctx = ws.get("u_ctx", (B, c_txt.shape[1], self.unet.ctx_total))
-            cn.ctx = ws.get("c_ctx", (B, c_txt.shape[1], self.cnet.ctx_total))
+            un.ctx = un.ws.get("ctx", (B, c_txt.shape[1], self.unet.ctx_total))
+            cn.ctx = cn.ws.get("ctx", (B, c_txt.shape[1], self.cnet.ctx_total))
         else:
             self._context(ws, un, cn, c_txt)
         un.time_embedding(t)
@@ -437,6 +465,37 @@ class CldmEngine:
         ops.nchw_to_nhwc(x, xc, 0)
         ops.nchw_to_nhwc(c_img, xc, self.zc)
 
+        # The UNet encoder+middle and the whole ControlNet are independent until the zero-conv accumulation
+        # (model/controlnet.py:25-31 vs :263-277), so they run concurrently: the ControlNet on a side stream with
+        # its own scratch buffers and split-K workspace (fork/join is capturable into the CUDA graph).  Many of
+        # their kernels (16x16 / 8x8 levels, short-K GEMMs, norms) cannot fill 148 SMs alone.
+        overlap = self.overlap and x.is_cuda
+        if overlap:
+            main = torch.cuda.current_stream()
+            side = self._side_stream()
+            side.wait_stream(main)
+        w = self.cnet.w
+        couts = []
+
+        def run_controlnet():
+            h = xc
+            for s, blk in enumerate(self.cnet.inputs):
+                d = self.in_ds[s]
+                dst = ws.get(f"c_out{s}", (B, H // d, W // d, self.in_ch[s]))
+                cn.block(f"input_blocks.{s}.", blk, h, dst)
+                h = dst
+                couts.append(dst)
+            d = self.in_ds[-1]
+            dst = ws.get("c_mid", (B, H // d, W // d, self.mid_ch))
+            cn.block("middle_block.", self.cnet.middle, h, dst)
+            couts.append(dst)
+
+        if overlap:
+            with torch.cuda.stream(side):
+                ops.use_workspace(1)
+                run_controlnet()
+            ops.use_workspace(0)
+
         # UNet encoder + middle (model/controlnet.py:25-28)
         h = xu
         for s, blk in enumerate(self.unet.inputs):
@@ -445,19 +504,14 @@ class CldmEngine:
         mid = cats[0][..., :self.cat_geom[0][1]]
         un.block("middle_block.", self.unet.middle, h, mid)
 
-        # ControlNet; zero-conv epilogues accumulate into the UNet tensors (model/controlnet.py:263-277,31,37)
-        w = self.cnet.w
-        h = xc
-        for s, blk in enumerate(self.cnet.inputs):
-            d = self.in_ds[s]
-            dst = ws.get(f"c_h{s % 2}", (B, H // d, W // d, self.in_ch[s]))
-            cn.block(f"input_blocks.{s}.", blk, h, dst)
-            h = dst
-            self._zero_conv(w, f"zero_convs.{s}.0.", h, hs_view(s), control_scales[s])
-        d = self.in_ds[-1]
-        dst = ws.get("c_mid", (B, H // d, W // d, self.mid_ch))
-        cn.block("middle_block.", self.cnet.middle, h, dst)
-        self._zero_conv(w, "middle_block_out.0.", dst, mid, control_scales[n_in])
+        if overlap:
+            main.wait_stream(side)
+        else:
+            run_controlnet()
+        # zero-conv epilogues accumulate into the UNet tensors (model/controlnet.py:270-275,31,37)
+        for s in range(n_in):
+            self._zero_conv(w, f"zero_convs.{s}.0.", couts[s], hs_view(s), control_scales[s])
+        self._zero_conv(w, "middle_block_out.0.", couts[n_in], mid, control_scales[n_in])
 
         # UNet decoder (model/controlnet.py:33-38)
         n_out = len(self.unet.outputs)

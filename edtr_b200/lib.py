@@ -158,6 +158,13 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         return _lib
 
 
+def use_workspace(index: int) -> None:
+    """Select which of the two split-K scratch buffers later launches use (one per concurrent stream)."""
+    lib = device_lib()
+    check(lib.edtr_set_workspace(_workspace[index].data_ptr(), WORKSPACE_BYTES), "edtr_set_workspace")
+    LAUNCHES[0] -= 1  # not a kernel launch
+
+
 def last_error() -> str:
     return load().edtr_last_error().decode("utf-8", "replace")
 
@@ -188,7 +195,7 @@ def device_lib() -> ctypes.CDLL:
         check(lib.edtr_init(), "edtr_init")
         # split-K scratch (stream-ordered use on the current stream; kept alive for the process lifetime)
         global _workspace
-        _workspace = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device="cuda")
-        check(lib.edtr_set_workspace(_workspace.data_ptr(), WORKSPACE_BYTES), "edtr_set_workspace")
+        _workspace = [torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device="cuda") for _ in range(2)]
+        check(lib.edtr_set_workspace(_workspace[0].data_ptr(), WORKSPACE_BYTES), "edtr_set_workspace")
         _initialised = True
     return lib

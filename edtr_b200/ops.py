@@ -31,6 +31,11 @@ def geglu_tile_n() -> int:
     return int(_lib.load().edtr_gemm_tile_n(128, 1024, 64, ACT_GEGLU))
 
 
+def use_workspace(index: int) -> None:
+    """Split-K scratch selection for launches issued from now on (0: main stream, 1: side stream)."""
+    _lib.use_workspace(index)
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
