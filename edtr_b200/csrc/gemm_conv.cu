@@ -416,75 +416,6 @@ extern "C" int edtr_gemm_bf16(const void* A, int lda, const void* Wt, int ldw, i
   return dispatch_gemm(bn, tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 
-// Direct 3x3 / pad-1 convolution for very few output channels (the UNet's 320->4 and the VAE's 128->3 output
-// convolutions): a 128-wide tensor-core tile would be >95 % padding, so one thread computes one pixel on the
-// FMA pipe; the filter lives in shared memory as fp32 (broadcast reads), activations stream through L1, and
-// the result is stored NCHW fp32 (coalesced per channel plane).
-template <int COUT>
-__global__ void __launch_bounds__(256)
-conv3x3_small_cout_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int H, int W, int Cin,
-                          const __nv_bfloat16* __restrict__ Wt, const float* __restrict__ bias,
-                          float* __restrict__ out, size_t total_pix) {
-  pdl_launch_dependents();
-  pdl_wait();
-  extern __shared__ float wsm[];  // [COUT][9][Cin]
-  const int K = 9 * Cin;
-  for (int i = threadIdx.x; i < COUT * K; i += blockDim.x) wsm[i] = __bfloat162float(Wt[i]);
-  __syncthreads();
-  const size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (pix >= total_pix) return;
-  const int x = static_cast<int>(pix % W);
-  const int y = static_cast<int>((pix / W) % H);
-  const size_t b = pix / (static_cast<size_t>(W) * H);
-  float acc[COUT];
-#pragma unroll
-  for (int co = 0; co < COUT; ++co) acc[co] = bias != nullptr ? __ldg(bias + co) : 0.f;
-#pragma unroll 1
-  for (int tap = 0; tap < 9; ++tap) {
-    const int iy = y + tap / 3 - 1, ix = x + tap % 3 - 1;
-    if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
-    const uint4* src = reinterpret_cast<const uint4*>(X + ((b * H + iy) * W + ix) * ldx);
-    const float* wt = wsm + tap * Cin;
-#pragma unroll 2
-    for (int c8 = 0; c8 < Cin / 8; ++c8) {
-      const uint4 u = __ldg(src + c8);
-      const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
-#pragma unroll
-      for (int co = 0; co < COUT; ++co) {
-        const float4 w0 = *reinterpret_cast<const float4*>(wt + co * K + c8 * 8);
-        const float4 w1 = *reinterpret_cast<const float4*>(wt + co * K + c8 * 8 + 4);
-        float a = acc[co];
-        a = fmaf(f0.x, w0.x, a); a = fmaf(f0.y, w0.y, a); a = fmaf(f1.x, w0.z, a); a = fmaf(f1.y, w0.w, a);
-        a = fmaf(f2.x, w1.x, a); a = fmaf(f2.y, w1.y, a); a = fmaf(f3.x, w1.z, a); a = fmaf(f3.y, w1.w, a);
-        acc[co] = a;
-      }
-    }
-  }
-  const size_t hw = static_cast<size_t>(H) * W;
-#pragma unroll
-  for (int co = 0; co < COUT; ++co) out[(b * COUT + co) * hw + (pix - b * hw)] = acc[co];
-}
-
-template <int COUT>
-static int launch_small_cout(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wt, const float* bias,
-                             float* out, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(COUT) * 9 * Cin * sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_small_cout_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) {
-      set_error("cudaFuncSetAttribute(conv3x3_small_cout): %s", cudaGetErrorString(e));
-      return EDTR_ERR_CUDA;
-    }
-    attr_set = true;
-  }
-  const size_t total = static_cast<size_t>(B) * H * W;
-  EDTR_LAUNCH((conv3x3_small_cout_kernel<COUT>), static_cast<unsigned>((total + 255) / 256), 256, smem, stream,
-              reinterpret_cast<const __nv_bfloat16*>(X), ldx, H, W, Cin, reinterpret_cast<const __nv_bfloat16*>(Wt), bias,
-              out, total);
-  return check_launch("conv3x3_small_cout_kernel");
-}
-
 // 2x nearest up-sampling followed by a 3x3 / pad-1 convolution, evaluated as four 2x2-tap convolutions on the
 // low-resolution input (one per output phase (py, px)): out[b, 2y+py, 2x+px] = sum over the 2x2 taps of
 // Wp[py][px] * in[b, y+dy, x+dx].  2.25x fewer MACs and operand bytes than convolving the up-sampled tensor.
@@ -574,17 +505,6 @@ extern "C" int edtr_conv3x3_bf16(const void* X, int ldx, int B, int H, int W, in
   int rc = check_epilogue(ep, M, Cout);
   if (rc) return rc;
   EDTR_REQUIRE(ep->act != EDTR_ACT_GEGLU, "GEGLU is not defined for convolutions");
-  if (Cout <= 4 && ep->out_mode == EDTR_OUT_NCHW_F32 && ep->act == EDTR_ACT_NONE && ep->residual == nullptr &&
-      ep->rowvec == nullptr && ep->alpha == 1.f && static_cast<size_t>(Cout) * 9 * Cin * 4 <= 200 * 1024) {
-    float* o = reinterpret_cast<float*>(ep->out);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    switch (Cout) {
-      case 1: return launch_small_cout<1>(X, ldx, B, H, W, Cin, Wt, ep->bias, o, st);
-      case 2: return launch_small_cout<2>(X, ldx, B, H, W, Cin, Wt, ep->bias, o, st);
-      case 3: return launch_small_cout<3>(X, ldx, B, H, W, Cin, Wt, ep->bias, o, st);
-      default: return launch_small_cout<4>(X, ldx, B, H, W, Cin, Wt, ep->bias, o, st);
-    }
-  }
   const int bn = pick_bn(M, Cout, ep->act);
   CUtensorMap tmA, tmB;
   {
