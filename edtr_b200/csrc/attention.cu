@@ -54,8 +54,9 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* kv_full = bars + 1;                    // [stages]
   uint64_t* kv_empty = kv_full + kKvStages;        // [stages]
   uint64_t* s_full = kv_empty + kKvStages;         // [2]
-  uint64_t* p_full = s_full + 2;                   // 128 arrivals per tile
-  uint64_t* pv_done = p_full + 1;                  // [2] PV of the tile that used P buffer b has retired
+  uint64_t* p_full = s_full + 2;                   // [2] 128 arrivals per tile; one barrier per P buffer, so a warp
+                                                   //     that runs one tile ahead cannot complete the wrong phase
+  uint64_t* pv_done = p_full + 2;                  // [2] PV of the tile that used P buffer b has retired
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5;
@@ -77,8 +78,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&pv_done[i], 1);
+      mbar_init(&p_full[i], 128);
     }
-    mbar_init(p_full, 128);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -124,7 +125,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int j = 0; j < nkv; ++j) {
         const int st = j % kKvStages;
         if (j + 1 < nkv) issue_s(j + 1);
-        mbar_wait(p_full, j & 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         tc_fence_after();
         const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP + (j & 1) * kQT * kKT * 2));
         const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV + st * kTileBytes));
@@ -222,7 +223,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       l += sum + sum1;
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[b]);
     }
     // last PV retired -> O complete
     mbar_wait(&pv_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
