@@ -117,6 +117,23 @@ class ControlLDM(nn.Module):
         return self._engine
 
     # ----------------------------------------------------------------- reference API
+    @torch.no_grad()
+    def forward_tiled(self, x_noisy, t, cond, tile_size: int, tile_stride: int) -> torch.Tensor:
+        """Batched equivalent of the sampler's tiled wrapper (utils/sampler.py:288-303): all latent tiles of the step
+        in one forward, gaussian-blended on the device; tiles are spread over the ranks of the default process
+        group when torch.distributed is initialised with more than one rank (config C4)."""
+        import torch.distributed as dist
+
+        rank, world, red = 0, 1, None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            rank, world = dist.get_rank(), dist.get_world_size()
+            red = lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        eps = self.engine().forward_tiled(x_noisy.float().contiguous(), t.long().contiguous(),
+                                          cond["c_img"].float().contiguous(), cond["c_txt"].float().contiguous(),
+                                          tile_size, tile_stride, control_scales=self.control_scales, rank=rank,
+                                          world=world, reduce_fn=red)
+        return eps.to(x_noisy.dtype)
+
     def vae_encode(self, image, sample=True, tiled=False, tile_size=-1):
         raise NotImplementedError("vae_encode precedes the accelerated path (SURVEY §8f rank 1); run the "
                                   "reference encoder and pass c_img")

@@ -151,6 +151,28 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
   if (pred_x0 != nullptr) pred_x0[i] = x0;
 }
 
+// Partial gaussian blend of latent tiles: out[b, c, y, x] = sum over the given tiles that cover (y, x) of
+// weight[y - hi, x - wi] * tiles[t, b, c, y - hi, x - wi]   (numerator of make_tiled_fn, utils/common.py:414-424).
+__global__ void tile_blend_kernel(const float* __restrict__ tiles, const int* __restrict__ coords, int ntiles,
+                                  const float* __restrict__ weight, float* __restrict__ out, int BC, int H, int W,
+                                  int th, int tw, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % W);
+  const int y = static_cast<int>((i / W) % H);
+  const int bc = static_cast<int>(i / (static_cast<size_t>(W) * H));
+  float acc = 0.f;
+  for (int t = 0; t < ntiles; ++t) {
+    const int hi = __ldg(coords + 2 * t), wi = __ldg(coords + 2 * t + 1);
+    const int ty = y - hi, tx = x - wi;
+    if (ty >= 0 && ty < th && tx >= 0 && tx < tw)
+      acc += __ldg(weight + ty * tw + tx) * __ldg(tiles + ((static_cast<size_t>(t) * BC + bc) * th + ty) * tw + tx);
+  }
+  out[i] = acc;
+}
+
 static inline unsigned blocks_for(size_t n, int threads) {
   return static_cast<unsigned>((n + threads - 1) / threads);
 }
@@ -227,6 +249,16 @@ extern "C" int edtr_im2col_bf16(const void* X, int ldx, void* Y, int B, int H, i
       reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), H, W, vpr, KH, KW,
       stride, pad_top, pad_left, Ho, Wo, total);
   return check_launch("im2col_kernel");
+}
+
+extern "C" int edtr_tile_blend(const float* tiles, const int32_t* coords, int ntiles, const float* weight, float* out,
+                               int BC, int H, int W, int th, int tw, void* stream) {
+  EDTR_REQUIRE(tiles && coords && weight && out, "NULL argument");
+  EDTR_REQUIRE(ntiles > 0 && BC > 0 && H > 0 && W > 0 && th > 0 && tw > 0 && th <= H && tw <= W, "bad tile-blend shape");
+  const size_t total = static_cast<size_t>(BC) * H * W;
+  EDTR_LAUNCH(tile_blend_kernel, blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), tiles, coords, ntiles,
+              weight, out, BC, H, W, th, tw, total);
+  return check_launch("tile_blend_kernel");
 }
 
 extern "C" int edtr_timestep_embedding(const int64_t* t, void* Y, int B, int dim, float max_period,

@@ -581,6 +581,46 @@ class CldmEngine:
             run()
         return eps.clone()
 
+    def forward_tiled(self, x_noisy, t, c_img, c_txt, tile_size: int, tile_stride: int, control_scales=None,
+                      rank: int = 0, world: int = 1, reduce_fn=None, use_graph: bool = True) -> torch.Tensor:
+        """cldm-tiled evaluation (utils/sampler.py:288-303 + make_tiled_fn, utils/common.py:367-427): the latent is cut
+        into overlapping windows, every window is one image of a BATCHED forward (the reference runs them one by one
+        at batch 1), and the outputs are blended with the gaussian weights by one kernel.  With world > 1 rank r
+        evaluates tiles r, r+world, ... and `reduce_fn` (an all-reduce SUM over ranks) merges the partial blends —
+        the only exchange of the step."""
+        from .tiling import gaussian_weights, sliding_windows
+
+        self._check_inputs(x_noisy, t, c_img, c_txt)
+        B, C, H, W = x_noisy.shape
+        if tile_size > min(H, W):
+            raise ValueError(f"tile_size {tile_size} exceeds the latent {H}x{W}")
+        coords = sliding_windows(H, W, tile_size, tile_stride)
+        mine = coords[rank::world]
+        dev = x_noisy.device
+        wnp = gaussian_weights(tile_size, tile_size)
+        weight = torch.tensor(wnp, dtype=F32, device=dev)
+        # the weight sum is data independent: computed once on the host (fp64), as `count` in the reference
+        cnt = torch.zeros((H, W), dtype=torch.float64)
+        wt = torch.tensor(wnp, dtype=torch.float64)
+        for hi, he, wi, we in coords:
+            cnt[hi:he, wi:we] += wt
+        inv_count = (1.0 / cnt).to(F32).to(dev)
+        out = torch.zeros((B, self.out_c, H, W), dtype=F32, device=dev)
+        if mine:
+            xt = torch.stack([x_noisy[..., hi:he, wi:we] for hi, he, wi, we in mine], 0)        # [T, B, C, th, tw]
+            ct = torch.stack([c_img[..., hi:he, wi:we] for hi, he, wi, we in mine], 0)
+            T = len(mine)
+            eps = self.forward(xt.reshape(T * B, C, tile_size, tile_size).contiguous(), t.repeat(T),
+                               ct.reshape(T * B, -1, tile_size, tile_size).contiguous(),
+                               c_txt.repeat(T, 1, 1), control_scales=control_scales, use_graph=use_graph)
+            cd = torch.tensor([[hi, wi] for hi, _, wi, _ in mine], dtype=torch.int32, device=dev)
+            self.ops.tile_blend(eps.view(T, B, self.out_c, tile_size, tile_size), cd, weight, out)
+        if world > 1:
+            if reduce_fn is None:
+                raise ValueError("reduce_fn (all-reduce SUM) is required when world > 1")
+            reduce_fn(out)
+        return out * inv_count
+
     def sample(self, x_T, timesteps: Sequence[int], tables: Dict[str, torch.Tensor], c_img, c_txt,
                noise: Sequence[torch.Tensor], control_scales=None, use_graph: bool = True,
                return_intermediates: bool = False):

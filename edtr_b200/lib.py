@@ -32,7 +32,7 @@ EXPORTED = [
     "edtr_conv3x3_bf16", "edtr_conv3x3_up2x_bf16", "edtr_attention_bf16", "edtr_groupnorm_partial_size", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
     "edtr_layernorm_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
     "edtr_nchw_f32_to_nhwc_bf16", "edtr_pointwise_nchw_f32_to_nhwc_bf16", "edtr_nhwc_bf16_to_nchw", "edtr_cast_f32_to_bf16",
-    "edtr_timestep_embedding", "edtr_sampler_update",
+    "edtr_tile_blend", "edtr_timestep_embedding", "edtr_sampler_update",
 ]
 
 
@@ -137,6 +137,8 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_nhwc_bf16_to_nchw.argtypes = [vp, ci, vp, ci, ci, ci, ci, vp]
     lib.edtr_cast_f32_to_bf16.restype = ci
     lib.edtr_cast_f32_to_bf16.argtypes = [vp, vp, c_size_t, vp]
+    lib.edtr_tile_blend.restype = ci
+    lib.edtr_tile_blend.argtypes = [vp, vp, ci, vp, vp, ci, ci, ci, ci, ci, vp]
     lib.edtr_timestep_embedding.restype = ci
     lib.edtr_timestep_embedding.argtypes = [vp, vp, ci, ci, c_float, vp]
     lib.edtr_sampler_update.restype = ci

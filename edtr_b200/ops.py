@@ -386,6 +386,26 @@ def cast_bf16(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tens
     return out
 
 
+def tile_blend(tiles: torch.Tensor, coords: torch.Tensor, weight: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """out[b,c,y,x] = sum_t weight * tiles[t,b,c,...] over the tiles covering (y,x). tiles [T,B,C,th,tw] fp32,
+    coords int32 [T,2] = (hi, wi), weight [th,tw] fp32, out [B,C,H,W] fp32."""
+    _require_cuda(tiles, coords, weight, out)
+    if tiles.dim() != 5 or tiles.dtype != torch.float32 or not tiles.is_contiguous():
+        raise ValueError("tiles must be a contiguous fp32 [T, B, C, th, tw] tensor")
+    T, B, C, th, tw = tiles.shape
+    if coords.dtype != torch.int32 or tuple(coords.shape) != (T, 2) or not coords.is_contiguous():
+        raise ValueError("coords must be a contiguous int32 [T, 2] tensor")
+    if weight.dtype != torch.float32 or tuple(weight.shape) != (th, tw) or not weight.is_contiguous():
+        raise ValueError("weight must be a contiguous fp32 [th, tw] tensor")
+    if out.dtype != torch.float32 or not out.is_contiguous() or out.dim() != 4 or tuple(out.shape[:2]) != (B, C):
+        raise ValueError("out must be a contiguous fp32 [B, C, H, W] tensor")
+    H, W = out.shape[2:]
+    L = _lib.device_lib()
+    _lib.check(L.edtr_tile_blend(tiles.data_ptr(), coords.data_ptr(), T, weight.data_ptr(), out.data_ptr(), B * C, H, W,
+                                 th, tw, _stream()), "edtr_tile_blend")
+    return out
+
+
 def timestep_embedding(t: torch.Tensor, dim: int, max_period: float = 10000.0,
                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _require_cuda(t, out)

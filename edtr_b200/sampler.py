@@ -152,6 +152,22 @@ class SpacedSampler(nn.Module):
             if return_intermediates:
                 return out[0], out[1]
             return out
+        ours = isinstance(model, ControlLDM) and type(model).forward is ControlLDM.forward and "forward" not in model.__dict__
+        if tiled and ours and (uncond is None or cfg_scale == 1.):
+            # batched tiles + on-device blend instead of the per-tile Python loop
+            intermediates = []
+            for i, step in enumerate(timesteps):
+                ts = torch.full((batch_size,), int(step), device=device, dtype=torch.long)
+                index = torch.full_like(ts, fill_value=total - i - 1)
+                eps = model.forward_tiled(img, ts, cond, tile_size, tile_stride)
+                noise = torch.randn_like(img)
+                from . import ops
+
+                img, pred_x0 = ops.sampler_update(img.float().contiguous(), eps.float().contiguous(),
+                                                  noise.float().contiguous(), index, self._tables_for_kernel())
+                if return_intermediates:
+                    intermediates.append(pred_x0)
+            return (img, intermediates) if return_intermediates else img
         if tiled:
             from .tiling import make_tiled_fn
 

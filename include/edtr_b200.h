@@ -181,6 +181,13 @@ int edtr_nhwc_bf16_to_nchw(const void* X, int ldx, void* Y, int B, int C, int HW
 /* fp32 -> bf16 element cast (n elements). */
 int edtr_cast_f32_to_bf16(const float* X, void* Y, size_t n, void* stream);
 
+/* Numerator of the gaussian tile blend of the cldm-tiled path: out[bc, y, x] = sum over the `ntiles` given
+ * tiles covering (y, x) of weight[y-hi, x-wi] * tiles[t, bc, y-hi, x-wi]; coords = int32 [ntiles, 2] (hi, wi),
+ * all fp32.  The caller divides by the (data-independent) weight sum, after the all-reduce when the tiles are
+ * spread over ranks.  replaces: out[..] += fn(tile) * weights — utils/common.py:414-424. */
+int edtr_tile_blend(const float* tiles, const int32_t* coords, int ntiles, const float* weight, float* out,
+                    int BC, int H, int W, int th, int tw, void* stream);
+
 /* Sinusoidal timestep embedding [B, dim] = [cos(t f_k) | sin(t f_k)],
  * f_k = exp(-ln(max_period) k / (dim/2)), computed in fp32, stored bf16.
  * replaces: timestep_embedding — model/util.py:98-118. */

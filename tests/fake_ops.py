@@ -221,6 +221,16 @@ def cast_bf16(x, out=None):
     return out
 
 
+def tile_blend(tiles, coords, weight, out):
+    LAUNCHES[0] += 1
+    out.zero_()
+    th, tw = weight.shape
+    for t in range(tiles.shape[0]):
+        hi, wi = int(coords[t, 0]), int(coords[t, 1])
+        out[..., hi:hi + th, wi:wi + tw] += tiles[t] * weight
+    return out
+
+
 def timestep_embedding(t, dim, max_period=10000.0, out=None):
     LAUNCHES[0] += 1
     half = dim // 2

@@ -82,6 +82,24 @@ def test_tiny_odd_batch_and_rectangular_latent(tiny):
         assert O.psnr((img.cpu() + 1) / 2, (iref + 1) / 2) >= PSNR_MIN, (B, H, W)
 
 
+def test_tiny_tiled_sampling_against_oracle(tiny):
+    """cldm-tiled path through the drop-in sampler (batched tiles, device blend) vs the reference tiling semantics
+    evaluated with the oracle tile by tile."""
+    from edtr_b200.tiling import make_tiled_fn
+
+    w, _, _, _, _, (eng, vd) = tiny
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1, 4, 32, 32, generator=g)
+    cond = dict(c_img=0.8 * torch.randn(1, 4, 32, 32, generator=g), c_txt=torch.randn(1, 77, 128, generator=g))
+    t = torch.full((1,), 150, dtype=torch.long)
+    with torch.no_grad():
+        fn = make_tiled_fn(lambda xt, tt, c, hi, hi_end, wi, wi_end: O.cldm_forward(
+            w, O.TINY, xt, tt, {"c_txt": c["c_txt"], "c_img": c["c_img"][..., hi:hi_end, wi:wi_end]}), 16, 8)
+        ref = fn(x, t, cond)
+    out = eng.forward_tiled(x.cuda(), t.cuda(), cond["c_img"].cuda(), cond["c_txt"].cuda(), 16, 8)
+    assert O.max_rel_err(out.cpu(), ref) < 3e-2
+
+
 @pytest.fixture(scope="module")
 def s4():
     w = O.make_cldm_weights(O.S4, seed=0)
