@@ -125,44 +125,62 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int w = cluster_id; w < num_work; w += num_clusters) {
-        const int tile = w / p.splits, ks = w - tile * p.splits;
-        const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
-        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-        const int m0 = tm * (2 * k2BM) + static_cast<int>(rank) * k2BM;
-        const int n_tile0 = tn * p.bn_base;
-        const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
-        const int nrow0 = n_tile0 + static_cast<int>(rank) * (bn >> 1);
-        int cx = 0, cy = 0, cn = 0;
-        if (p.mode == 1) {
-          cx = (p.W >= k2BM) ? (m0 % p.W) : 0;
-          cy = (m0 / p.W) % p.H;
-          cn = m0 / (p.W * p.H);
-        }
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % nstages;
-          const uint32_t ph = (it / nstages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+    // The whole warp walks the loop with warp-uniform state (stage counter, tap / channel-block counters: no
+    // divisions per k-block) so the addresses live in uniform registers; one elected lane issues.
+    const uint32_t pipe_u32 = smem_u32(sPipe);
+    const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[0]), 0);
+    const uint32_t empty_u32 = smem_u32(&empty_bar[0]);
+    uint32_t s = 0, ph = 0;
+    for (int w = cluster_id; w < num_work; w += num_clusters) {
+      const int tile = w / p.splits, ks = w - tile * p.splits;
+      const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int m0 = tm * (2 * k2BM) + static_cast<int>(rank) * k2BM;
+      const int n_tile0 = tn * p.bn_base;
+      const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
+      const int nrow0 = n_tile0 + static_cast<int>(rank) * (bn >> 1);
+      int cx = 0, cy = 0, cn = 0, cb = 0, tx = 0, ty = 0;
+      if (p.mode == 1) {
+        cx = (p.W >= k2BM) ? (m0 % p.W) : 0;
+        cy = (m0 / p.W) % p.H;
+        cn = m0 / (p.W * p.H);
+        const int tap0 = kb0 / p.cblocks;
+        cb = kb0 - tap0 * p.cblocks;
+        ty = tap0 / p.taps_x;
+        tx = tap0 - ty * p.taps_x;
+        cx += p.tap_dx0;
+        cy += p.tap_dy0;
+      }
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_u32(empty_u32 + s * 8, ph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = full_leader + s * 8;
+          const uint32_t sa = pipe_u32 + s * p.stage_bytes;
           mbar_arrive_expect_tx_cluster(fb, p.stage_bytes);
-          uint8_t* sa = sPipe + s * p.stage_bytes;
           if (p.mode == 0) {
-            tma_load_2d_pair(sa, &tmA, fb, kb * k2BK, m0);
+            tma_load_2d_pair_u32(sa, &tmA, fb, kb * k2BK, m0);
           } else {
-            const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-            const int dy = tap / p.taps_x + p.tap_dy0, dx = tap % p.taps_x + p.tap_dx0;
-            tma_load_4d_pair(sa, &tmA, fb, cb * k2BK, cx + dx, cy + dy, cn);
+            tma_load_4d_pair_u32(sa, &tmA, fb, cb * k2BK, cx + tx, cy + ty, cn);
           }
-          tma_load_2d_pair(sa + k2ABytes, &tmB, fb, kb * k2BK, nrow0);
+          tma_load_2d_pair_u32(sa + k2ABytes, &tmB, fb, kb * k2BK, nrow0);
         }
+        __syncwarp();
+        if (++cb == p.cblocks) {
+          cb = 0;
+          if (++tx == p.taps_x) { tx = 0; ++ty; }
+        }
+        if (++s == static_cast<uint32_t>(nstages)) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------- UMMA issuer (leader only)
-    if (lane == 0 && leader) {
-      uint32_t it = 0, ti = 0;
+    if (leader) {
+      const uint32_t pipe_u32 = smem_u32(sPipe);
+      const uint32_t full_u32 = smem_u32(&full_bar[0]);
+      const uint32_t empty_u32 = smem_u32(&empty_bar[0]);
+      const uint32_t tfull_u32 = smem_u32(&tfull_bar[0]);
+      const uint32_t tempty_u32 = smem_u32(&tempty_bar[0]);
+      uint32_t s = 0, ph = 0, ti = 0;
       for (int w = cluster_id; w < num_work; w += num_clusters, ++ti) {
         const int tile = w / p.splits, ks = w - tile * p.splits;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
@@ -171,23 +189,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
         const uint32_t idesc = umma_idesc_bf16(2 * k2BM, bn);
         const uint32_t a = ti & 1, aph = (ti >> 1) & 1;
-        mbar_wait(&tempty_bar[a], aph ^ 1);
+        mbar_wait_u32(tempty_u32 + a * 8, aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * k2MaxBN;
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % nstages;
-          const uint32_t ph = (it / nstages) & 1;
-          mbar_wait(&full_bar[s], ph);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait_u32(full_u32 + s * 8, ph);
           tc_fence_after();
-          const uint32_t sa = smem_u32(sPipe + s * p.stage_bytes);
-          const uint64_t adesc = umma_smem_desc_sw128(sa);
-          const uint64_t bdesc = umma_smem_desc_sw128(sa + k2ABytes);
+          if (elect_one()) {
+            const uint32_t sa = pipe_u32 + s * p.stage_bytes;
+            const uint64_t adesc = umma_smem_desc_sw128(sa);
+            const uint64_t bdesc = umma_smem_desc_sw128(sa + k2ABytes);
+            umma_ss_pair(d_tmem, adesc, bdesc, idesc, kb > kb0);
 #pragma unroll
-          for (int k = 0; k < k2BK / 16; ++k)
-            umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb0) || (k != 0));
-          umma_commit_pair(&empty_bar[s], 0x3);
+            for (int k = 1; k < k2BK / 16; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+            umma_commit_pair_u32(empty_u32 + s * 8, 0x3);
+          }
+          __syncwarp();
+          if (++s == static_cast<uint32_t>(nstages)) { s = 0; ph ^= 1; }
         }
-        umma_commit_pair(&tfull_bar[a], 0x3);
+        if (elect_one()) umma_commit_pair_u32(tfull_u32 + a * 8, 0x3);
+        __syncwarp();
       }
     }
   } else {

@@ -72,6 +72,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, on a shared-window address (keeps warp-uniform callers in uniform registers).
+__device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_u32(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_u32(bar, parity)) {
+    if (clock64() - t0 > 40000000000LL) {
+      printf("edtr: mbarrier timeout block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -241,6 +265,22 @@ __device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_pair_u32(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                     int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair_u32(uint32_t dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                     int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // TMA store smem -> global (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -294,6 +334,13 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t cta_mas
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
           smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_pair_u32(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
       "h"(cta_mask)
       : "memory");
 }

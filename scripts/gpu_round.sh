@@ -12,7 +12,7 @@ EDTR_NCU=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none
     --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 echo "== ncu launches exit $?"; wc -l gpurun_out/launches.csv
 EDTR_NCU=1 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
-    -k regex:gemm_conv_kernel -s 300 -c 3 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+    -k regex:gemm2_kernel -s 300 -c 3 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 echo "== ncu full exit $?"; ls -la gpurun_out/*.ncu-rep
 fi
 timeout 600 python scripts/profile_step.py --batch 8 > gpurun_out/profile_step.log 2>&1

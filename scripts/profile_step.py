@@ -41,7 +41,8 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--out", default="gpurun_out/profile_step.txt")
     ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--shapes", action="store_true", help="eager per-shape timing of the tensor-core launches")
+    ap.add_argument("--shapes", action="store_true", help="per-shape kernel time of one graph replay (single stream)")
+    ap.add_argument("--no-overlap", action="store_true", help="run the ControlNet on the main stream")
     a = ap.parse_args()
     B = a.batch
     cn_cfg = dict(S4_NET, hint_channels=4)
@@ -50,6 +51,8 @@ def main():
                      rand_sd(T.unet_param_shapes(cn_cfg, True), 1), "cuda")
     vd = VaeDecoderEngine(S4_DD, 4, rand_sd(T.vae_decoder_param_shapes(S4_DD, 4), 2), "cuda")
     print("pack s", time.time() - t0, flush=True)
+    if a.no_overlap or a.shapes:   # launch order == time order, so kernels can be attributed to ops
+        eng.overlap = False
     g = torch.Generator(device="cuda").manual_seed(3)
     x_T = torch.randn(B, 4, 64, 64, generator=g, device="cuda")
     c_img = 0.8 * torch.randn(B, 4, 64, 64, generator=g, device="cuda")
@@ -102,12 +105,24 @@ def main():
         from edtr_b200 import ops
 
         seq = []
-        names = ("gemm", "conv3x3", "attention", "groupnorm", "layernorm", "softmax_rows", "upsample2x", "im2col",
-                 "nchw_to_nhwc", "pointwise_nchw_to_nhwc", "cast_bf16", "timestep_embedding", "sampler_update")
+        names = ("gemm", "conv3x3", "conv3x3_up2x", "attention", "groupnorm", "layernorm", "softmax_rows", "upsample2x",
+                 "im2col", "nchw_to_nhwc", "pointwise_nchw_to_nhwc", "cast_bf16", "timestep_embedding", "sampler_update",
+                 "tile_blend")
         orig = {n: getattr(ops, n) for n in names}
+        # kernels an op launches first ("primary", counted) — the rest (split-K reduce, GN apply) follow their primary
+        PRIMARY = {"gemm": ("gemm2_kernel", "gemm_conv_kernel"), "conv3x3": ("gemm2_kernel", "gemm_conv_kernel"),
+                   "conv3x3_up2x": ("gemm2_kernel",), "attention": ("attention_kernel",),
+                   "groupnorm": ("groupnorm_stats_kernel",), "layernorm": ("layernorm_kernel",),
+                   "softmax_rows": ("softmax_rows_kernel",), "upsample2x": ("upsample2x_kernel",),
+                   "im2col": ("im2col_kernel",), "nchw_to_nhwc": ("nchw_to_nhwc_kernel",),
+                   "pointwise_nchw_to_nhwc": ("pointwise_nchw_kernel",), "cast_bf16": ("cast_f32_bf16_kernel",),
+                   "timestep_embedding": ("timestep_embedding_kernel",), "sampler_update": ("sampler_update_kernel",),
+                   "tile_blend": ("tile_blend_kernel",)}
+        SECONDARY = ("splitk_reduce_kernel", "groupnorm_apply_kernel")
 
         def wrap(name, fn):
             def w(*args, **kw):
+                nk = 1
                 if name == "gemm":
                     A, Wt = args[0], args[1]
                     M = A.numel() // A.shape[-1]
@@ -119,6 +134,12 @@ def main():
                     M = X.numel() // X.shape[-1]
                     key = (name, M, Wt.shape[0], Wt.shape[1], "res" if kw.get("residual") is not None else "")
                     fl = 2.0 * M * Wt.shape[0] * Wt.shape[1]
+                elif name == "conv3x3_up2x":   # 4 phase GEMMs; FLOPs counted as the reference's 3x3 conv on the 2x grid
+                    X, Wt = args[0], args[1]
+                    M = X.numel() // X.shape[-1]
+                    key = (name, 4 * M, Wt.shape[1], 9 * X.shape[-1], "")
+                    fl = 2.0 * 4 * M * Wt.shape[1] * 9 * X.shape[-1]
+                    nk = 4
                 elif name == "attention":
                     q, k_ = args[0], args[1]
                     key = (name, q.shape[0] * q.shape[1], k_.shape[1], q.shape[2], "")
@@ -126,21 +147,14 @@ def main():
                 elif name in ("groupnorm", "layernorm"):
                     x = args[0]
                     key = (name, x.numel() // x.shape[-1], x.shape[-1], 0, "")
-                    fl = 4.0 * x.numel()
+                    fl = 4.0 * x.numel()   # bytes: bf16 in + out
                 else:
                     key = (name, 0, 0, 0, "")
                     fl = 0.0
-                seq.append((key, fl))
+                seq.append((key, fl, nk))
                 return fn(*args, **kw)
             return w
 
-        KCLASS = {"gemm2_kernel": ("gemm", "conv3x3"), "gemm_conv_kernel": ("gemm", "conv3x3"),
-                  "attention_kernel": ("attention",), "groupnorm_stats_kernel": ("groupnorm",),
-                  "layernorm_kernel": ("layernorm",), "softmax_rows_kernel": ("softmax_rows",),
-                  "upsample2x_kernel": ("upsample2x",), "im2col_kernel": ("im2col",),
-                  "nchw_to_nhwc_kernel": ("nchw_to_nhwc",), "pointwise_nchw_kernel": ("pointwise_nchw_to_nhwc",),
-                  "cast_f32_bf16_kernel": ("cast_bf16",), "timestep_embedding_kernel": ("timestep_embedding",),
-                  "sampler_update_kernel": ("sampler_update",)}
         for phase, eager, replay in (
                 ("sample", lambda: eng.sample(x_T, ts, tabs, c_img, c_txt, noise, use_graph=False),
                  lambda: eng.sample(x_T, ts, tabs, c_img, c_txt, noise)),
@@ -162,30 +176,38 @@ def main():
             evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and "edtr::" in e.name]
             evs.sort(key=lambda e: e.time_range.start)
             agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
-            i = 0
-            bad = 0
+            i, left, bad, last = 0, (seq[0][2] if seq else 0), 0, None
             for e in evs:
-                kname = next((k for k in KCLASS if k in e.name), None)
                 us = e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
-                if kname is None:   # splitk_reduce / groupnorm_apply: belongs to the previous op
-                    if i > 0:
-                        agg[seq[i - 1][0]][1] += us
+                if any(k in e.name for k in SECONDARY):
+                    if last is not None:
+                        agg[last][1] += us
                     continue
-                while i < len(seq) and seq[i][0][0] not in KCLASS[kname]:
+                while i < len(seq) and not any(k in e.name for k in PRIMARY[seq[i][0][0]]):
                     i += 1
                     bad += 1
+                    left = seq[i][2] if i < len(seq) else 0
                 if i >= len(seq):
-                    break
-                key, fl = seq[i]
-                agg[key][0] += 1
+                    bad += 1
+                    continue
+                key, fl, nk = seq[i]
                 agg[key][1] += us
-                agg[key][2] += fl
-                i += 1
+                last = key
+                left -= 1
+                if left == 0:
+                    agg[key][0] += 1
+                    agg[key][2] += fl
+                    i += 1
+                    left = seq[i][2] if i < len(seq) else 0
             tot = sum(v[1] for v in agg.values())
-            lines.append(f"--- {phase}: graph-replay kernel time by op/shape: {tot / 1e3:.2f} ms, {len(evs)} kernels, "
-                         f"{len(seq)} ops, {bad} skipped  (op, M, N, K|Lk, flag): count, ms, TFLOP/s (norms: GB/s)")
-            for key, (n, us, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
-                lines.append(f"{us / 1e3:8.3f} ms {100 * us / tot:5.1f}% x{n:<4d} avg {us / max(n, 1):7.1f} us {fl / max(us, 1e-9) / 1e6:8.1f}  {key}")
+            span = (max(e.time_range.end for e in evs) - min(e.time_range.start for e in evs)) if evs else 0.0
+            lines.append(f"--- {phase}: graph-replay kernel time by op/shape: {tot / 1e3:.2f} ms busy, {span / 1e3:.2f} ms span, "
+                         f"{len(evs)} kernels, {len(seq)} ops, {bad} unmatched  (op, M, N, K|Lk, flag): count, ms, TFLOP/s "
+                         f"(norms: GB/s), ms at the sustained bf16 peak")
+            for key, (n, us, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+                ideal = fl / 1382.9e12 * 1e3 if key[0] not in ("groupnorm", "layernorm") else fl / 6539.2e9 * 1e3
+                lines.append(f"{us / 1e3:8.3f} ms {100 * us / tot:5.1f}% x{n:<4d} avg {us / max(n, 1):7.1f} us "
+                             f"{fl / max(us, 1e-9) / 1e6:8.1f}  ideal {ideal:7.3f} ms  {key}")
     if not a.no_profile:
         from torch.profiler import ProfilerActivity, profile
 
