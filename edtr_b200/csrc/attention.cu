@@ -93,50 +93,67 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   pdl_wait();  // PDL: everything above overlapped the previous kernel; global memory is touched only below
 
   if (warp == 0) {
-    if (lane == 0) {
+    // TMA producer: warp-uniform loop state (uniform registers), one elected lane issues
+    const uint32_t sK_u32 = smem_u32(sK), sV_u32 = smem_u32(sV);
+    const uint32_t full_u32 = smem_u32(kv_full), empty_u32 = smem_u32(kv_empty);
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, kQT * kD * 2);
       tma_load_4d(sQ, &tmQ, q_full, 0, q0, head, img);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j % kKvStages;
-        const uint32_t ph = (j / kKvStages) & 1;
-        mbar_wait(&kv_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * kTileBytes);
-        tma_load_4d(sK + st * kTileBytes, &tmK, &kv_full[st], 0, j * kKT, head, img);
-        tma_load_4d(sV + st * kTileBytes, &tmV, &kv_full[st], 0, j * kKT, head, img);
+    }
+    __syncwarp();
+    uint32_t st = 0, ph = 0;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait_u32(empty_u32 + st * 8, ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_u32(full_u32 + st * 8, 2 * kTileBytes);
+        tma_load_4d_u32(sK_u32 + st * kTileBytes, &tmK, full_u32 + st * 8, 0, j * kKT, head, img);
+        tma_load_4d_u32(sV_u32 + st * kTileBytes, &tmV, full_u32 + st * 8, 0, j * kKT, head, img);
       }
+      __syncwarp();
+      if (++st == kKvStages) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(kQT, kKT, false);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kD, true);
-      const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ));
-      auto issue_s = [&](int j) {
-        const int st = j % kKvStages;
-        mbar_wait(&kv_full[st], (j / kKvStages) & 1);
-        tc_fence_after();
-        const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK + st * kTileBytes));
+    // UMMA issuer: the whole warp waits on the barriers (uniform control flow), one elected lane issues
+    constexpr uint32_t idesc_s = umma_idesc_bf16(kQT, kKT, false);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kD, true);
+    const uint32_t sQ_u32 = smem_u32(sQ), sK_u32 = smem_u32(sK), sV_u32 = smem_u32(sV), sP_u32 = smem_u32(sP);
+    const uint32_t full_u32 = smem_u32(kv_full), empty_u32 = smem_u32(kv_empty);
+    const uint32_t sfull_u32 = smem_u32(s_full), pfull_u32 = smem_u32(p_full), pvdone_u32 = smem_u32(pv_done);
+    uint32_t st_s = 0, ph_s = 0;   // K/V ring position of the next S = Q K^T
+    auto issue_s = [&](int j) {
+      mbar_wait_u32(full_u32 + st_s * 8, ph_s);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t qdesc = umma_smem_desc_sw128(sQ_u32);
+        const uint64_t kdesc = umma_smem_desc_sw128(sK_u32 + st_s * kTileBytes);
 #pragma unroll
         for (int k = 0; k < kD / 16; ++k)
           umma_ss(tmem_base + (j & 1) * kKT, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit(&s_full[j & 1]);
-      };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        const int st = j % kKvStages;
-        if (j + 1 < nkv) issue_s(j + 1);
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
-        const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP + (j & 1) * kQT * kKT * 2));
-        const uint64_t vdesc = umma_smem_desc_sw128(smem_u32(sV + st * kTileBytes));
+        umma_commit_u32(sfull_u32 + (j & 1) * 8);
+      }
+      __syncwarp();
+      if (++st_s == kKvStages) { st_s = 0; ph_s ^= 1; }
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    uint32_t st = 0;
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) issue_s(j + 1);
+      mbar_wait_u32(pfull_u32 + (j & 1) * 8, (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t pdesc = umma_smem_desc_sw128(sP_u32 + (j & 1) * (kQT * kKT * 2));
+        const uint64_t vdesc = umma_smem_desc_sw128(sV_u32 + st * kTileBytes);
 #pragma unroll
         for (int k = 0; k < kKT / 16; ++k) {
           // A: +32 B per 16 keys (K-major P); B: +16 rows * 128 B (MN-major V)
           umma_ss(tmem_base + 128, pdesc + 2 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
         }
-        umma_commit(&pv_done[j & 1]);
-        umma_commit(&kv_empty[st]);
+        umma_commit_u32(pvdone_u32 + (j & 1) * 8);
+        umma_commit_u32(empty_u32 + st * 8);
       }
+      __syncwarp();
+      if (++st == kKvStages) st = 0;
     }
   } else {
     const int lg = warp & 3;

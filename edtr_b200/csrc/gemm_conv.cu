@@ -175,48 +175,59 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int cx = 0, cy = 0, cn = 0;
-      if (p.mode == 1) {
-        cx = (p.W >= kBM) ? (m0 % p.W) : 0;
-        cy = (m0 / p.W) % p.H;
-        cn = m0 / (p.W * p.H);
-      }
-      for (int kb = 0; kb < p.num_kblocks; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::kABytes + Cfg::kBBytes);
+    // warp-uniform loop state (stage / tap / channel-block counters, no divisions), one elected lane issues
+    const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+    const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
+    int cx = 0, cy = 0, cn = 0;
+    if (p.mode == 1) {
+      cx = ((p.W >= kBM) ? (m0 % p.W) : 0) - 1;
+      cy = (m0 / p.W) % p.H - 1;
+      cn = m0 / (p.W * p.H);
+    }
+    uint32_t s = 0, ph = 0;
+    int cb = 0, tx = 0, ty = 0;
+    for (int kb = 0; kb < p.num_kblocks; ++kb) {
+      mbar_wait_u32(empty_u32 + s * 8, ph ^ 1);
+      if (elect_one()) {
+        const uint32_t fb = full_u32 + s * 8;
+        mbar_arrive_expect_tx_u32(fb, Cfg::kABytes + Cfg::kBBytes);
         if (p.mode == 0) {
-          tma_load_2d(sA + s * Cfg::kABytes, &tmA, &full_bar[s], kb * kBK, m0);
+          tma_load_2d_u32(sA_u32 + s * Cfg::kABytes, &tmA, fb, kb * kBK, m0);
         } else {
-          const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-          const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-          tma_load_4d(sA + s * Cfg::kABytes, &tmA, &full_bar[s], cb * kBK, cx + dx, cy + dy, cn);
+          tma_load_4d_u32(sA_u32 + s * Cfg::kABytes, &tmA, fb, cb * kBK, cx + tx, cy + ty, cn);
         }
-        tma_load_2d(sB + s * Cfg::kBBytes, &tmB, &full_bar[s], kb * kBK, n0);
+        tma_load_2d_u32(sB_u32 + s * Cfg::kBBytes, &tmB, fb, kb * kBK, n0);
       }
+      __syncwarp();
+      if (++cb == p.cblocks) {
+        cb = 0;
+        if (++tx == 3) { tx = 0; ++ty; }
+      }
+      if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------- UMMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
-      for (int kb = 0; kb < p.num_kblocks; ++kb) {
-        const int s = kb % Cfg::kStages;
-        const uint32_t ph = (kb / Cfg::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint64_t adesc = umma_smem_desc_sw128(smem_u32(sA + s * Cfg::kABytes));
-        const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(sB + s * Cfg::kBBytes));
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN);
+    const uint32_t sA_u32 = smem_u32(sA), sB_u32 = smem_u32(sB);
+    const uint32_t full_u32 = smem_u32(full_bar), empty_u32 = smem_u32(empty_bar);
+    uint32_t s = 0, ph = 0;
+    for (int kb = 0; kb < p.num_kblocks; ++kb) {
+      mbar_wait_u32(full_u32 + s * 8, ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = umma_smem_desc_sw128(sA_u32 + s * Cfg::kABytes);
+        const uint64_t bdesc = umma_smem_desc_sw128(sB_u32 + s * Cfg::kBBytes);
+        // +32 B per 16-element K step inside the 128 B swizzle row (encoded >>4)
+        umma_ss(tmem_base, adesc, bdesc, idesc, kb != 0);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // +32 B per 16-element K step inside the 128 B swizzle row (encoded >>4)
-          umma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-        }
-        umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+        for (int k = 1; k < kBK / 16; ++k) umma_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+        umma_commit_u32(empty_u32 + s * 8);  // frees the smem stage when these MMAs retire
       }
-      umma_commit(accum_bar);        // accumulator complete
+      __syncwarp();
+      if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
     }
+    if (elect_one()) umma_commit(accum_bar);  // accumulator complete
+    __syncwarp();
   } else {
     // ---------------------------------------------------------- epilogue
     const int lg = warp & 3;  // TMEM lane group this warp may access
