@@ -334,7 +334,7 @@ def run_ours(args):
     gemm_n = tot["gemm"][0] + tot["conv3x3"][0]
     achieved = GF_GEMM_PER_IMAGE * B / gemm_ms  # GF / ms = TFLOP/s
     roofline = {
-        "bound": "tensor", "kernel": "edtr::gemm_conv_kernel (tcgen05 implicit-GEMM: all conv3x3 / 1x1 / Linear launches)",
+        "bound": "tensor", "kernel": "edtr::gemm2_kernel (CTA-pair tcgen05 implicit-GEMM: all conv3x3 / 1x1 / Linear launches)",
         "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
         "traffic": None, "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
         "launches_per_step": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),

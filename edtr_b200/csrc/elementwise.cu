@@ -9,8 +9,7 @@ namespace edtr {
 // Y[(b,p), coff+c] = X[b,c,p]; one thread per pixel, coalesced reads per channel plane.
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ Y, int ldy,
                                     int coff, int C, int HW, size_t total_pix) {
-  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
-  pdl_wait();                // ... and wait for the previous kernel's results
+  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total_pix) return;
   const size_t b = i / HW, pix = i - b * HW;
@@ -24,8 +23,7 @@ __global__ void pointwise_nchw_kernel(const float* __restrict__ X, const float* 
                                       const float* __restrict__ bias, float scale,
                                       __nv_bfloat16* __restrict__ Y, int ldy, int coff, int Cin, int Cout, int HW,
                                       size_t total_pix) {
-  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
-  pdl_wait();                // ... and wait for the previous kernel's results
+  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total_pix) return;
   const size_t b = i / HW, pix = i - b * HW;
@@ -44,8 +42,7 @@ __global__ void pointwise_nchw_kernel(const float* __restrict__ X, const float* 
 template <typename OutT>
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ X, int ldx, OutT* __restrict__ Y, int C,
                                     int HW) {
-  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
-  pdl_wait();                // ... and wait for the previous kernel's results
+  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -67,8 +64,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ X, int ldx
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ X, __nv_bfloat16* __restrict__ Y, size_t n) {
-  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
-  pdl_wait();                // ... and wait for the previous kernel's results
+  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) Y[i] = __float2bfloat16(X[i]);
 }
@@ -76,8 +72,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ X, __nv_bfloat16*
 // One thread per (output pixel, 16-byte channel vector).
 __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y,
                                   int ldy, int H, int W, int vpr, size_t total) {
-  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
-  pdl_wait();                // ... and wait for the previous kernel's results
+  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int v = static_cast<int>(i % vpr);
@@ -95,8 +90,7 @@ __global__ void upsample2x_kernel(const __nv_bfloat16* __restrict__ X, int ldx, 
 __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y,
                               int H, int W, int vpr, int KH, int KW, int stride, int pad_top, int pad_left,
                               int Ho, int Wo, size_t total) {
-  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
-  pdl_wait();                // ... and wait for the previous kernel's results
+  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int v = static_cast<int>(i % vpr);
@@ -117,8 +111,7 @@ __global__ void im2col_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv
 
 __global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ Y, int dim,
                                           float log_max_period) {
-  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
-  pdl_wait();                // ... and wait for the previous kernel's results
+  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   const int b = blockIdx.x;
   const int half = dim / 2;
   const float tv = static_cast<float>(t[b]);
@@ -137,8 +130,7 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
                                       const float* __restrict__ coef1, const float* __restrict__ coef2,
                                       const float* __restrict__ var, float* __restrict__ x_prev,
                                       float* __restrict__ pred_x0, int n_per_image, size_t total) {
-  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
-  pdl_wait();                // ... and wait for the previous kernel's results
+  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int64_t idx = index[i / n_per_image];
@@ -156,8 +148,7 @@ __global__ void sampler_update_kernel(const float* __restrict__ x, const float* 
 __global__ void tile_blend_kernel(const float* __restrict__ tiles, const int* __restrict__ coords, int ntiles,
                                   const float* __restrict__ weight, float* __restrict__ out, int BC, int H, int W,
                                   int th, int tw, size_t total) {
-  pdl_launch_dependents();
-  pdl_wait();
+  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = static_cast<int>(i % W);

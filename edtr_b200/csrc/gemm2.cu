@@ -75,7 +75,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
              const Gemm2Params p) {
-  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sPipe = smem;                             // stage s: A at s*stage_bytes, B right after it
@@ -172,6 +171,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++s == static_cast<uint32_t>(nstages)) { s = 0; ph ^= 1; }
       }
     }
+    // PDL trigger, late on purpose: every operand load of this CTA has been issued, so the next kernel may be
+    // scheduled now and run its prologue under this kernel's last MMAs / epilogue.  (A trigger at kernel entry
+    // lets waiting dependents grab registers / warp slots that a multi-wave predecessor still needs.)
+    pdl_launch_dependents();
   } else if (warp == 1) {
     // ------------------------------------------------------------- UMMA issuer (leader only)
     if (leader) {
@@ -417,6 +420,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     (void)n_out;
   }
   __syncwarp();  // role branches diverge inside a warp; the cluster barrier below is .aligned
+  pdl_launch_dependents();
   tc_fence_before();
   cluster_sync_all();
   if (warp == 1) {
@@ -432,8 +436,7 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, flo
                      const float* __restrict__ bias, const float* __restrict__ rowvec, int rowvec_ld,
                      int rows_per_group, const __nv_bfloat16* residual, int ldr, __nv_bfloat16* out, int ldc,
                      int act) {
-  pdl_launch_dependents();  // PDL: let the next kernel's prologue overlap this kernel
-  pdl_wait();                // ... and wait for the previous kernel's results
+  pdl_wait();  // PDL: wait for the previous kernel's results (the trigger is at the end of the body)
   const int vpr = N >> 3;
   const size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<size_t>(M) * vpr) return;
@@ -473,6 +476,7 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, flo
   uint4 o;
   o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
   *reinterpret_cast<uint4*>(out + static_cast<size_t>(row) * ldc + col) = o;
+  pdl_launch_dependents();
 }
 
 static float* g_ws = nullptr;      // split-K workspace registered by the host (edtr_set_workspace)
@@ -572,7 +576,8 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   p.ws = g_ws;
   p.b_box_rows = p.bn_base / 2;
   p.stage_bytes = k2ABytes + p.b_box_rows * k2BK * 2;
-  // short main loops are epilogue-bound: give the epilogue a deeper staging ring, the operands fewer stages
+  // two staging buffers per epilogue warp; a ring of four (residual requested two chunks ahead) was measured on
+  // B200 and changes nothing: the short-K GEMMs are bound by launch / fill / drain latency, not by the residual
   p.ring = 2;
   p.stages = (k2DataBytes - k2EpiWarps * p.ring * k2WarpStageBytes) / p.stage_bytes;
   if (p.stages > k2MaxStages) p.stages = k2MaxStages;

@@ -137,7 +137,6 @@ __global__ void __launch_bounds__(kGemmThreads, (BN <= 160) ? 2 : 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmKernelParams p) {
   using Cfg = GemmCfg<BN>;
-  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -291,6 +290,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     tc_fence_before();
   }
+  pdl_launch_dependents();  // late trigger (see gemm2.cu)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();

@@ -29,6 +29,14 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Memory-bound kernels: wait on entry; trigger at the END of the body.  A trigger at entry lets the dependent
+// kernel's CTAs become resident (and sit in griddepcontrol.wait) while a multi-wave predecessor still needs the
+// registers / warp slots — measured slower than no PDL at all.
+struct PdlScope {
+  __device__ __forceinline__ PdlScope() { pdl_wait(); }
+  __device__ __forceinline__ ~PdlScope() { pdl_launch_dependents(); }
+};
+
 // ----------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

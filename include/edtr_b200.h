@@ -142,6 +142,14 @@ int edtr_groupnorm_stats(const void* X, int ldx, int B, int HW, int C, int group
 int edtr_groupnorm_apply(const void* X, int ldx, void* Y, int ldy, int B, int HW, int C,
                          int groups, const float* stats, const float* gamma, const float* beta,
                          float eps, int silu, void* stream);
+
+/* Single-launch GroupNorm (+SiLU) for small L2-resident tensors (<= 1 MB per image): a thread-block cluster per
+ * image, statistics exchanged through distributed shared memory, deterministic.  Same arithmetic as
+ * edtr_groupnorm_stats + edtr_groupnorm_apply (reference: model/util.py:161-163, model/attention.py:50-51).
+ * edtr_groupnorm_fused_supported returns 1 when the shape is eligible. */
+int edtr_groupnorm_fused_supported(int B, int HW, int C, int groups);
+int edtr_groupnorm_fused(const void* X, int ldx, void* Y, int ldy, int B, int HW, int C, int groups,
+                         const float* gamma, const float* beta, float eps, int silu, void* stream);
 /* Row-wise LayerNorm over C (biased variance, eps 1e-5 typical), bf16 in/out.
  * replaces: nn.LayerNorm — model/attention.py:222-224. */
 int edtr_layernorm_bf16(const void* X, int ldx, void* Y, int ldy, int M, int C,

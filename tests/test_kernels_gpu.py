@@ -237,11 +237,18 @@ def test_attention_growing_scores_exercise_lazy_rescale(ops, Lq, Lk):
 @pytest.mark.parametrize("B,HW,C,silu,eps", [(2, 4096, 320, True, 1e-5), (2, 64, 2560, True, 1e-5),
                                               (1, 1024, 1920, False, 1e-6), (3, 256, 960, True, 1e-5),
                                               (1, 65536, 128, True, 1e-6), (2, 4096, 512, True, 1e-6)])
-def test_groupnorm(ops, B, HW, C, silu, eps):
+@pytest.mark.parametrize("fused", [True, False])
+def test_groupnorm(ops, B, HW, C, silu, eps, fused):
+    """fused=True: single-launch cluster kernel where eligible (L2-resident tensors); False: two-pass kernels."""
     x = (rnd(B, HW, C, seed=1).float() * 1.5 + 0.7).to(BF)
     gamma = torch.randn(C, device="cuda")
     beta = torch.randn(C, device="cuda")
-    out = ops.groupnorm(x, gamma, beta, 32, eps, silu)
+    old = ops.GROUPNORM_FUSED
+    ops.GROUPNORM_FUSED = fused
+    try:
+        out = ops.groupnorm(x, gamma, beta, 32, eps, silu)
+    finally:
+        ops.GROUPNORM_FUSED = old
     ref = F.group_norm(x.float().permute(0, 2, 1), 32, gamma, beta, eps)
     if silu:
         ref = F.silu(ref)
