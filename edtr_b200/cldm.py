@@ -140,10 +140,20 @@ class ControlLDM(nn.Module):
 
     @torch.no_grad()
     def vae_decode(self, z: torch.Tensor, tiled: bool = False, tile_size: int = -1) -> torch.Tensor:
-        """model/cldm.py:136-156 (untiled).  Returns fp32 NCHW in [-1, 1]."""
-        if tiled:
-            raise NotImplementedError("tiled VAE decode (VAEHook) is not implemented in this round")
-        return self.vae._decoder_engine().decode(z.float().contiguous(), float(self.scale_factor))
+        """model/cldm.py:136-156.  Returns fp32 NCHW in [-1, 1].  tiled=True is the reference's VAEHook decode
+        (utils/tilevae/tilevae.py:307-579, pooled GroupNorm statistics); its tiles are spread over the ranks of the
+        default process group when torch.distributed is initialised with more than one rank (config C4)."""
+        eng = self.vae._decoder_engine()
+        if not tiled:
+            return eng.decode(z.float().contiguous(), float(self.scale_factor))
+        import torch.distributed as dist
+
+        rank, world, red = 0, 1, None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            rank, world = dist.get_rank(), dist.get_world_size()
+            red = lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        return eng.decode_tiled(z.float().contiguous(), float(self.scale_factor), int(tile_size), rank=rank,
+                                world=world, reduce_fn=red)
 
     def prepare_condition(self, clean: torch.Tensor, prompt: List[str]) -> Dict[str, torch.Tensor]:
         raise NotImplementedError("prepare_condition = CLIP text tower + VAE encoder, both inputs of the path")

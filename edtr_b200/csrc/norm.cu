@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y, int ldy,
                        int HW, int C, int groups, int rows_per_cta, int vslab, int nchunks_stats, int nslab_stats,
                        int cslab_stats, const float* __restrict__ partial, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float eps, int silu) {
+                       const float* __restrict__ beta, float eps, int silu, int direct) {
   PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   __shared__ float g_mean[64], g_rstd[64];  // groups intersecting this slab (<= 64)
   const int cslab = vslab * 8;
@@ -112,7 +112,14 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
   const int g_first = c0 / cpg;
   const int g_last = (min(C, c0 + cslab) - 1) / cpg;
   const float inv_n = 1.f / (static_cast<float>(cpg) * static_cast<float>(HW));
-  {
+  if (direct) {
+    // `partial` holds given statistics [B][groups][2] = (mean, biased variance): tiled VAE, pooled over tiles
+    for (int g = g_first + threadIdx.x; g <= g_last; g += blockDim.x) {
+      const float2 mv = __ldg(reinterpret_cast<const float2*>(partial + (static_cast<size_t>(b) * groups + g) * 2));
+      g_mean[g - g_first] = mv.x;
+      g_rstd[g - g_first] = rsqrtf(mv.y + eps);
+    }
+  } else {
     // one warp per group: lanes stride over the (chunk, slab) partial sums, then a fixed shuffle tree
     // (only full warps take part: the block size need not be a multiple of 32)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -179,6 +186,34 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
       }
     }
   }
+}
+
+// ------------------------------------------------- GroupNorm statistics pooling (tiled VAE)
+// Folds the partial sums of one tile (groupnorm_stats_kernel) into that tile's (mean, biased variance) per
+// (image, group) and accumulates weight * (mean, var) into acc[B][groups][2] — the pixel-weighted average of
+// per-tile means AND per-tile variances of GroupNormParam.summary (utils/tilevae/tilevae.py:263-278).  One
+// thread per (image, group), fixed order, no atomics: launches on one stream accumulate deterministically.
+__global__ void groupnorm_pool_kernel(const float* __restrict__ partial, int B, int HW, int C, int groups,
+                                      int nchunks, int nslab, int cslab, float weight, float* __restrict__ acc) {
+  PdlScope pdl_scope;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * groups) return;
+  const int b = i / groups, g = i - b * groups;
+  const int cpg = C / groups;
+  const int s_lo = (g * cpg) / cslab, s_hi = ((g + 1) * cpg - 1) / cslab;
+  float a = 0.f, a2 = 0.f;
+  for (int ch = 0; ch < nchunks; ++ch)
+    for (int sl = s_lo; sl <= s_hi; ++sl) {
+      const float2 pr = __ldg(reinterpret_cast<const float2*>(
+          partial + ((((static_cast<size_t>(b) * nchunks + ch) * nslab + sl) * groups + g) * 2)));
+      a += pr.x;
+      a2 += pr.y;
+    }
+  const float inv_n = 1.f / (static_cast<float>(cpg) * static_cast<float>(HW));
+  const float mean = a * inv_n;
+  const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
+  acc[2 * i] += weight * mean;
+  acc[2 * i + 1] += weight * var;
 }
 
 // ------------------------------------------------------------------ LayerNorm
@@ -501,8 +536,38 @@ extern "C" int edtr_groupnorm_apply(const void* X, int ldx, void* Y, int ldy, in
   dim3 grid(g.nchunks, B, g.nslab);
   EDTR_LAUNCH(groupnorm_apply_kernel, grid, g.threads, 0, static_cast<cudaStream_t>(stream), 
       reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
-      g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, stats, gamma, beta, eps, silu);
+      g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, stats, gamma, beta, eps, silu, 0);
   return check_launch("groupnorm_apply_kernel");
+}
+
+extern "C" int edtr_groupnorm_apply_stats(const void* X, int ldx, void* Y, int ldy, int B, int HW, int C, int groups,
+                                          const float* mean_var, const float* gamma, const float* beta, float eps,
+                                          int silu, void* stream) {
+  int rc = check_gn_args(X, ldx, B, HW, C, groups);
+  if (rc) return rc;
+  EDTR_REQUIRE(Y && mean_var && gamma && beta, "Y/mean_var/gamma/beta is NULL");
+  EDTR_REQUIRE(ldy % 8 == 0 && ldy >= C && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "bad Y stride/alignment");
+  EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0,
+               "gamma/beta must be 16-byte aligned");
+  EDTR_REQUIRE((reinterpret_cast<uintptr_t>(mean_var) & 7) == 0, "mean_var must be 8-byte aligned");
+  const GnGeom g = gn_geom(B, HW, C);
+  EDTR_REQUIRE(g.vslab * 8 / (C / groups) + 2 <= 64, "too many groups per channel slab");
+  dim3 grid(g.nchunks, B, g.nslab);
+  EDTR_LAUNCH(groupnorm_apply_kernel, grid, g.threads, 0, static_cast<cudaStream_t>(stream),
+      reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
+      g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, mean_var, gamma, beta, eps, silu, 1);
+  return check_launch("groupnorm_apply_kernel");
+}
+
+extern "C" int edtr_groupnorm_pool(const float* stats, int B, int HW, int C, int groups, float weight, float* acc,
+                                   void* stream) {
+  EDTR_REQUIRE(stats && acc, "stats/acc is NULL");
+  EDTR_REQUIRE(B > 0 && HW > 0 && C > 0 && groups > 0 && C % 8 == 0 && C % groups == 0, "bad GroupNorm shape");
+  const GnGeom g = gn_geom(B, HW, C);
+  const int n = B * groups;
+  EDTR_LAUNCH(groupnorm_pool_kernel, (n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), stats, B, HW, C,
+              groups, g.nchunks, g.nslab, g.vslab * 8, weight, acc);
+  return check_launch("groupnorm_pool_kernel");
 }
 
 extern "C" int edtr_groupnorm_fused_supported(int B, int HW, int C, int groups) {

@@ -827,6 +827,150 @@ class VaeDecoderEngine:
         ops.conv3x3(y, w["decoder.conv_out.weight"], bias=w["decoder.conv_out.bias"],
                     out=img_out.view(B, self.dd["out_ch"], H * W), out_mode=ops.OUT_NCHW_F32)
 
+    # ------------------------------------------------------------------ tiled decode (VAEHook)
+    def _conv_any(self, ws: Workspace, x: torch.Tensor, wk: str, **kw) -> torch.Tensor:
+        """3x3/p1 convolution at any tile geometry: the TMA implicit-GEMM kernel when the tile fits its box
+        rules, else im2col + GEMM (tiled-VAE tiles are e.g. 86x86 latent pixels)."""
+        ops, w = self.ops, self.w
+        B, H, W, C = x.shape
+        if ops.conv3x3_supported(H, W, C):
+            return ops.conv3x3(x, w[wk + "weight"], bias=w[wk + "bias"], **kw)
+        col = ops.im2col(x, 3, 3, 1, 1, 1, H, W, out=ws.get("col", (B * H * W, 9 * C)))
+        if kw.get("out_mode", ops.OUT_BF16) in (ops.OUT_NCHW_F32, ops.OUT_NCHW_BF16):
+            kw["hw"] = H * W
+        return ops.gemm(col, w[wk + "weight"], bias=w[wk + "bias"], **kw)
+
+    def _tile_program(self, ws: Workspace, x: torch.Tensor):
+        """Decoder.forward of ONE tile as the task queue of build_task_queue (utils/tilevae/tilevae.py:72-165):
+        a generator that yields (tensor, norm-key, silu) at every `pre_norm` task, is resumed with the tensor
+        normalised by the pooled statistics, and returns the decoded tile [B, out_ch, 8h, 8w] fp32."""
+        ops, w = self.ops, self.w
+        dev = x.device
+        new = lambda shape: torch.empty(shape, dtype=BF16, device=dev)
+
+        def res(p, x):
+            B, H, W, cin = x.shape
+            cout = w[p + "conv1.bias"].shape[0]
+            y = yield (x, p + "norm1.", True)
+            h = self._conv_any(ws, y, p + "conv1.", out=new((B, H, W, cout)))
+            y2 = yield (h, p + "norm2.", True)
+            if (p + "nin_shortcut.weight") in w:
+                skip = ops.gemm(x, w[p + "nin_shortcut.weight"], bias=w[p + "nin_shortcut.bias"],
+                                out=new((B, H, W, cout)))
+            else:
+                skip = x
+            return self._conv_any(ws, y2, p + "conv2.", residual=skip, out=new((B, H, W, cout)))
+
+        def attn(p, x):
+            # tile-local single-head attention (utils/tilevae/attn.py:95-124); tokens padded to a multiple of 64
+            # (zero probability columns, ignored rows) so that L = h*w may be anything
+            B, H, W, C = x.shape
+            L = H * W
+            Lp = _ceil(L, 64)
+            y = yield (x, p + "norm.", False)
+            o = new((B, L, C))
+            ypad = ws.get("ta_y", (Lp, C))
+            s = ws.get("ta_s", (Lp, Lp), F32)
+            pm = ws.get("ta_p", (Lp, Lp))
+            ypad[L:].zero_()        # padding tokens: zero features, zero probability columns
+            pm[:, L:].zero_()
+            for b in range(B):
+                ypad[:L].copy_(y[b].reshape(L, C))
+                qk = ops.gemm(ypad, w[p + "qk.weight"], bias=w[p + "qk.bias"], out=ws.get("ta_qk", (Lp, 2 * C)))
+                vt = ops.gemm(ypad, w[p + "v.weight"], bias=w[p + "v.bias"], out_mode=ops.OUT_NCHW_BF16, hw=Lp,
+                              out=ws.get("ta_vt", (1, C, Lp)))
+                ops.gemm(qk[:, :C], qk[:, C:], out_mode=ops.OUT_F32, out=s)
+                ops.softmax_rows(s[:, :L], float(C) ** -0.5, out=pm[:, :L])
+                ob = ops.gemm(pm, vt[0], out=ws.get("ta_o", (Lp, C)))
+                o[b].copy_(ob[:L])
+            return ops.gemm(o, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x.reshape(B, L, C),
+                            out=new((B, L, C))).view(B, H, W, C)
+
+        B, H, W, _ = x.shape
+        h = self._conv_any(ws, x, "decoder.conv_in.", out=new((B, H, W, self.top)))
+        h = yield from res("decoder.mid.block_1.", h)
+        h = yield from attn("decoder.mid.attn_1.", h)
+        h = yield from res("decoder.mid.block_2.", h)
+        for level, blocks, has_up in self.levels:
+            for i in range(len(blocks)):
+                h = yield from res(f"decoder.up.{level}.block.{i}.", h)
+            if has_up:
+                c = h.shape[-1]
+                u = ops.upsample2x(h, out=new((B, 2 * H, 2 * W, c)))
+                H, W = 2 * H, 2 * W
+                h = self._conv_any(ws, u, f"decoder.up.{level}.upsample.conv.", out=new((B, H, W, c)))
+        y = yield (h, "decoder.norm_out.", True)
+        img = torch.empty((B, self.dd["out_ch"], H, W), dtype=F32, device=dev)
+        self._conv_any(ws, y, "decoder.conv_out.", out=img.view(B, self.dd["out_ch"], H * W), out_mode=ops.OUT_NCHW_F32)
+        return img
+
+    def decode_tiled(self, z: torch.Tensor, scale_factor: float, tile_size: int, rank: int = 0, world: int = 1,
+                     reduce_fn=None, use_graph: bool = True) -> torch.Tensor:
+        """ControlLDM.vae_decode(tiled=True) (model/cldm.py:142-156): VAEHook in its default (non-fast) mode
+        (utils/tilevae/tilevae.py:307-323, :442-579).  post_quant_conv runs on the whole latent, the latent is cut
+        into overlapping tiles (pad 11), all tiles advance layer by layer, and at every GroupNorm the statistics
+        are the pixel-weighted average of the per-tile means and per-tile variances (GroupNormParam.summary —
+        an approximation of the reference that is reproduced, not fixed).  The reference's CPU<->GPU tile
+        shuffling is not: every tile stays in HBM.  With world > 1 rank r owns tiles r, r+world, ...; `reduce_fn`
+        (all-reduce SUM) is called on the [B, 32, 2] pooled statistics at each of the 30 GroupNorms and once on
+        the output image."""
+        from .tiling import VAE_TILE_PAD_DECODER, vae_split_tiles
+
+        if z.dim() != 4 or z.shape[1] != self.embed_dim:
+            raise ValueError(f"z must be [B, {self.embed_dim}, H, W], got {tuple(z.shape)}")
+        if getattr(self.ops, "REQUIRES_CUDA", True) and not z.is_cuda:
+            raise RuntimeError("edtr_b200 has no CPU path: z must be a CUDA tensor")
+        if len(self.levels) != 4:
+            raise NotImplementedError("the tiled VAE hook assumes the x8 decoder (4 resolution levels)")
+        if world > 1 and reduce_fn is None:
+            raise ValueError("reduce_fn (all-reduce SUM) is required when world > 1")
+        ops, w = self.ops, self.w
+        B, _, H, W = z.shape
+        pad = VAE_TILE_PAD_DECODER
+        if max(H, W) <= pad * 2 + tile_size:      # "tiny and unnecessary to tile" (utils/tilevae/tilevae.py:319-321)
+            return self.decode(z, scale_factor, use_graph=use_graph)
+        in_boxes, out_boxes = vae_split_tiles(H, W, tile_size, pad, True)
+        ws = self._ws.get(("tiled", B))
+        if ws is None:
+            ws = self._ws[("tiled", B)] = Workspace(self.device)
+        zin = torch.zeros((B, H, W, 64), dtype=BF16, device=z.device)
+        ops.pointwise_nchw_to_nhwc(z.contiguous().float(), w["post_quant_conv.weight"], w["post_quant_conv.bias"],
+                                   1.0 / scale_factor, zin, 0)
+        mine = list(range(rank, len(in_boxes), world))
+        pix_total = float(sum((b[1] - b[0]) * (b[3] - b[2]) for b in in_boxes))
+        wgt = {i: (in_boxes[i][1] - in_boxes[i][0]) * (in_boxes[i][3] - in_boxes[i][2]) / pix_total for i in mine}
+        progs = {i: self._tile_program(ws, zin[:, in_boxes[i][2]:in_boxes[i][3], in_boxes[i][0]:in_boxes[i][1]].contiguous())
+                 for i in mine}
+        pending = {i: next(g) for i, g in progs.items()}
+        done: Dict[int, torch.Tensor] = {}
+        acc = torch.zeros((B, 32, 2), dtype=F32, device=z.device)
+        # every rank walks the same number of synchronisation points (one per GroupNorm of the decoder)
+        n_sync = 2 * (2 + sum(len(b) for _, b, _ in self.levels)) + 2
+        for _ in range(n_sync):
+            acc.zero_()
+            for i in mine:
+                x = pending[i][0]
+                ops.groupnorm_pool(x, 32, wgt[i], acc, stats=ws.gn_scratch(ops, x))
+            if world > 1:
+                reduce_fn(acc)
+            for i in mine:
+                x, key, silu = pending[i]
+                y = ops.groupnorm_apply_stats(x, acc, w[key + "weight"], w[key + "bias"], 32, 1e-6, silu)
+                try:
+                    pending[i] = progs[i].send(y)
+                except StopIteration as fin:
+                    done[i] = fin.value
+        if len(done) != len(mine):
+            raise RuntimeError("internal: tile programs did not finish after the last GroupNorm")
+        out = torch.zeros((B, self.dd["out_ch"], H * 8, W * 8), dtype=F32, device=z.device)
+        for i in mine:
+            ib, ob, t = in_boxes[i], out_boxes[i], done[i]
+            m = [ob[k] - ib[k] * 8 for k in range(4)]          # crop_valid_region (utils/tilevae/tilevae.py:218-229)
+            out[:, :, ob[2]:ob[3], ob[0]:ob[1]] = t[:, :, m[2]:t.shape[2] + m[3], m[0]:t.shape[3] + m[1]]
+        if world > 1:
+            reduce_fn(out)      # valid regions are disjoint: the sum assembles the image on every rank
+        return out
+
     def decode(self, z: torch.Tensor, scale_factor: float, use_graph: bool = True) -> torch.Tensor:
         if z.dim() != 4 or z.shape[1] != self.embed_dim:
             raise ValueError(f"z must be [B, {self.embed_dim}, H, W], got {tuple(z.shape)}")

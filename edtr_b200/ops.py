@@ -279,6 +279,56 @@ def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: 
     return out
 
 
+def groupnorm_pool(x: torch.Tensor, groups: int, weight: float, acc: torch.Tensor,
+                   stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Tiled VAE: acc[B, groups, 2] += weight * (mean, biased var) of tile x [B, HW..., C] per (image, group)
+    (GroupNormParam.add_tile / summary, utils/tilevae/tilevae.py:241-278)."""
+    _require_cuda(x, acc, stats)
+    B = x.shape[0]
+    M, C, ldx = rows_view(x)
+    HW = M // B
+    if C % 8 != 0 or C % groups != 0:
+        raise ValueError(f"C ({C}) must be a multiple of 8 and of groups ({groups})")
+    if acc.dtype != torch.float32 or tuple(acc.shape) != (B, groups, 2) or not acc.is_contiguous():
+        raise ValueError(f"acc must be a contiguous fp32 [{B}, {groups}, 2] tensor")
+    need = groupnorm_partial_size(B, HW, C, groups)
+    if stats is None:
+        stats = torch.empty((need,), dtype=torch.float32, device=x.device)
+    elif stats.dtype != torch.float32 or stats.numel() < need or not stats.is_contiguous():
+        raise ValueError(f"stats must be a contiguous fp32 scratch tensor with >= {need} elements")
+    L = _lib.device_lib()
+    st = _stream()
+    _lib.check(L.edtr_groupnorm_stats(x.data_ptr(), ldx, B, HW, C, groups, stats.data_ptr(), st),
+               "edtr_groupnorm_stats")
+    _lib.check(L.edtr_groupnorm_pool(stats.data_ptr(), B, HW, C, groups, float(weight), acc.data_ptr(), st),
+               "edtr_groupnorm_pool")
+    return acc
+
+
+def groupnorm_apply_stats(x: torch.Tensor, mean_var: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                          groups: int, eps: float, silu: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm (+SiLU) with GIVEN statistics mean_var [B, groups, 2] = (mean, biased var)
+    (custom_group_norm, utils/tilevae/tilevae.py:188-215)."""
+    _require_cuda(x, mean_var, gamma, beta, out)
+    B = x.shape[0]
+    M, C, ldx = rows_view(x)
+    HW = M // B
+    if C % 8 != 0 or C % groups != 0:
+        raise ValueError(f"C ({C}) must be a multiple of 8 and of groups ({groups})")
+    if mean_var.dtype != torch.float32 or tuple(mean_var.shape) != (B, groups, 2) or not mean_var.is_contiguous():
+        raise ValueError(f"mean_var must be a contiguous fp32 [{B}, {groups}, 2] tensor")
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    Mo, Co, ldy = rows_view(out)
+    if Mo != M or Co != C:
+        raise ValueError("out shape mismatch")
+    L = _lib.device_lib()
+    _lib.check(L.edtr_groupnorm_apply_stats(x.data_ptr(), ldx, out.data_ptr(), ldy, B, HW, C, groups,
+                                            mean_var.data_ptr(), _f32(gamma, C, "gamma"), _f32(beta, C, "beta"),
+                                            eps, 1 if silu else 0, _stream()), "edtr_groupnorm_apply_stats")
+    return out
+
+
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _require_cuda(x, gamma, beta, out)

@@ -1,14 +1,53 @@
-"""Latent tiling helpers of the cldm-tiled path (utils/common.py:151-165, 351-427).
+"""Tiling helpers: latent windows of the cldm-tiled path (utils/common.py:151-165, 351-427) and the tile
+split of the tiled VAE (utils/tilevae/tilevae.py:325-399).  Host-side index arithmetic only.
 
 Same numerics as the reference: overlapped windows, gaussian weights, ``out / count``; tiles are
 evaluated one by one exactly as the reference does (batching the tiles of a step is planned).
 """
 from __future__ import annotations
 
+import math
 from typing import Callable, List, Tuple
 
 import numpy as np
 import torch
+
+VAE_TILE_PAD_DECODER = 11   # latent pixels (utils/tilevae/tilevae.py:315)
+VAE_TILE_PAD_ENCODER = 32   # image pixels
+
+
+def best_tile_size(lowerbound: int, upperbound: int) -> int:
+    """VAEHook.get_best_tile_size (utils/tilevae/tilevae.py:325-338): smallest size >= lowerbound that is a
+    multiple of the largest possible power of two (32 ... 2) and still <= upperbound."""
+    divider = 32
+    while divider >= 2:
+        rem = lowerbound % divider
+        if rem == 0:
+            return lowerbound
+        cand = lowerbound - rem + divider
+        if cand <= upperbound:
+            return cand
+        divider //= 2
+    return lowerbound
+
+
+def vae_split_tiles(h: int, w: int, tile_size: int, pad: int, is_decoder: bool):
+    """VAEHook.split_tiles (utils/tilevae/tilevae.py:340-399).  Boxes are [x1, x2, y1, y2]; returns the input
+    boxes (tile + `pad` context, clipped to the tensor) and the output boxes (x8 for the decoder, //8 for the
+    encoder) each tile's valid region is pasted into."""
+    nh = max(math.ceil((h - 2 * pad) / tile_size), 1)
+    nw = max(math.ceil((w - 2 * pad) / tile_size), 1)
+    th = best_tile_size(math.ceil((h - 2 * pad) / nh), tile_size)
+    tw = best_tile_size(math.ceil((w - 2 * pad) / nw), tile_size)
+    in_boxes, out_boxes = [], []
+    for i in range(nh):
+        for j in range(nw):
+            ib = [pad + j * tw, min(pad + (j + 1) * tw, w), pad + i * th, min(pad + (i + 1) * th, h)]
+            ob = [ib[0] if ib[0] > pad else 0, ib[1] if ib[1] < w - pad else w,
+                  ib[2] if ib[2] > pad else 0, ib[3] if ib[3] < h - pad else h]
+            out_boxes.append([v * 8 if is_decoder else v // 8 for v in ob])
+            in_boxes.append([max(0, ib[0] - pad), min(w, ib[1] + pad), max(0, ib[2] - pad), min(h, ib[3] + pad)])
+    return in_boxes, out_boxes
 
 
 def gaussian_weights(tile_width: int, tile_height: int) -> np.ndarray:

@@ -143,6 +143,17 @@ int edtr_groupnorm_apply(const void* X, int ldx, void* Y, int ldy, int B, int HW
                          int groups, const float* stats, const float* gamma, const float* beta,
                          float eps, int silu, void* stream);
 
+/* Tiled VAE (utils/tilevae/tilevae.py:232-304): every GroupNorm of a tiled decode uses statistics pooled over
+ * the tiles.  edtr_groupnorm_pool folds the partial sums edtr_groupnorm_stats wrote for ONE tile (same B, HW, C,
+ * groups) into that tile's mean / biased variance per (image, group) and adds weight * (mean, var) into
+ * acc[B][groups][2] (fp32, zeroed by the caller before the first tile; stream-ordered, deterministic).
+ * edtr_groupnorm_apply_stats normalises with given statistics mean_var[B][groups][2] instead of the tensor's own
+ * (custom_group_norm, :188-215). */
+int edtr_groupnorm_pool(const float* stats, int B, int HW, int C, int groups, float weight, float* acc, void* stream);
+int edtr_groupnorm_apply_stats(const void* X, int ldx, void* Y, int ldy, int B, int HW, int C, int groups,
+                               const float* mean_var, const float* gamma, const float* beta, float eps, int silu,
+                               void* stream);
+
 /* Single-launch GroupNorm (+SiLU) for small L2-resident tensors (<= 1 MB per image): a thread-block cluster per
  * image, statistics exchanged through distributed shared memory, deterministic.  Same arithmetic as
  * edtr_groupnorm_stats + edtr_groupnorm_apply (reference: model/util.py:161-163, model/attention.py:50-51).

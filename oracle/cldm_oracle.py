@@ -53,6 +53,8 @@ TINY = dict(
     diffusion=dict(linear_start=0.00085, linear_end=0.0120, timesteps=1000),
     used_timesteps=(50, 100, 150, 200),
 )
+# 4-level toy VAE (the tiled-VAE hook hard-codes the x8 latent->pixel factor, utils/tilevae/tilevae.py:389,226)
+TINY_VAE8 = dict(z_channels=4, embed_dim=4, in_channels=3, out_ch=3, ch=64, ch_mult=(1, 1, 2, 2), num_res_blocks=1)
 
 
 # ------------------------------------------------------------------- UNet topology
@@ -524,6 +526,132 @@ def vae_decode(sd: SD, cfg: dict, z: Tensor, scale_factor: float) -> Tensor:
         if has_up:
             h = _conv(sd, f"decoder.up.{level}.upsample.conv.", F.interpolate(h, scale_factor=2.0, mode="nearest"))
     return _conv(sd, "decoder.conv_out.", F.silu(_gn(sd, "decoder.norm_out.", h, 1e-6)))
+
+
+# ------------------------------------------------------------- tiled VAE decoder
+VAE_TILE_PAD_DECODER = 11   # utils/tilevae/tilevae.py:315 (latent pixels)
+
+
+def _best_tile_size(lowerbound: int, upperbound: int) -> int:
+    """VAEHook.get_best_tile_size (utils/tilevae/tilevae.py:325-338)."""
+    divider = 32
+    while divider >= 2:
+        rem = lowerbound % divider
+        if rem == 0:
+            return lowerbound
+        cand = lowerbound - rem + divider
+        if cand <= upperbound:
+            return cand
+        divider //= 2
+    return lowerbound
+
+
+def vae_split_tiles(h: int, w: int, tile_size: int, pad: int = VAE_TILE_PAD_DECODER, is_decoder: bool = True):
+    """VAEHook.split_tiles (utils/tilevae/tilevae.py:340-399): ([x1,x2,y1,y2] input boxes grown by `pad`,
+    output boxes in output pixels)."""
+    nh = max(math.ceil((h - 2 * pad) / tile_size), 1)
+    nw = max(math.ceil((w - 2 * pad) / tile_size), 1)
+    th = _best_tile_size(math.ceil((h - 2 * pad) / nh), tile_size)
+    tw = _best_tile_size(math.ceil((w - 2 * pad) / nw), tile_size)
+    in_boxes, out_boxes = [], []
+    for i in range(nh):
+        for j in range(nw):
+            ib = [pad + j * tw, min(pad + (j + 1) * tw, w), pad + i * th, min(pad + (i + 1) * th, h)]
+            ob = [ib[0] if ib[0] > pad else 0, ib[1] if ib[1] < w - pad else w,
+                  ib[2] if ib[2] > pad else 0, ib[3] if ib[3] < h - pad else h]
+            out_boxes.append([v * 8 if is_decoder else v // 8 for v in ob])
+            in_boxes.append([max(0, ib[0] - pad), min(w, ib[1] + pad), max(0, ib[2] - pad), min(h, ib[3] + pad)])
+    return in_boxes, out_boxes
+
+
+def _tile_group_stats(x: Tensor, groups: int = 32):
+    """get_var_mean (utils/tilevae/tilevae.py:177-185): biased var / mean per (sample, group) of one tile."""
+    b, c = x.shape[:2]
+    xr = x.reshape(b * groups, -1)
+    var, mean = torch.var_mean(xr, dim=1, unbiased=False)
+    return var, mean
+
+
+def _apply_group_stats(sd: SD, p: str, x: Tensor, mean: Tensor, var: Tensor, groups: int = 32) -> Tensor:
+    """custom_group_norm (utils/tilevae/tilevae.py:188-215): fixed statistics, eps 1e-6, then the affine."""
+    b, c = x.shape[:2]
+    xr = x.reshape(b * groups, -1)
+    y = (xr - mean[:, None]) / torch.sqrt(var[:, None] + 1e-6)
+    y = y.reshape(x.shape)
+    return y * sd[p + "weight"].view(1, -1, 1, 1) + sd[p + "bias"].view(1, -1, 1, 1)
+
+
+def _vae_decoder_program(sd: SD, cfg: dict, x: Tensor):
+    """Decoder.forward as the task queue of build_task_queue (utils/tilevae/tilevae.py:72-165) for ONE tile:
+    a generator that yields (tensor, norm-prefix) at every `pre_norm` task and is resumed with the normalised
+    tensor; returns the decoded tile."""
+
+    def res(p, x):
+        h = yield (x, p + "norm1.")
+        h = _conv(sd, p + "conv1.", F.silu(h))
+        h = yield (h, p + "norm2.")
+        h = _conv(sd, p + "conv2.", F.silu(h))
+        if (p + "nin_shortcut.weight") in sd:
+            x = _conv(sd, p + "nin_shortcut.", x, padding=0)
+        return x + h
+
+    def attn(p, x):
+        b, c, hh, ww = x.shape
+        h = yield (x, p + "norm.")
+        q, k, v = (_conv(sd, p + n + ".", h, padding=0).reshape(b, c, hh * ww).permute(0, 2, 1) for n in "qkv")
+        w = torch.softmax(q @ k.transpose(1, 2) * (c ** -0.5), dim=-1)
+        o = (w @ v).permute(0, 2, 1).reshape(b, c, hh, ww)
+        return x + _conv(sd, p + "proj_out.", o, padding=0)
+
+    h = _conv(sd, "decoder.conv_in.", x)
+    h = yield from res("decoder.mid.block_1.", h)
+    h = yield from attn("decoder.mid.attn_1.", h)
+    h = yield from res("decoder.mid.block_2.", h)
+    plan, _ = vae_decoder_plan(cfg)
+    for level, blocks, has_up in plan:
+        for i in range(len(blocks)):
+            h = yield from res(f"decoder.up.{level}.block.{i}.", h)
+        if has_up:
+            h = _conv(sd, f"decoder.up.{level}.upsample.conv.", F.interpolate(h, scale_factor=2.0, mode="nearest"))
+    h = yield (h, "decoder.norm_out.")
+    return _conv(sd, "decoder.conv_out.", F.silu(h))
+
+
+def vae_decode_tiled(sd: SD, cfg: dict, z: Tensor, scale_factor: float, tile_size: int) -> Tensor:
+    """ControlLDM.vae_decode(tiled=True) (model/cldm.py:142-156) -> VAEHook.__call__ / vae_tile_forward in the
+    default (non-fast) mode (utils/tilevae/tilevae.py:317-323, :442-579): post_quant_conv on the whole latent,
+    overlapping latent tiles, every GroupNorm uses the pixel-weighted average of the per-tile mean AND of the
+    per-tile variance (GroupNormParam.summary, :263-278), attention is tile-local, valid regions are pasted."""
+    pad = VAE_TILE_PAD_DECODER
+    zq = _conv(sd, "post_quant_conv.", z / scale_factor, padding=0)
+    n, _, hh, ww = zq.shape
+    if max(hh, ww) <= pad * 2 + tile_size:          # "tiny and unnecessary to tile" (:319-321)
+        return vae_decode(sd, cfg, z, scale_factor)
+    in_boxes, out_boxes = vae_split_tiles(hh, ww, tile_size, pad, True)
+    progs = [_vae_decoder_program(sd, cfg, zq[:, :, b[2]:b[3], b[0]:b[1]]) for b in in_boxes]
+    pending = [next(g) for g in progs]
+    done: List[Optional[Tensor]] = [None] * len(progs)
+    while any(d is None for d in done):
+        stats = [_tile_group_stats(x) for x, _ in pending]
+        pix = torch.tensor([float(x.shape[2] * x.shape[3]) for x, _ in pending])
+        wgt = pix / pix.max()
+        wgt = wgt / wgt.sum()
+        var = sum(wt * st[0] for wt, st in zip(wgt, stats))
+        mean = sum(wt * st[1] for wt, st in zip(wgt, stats))
+        nxt = []
+        for i, (g, (x, p)) in enumerate(zip(progs, pending)):
+            try:
+                nxt.append(g.send(_apply_group_stats(sd, p, x, mean, var)))
+            except StopIteration as fin:     # every tile runs the same queue, so all finish together
+                done[i] = fin.value
+                nxt.append(None)
+        pending = nxt
+    out = torch.zeros((n, done[0].shape[1], hh * 8, ww * 8), dtype=done[0].dtype)
+    for tile, ib, ob in zip(done, in_boxes, out_boxes):
+        # crop_valid_region (:218-229)
+        m = [ob[i] - ib[i] * 8 for i in range(4)]
+        out[:, :, ob[2]:ob[3], ob[0]:ob[1]] = tile[:, :, m[2]:tile.shape[2] + m[3], m[0]:tile.shape[3] + m[1]]
+    return out
 
 
 def restore(w, cfg: dict, x_T: Tensor, cond, noise):

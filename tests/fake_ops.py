@@ -153,6 +153,44 @@ def groupnorm(x, gamma, beta, groups, eps, silu, stats=None, out=None):
     return out
 
 
+def groupnorm_pool(x, groups, weight, acc, stats=None):
+    LAUNCHES[0] += 2
+    B, C = x.shape[0], x.shape[-1]
+    v = x.float().reshape(B, -1, groups, C // groups).permute(0, 2, 1, 3).reshape(B, groups, -1)
+    var, mean = torch.var_mean(v, dim=2, unbiased=False)
+    acc[..., 0] += weight * mean
+    acc[..., 1] += weight * var
+    return acc
+
+
+def groupnorm_apply_stats(x, mean_var, gamma, beta, groups, eps, silu, out=None):
+    LAUNCHES[0] += 1
+    B, C = x.shape[0], x.shape[-1]
+    cpg = C // groups
+    v = x.float().reshape(B, -1, groups, cpg)
+    mean = mean_var[..., 0].view(B, 1, groups, 1)
+    var = mean_var[..., 1].view(B, 1, groups, 1)
+    y = (v - mean) * torch.rsqrt(var + eps)
+    y = y.reshape(B, -1, C) * gamma.float() + beta.float()
+    if silu:
+        y = F.silu(y)
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.bfloat16)
+    out.copy_(y.view(out.shape))
+    return out
+
+
+def conv3x3_supported(H, W, Cin):
+    if Cin % 64 != 0:
+        return False
+    if W >= 128:
+        return W % 128 == 0
+    if W < 8 or 128 % W != 0:
+        return False
+    rows = 128 // W
+    return H % rows == 0 if H >= rows else rows % H == 0
+
+
 def layernorm(x, gamma, beta, eps, out=None):
     LAUNCHES[0] += 1
     y = F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps)

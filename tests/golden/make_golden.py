@@ -13,6 +13,7 @@ enumeration), then the reference's own public API is executed on CPU in fp32:
 four per-step noise draws are the seeded tensors the oracle receives explicitly.
 
 Outputs:  golden_tiny.npz  (TINY config, B=2, 16x16 latent; everything in fp32)
+          golden_vae_tiled.npz  (TINY_VAE8 decoder, B=2, 40x48 latent, vae_decode(tiled=True, tile_size=16))
           golden_s4.npz    (s4 config, B=1, 64x64 latent; --full; image stored as fp16)
 """
 import argparse
@@ -133,6 +134,33 @@ def run_reference(cfg, batch, latent_hw):
     return dict(eps0=eps0, xs=torch.stack(xs), x0s=torch.stack(x0s), img=img, sched=sched)
 
 
+def run_reference_tiled_vae(vae_cfg, batch, latent_h, latent_w, tile_size):
+    """ControlLDM.vae_decode(z, tiled=True, tile_size) of the unmodified reference (VAEHook, non-fast mode)."""
+    from oracle import cldm_oracle as O
+
+    _stub_missing_packages()
+    from model.cldm import ControlLDM
+    from model.vae import AutoencoderKL
+
+    sd = O.make_weights(O.vae_decoder_param_shapes(vae_cfg), seed=2)
+    m = ControlLDM.__new__(ControlLDM)
+    torch.nn.Module.__init__(m)
+    m.vae = AutoencoderKL(ddconfig=dict(double_z=True, z_channels=vae_cfg["z_channels"], resolution=256,
+                                        in_channels=vae_cfg["in_channels"], out_ch=vae_cfg["out_ch"], ch=vae_cfg["ch"],
+                                        ch_mult=list(vae_cfg["ch_mult"]), num_res_blocks=vae_cfg["num_res_blocks"],
+                                        attn_resolutions=[], dropout=0.0), embed_dim=vae_cfg["embed_dim"])
+    res = m.vae.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    m.scale_factor = 0.18215
+    m.eval()
+    g = torch.Generator().manual_seed(11)
+    z = 0.9 * torch.randn(batch, vae_cfg["embed_dim"], latent_h, latent_w, generator=g)
+    with torch.no_grad():
+        img = m.vae_decode(z, tiled=True, tile_size=tile_size)
+        img_untiled = m.vae_decode(z)
+    return z, img, img_untiled
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also generate the s4 (full-size) fixture; ~2 min")
@@ -144,6 +172,11 @@ def main():
     np.savez_compressed(os.path.join(HERE, "golden_tiny.npz"), eps0=r["eps0"].numpy(), xs=r["xs"].numpy(),
                         x0s=r["x0s"].numpy(), img=r["img"].numpy(), **{"sched_" + k: v for k, v in r["sched"].items()})
     print("tiny:", {k: tuple(v.shape) for k, v in r.items() if hasattr(v, "shape")})
+    z, img, img_u = run_reference_tiled_vae(O.TINY_VAE8, batch=2, latent_h=40, latent_w=48, tile_size=16)
+    np.savez_compressed(os.path.join(HERE, "golden_vae_tiled.npz"), z=z.numpy(), img=img.numpy().astype(np.float32),
+                        tile_size=np.int64(16))
+    print("tiled vae:", tuple(z.shape), tuple(img.shape), "tiled vs untiled max diff",
+          float((img - img_u).abs().max()))
     if args.full:
         r = run_reference(O.S4, batch=1, latent_hw=64)
         np.savez_compressed(os.path.join(HERE, "golden_s4.npz"), eps0=r["eps0"].numpy(), xs=r["xs"].numpy(),

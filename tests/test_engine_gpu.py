@@ -165,3 +165,21 @@ def _oracle_sample_cuda(wd, x_T, cond, noise):
         x, _ = O.p_sample_update(sched, x, eps, len(ts) - i - 1, noise[i])
         xs.append(x)
     return x, xs, None
+
+
+# ----------------------------------------------------------------------------- tiled VAE decode (config C4)
+def test_tiled_vae_decode_against_reference_fixture():
+    """ControlLDM.vae_decode(tiled=True) semantics (VAEHook, pooled GroupNorm statistics, tile-local attention)
+    on the CUDA kernels vs the fixture recorded from the live reference; odd tile sizes (38x38, 24x38, ...) take
+    the im2col + GEMM route, the padded-token attention and the statistics-pool / apply-with-statistics kernels."""
+    from edtr_b200.engine import VaeDecoderEngine
+
+    g = np.load(os.path.join(GOLD, "golden_vae_tiled.npz"))
+    sd = O.make_weights(O.vae_decoder_param_shapes(O.TINY_VAE8), seed=2)
+    vd = VaeDecoderEngine(_dd(O.TINY_VAE8), O.TINY_VAE8["embed_dim"], sd, "cuda")
+    z = torch.from_numpy(g["z"]).cuda()
+    img = vd.decode_tiled(z, 0.18215, int(g["tile_size"]))
+    ref = torch.from_numpy(g["img"])
+    assert img.shape == ref.shape and bool(torch.isfinite(img).all())
+    assert O.psnr((img.cpu() + 1) / 2, (ref + 1) / 2) >= PSNR_MIN
+    assert O.max_rel_err(img.cpu(), ref) < 5e-2

@@ -255,6 +255,33 @@ def test_groupnorm(ops, B, HW, C, silu, eps, fused):
     assert relerr(out, ref.permute(0, 2, 1)) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 38, 24, 128), (1, 86, 75, 64), (3, 16, 16, 512)])
+def test_groupnorm_pool_and_apply_stats(ops, B, H, W, C):
+    """Tiled-VAE GroupNorm: pooled (mean, var) over two tiles with pixel weights, then apply with given statistics
+    (GroupNormParam.summary + custom_group_norm, utils/tilevae/tilevae.py:188-215, 263-278)."""
+    tiles = [(rnd(B, H, W, C, seed=1).float() * 1.3 + 0.4).to(BF), (rnd(B, H // 2, W, C, seed=2).float() * 0.7 - 0.2).to(BF)]
+    pix = [t.shape[1] * t.shape[2] for t in tiles]
+    acc = torch.zeros(B, 32, 2, device="cuda")
+    ref = torch.zeros(B, 32, 2, device="cuda")
+    for t, p in zip(tiles, pix):
+        wgt = p / sum(pix)
+        ops.groupnorm_pool(t, 32, wgt, acc)
+        v = t.float().reshape(B, -1, 32, C // 32).permute(0, 2, 1, 3).reshape(B, 32, -1)
+        var, mean = torch.var_mean(v, dim=2, unbiased=False)
+        ref[..., 0] += wgt * mean
+        ref[..., 1] += wgt * var
+    assert relerr(acc, ref) < 1e-4
+    gamma, beta = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    for silu in (False, True):
+        out = ops.groupnorm_apply_stats(tiles[0], acc, gamma, beta, 32, 1e-6, silu)
+        x = tiles[0].float().reshape(B, -1, 32, C // 32)
+        y = (x - ref[..., 0].view(B, 1, 32, 1)) * torch.rsqrt(ref[..., 1].view(B, 1, 32, 1) + 1e-6)
+        y = y.reshape(B, H, W, C) * gamma + beta
+        if silu:
+            y = F.silu(y)
+        assert relerr(out, y) < 1e-2
+
+
 def test_groupnorm_on_channel_slice(ops):
     B, HW = 2, 256
     buf = rnd(B, HW, 640, seed=1)

@@ -66,3 +66,23 @@ def test_s4_fixture_is_sane():
     g = np.load(os.path.join(GOLD, "golden_s4.npz"))
     assert g["xs"].shape == (4, 1, 4, 64, 64) and g["img"].shape == (1, 3, 512, 512)
     assert np.isfinite(g["xs"]).all() and np.abs(g["eps0"]).max() > 0.05
+
+
+def test_oracle_tiled_vae_matches_reference():
+    """vae_decode(tiled=True) of the live reference (VAEHook, pooled GroupNorm statistics) vs the restatement."""
+    g = np.load(os.path.join(GOLD, "golden_vae_tiled.npz"))
+    sd = O.make_weights(O.vae_decoder_param_shapes(O.TINY_VAE8), seed=2)
+    z = torch.from_numpy(g["z"])
+    with torch.no_grad():
+        img = O.vae_decode_tiled(sd, O.TINY_VAE8, z, 0.18215, int(g["tile_size"]))
+        img_untiled = O.vae_decode(sd, O.TINY_VAE8, z, 0.18215)
+    assert O.max_rel_err(img, torch.from_numpy(g["img"])) < 1e-5
+    # the pooled statistics are an approximation: tiled != untiled, so the test is not vacuous
+    assert O.max_rel_err(img, img_untiled) > 1e-3
+
+
+def test_vae_split_tiles_matches_survey():
+    """a 256x256 latent with decoder tile 64 -> 16 tiles of <= 86x86 latent pixels."""
+    ib, ob = O.vae_split_tiles(256, 256, 64)
+    assert len(ib) == 16 and ib[5] == [64, 150, 64, 150] and ob[5] == [600, 1112, 600, 1112]
+    assert ob[-1] == [1624, 2048, 1624, 2048]
