@@ -476,8 +476,10 @@ static GnGeom gn_geom(int B, int HW, int C) {
   g.ppar = 256 / g.vslab;
   if (g.ppar < 1) g.ppar = 1;
   g.threads = g.vslab * g.ppar;
-  // aim for >= 2 CTAs per SM over the whole launch, at least 4 rows per thread-row
-  const int want_ctas = 2 * 148;
+  // aim for >= 2 CTAs per SM over the whole launch, at least 4 rows per thread-row; tensors that stream from HBM
+  // (VAE decoder, >= 64 MB; measured: 33 MB tensors are faster with 2) get 8 CTAs per SM so that enough 16-byte loads are in flight to cover the DRAM latency
+  const size_t bytes = static_cast<size_t>(B) * HW * C * 2;
+  const int want_ctas = (bytes >= (64u << 20) ? 8 : 2) * 148;
   int chunks = (want_ctas + B * g.nslab - 1) / (B * g.nslab);
   int rows = (HW + chunks - 1) / chunks;
   const int min_rows = 4 * g.ppar;
