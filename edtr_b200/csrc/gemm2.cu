@@ -39,7 +39,10 @@ struct Gemm2Params {
   int taps_x, tap_dy0, tap_dx0;
   int up2x;                // 1: rows are low-resolution pixels of one 2x-upsample phase; D is a 4-D map over the
                            //    phase's output pixels (x and y strides of two pixels)
-  int tiles_m, tiles_n;    // 256-row pair tiles, column tiles
+  int tiles_m, tiles_n;    // 256-row pair tiles, column tiles.  Work items are numbered column-tile major (all row
+                           // tiles of column tile 0, then of column tile 1, ...): the only narrower tile is the
+                           // last column tile, so the round-robin hands the wide (expensive) tiles out first and
+                           // every cluster gets the same mix instead of one parity of clusters taking all wide tiles
   int bn_base;             // width of every column tile but the last (multiple of 64, <= 256)
   int b_box_rows;          // rows of the weight TMA box (= bn_base / 2)
   int splits;              // split-K factor (1 = none); partial tiles go to `ws` as fp32 [splits][M][N]
@@ -133,7 +136,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int w = cluster_id; w < num_work; w += num_clusters) {
       const int tile = w / p.splits, ks = w - tile * p.splits;
       const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
-      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int tn = tile / p.tiles_m, tm = tile - tn * p.tiles_m;   // column-tile major: see Gemm2Params::tiles_m
       const int m0 = tm * (2 * k2BM) + static_cast<int>(rank) * k2BM;
       const int n_tile0 = tn * p.bn_base;
       const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
@@ -187,7 +190,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int w = cluster_id; w < num_work; w += num_clusters, ++ti) {
         const int tile = w / p.splits, ks = w - tile * p.splits;
         const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kblocks, kb0 + p.kb_per_split);
-        const int tn = tile % p.tiles_n;
+        const int tn = tile / p.tiles_m;
         const int n_tile0 = tn * p.bn_base;
         const int bn = min(p.bn_base, ((p.N - n_tile0) + 63) & ~63);
         const uint32_t idesc = umma_idesc_bf16(2 * k2BM, bn);
@@ -233,8 +236,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int row_off = static_cast<int>(rank) * k2BM + lg * 32;
 
     // (work item, chunk) -> coordinates; shared by the processing loop and the residual look-ahead
-    auto tile_m0 = [&](int w) { return ((w / p.splits) / p.tiles_n) * (2 * k2BM) + row_off; };
-    auto tile_n0 = [&](int w) { return ((w / p.splits) % p.tiles_n) * p.bn_base; };
+    auto tile_m0 = [&](int w) { return ((w / p.splits) % p.tiles_m) * (2 * k2BM) + row_off; };
+    auto tile_n0 = [&](int w) { return ((w / p.splits) / p.tiles_m) * p.bn_base; };
     auto tile_bn = [&](int w) { return min(p.bn_base, ((p.N - tile_n0(w)) + 63) & ~63); };
     auto tile_chunks = [&](int w) { return (p.geglu ? (tile_bn(w) >> 1) : tile_bn(w)) >> 6; };
     auto tile_outcol0 = [&](int w) { return p.geglu ? (tile_n0(w) >> 1) : tile_n0(w); };
