@@ -134,9 +134,15 @@ class ControlLDM(nn.Module):
                                           world=world, reduce_fn=red)
         return eps.to(x_noisy.dtype)
 
-    def vae_encode(self, image, sample=True, tiled=False, tile_size=-1):
-        raise NotImplementedError("vae_encode precedes the accelerated path (SURVEY §8f rank 1); run the "
-                                  "reference encoder and pass c_img")
+    @torch.no_grad()
+    def vae_encode(self, image: torch.Tensor, sample: bool = True, tiled: bool = False, tile_size: int = -1):
+        """model/cldm.py:107-134 (untiled): posterior sample or mode, times the latent scale factor."""
+        if tiled:
+            raise NotImplementedError("tiled VAE *encode* (VAEHook with the encoder, pad 32) is not built yet; the "
+                                      "tiled decode is (vae_decode(tiled=True))")
+        posterior = self.vae.encode(image)
+        z = posterior.sample() if sample else posterior.mode()
+        return z * self.scale_factor
 
     @torch.no_grad()
     def vae_decode(self, z: torch.Tensor, tiled: bool = False, tile_size: int = -1) -> torch.Tensor:

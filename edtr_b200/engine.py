@@ -706,7 +706,61 @@ class _Graph:
 
 
 # ------------------------------------------------------------------------ VAE decoder
-class VaeDecoderEngine:
+class _VaeBlocks:
+    """Leaf blocks shared by the VAE decoder and encoder engines (model/vae.py:64-124, :250-308); the kernels are
+    reached through ``self.ops`` and the packed weights through ``self.w``."""
+
+    def _res(self, ws: Workspace, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
+        """ResnetBlock.forward, temb=None (model/vae.py:103-124)."""
+        ops, w = self.ops, self.w
+        B, H, W, cin = x.shape
+        cout = out.shape[-1]
+        y = ops.groupnorm(x, w[p + "norm1.weight"], w[p + "norm1.bias"], 32, 1e-6, True, stats=ws.gn_scratch(ops, x),
+                          out=ws.get("gn", (B, H, W, cin)))
+        h = self._conv_any(ws, y, p + "conv1.", out=ws.get("res_h", (B, H, W, cout)))
+        y2 = ops.groupnorm(h, w[p + "norm2.weight"], w[p + "norm2.bias"], 32, 1e-6, True, stats=ws.gn_scratch(ops, h),
+                           out=ws.get("gn", (B, H, W, cout)))
+        if (p + "nin_shortcut.weight") in w:
+            skip = ops.gemm(x, w[p + "nin_shortcut.weight"], bias=w[p + "nin_shortcut.bias"],
+                            out=ws.get("res_skip", (B, H, W, cout)))
+        else:
+            skip = x
+        self._conv_any(ws, y2, p + "conv2.", residual=skip, out=out)
+
+    def _attn(self, ws: Workspace, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
+        """SDPAttnBlock.forward: one head of width C (model/vae.py:279-308)."""
+        ops, w = self.ops, self.w
+        B, H, W, C = x.shape
+        L = H * W
+        y = ops.groupnorm(x, w[p + "norm.weight"], w[p + "norm.bias"], 32, 1e-6, False, stats=ws.gn_scratch(ops, x),
+                          out=ws.get("gn", (B, L, C)))
+        qk = ops.gemm(y, w[p + "qk.weight"], bias=w[p + "qk.bias"], out=ws.get("va_qk", (B, L, 2 * C)))
+        # V^T per image ([C, L], keys contiguous) is the K-major B operand of P @ V
+        vt = ops.gemm(y, w[p + "v.weight"], bias=w[p + "v.bias"], out_mode=ops.OUT_NCHW_BF16, hw=L,
+                      out=ws.get("va_vt", (B, C, L)))
+        o = ws.get("va_o", (B, L, C))
+        s = ws.get("va_s", (L, L), F32)
+        pm = ws.get("va_p", (L, L))
+        for b in range(B):
+            ops.gemm(qk[b, :, :C], qk[b, :, C:], out_mode=ops.OUT_F32, out=s)
+            ops.softmax_rows(s, float(C) ** -0.5, out=pm)
+            ops.gemm(pm, vt[b], out=o[b])
+        ops.gemm(o, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out)
+
+    def _conv_any(self, ws: Workspace, x: torch.Tensor, wk: str, **kw) -> torch.Tensor:
+        """3x3/p1 convolution at any tile geometry: the TMA implicit-GEMM kernel when the tile fits its box
+        rules, else im2col + GEMM (tiled-VAE tiles are e.g. 86x86 latent pixels)."""
+        ops, w = self.ops, self.w
+        B, H, W, C = x.shape
+        if ops.conv3x3_supported(H, W, C):
+            return ops.conv3x3(x, w[wk + "weight"], bias=w[wk + "bias"], **kw)
+        col = ops.im2col(x, 3, 3, 1, 1, 1, H, W, out=ws.get("col", (B * H * W, 9 * C)))
+        if kw.get("out_mode", ops.OUT_BF16) in (ops.OUT_NCHW_F32, ops.OUT_NCHW_BF16):
+            kw["hw"] = H * W
+        return ops.gemm(col, w[wk + "weight"], bias=w[wk + "bias"], **kw)
+
+
+class VaeDecoderEngine(_VaeBlocks):
     """ControlLDM.vae_decode (untiled): z / scale -> post_quant_conv -> Decoder.forward
     (model/cldm.py:136-156, model/vae.py:731-734, :527-560)."""
 
@@ -750,43 +804,6 @@ class VaeDecoderEngine:
         self._ws: Dict[Tuple[int, int, int], Workspace] = {}
         self._graphs: Dict[Tuple, _Graph] = {}
 
-    def _res(self, ws: Workspace, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
-        """ResnetBlock.forward, temb=None (model/vae.py:103-124)."""
-        ops, w = self.ops, self.w
-        B, H, W, cin = x.shape
-        cout = out.shape[-1]
-        y = ops.groupnorm(x, w[p + "norm1.weight"], w[p + "norm1.bias"], 32, 1e-6, True, stats=ws.gn_scratch(ops, x),
-                          out=ws.get("gn", (B, H, W, cin)))
-        h = ops.conv3x3(y, w[p + "conv1.weight"], bias=w[p + "conv1.bias"], out=ws.get("res_h", (B, H, W, cout)))
-        y2 = ops.groupnorm(h, w[p + "norm2.weight"], w[p + "norm2.bias"], 32, 1e-6, True, stats=ws.gn_scratch(ops, h),
-                           out=ws.get("gn", (B, H, W, cout)))
-        if (p + "nin_shortcut.weight") in w:
-            skip = ops.gemm(x, w[p + "nin_shortcut.weight"], bias=w[p + "nin_shortcut.bias"],
-                            out=ws.get("res_skip", (B, H, W, cout)))
-        else:
-            skip = x
-        ops.conv3x3(y2, w[p + "conv2.weight"], bias=w[p + "conv2.bias"], residual=skip, out=out)
-
-    def _attn(self, ws: Workspace, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
-        """SDPAttnBlock.forward: one head of width C (model/vae.py:279-308)."""
-        ops, w = self.ops, self.w
-        B, H, W, C = x.shape
-        L = H * W
-        y = ops.groupnorm(x, w[p + "norm.weight"], w[p + "norm.bias"], 32, 1e-6, False, stats=ws.gn_scratch(ops, x),
-                          out=ws.get("gn", (B, L, C)))
-        qk = ops.gemm(y, w[p + "qk.weight"], bias=w[p + "qk.bias"], out=ws.get("va_qk", (B, L, 2 * C)))
-        # V^T per image ([C, L], keys contiguous) is the K-major B operand of P @ V
-        vt = ops.gemm(y, w[p + "v.weight"], bias=w[p + "v.bias"], out_mode=ops.OUT_NCHW_BF16, hw=L,
-                      out=ws.get("va_vt", (B, C, L)))
-        o = ws.get("va_o", (B, L, C))
-        s = ws.get("va_s", (L, L), F32)
-        pm = ws.get("va_p", (L, L))
-        for b in range(B):
-            ops.gemm(qk[b, :, :C], qk[b, :, C:], out_mode=ops.OUT_F32, out=s)
-            ops.softmax_rows(s, float(C) ** -0.5, out=pm)
-            ops.gemm(pm, vt[b], out=o[b])
-        ops.gemm(o, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out)
-
     def _decode(self, ws: Workspace, z: torch.Tensor, scale_factor: float, img_out: torch.Tensor) -> None:
         ops, w = self.ops, self.w
         B, _, H, W = z.shape
@@ -828,18 +845,6 @@ class VaeDecoderEngine:
                     out=img_out.view(B, self.dd["out_ch"], H * W), out_mode=ops.OUT_NCHW_F32)
 
     # ------------------------------------------------------------------ tiled decode (VAEHook)
-    def _conv_any(self, ws: Workspace, x: torch.Tensor, wk: str, **kw) -> torch.Tensor:
-        """3x3/p1 convolution at any tile geometry: the TMA implicit-GEMM kernel when the tile fits its box
-        rules, else im2col + GEMM (tiled-VAE tiles are e.g. 86x86 latent pixels)."""
-        ops, w = self.ops, self.w
-        B, H, W, C = x.shape
-        if ops.conv3x3_supported(H, W, C):
-            return ops.conv3x3(x, w[wk + "weight"], bias=w[wk + "bias"], **kw)
-        col = ops.im2col(x, 3, 3, 1, 1, 1, H, W, out=ws.get("col", (B * H * W, 9 * C)))
-        if kw.get("out_mode", ops.OUT_BF16) in (ops.OUT_NCHW_F32, ops.OUT_NCHW_BF16):
-            kw["hw"] = H * W
-        return ops.gemm(col, w[wk + "weight"], bias=w[wk + "bias"], **kw)
-
     def _tile_program(self, ws: Workspace, x: torch.Tensor):
         """Decoder.forward of ONE tile as the task queue of build_task_queue (utils/tilevae/tilevae.py:72-165):
         a generator that yields (tensor, norm-key, silu) at every `pre_norm` task, is resumed with the tensor
@@ -995,3 +1000,122 @@ class VaeDecoderEngine:
         else:
             run()
         return img.clone()
+
+
+# ------------------------------------------------------------------------ VAE encoder
+class VaeEncoderEngine(_VaeBlocks):
+    """AutoencoderKL.encode up to the posterior moments (model/vae.py:725-729, Encoder.forward :421-446):
+    conv_in -> per level [ResnetBlock x num_res_blocks, Downsample] -> mid (ResnetBlock, attention, ResnetBlock)
+    -> GroupNorm + swish -> conv_out -> quant_conv.  Downsample is `pad (0,1,0,1)` + 3x3 stride 2 (model/vae.py:54-58)
+    = an im2col gather whose out-of-image taps are zero + GEMM.  conv_out (3x3) and quant_conv (1x1) are both
+    linear with nothing in between, so they are folded into one 3x3 convolution at pack time (fp32)."""
+
+    def __init__(self, ddconfig: Dict, embed_dim: int, sd: Dict[str, torch.Tensor], device, ops=None):
+        if ops is None:
+            from . import ops as _ops
+            ops = _ops
+        self.ops = ops
+        self.device = torch.device(device)
+        self.dd = ddconfig
+        self.embed_dim = embed_dim
+        if ddconfig.get("attn_resolutions"):
+            raise NotImplementedError("per-level VAE attention (attn_resolutions) is not used by EDTR configs")
+        if ddconfig["ch"] % 64 != 0:
+            raise NotImplementedError("VAE base width must be a multiple of 64")
+        if not ddconfig.get("double_z", True):
+            raise NotImplementedError("the encoder path expects double_z (mean | logvar)")
+        self.levels, self.top = T.vae_encoder_levels(ddconfig)
+        w: Dict[str, torch.Tensor] = {}
+        dev = self.device
+        want = [(k, shp) for k, shp in T.vae_param_shapes(ddconfig, embed_dim)
+                if k.startswith(("encoder.", "quant_conv."))]
+        for k, shp in want:
+            if k not in sd:
+                raise KeyError(f"state-dict is missing {k}")
+            if tuple(sd[k].shape) != tuple(shp):
+                raise ValueError(f"{k}: expected shape {tuple(shp)}, got {tuple(sd[k].shape)}")
+            v = sd[k]
+            if k.startswith(("quant_conv.", "encoder.conv_out.")):
+                continue
+            if v.dim() == 4 and v.shape[-1] == 3:
+                w[k] = pack_conv3x3(v, dev)
+            elif v.dim() == 4:
+                w[k] = pack_matrix(v, dev)
+            else:
+                w[k] = vec(v, dev)
+        # quant_conv(conv_out(x)) = (Wq . Wc) * x + (Wq . bc + bq)
+        wq = sd["quant_conv.weight"].detach().double().cpu().reshape(2 * embed_dim, -1)
+        wc = sd["encoder.conv_out.weight"].detach().double().cpu()
+        wf = torch.einsum("om,mckl->ockl", wq, wc)
+        bf = wq @ sd["encoder.conv_out.bias"].detach().double().cpu() + sd["quant_conv.bias"].detach().double().cpu()
+        w["encoder.moments.weight"] = pack_conv3x3(wf.float(), dev)
+        w["encoder.moments.bias"] = vec(bf.float(), dev)
+        a = "encoder.mid.attn_1."
+        w[a + "qk.weight"] = torch.cat([w[a + "q.weight"], w[a + "k.weight"]], 0).contiguous()
+        w[a + "qk.bias"] = torch.cat([w[a + "q.bias"], w[a + "k.bias"]], 0).contiguous()
+        self.w = w
+        self._ws: Dict[Tuple[int, int, int], Workspace] = {}
+        self._graphs: Dict[Tuple, _Graph] = {}
+
+    def _encode(self, ws: Workspace, image: torch.Tensor, moments: torch.Tensor) -> None:
+        ops, w = self.ops, self.w
+        B, cin, H, W = image.shape
+        xin = ws.zeros("e_xin", (B, H, W, 64))
+        ops.nchw_to_nhwc(image, xin, 0)
+        ping = lambda i, shape: ws.get(f"e_h{i % 2}", shape)
+        n = 0
+        h = self._conv_any(ws, xin, "encoder.conv_in.", out=ping(n, (B, H, W, self.dd["ch"])))
+        for level, blocks, has_down in self.levels:
+            for i, (ci, co) in enumerate(blocks):
+                n += 1
+                o = ping(n, (B, H, W, co))
+                self._res(ws, f"encoder.down.{level}.block.{i}.", h, o)
+                h = o
+            if has_down:   # Downsample: pad right/bottom by one, 3x3 stride 2 (model/vae.py:54-58)
+                c = h.shape[-1]
+                Ho, Wo = H // 2, W // 2
+                q = f"encoder.down.{level}.downsample.conv."
+                col = ops.im2col(h, 3, 3, 2, 0, 0, Ho, Wo, out=ws.get("col", (B * Ho * Wo, 9 * c)))
+                n += 1
+                h = ops.gemm(col, w[q + "weight"], bias=w[q + "bias"], out=ping(n, (B, Ho, Wo, c)))
+                H, W = Ho, Wo
+        for name in ("block_1", "attn_1", "block_2"):
+            n += 1
+            o = ping(n, (B, H, W, self.top))
+            if name == "attn_1":
+                self._attn(ws, "encoder.mid.attn_1.", h, o)
+            else:
+                self._res(ws, f"encoder.mid.{name}.", h, o)
+            h = o
+        y = ops.groupnorm(h, w["encoder.norm_out.weight"], w["encoder.norm_out.bias"], 32, 1e-6, True,
+                          stats=ws.gn_scratch(ops, h), out=ws.get("gn", (B, H, W, self.top)))
+        self._conv_any(ws, y, "encoder.moments.", out=moments.view(B, 2 * self.embed_dim, H * W),
+                       out_mode=ops.OUT_NCHW_F32)
+
+    def encode(self, image: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
+        """image [B, in_channels, H, W] fp32 in [-1, 1] -> posterior moments [B, 2*embed_dim, H/f, W/f] fp32
+        (mean | logvar), f = 2^(levels-1)."""
+        if image.dim() != 4 or image.shape[1] != self.dd["in_channels"]:
+            raise ValueError(f"image must be [B, {self.dd['in_channels']}, H, W], got {tuple(image.shape)}")
+        if getattr(self.ops, "REQUIRES_CUDA", True) and not image.is_cuda:
+            raise RuntimeError("edtr_b200 has no CPU path: image must be a CUDA tensor")
+        B, _, H, W = image.shape
+        f = 2 ** (len(self.levels) - 1)
+        if H % f or W % f:
+            raise ValueError(f"image size {H}x{W} must be a multiple of {f}")
+        key = (B, H, W)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = self._ws[key] = Workspace(self.device)
+        si = ws.get("in_img", tuple(image.shape), F32)
+        mo = ws.get("out_moments", (B, 2 * self.embed_dim, H // f, W // f), F32)
+        si.copy_(image)
+        run = lambda: self._encode(ws, si, mo)
+        if use_graph:
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._graphs[key] = _Graph(run)
+            g.replay()
+        else:
+            run()
+        return mo.clone()

@@ -162,8 +162,29 @@ class ControlNet(_UNetFamily):
             "UNet skip tensors by the zero-conv GEMM epilogues and never materialised")
 
 
+class DiagonalGaussianDistribution:
+    """model/distributions.py:24-65 (the members the EDTR scripts use): mean | logvar split, logvar clamped to
+    [-30, 20], ``sample()`` = mean + std * randn (torch.randn on the host RNG, as the reference), ``mode()`` = mean."""
+
+    def __init__(self, parameters: torch.Tensor, deterministic: bool = False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self) -> torch.Tensor:
+        return self.mean + self.std * torch.randn(self.mean.shape).to(device=self.parameters.device)
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
 class AutoencoderKL(nn.Module):
-    """model/vae.py:681-743 — parameter holder; ``decode`` runs on the CUDA engine."""
+    """model/vae.py:681-743 — parameter holder; ``encode`` / ``decode`` run on the CUDA engines."""
 
     def __init__(self, ddconfig: Dict, embed_dim: int, train_encoder: bool = False, train_decoder: bool = False):
         super().__init__()
@@ -198,8 +219,22 @@ class AutoencoderKL(nn.Module):
         """post_quant_conv + Decoder.forward (model/vae.py:731-734)."""
         return self._decoder_engine().decode(z.float().contiguous(), 1.0)
 
-    def encode(self, x):
-        raise NotImplementedError("the VAE encoder is outside the accelerated path in this round (SURVEY §8f rank 1)")
+    def _encoder_engine(self):
+        from .engine import VaeEncoderEngine
+
+        ver = state_version(self)
+        dev = next(self.parameters()).device
+        if getattr(self, "_enc_engine", None) is None or self._enc_engine_version != (ver, dev):
+            if dev.type != "cuda":
+                raise RuntimeError("edtr_b200 has no CPU path: move the model to a CUDA device first")
+            self._enc_engine = VaeEncoderEngine(self.ddconfig, self.embed_dim, self.state_dict(), dev)
+            self._enc_engine_version = (ver, dev)
+        return self._enc_engine
+
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor) -> "DiagonalGaussianDistribution":
+        """Encoder.forward + quant_conv -> posterior (model/vae.py:725-729)."""
+        return DiagonalGaussianDistribution(self._encoder_engine().encode(x.float().contiguous()))
 
     def forward(self, input, sample_posterior=True):
         raise NotImplementedError("AutoencoderKL.forward (encode + decode) is a training-time call, out of scope")

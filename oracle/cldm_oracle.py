@@ -528,6 +528,80 @@ def vae_decode(sd: SD, cfg: dict, z: Tensor, scale_factor: float) -> Tensor:
     return _conv(sd, "decoder.conv_out.", F.silu(_gn(sd, "decoder.norm_out.", h, 1e-6)))
 
 
+# ---------------------------------------------------------------------- VAE encoder
+def vae_encoder_plan(cfg: dict):
+    """[(level, [(cin, cout), ...], has_downsample)] from the image side (model/vae.py:376-399)."""
+    ch, mult, nrb = cfg["ch"], cfg["ch_mult"], cfg["num_res_blocks"]
+    in_mult = (1,) + tuple(mult)
+    plan = []
+    for level in range(len(mult)):
+        cin, cout = ch * in_mult[level], ch * mult[level]
+        blocks = []
+        for _ in range(nrb):
+            blocks.append((cin, cout))
+            cin = cout
+        plan.append((level, blocks, level != len(mult) - 1))
+    return plan, ch * mult[-1]
+
+
+def vae_encoder_param_shapes(cfg: dict):
+    """(key, shape) list of the AutoencoderKL keys the encode path reads (model/vae.py:326-420, :687-688)."""
+    z, ed = cfg["z_channels"], cfg["embed_dim"]
+    plan, top = vae_encoder_plan(cfg)
+    s = [("encoder.conv_in.weight", (cfg["ch"], cfg["in_channels"], 3, 3)), ("encoder.conv_in.bias", (cfg["ch"],))]
+    for level, blocks, has_down in plan:
+        for i, (cin, cout) in enumerate(blocks):
+            s += _vae_res_shapes(f"encoder.down.{level}.block.{i}.", cin, cout)
+        if has_down:
+            c = blocks[-1][1]
+            s += [(f"encoder.down.{level}.downsample.conv.weight", (c, c, 3, 3)),
+                  (f"encoder.down.{level}.downsample.conv.bias", (c,))]
+    s += _vae_res_shapes("encoder.mid.block_1.", top, top)
+    s += [("encoder.mid.attn_1.norm.weight", (top,)), ("encoder.mid.attn_1.norm.bias", (top,))]
+    for n in ("q", "k", "v", "proj_out"):
+        s += [(f"encoder.mid.attn_1.{n}.weight", (top, top, 1, 1)), (f"encoder.mid.attn_1.{n}.bias", (top,))]
+    s += _vae_res_shapes("encoder.mid.block_2.", top, top)
+    s += [("encoder.norm_out.weight", (top,)), ("encoder.norm_out.bias", (top,)),
+          ("encoder.conv_out.weight", (2 * z, top, 3, 3)), ("encoder.conv_out.bias", (2 * z,)),
+          ("quant_conv.weight", (2 * ed, 2 * z, 1, 1)), ("quant_conv.bias", (2 * ed,))]
+    return s
+
+
+def vae_encode_moments(sd: SD, cfg: dict, image: Tensor) -> Tensor:
+    """AutoencoderKL.encode up to the posterior parameters: Encoder.forward + quant_conv
+    (model/vae.py:421-446, :725-729).  Downsample = F.pad(x, (0,1,0,1)) + conv3x3 stride 2 pad 0 (:54-58)."""
+    h = _conv(sd, "encoder.conv_in.", image)
+    plan, _ = vae_encoder_plan(cfg)
+    for level, blocks, has_down in plan:
+        for i in range(len(blocks)):
+            h = _vae_resblock(sd, f"encoder.down.{level}.block.{i}.", h)
+        if has_down:
+            h = _conv(sd, f"encoder.down.{level}.downsample.conv.", F.pad(h, (0, 1, 0, 1)), stride=2, padding=0)
+    h = _vae_resblock(sd, "encoder.mid.block_1.", h)
+    h = _vae_attn(sd, "encoder.mid.attn_1.", h)
+    h = _vae_resblock(sd, "encoder.mid.block_2.", h)
+    h = _conv(sd, "encoder.conv_out.", F.silu(_gn(sd, "encoder.norm_out.", h, 1e-6)))
+    return _conv(sd, "quant_conv.", h, padding=0)
+
+
+def vae_encode(sd: SD, cfg: dict, image: Tensor, scale_factor: float, noise: Optional[Tensor] = None) -> Tensor:
+    """ControlLDM.vae_encode untiled (model/cldm.py:107-134): posterior.mode() (noise=None, `sample=False`) or
+    posterior.sample() with the given N(0,1) draw, times the latent scale (model/distributions.py:24-65)."""
+    mean, logvar = torch.chunk(vae_encode_moments(sd, cfg, image), 2, dim=1)
+    if noise is None:
+        return mean * scale_factor
+    std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+    return (mean + std * noise) * scale_factor
+
+
+def q_sample(betas: np.ndarray, x_start: Tensor, t: Tensor, noise: Tensor) -> Tensor:
+    """Diffusion.q_sample (model/gaussian_diffusion.py:80-84): sqrt(ac[t]) x0 + sqrt(1 - ac[t]) noise."""
+    ac = np.cumprod(1.0 - betas, axis=0)
+    a = torch.from_numpy(np.sqrt(ac)).float()[t].view(-1, 1, 1, 1)
+    b = torch.from_numpy(np.sqrt(1.0 - ac)).float()[t].view(-1, 1, 1, 1)
+    return a * x_start + b * noise
+
+
 # ------------------------------------------------------------- tiled VAE decoder
 VAE_TILE_PAD_DECODER = 11   # utils/tilevae/tilevae.py:315 (latent pixels)
 

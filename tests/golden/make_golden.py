@@ -13,6 +13,7 @@ enumeration), then the reference's own public API is executed on CPU in fp32:
 four per-step noise draws are the seeded tensors the oracle receives explicitly.
 
 Outputs:  golden_tiny.npz  (TINY config, B=2, 16x16 latent; everything in fp32)
+          golden_vae_encode.npz (TINY VAE encoder, B=2, 64x64 image: vae_encode mode / sample, q_sample at t=200)
           golden_vae_tiled.npz  (TINY_VAE8 decoder, B=2, 40x48 latent, vae_decode(tiled=True, tile_size=16))
           golden_s4.npz    (s4 config, B=1, 64x64 latent; --full; image stored as fp16)
 """
@@ -161,6 +162,46 @@ def run_reference_tiled_vae(vae_cfg, batch, latent_h, latent_w, tile_size):
     return z, img, img_untiled
 
 
+def run_reference_vae_encode(vae_cfg, batch, hw):
+    """ControlLDM.vae_encode(image, sample=False / True) and Diffusion.q_sample of the unmodified reference."""
+    from oracle import cldm_oracle as O
+
+    _stub_missing_packages()
+    from model.cldm import ControlLDM
+    from model.gaussian_diffusion import Diffusion
+    from model.vae import AutoencoderKL
+
+    sd = O.make_weights(O.vae_encoder_param_shapes(vae_cfg), seed=3)
+    m = ControlLDM.__new__(ControlLDM)
+    torch.nn.Module.__init__(m)
+    m.vae = AutoencoderKL(ddconfig=dict(double_z=True, z_channels=vae_cfg["z_channels"], resolution=256,
+                                        in_channels=vae_cfg["in_channels"], out_ch=vae_cfg["out_ch"], ch=vae_cfg["ch"],
+                                        ch_mult=list(vae_cfg["ch_mult"]), num_res_blocks=vae_cfg["num_res_blocks"],
+                                        attn_resolutions=[], dropout=0.0), embed_dim=vae_cfg["embed_dim"])
+    res = m.vae.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    assert all(k.startswith(("decoder.", "post_quant_conv.")) for k in res.missing_keys), res.missing_keys
+    m.scale_factor = 0.18215
+    m.eval()
+    g = torch.Generator().manual_seed(21)
+    image = torch.rand(batch, 3, hw, hw, generator=g) * 2 - 1
+    with torch.no_grad():
+        z_mode = m.vae_encode(image, sample=False)
+        draw = torch.randn(z_mode.shape, generator=g)
+        real = torch.randn
+        torch.randn = lambda *a, **k: draw          # DiagonalGaussianDistribution.sample draws torch.randn(mean.shape)
+        try:
+            z_sample = m.vae_encode(image, sample=True)
+        finally:
+            torch.randn = real
+        diffusion = Diffusion(timesteps=1000, beta_schedule="linear", loss_type="l2", linear_start=0.00085,
+                              linear_end=0.0120, cosine_s=8e-3, parameterization="eps")
+        t = torch.full((batch,), 200, dtype=torch.long)
+        n2 = torch.randn(z_mode.shape, generator=g)
+        x_T = diffusion.q_sample(x_start=z_mode, t=t, noise=n2)
+    return image, z_mode, draw, z_sample, n2, x_T
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also generate the s4 (full-size) fixture; ~2 min")
@@ -175,6 +216,10 @@ def main():
     z, img, img_u = run_reference_tiled_vae(O.TINY_VAE8, batch=2, latent_h=40, latent_w=48, tile_size=16)
     np.savez_compressed(os.path.join(HERE, "golden_vae_tiled.npz"), z=z.numpy(), img=img.numpy().astype(np.float32),
                         tile_size=np.int64(16))
+    image, z_mode, draw, z_sample, n2, x_T = run_reference_vae_encode(O.TINY["vae"], batch=2, hw=64)
+    np.savez_compressed(os.path.join(HERE, "golden_vae_encode.npz"), image=image.numpy(), z_mode=z_mode.numpy(),
+                        draw=draw.numpy(), z_sample=z_sample.numpy(), q_noise=n2.numpy(), x_T=x_T.numpy())
+    print("vae encode:", tuple(image.shape), "->", tuple(z_mode.shape))
     print("tiled vae:", tuple(z.shape), tuple(img.shape), "tiled vs untiled max diff",
           float((img - img_u).abs().max()))
     if args.full:

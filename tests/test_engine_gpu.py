@@ -183,3 +183,42 @@ def test_tiled_vae_decode_against_reference_fixture():
     assert img.shape == ref.shape and bool(torch.isfinite(img).all())
     assert O.psnr((img.cpu() + 1) / 2, (ref + 1) / 2) >= PSNR_MIN
     assert O.max_rel_err(img.cpu(), ref) < 5e-2
+
+
+# ----------------------------------------------------------------------------- VAE encoder
+def test_vae_encoder_against_reference_fixture():
+    from edtr_b200.engine import VaeEncoderEngine
+
+    g = np.load(os.path.join(GOLD, "golden_vae_encode.npz"))
+    v = O.TINY["vae"]
+    sd = O.make_weights(O.vae_encoder_param_shapes(v), seed=3)
+    ve = VaeEncoderEngine(_dd(v), v["embed_dim"], sd, "cuda")
+    image = torch.from_numpy(g["image"]).cuda()
+    for use_graph in (False, True):
+        mo = ve.encode(image, use_graph=use_graph).cpu()
+        mean, logvar = torch.chunk(mo, 2, dim=1)
+        assert O.max_rel_err(mean * 0.18215, torch.from_numpy(g["z_mode"])) < STEP_TOL
+        std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+        z_s = (mean + std * torch.from_numpy(g["draw"])) * 0.18215
+        assert O.max_rel_err(z_s, torch.from_numpy(g["z_sample"])) < STEP_TOL
+
+
+def test_vae_encoder_s4_against_oracle():
+    """Full-width encoder (128..512 channels, 512x512 image, B=1) vs the oracle evaluated in fp32 on the GPU;
+    also the odd image size that takes the im2col route."""
+    from edtr_b200.engine import VaeEncoderEngine
+
+    v = dict(O.S4["vae"])
+    sd = O.make_weights(O.vae_encoder_param_shapes(v), seed=3)
+    ve = VaeEncoderEngine(_dd(v), v["embed_dim"], sd, "cuda")
+    sdg = {k: t.cuda() for k, t in sd.items()}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    for hw in ((512, 512), (256, 384)):   # 384 -> 192 -> 96 -> 48 wide levels: TMA boxes do not fit, im2col route
+        g = torch.Generator().manual_seed(5)
+        image = (torch.rand(1, 3, *hw, generator=g) * 2 - 1).cuda()
+        mo = ve.encode(image, use_graph=False)
+        with torch.no_grad():
+            ref = O.vae_encode_moments(sdg, v, image)
+        mean, ref_mean = mo[:, :4], ref[:, :4]
+        assert O.max_rel_err(mean.cpu(), ref_mean.cpu()) < STEP_TOL, hw

@@ -360,3 +360,28 @@ def test_tiled_vae_decode_two_ranks_gloo():
     # bf16 roundings downstream — compared by PSNR, not bit for bit)
     for _, ps_vs_one_rank, ps_vs_reference in res:
         assert ps_vs_one_rank > 45.0 and ps_vs_reference > 40.0
+
+
+# ----------------------------------------------------------------------------- VAE encoder + q_sample
+def test_vae_encoder_dataflow_and_q_sample_match_reference_fixture():
+    """VaeEncoderEngine on the torch stand-in kernels (folded conv_out . quant_conv, asymmetric-pad stride-2
+    im2col) and the drop-in Diffusion.q_sample vs the fixture recorded from the live reference."""
+    from edtr_b200.diffusion import Diffusion
+    from edtr_b200.engine import VaeEncoderEngine
+    from edtr_b200.nets import DiagonalGaussianDistribution
+
+    g = np.load(os.path.join(GOLD, "golden_vae_encode.npz"))
+    v = O.TINY["vae"]
+    sd = O.make_weights(O.vae_encoder_param_shapes(v), seed=3)
+    ve = VaeEncoderEngine(_dd(v), v["embed_dim"], sd, "cpu", ops=fake_ops)
+    mo = ve.encode(torch.from_numpy(g["image"]), use_graph=False)
+    post = DiagonalGaussianDistribution(mo)
+    z_mode = post.mode() * 0.18215
+    assert O.max_rel_err(z_mode, torch.from_numpy(g["z_mode"])) < 3e-2
+    z_s = (post.mean + post.std * torch.from_numpy(g["draw"])) * 0.18215
+    assert O.max_rel_err(z_s, torch.from_numpy(g["z_sample"])) < 3e-2
+    d = Diffusion(timesteps=1000, beta_schedule="linear", linear_start=0.00085, linear_end=0.0120)
+    t = torch.full((2,), 200, dtype=torch.long)
+    x_T = d.q_sample(torch.from_numpy(g["z_mode"]), t, torch.from_numpy(g["q_noise"]))
+    assert torch.equal(x_T, torch.from_numpy(g["x_T"]))
+    assert np.array_equal(d.betas, O.make_betas(**O.TINY["diffusion"]))

@@ -86,3 +86,18 @@ def test_vae_split_tiles_matches_survey():
     ib, ob = O.vae_split_tiles(256, 256, 64)
     assert len(ib) == 16 and ib[5] == [64, 150, 64, 150] and ob[5] == [600, 1112, 600, 1112]
     assert ob[-1] == [1624, 2048, 1624, 2048]
+
+
+def test_oracle_vae_encode_and_q_sample_match_reference():
+    """ControlLDM.vae_encode (mode and sample) and Diffusion.q_sample of the live reference vs the restatement."""
+    g = np.load(os.path.join(GOLD, "golden_vae_encode.npz"))
+    sd = O.make_weights(O.vae_encoder_param_shapes(O.TINY["vae"]), seed=3)
+    image = torch.from_numpy(g["image"])
+    with torch.no_grad():
+        z_mode = O.vae_encode(sd, O.TINY["vae"], image, 0.18215)
+        z_sample = O.vae_encode(sd, O.TINY["vae"], image, 0.18215, noise=torch.from_numpy(g["draw"]))
+    assert O.max_rel_err(z_mode, torch.from_numpy(g["z_mode"])) < 1e-5
+    assert O.max_rel_err(z_sample, torch.from_numpy(g["z_sample"])) < 1e-5
+    t = torch.full((2,), 200, dtype=torch.long)
+    x_T = O.q_sample(O.make_betas(**O.TINY["diffusion"]), z_mode, t, torch.from_numpy(g["q_noise"]))
+    assert O.max_rel_err(x_T, torch.from_numpy(g["x_T"])) < 1e-5
