@@ -164,6 +164,44 @@ __global__ void tile_blend_kernel(const float* __restrict__ tiles, const int* __
   out[i] = acc;
 }
 
+
+// One level of the wavelet colour fix (utils/common.py:99-147): low = 3x3 binomial blur with dilation `radius` and
+// replicate padding (clamped coordinates) of every plane of a [planes, H, W] fp32 tensor.
+//   mode 0: out = low                                   (style image, levels 0..3)
+//   mode 1: out = low, high (+)= in - low               (content image; `first` level stores instead of adding)
+//   mode 2: out = high + low                            (last style level: content_high + style_low)
+__global__ void wavelet_level_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ high,
+                                     int H, int W, int radius, int mode, int first, size_t total) {
+  PdlScope pdl_scope;
+  const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = static_cast<int>(i % W);
+  const int y = static_cast<int>((i / W) % H);
+  const float* plane = in + (i - static_cast<size_t>(y) * W - x);
+  const int ym = max(y - radius, 0), yp = min(y + radius, H - 1);
+  const int xm = max(x - radius, 0), xp = min(x + radius, W - 1);
+  const float* r0 = plane + static_cast<size_t>(ym) * W;
+  const float* r1 = plane + static_cast<size_t>(y) * W;
+  const float* r2 = plane + static_cast<size_t>(yp) * W;
+  // same tap order as a row-major 3x3 correlation
+  float low = 0.0625f * __ldg(r0 + xm);
+  low = fmaf(0.125f, __ldg(r0 + x), low);
+  low = fmaf(0.0625f, __ldg(r0 + xp), low);
+  low = fmaf(0.125f, __ldg(r1 + xm), low);
+  const float centre = __ldg(r1 + x);
+  low = fmaf(0.25f, centre, low);
+  low = fmaf(0.125f, __ldg(r1 + xp), low);
+  low = fmaf(0.0625f, __ldg(r2 + xm), low);
+  low = fmaf(0.125f, __ldg(r2 + x), low);
+  low = fmaf(0.0625f, __ldg(r2 + xp), low);
+  if (mode == 2) {
+    out[i] = high[i] + low;
+    return;
+  }
+  out[i] = low;
+  if (mode == 1) high[i] = first ? (centre - low) : (high[i] + (centre - low));
+}
+
 static inline unsigned blocks_for(size_t n, int threads) {
   return static_cast<unsigned>((n + threads - 1) / threads);
 }
@@ -271,4 +309,17 @@ extern "C" int edtr_sampler_update(const float* x, const float* eps, const float
   EDTR_LAUNCH(sampler_update_kernel, blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       x, eps, noise, index, sqrt_recip, sqrt_recipm1, coef1, coef2, var, x_prev, pred_x0, n_per_image, total);
   return check_launch("sampler_update_kernel");
+}
+
+extern "C" int edtr_wavelet_level(const float* in, float* out, float* high, int planes, int H, int W, int radius,
+                                  int mode, int first, void* stream) {
+  EDTR_REQUIRE(in && out, "in/out is NULL");
+  EDTR_REQUIRE(in != out, "the blur cannot run in place");
+  EDTR_REQUIRE(planes > 0 && H > 0 && W > 0 && radius > 0, "bad wavelet geometry");
+  EDTR_REQUIRE(mode >= 0 && mode <= 2, "bad mode %d", mode);
+  EDTR_REQUIRE(mode == 0 || high != nullptr, "high is NULL");
+  const size_t total = static_cast<size_t>(planes) * H * W;
+  EDTR_LAUNCH(wavelet_level_kernel, blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), in, out, high,
+              H, W, radius, mode, first, total);
+  return check_launch("wavelet_level_kernel");
 }

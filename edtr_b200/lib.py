@@ -33,7 +33,7 @@ EXPORTED = [
     "edtr_groupnorm_fused_supported", "edtr_groupnorm_fused", "edtr_groupnorm_pool", "edtr_groupnorm_apply_stats",
     "edtr_layernorm_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
     "edtr_nchw_f32_to_nhwc_bf16", "edtr_pointwise_nchw_f32_to_nhwc_bf16", "edtr_nhwc_bf16_to_nchw", "edtr_cast_f32_to_bf16",
-    "edtr_tile_blend", "edtr_timestep_embedding", "edtr_sampler_update",
+    "edtr_tile_blend", "edtr_timestep_embedding", "edtr_sampler_update", "edtr_wavelet_level",
 ]
 
 
@@ -124,6 +124,8 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_groupnorm_fused_supported.argtypes = [ci, ci, ci, ci]
     lib.edtr_groupnorm_fused.restype = ci
     lib.edtr_groupnorm_fused.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, vp, vp, c_float, ci, vp]
+    lib.edtr_wavelet_level.restype = ci
+    lib.edtr_wavelet_level.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
     lib.edtr_groupnorm_pool.restype = ci
     lib.edtr_groupnorm_pool.argtypes = [vp, ci, ci, ci, ci, c_float, vp, vp]
     lib.edtr_groupnorm_apply_stats.restype = ci

@@ -501,3 +501,34 @@ def sampler_update(x, eps, noise, index, tables, want_pred_x0: bool = True, x_pr
                                      pred.data_ptr() if pred is not None else None, B, n, _stream()),
                "edtr_sampler_update")
     return x_prev, pred
+
+
+def wavelet_reconstruction(content: torch.Tensor, style: torch.Tensor, levels: int = 5) -> torch.Tensor:
+    """utils/common.py:136-147: high frequencies of `content` + low frequencies of `style` (both [B, C, H, W] fp32),
+    five dilated binomial blurs per image, the final sum fused into the last style level."""
+    _require_cuda(content, style)
+    if content.shape != style.shape or content.dim() != 4:
+        raise ValueError(f"content / style must be equal-shaped [B, C, H, W], got {tuple(content.shape)} {tuple(style.shape)}")
+    if content.dtype != torch.float32 or style.dtype != torch.float32:
+        raise ValueError("the colour fix runs in fp32")
+    content, style = content.contiguous(), style.contiguous()
+    B, C, H, W = content.shape
+    L = _lib.device_lib()
+    st = _stream()
+    high = torch.empty_like(content)
+    ping = [torch.empty_like(content), torch.empty_like(content)]
+    cur = content
+    for i in range(levels):      # content: accumulate image - low
+        dst = ping[i % 2]
+        _lib.check(L.edtr_wavelet_level(cur.data_ptr(), dst.data_ptr(), high.data_ptr(), B * C, H, W, 2 ** i, 1,
+                                        1 if i == 0 else 0, st), "edtr_wavelet_level")
+        cur = dst
+    cur = style
+    out = torch.empty_like(content)
+    for i in range(levels):      # style: keep the low pass; the last level adds the content's high pass
+        last = i == levels - 1
+        dst = out if last else ping[i % 2]
+        _lib.check(L.edtr_wavelet_level(cur.data_ptr(), dst.data_ptr(), high.data_ptr(), B * C, H, W, 2 ** i,
+                                        2 if last else 0, 0, st), "edtr_wavelet_level")
+        cur = dst
+    return out

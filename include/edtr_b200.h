@@ -225,6 +225,13 @@ int edtr_sampler_update(const float* x, const float* eps, const float* noise,
                         const float* coef1, const float* coef2, const float* var, float* x_prev,
                         float* pred_x0, int B, int n_per_image, void* stream);
 
+/* One level of the wavelet colour fix applied after the decode (utils/common.py:99-147, wavelet_blur /
+ * wavelet_decomposition / wavelet_reconstruction): 3x3 binomial blur with dilation `radius`, replicate padding, on
+ * every plane of a contiguous fp32 [planes, H, W] tensor.  mode 0: out = low; mode 1: out = low and
+ * high (+)= in - low (`first` != 0 stores); mode 2: out = high + low.  `in` and `out` must not alias. */
+int edtr_wavelet_level(const float* in, float* out, float* high, int planes, int H, int W, int radius, int mode,
+                       int first, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -734,6 +734,32 @@ def restore(w, cfg: dict, x_T: Tensor, cond, noise):
     return vae_decode(w["vae"], cfg["vae"], z, cfg["latent_scale_factor"]), xs
 
 
+# ----------------------------------------------------------------- wavelet colour fix
+def wavelet_blur(image: Tensor, radius: int) -> Tensor:
+    """utils/common.py:99-118: depthwise 3x3 binomial kernel, dilation = radius, replicate padding."""
+    c = image.shape[1]
+    k = torch.tensor([[0.0625, 0.125, 0.0625], [0.125, 0.25, 0.125], [0.0625, 0.125, 0.0625]], dtype=image.dtype)
+    k = k[None, None].repeat(c, 1, 1, 1)
+    image = F.pad(image, (radius, radius, radius, radius), mode="replicate")
+    return F.conv2d(image, k, groups=c, dilation=radius)
+
+
+def wavelet_decomposition(image: Tensor, levels: int = 5):
+    """utils/common.py:121-133."""
+    high = torch.zeros_like(image)
+    low = image
+    for i in range(levels):
+        low = wavelet_blur(image, 2 ** i)
+        high = high + (image - low)
+        image = low
+    return high, low
+
+
+def wavelet_reconstruction(content: Tensor, style: Tensor) -> Tensor:
+    """utils/common.py:136-147."""
+    return wavelet_decomposition(content)[0] + wavelet_decomposition(style)[1]
+
+
 # -------------------------------------------------------------------------- metrics
 def max_rel_err(new: Tensor, ref: Tensor) -> float:
     """max|new - ref| / max|ref|."""

@@ -13,6 +13,7 @@ enumeration), then the reference's own public API is executed on CPU in fp32:
 four per-step noise draws are the seeded tensors the oracle receives explicitly.
 
 Outputs:  golden_tiny.npz  (TINY config, B=2, 16x16 latent; everything in fp32)
+          golden_wavelet.npz    (utils.common.wavelet_reconstruction on two random [2,3,40,56] images)
           golden_vae_encode.npz (TINY VAE encoder, B=2, 64x64 image: vae_encode mode / sample, q_sample at t=200)
           golden_vae_tiled.npz  (TINY_VAE8 decoder, B=2, 40x48 latent, vae_decode(tiled=True, tile_size=16))
           golden_s4.npz    (s4 config, B=1, 64x64 latent; --full; image stored as fp16)
@@ -216,6 +217,12 @@ def main():
     z, img, img_u = run_reference_tiled_vae(O.TINY_VAE8, batch=2, latent_h=40, latent_w=48, tile_size=16)
     np.savez_compressed(os.path.join(HERE, "golden_vae_tiled.npz"), z=z.numpy(), img=img.numpy().astype(np.float32),
                         tile_size=np.int64(16))
+    _stub_missing_packages()
+    from utils.common import wavelet_reconstruction as wr_ref
+    gg = torch.Generator().manual_seed(31)
+    content, style = torch.rand(2, 3, 40, 56, generator=gg), torch.rand(2, 3, 40, 56, generator=gg)
+    np.savez_compressed(os.path.join(HERE, "golden_wavelet.npz"), content=content.numpy(), style=style.numpy(),
+                        out=wr_ref(content, style).numpy())
     image, z_mode, draw, z_sample, n2, x_T = run_reference_vae_encode(O.TINY["vae"], batch=2, hw=64)
     np.savez_compressed(os.path.join(HERE, "golden_vae_encode.npz"), image=image.numpy(), z_mode=z_mode.numpy(),
                         draw=draw.numpy(), z_sample=z_sample.numpy(), q_noise=n2.numpy(), x_T=x_T.numpy())

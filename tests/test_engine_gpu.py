@@ -222,3 +222,73 @@ def test_vae_encoder_s4_against_oracle():
             ref = O.vae_encode_moments(sdg, v, image)
         mean, ref_mean = mo[:, :4], ref[:, :4]
         assert O.max_rel_err(mean.cpu(), ref_mean.cpu()) < STEP_TOL, hw
+
+
+# ----------------------------------------------------------------------------- whole restore pipeline, drop-in API
+def test_dropin_pipeline_encode_sample_decode_colorfix():
+    """The EDTR restore of main/det/test_edtr.py:121-135 through the drop-in classes only — vae_encode(sample=False)
+    -> Diffusion.q_sample(t=200) -> SpacedSampler.manual_sample_with_timesteps -> vae_decode ->
+    wavelet_reconstruction — against the oracle on the same weights, inputs and noise."""
+    from edtr_b200.cldm import ControlLDM
+    from edtr_b200.colorfix import wavelet_reconstruction
+    from edtr_b200.diffusion import Diffusion
+    from edtr_b200.sampler import SpacedSampler
+
+    cfg = O.TINY
+
+    def kw(c, controlnet):
+        d = dict(image_size=32, in_channels=c["in_channels"], model_channels=c["model_channels"],
+                 attention_resolutions=list(c["attention_resolutions"]), num_res_blocks=c["num_res_blocks"],
+                 channel_mult=list(c["channel_mult"]), num_head_channels=c["num_head_channels"],
+                 use_spatial_transformer=True, use_linear_in_transformer=True, transformer_depth=1,
+                 context_dim=c["context_dim"], legacy=False, use_checkpoint=True)
+        d["hint_channels" if controlnet else "out_channels"] = c["hint_channels" if controlnet else "out_channels"]
+        return d
+
+    v = cfg["vae"]
+    model = ControlLDM(kw(cfg["unet"], False), dict(ddconfig=dict(_dd(v), double_z=True), embed_dim=v["embed_dim"]),
+                       None, kw(cfg["controlnet"], True), cfg["latent_scale_factor"])
+    w = O.make_cldm_weights(cfg, seed=0)
+    vae_sd = dict(w["vae"])
+    vae_sd.update(O.make_weights(O.vae_encoder_param_shapes(v), seed=3))
+    model.unet.load_state_dict(w["unet"], strict=True)
+    model.controlnet.load_state_dict(w["controlnet"], strict=True)
+    model.vae.load_state_dict(vae_sd, strict=True)
+    model = model.cuda().eval()
+
+    B = 2
+    g = torch.Generator().manual_seed(9)
+    pre_res = torch.rand(B, 3, 32, 32, generator=g)              # stands for the SwinIR output in [0, 1]
+    c_txt = torch.randn(B, 77, cfg["unet"]["context_dim"], generator=g)
+    q_noise = torch.randn(B, 4, 16, 16, generator=g)
+    step_noise = [torch.randn(B, 4, 16, 16, generator=g) for _ in range(4)]
+    betas = O.make_betas(**cfg["diffusion"])
+
+    # oracle (CPU fp32)
+    with torch.no_grad():
+        z0 = O.vae_encode(vae_sd, v, pre_res * 2 - 1, cfg["latent_scale_factor"])
+        x_T = O.q_sample(betas, z0, torch.full((B,), 200, dtype=torch.long), q_noise)
+        cond = dict(c_txt=c_txt, c_img=z0)
+        z_ref, xs_ref, _ = O.sample(w, cfg, x_T, cond, step_noise)
+        dec_ref = O.vae_decode(w["vae"], v, z_ref, cfg["latent_scale_factor"])
+        res_ref = O.wavelet_reconstruction((dec_ref + 1) / 2, pre_res)
+
+    # drop-in path (CUDA)
+    dev = torch.device("cuda")
+    diffusion = Diffusion(timesteps=1000, beta_schedule="linear", linear_start=0.00085, linear_end=0.0120).to(dev)
+    sampler = SpacedSampler(diffusion.betas)
+    z = model.vae_encode(pre_res.to(dev) * 2 - 1, sample=False)
+    assert O.max_rel_err(z.cpu(), z0) < STEP_TOL
+    x = diffusion.q_sample(x_start=z, t=torch.full((B,), 200, dtype=torch.long, device=dev), noise=q_noise.to(dev))
+    draws = [n.to(dev) for n in step_noise]
+    real = torch.randn_like
+    torch.randn_like = lambda t, *a, **k: draws.pop(0)           # the sampler's per-step draw (utils/sampler.py:199)
+    try:
+        zz = sampler.manual_sample_with_timesteps(model, dev, x, 4, list(cfg["used_timesteps"]), B,
+                                                  dict(c_txt=c_txt.to(dev), c_img=z), None, 1.0, progress=False)
+    finally:
+        torch.randn_like = real
+    assert O.max_rel_err(zz.cpu(), z_ref) < 3e-2                 # latent after encode (bf16) + 4 steps
+    dec = model.vae_decode(zz)
+    res = wavelet_reconstruction((dec + 1) / 2, pre_res.to(dev))
+    assert O.psnr(res.cpu(), res_ref) >= PSNR_MIN

@@ -366,3 +366,20 @@ def test_validation_errors(ops):
         ops.gemm(rnd(128, 64).float(), rnd(64, 64))
     with pytest.raises(RuntimeError):
         ops.gemm(torch.zeros(128, 64, dtype=BF), torch.zeros(64, 64, dtype=BF))
+
+
+def test_wavelet_reconstruction_against_reference_fixture(ops):
+    """The colour fix after the decode (utils/common.py:136-147) vs the fixture recorded from the live reference,
+    and vs the same arithmetic in torch at 512x512."""
+    import os
+
+    import numpy as np
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_wavelet.npz"))
+    out = ops.wavelet_reconstruction(torch.from_numpy(g["content"]).cuda(), torch.from_numpy(g["style"]).cuda())
+    assert relerr(out.cpu(), torch.from_numpy(g["out"])) < 1e-5
+    from oracle import cldm_oracle as O
+
+    gen = torch.Generator().manual_seed(3)
+    c, s = torch.rand(2, 3, 512, 512, generator=gen), torch.rand(2, 3, 512, 512, generator=gen)
+    assert relerr(ops.wavelet_reconstruction(c.cuda(), s.cuda()).cpu(), O.wavelet_reconstruction(c, s)) < 1e-5

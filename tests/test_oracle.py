@@ -101,3 +101,9 @@ def test_oracle_vae_encode_and_q_sample_match_reference():
     t = torch.full((2,), 200, dtype=torch.long)
     x_T = O.q_sample(O.make_betas(**O.TINY["diffusion"]), z_mode, t, torch.from_numpy(g["q_noise"]))
     assert O.max_rel_err(x_T, torch.from_numpy(g["x_T"])) < 1e-5
+
+
+def test_oracle_wavelet_matches_reference():
+    g = np.load(os.path.join(GOLD, "golden_wavelet.npz"))
+    out = O.wavelet_reconstruction(torch.from_numpy(g["content"]), torch.from_numpy(g["style"]))
+    assert O.max_rel_err(out, torch.from_numpy(g["out"])) < 1e-6
