@@ -15,7 +15,7 @@
 
 namespace edtr {
 
-constexpr int kAttThreads = 192;
+constexpr int kAttThreads = 320;   // TMA warp, MMA warp, eight softmax warps
 constexpr int kQT = 128;   // query rows per CTA
 constexpr int kKT = 64;    // keys per tile
 constexpr int kD = 64;     // head dim
@@ -32,6 +32,9 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Measured on B200 (L = 4096, 5 heads, B = 8): one or two threads per row, generic or STS stores all land at
+// 0.31-0.32 ms (~550 TFLOP/s); moving a share of the exp2 to an FMA-pipe polynomial (FA4-style) makes the loop
+// slower in proportion (25 % -> 0.40 ms, 50 % -> 0.48 ms), so the MUFU unit (53 % busy in ncu) is not the limiter.
 struct AttParams {
   void* O;
   int ldo;
@@ -53,10 +56,12 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* kv_full = bars + 1;                    // [stages]
   uint64_t* kv_empty = kv_full + kKvStages;        // [stages]
   uint64_t* s_full = kv_empty + kKvStages;         // [2]
-  uint64_t* p_full = s_full + 2;                   // [2] 128 arrivals per tile; one barrier per P buffer, so a warp
+  uint64_t* p_full = s_full + 2;                   // [2] 256 arrivals per tile; one barrier per P buffer, so a warp
                                                    //     that runs one tile ahead cannot complete the wrong phase
   uint64_t* pv_done = p_full + 2;                  // [2] PV of the tile that used P buffer b has retired
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
+  __shared__ float mx_ex[2][2][kQT];   // [tile parity][column half][row]: tile maxima of the two halves of a row
+  __shared__ float l_ex[2][kQT];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -77,7 +82,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&pv_done[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], 256);
     }
     fence_barrier_init();
   }
@@ -155,42 +160,52 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       if (++st == kKvStages) st = 0;
     }
   } else {
-    const int lg = warp & 3;
-    const int r = lg * 32 + lane;  // query row inside the tile == TMEM lane
+    // Softmax: TWO threads per query row (warps w and w+4 share a TMEM lane quadrant and split the 64 key columns
+    // of a tile 32 / 32), i.e. eight softmax warps per CTA and four per SM sub-partition with two CTAs per SM:
+    // enough independent work to keep the exp2 unit busy while a warp waits on TMEM, a barrier or the fence.  The two
+    // halves of a row exchange their tile maximum through shared memory + a 64-thread named barrier; the row sums
+    // stay private until the end.
+    const int sw = warp - 2;               // 0..7
+    const int half = sw >> 2;              // which 32 of the 64 key columns
+    const int lg = warp & 3;               // TMEM lane quadrant this warp may access
+    const int r = lg * 32 + lane;          // query row inside the tile == TMEM lane
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    const int pair_bar = 1 + lg;           // named barrier of the two warps that share rows [lg*32, lg*32+32)
+    const uint32_t sP_base = smem_u32(sP);
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < nkv; ++j) {
       const int b = j & 1;
       mbar_wait(&s_full[b], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t sr[2][32];
-      tmem_ld32(trow + b * kKT, sr[0]);
-      tmem_ld32(trow + b * kKT + 32, sr[1]);
+      uint32_t sr[32];
+      tmem_ld32(trow + b * kKT + half * 32, sr);
       tmem_ld_wait();
-      const int valid = p.Lk - j * kKT;  // >= 1
-      float mx = -INFINITY;
-      if (valid >= kKT) {
-        // four independent chains instead of one 64-deep dependent chain
+      const int valid = p.Lk - j * kKT - half * 32;  // key columns of this half that exist (may be <= 0)
+      float mx;
+      if (valid >= 32) {
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          m0 = fmaxf(m0, __uint_as_float(sr[0][i]));
-          m1 = fmaxf(m1, __uint_as_float(sr[0][i + 1]));
-          m2 = fmaxf(m2, __uint_as_float(sr[1][i]));
-          m3 = fmaxf(m3, __uint_as_float(sr[1][i + 1]));
+        for (int i = 0; i < 32; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(sr[i]));
+          m1 = fmaxf(m1, __uint_as_float(sr[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(sr[i + 2]));
+          m3 = fmaxf(m3, __uint_as_float(sr[i + 3]));
         }
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       } else {
+        mx = -INFINITY;
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = __uint_as_float(sr[h][i]);
-            if (h * 32 + i >= valid) v = -INFINITY;
-            sr[h][i] = __float_as_uint(v);
-            mx = fmaxf(mx, v);
-          }
+        for (int i = 0; i < 32; ++i) {
+          float v = __uint_as_float(sr[i]);
+          if (i >= valid) v = -INFINITY;
+          sr[i] = __float_as_uint(v);
+          mx = fmaxf(mx, v);
+        }
       }
+      // tile maximum of the whole row: exchange with the other half (double-buffered by tile parity)
+      mx_ex[b][half][r] = mx;
+      named_bar_sync(pair_bar, 64);
+      mx = fmaxf(mx, mx_ex[b][half ^ 1][r]);
       if (j == 0) {
         m_used = mx;
       } else {
@@ -202,31 +217,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           const float f = need ? exp2f((m_used - mx) * p.scale_log2) : 1.f;
           if (need) m_used = mx;
           l *= f;
+          uint32_t o[32];
+          tmem_ld32(trow + 128 + half * 32, o);
+          tmem_ld_wait();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t o[32];
-            tmem_ld32(trow + 128 + h * 32, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st32(trow + 128 + h * 32, o);
-          }
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+          tmem_st32(trow + 128 + half * 32, o);
           tmem_st_wait();
         }
       }
       // P buffer b was last read by the PV MMA of tile j-2
       if (j >= 2) mbar_wait(&pv_done[b], ((j - 2) >> 1) & 1);
       const float mb = m_used * p.scale_log2;
-      uint8_t* prow = sP + b * (kQT * kKT * 2) + r * 128;
+      const uint32_t prow = sP_base + b * (kQT * kKT * 2) + r * 128;   // shared-window address: plain STS
       float sum = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {  // 8 chunks of 8 keys = 16 B
+      for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 keys = 16 B
         float pv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int idx = c * 8 + i;
-          pv[i] = fast_exp2(fmaf(__uint_as_float(sr[idx >> 5][idx & 31]), p.scale_log2, -mb));
-        }
+        for (int i = 0; i < 8; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(sr[c * 8 + i]), p.scale_log2, -mb));
         sum += (pv[0] + pv[1]) + (pv[2] + pv[3]);
         sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
         uint4 u;
@@ -234,25 +243,28 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         u.y = pack_bf16(pv[2], pv[3]);
         u.z = pack_bf16(pv[4], pv[5]);
         u.w = pack_bf16(pv[6], pv[7]);
-        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = u;
+        st_shared_v4(prow + (((half * 4 + c) ^ (r & 7)) << 4), u);
       }
       l += sum + sum1;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[b]);
     }
+    // row sum of both halves
+    l_ex[half][r] = l;
+    named_bar_sync(pair_bar, 64);
+    l += l_ex[half ^ 1][r];
     // last PV retired -> O complete
     mbar_wait(&pv_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
     tc_fence_after();
-    uint32_t o0[32], o1[32];
-    tmem_ld32(trow + 128, o0);
-    tmem_ld32(trow + 128 + 32, o1);
+    uint32_t o0[32];
+    tmem_ld32(trow + 128 + half * 32, o0);
     tmem_ld_wait();
     const int q = q0 + r;
     if (q < p.Lq) {
       const float inv = 1.f / l;
       __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.O) +
-                          (static_cast<size_t>(img) * p.Lq + q) * p.ldo + head * kD;
+                          (static_cast<size_t>(img) * p.Lq + q) * p.ldo + head * kD + half * 32;
       uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -262,15 +274,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         u.z = pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv);
         u.w = pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv);
         o4[c] = u;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(o1[8 * c + 0]) * inv, __uint_as_float(o1[8 * c + 1]) * inv);
-        u.y = pack_bf16(__uint_as_float(o1[8 * c + 2]) * inv, __uint_as_float(o1[8 * c + 3]) * inv);
-        u.z = pack_bf16(__uint_as_float(o1[8 * c + 4]) * inv, __uint_as_float(o1[8 * c + 5]) * inv);
-        u.w = pack_bf16(__uint_as_float(o1[8 * c + 6]) * inv, __uint_as_float(o1[8 * c + 7]) * inv);
-        o4[4 + c] = u;
       }
     }
     tc_fence_before();

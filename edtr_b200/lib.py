@@ -75,7 +75,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile the CUDA sources for sm_100a into ``libedtr_b200.so`` (in-tree)."""
     if not force and not _stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC_DIR, s) for s in SOURCES]
+    extra = os.environ.get("EDTR_NVCC_EXTRA", "").split()   # developer experiments (-DNAME=value)
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB_PATH] + [os.path.join(CSRC_DIR, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
