@@ -18,10 +18,15 @@ void set_error(const char* fmt, ...) {
 }
 
 bool pdl_enabled() {
-  // Measured on B200 (profiles/r01c): inside a CUDA graph the launch gaps are already ~0 and the programmatic
-  // edges cost ~1.5 us per kernel, so PDL is opt-in (EDTR_PDL=1).
-  const char* e = getenv("EDTR_PDL");
-  return e != nullptr && e[0] == '1';
+  // Programmatic dependent launch, with LATE triggers (see ptx.cuh / gemm2.cu).  Measured on B200 inside the
+  // CUDA graphs: triggers at kernel entry cost ~3 % (waiting dependents take registers / warp slots a multi-wave
+  // predecessor still needs), late triggers gain ~1.3 % on the 4-step sample; all GPU tests pass either way.
+  // EDTR_PDL=0 turns it off.
+  static const bool on = [] {
+    const char* e = getenv("EDTR_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 int check_launch(const char* what) {

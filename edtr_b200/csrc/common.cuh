@@ -23,7 +23,7 @@ int check_launch(const char* what);
 // Programmatic dependent launch: every kernel is launched with the stream-serialization attribute so its
 // prologue (barrier init, TMEM allocation, descriptor prefetch, index math) overlaps the tail of the previous
 // kernel; on the device every kernel calls pdl_launch_dependents() first and pdl_wait() before it touches
-// global memory.  Opt-in with EDTR_PDL=1 (without the attribute the device calls are no-ops).
+// global memory.  On by default, EDTR_PDL=0 disables it (without the attribute the device calls are no-ops).
 bool pdl_enabled();
 
 template <typename... KArgs, typename... Args>
