@@ -323,6 +323,12 @@ def run_ours(args):
     ms_fwd, _, _ = timed(lambda: eng.forward(x_T, t200, c_img, c_txt), 5, 3)
     unet_step_ms = ms_fwd / 5
 
+    # the steps either side of the path, timed for information: VAE encode and wavelet colour fix
+    from edtr_b200.colorfix import wavelet_reconstruction
+    img_dev = torch.rand(B, 3, 512, 512, device=dev)
+    ms_enc, _, _ = timed(lambda: model.vae_encode(img_dev * 2 - 1, sample=False), 5, 3)
+    ms_fix, _, _ = timed(lambda: wavelet_reconstruction(img_dev, img_dev), 5, 3)
+
     # dominant kernel family, measured live: one eager (non-graph) restore with every tensor-core launch bracketed
     pk = peaks()
     with TensorCoreTimer(ops) as tc:
@@ -333,10 +339,19 @@ def run_ours(args):
     gemm_ms = tot["gemm"][1] + tot["conv3x3"][1]
     gemm_n = tot["gemm"][0] + tot["conv3x3"][0]
     achieved = GF_GEMM_PER_IMAGE * B / gemm_ms  # GF / ms = TFLOP/s
+    # DRAM bytes per launch of the dominant kernel, from the committed ncu launch list of this same command
+    # (profiles/gemm2_traffic.json, written by scripts/summarize_launches.py); null when no capture is committed
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "gemm2_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath))["dram_bytes_per_launch"]
+        except (OSError, ValueError, KeyError):
+            traffic = None
     roofline = {
         "bound": "tensor", "kernel": "edtr::gemm2_kernel (CTA-pair tcgen05 implicit-GEMM: all conv3x3 / 1x1 / Linear launches)",
         "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-        "traffic": None, "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
+        "traffic": traffic, "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
         "launches_per_step": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
         "algorithmic_gflop_per_step": GF_GEMM_PER_IMAGE * B,
         "attention": {"launches_per_step": tot["attention"][0], "ms_per_step": tot["attention"][1],
@@ -365,6 +380,8 @@ def run_ours(args):
         if cpu is not None:
             line["cpu_baseline"] = cpu
         line["config"]["unet_step_ms"] = unet_step_ms
+        line["config"]["vae_encode_ms"] = ms_enc / 5
+        line["config"]["colorfix_ms"] = ms_fix / 5
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

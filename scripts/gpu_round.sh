@@ -8,9 +8,10 @@ echo "== gpu tests exit $?"; tail -n 30 gpurun_out/gpu_tests.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 echo "== bench exit $?"; cat gpurun_out/bench.json; tail -n 5 gpurun_out/bench.err
 if [ "${SKIP_NCU:-0}" != "1" ]; then
-EDTR_NCU=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+EDTR_NCU=1 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 echo "== ncu launches exit $?"; wc -l gpurun_out/launches.csv
+python scripts/summarize_launches.py gpurun_out/launches.csv gpurun_out/gemm2_traffic.json > gpurun_out/launches_summary.txt; head -n 12 gpurun_out/launches_summary.txt
 EDTR_NCU=1 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
     -k regex:gemm2_kernel -s 300 -c 3 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 echo "== ncu full exit $?"; ls -la gpurun_out/*.ncu-rep
