@@ -143,8 +143,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "4-step ControlLDM (s4) restore + VAE decode of 512x512 images, batch 1 per step, "
-                               "random-init weights, fp32 on host CPU", "steps_requested": args.steps},
+        # the same workload as the CUDA arm's line; each reference step is a bounded sample of it (one image)
+        "config": dict(workload_config(args.batch, 1), sample="one 512x512 image per step (B=1), fp32 on the host CPU",
+                       steps_requested=args.steps),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{len(times)} x (1 image: 4 ControlLDM steps + VAE decode), oracle/cldm_oracle.py "
                                    f"with torch CPU ops on {cores} threads"},
@@ -166,6 +167,12 @@ def cpu_baseline_sample():
     return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"1 image (4 ControlLDM steps + VAE decode, fp32) in {dt:.1f} s, oracle/cldm_oracle.py on "
                       f"{cores} torch CPU threads, no warm-up"}
+
+
+def workload_config(B, world):
+    return {"workload": f"4-step ControlLDM (SD-2.1 UNet + ControlNet, s4) + VAE decode, batch {B} per GPU, "
+                        f"512x512 (64x64x4 latent), random-init weights", "batch_per_gpu": B,
+            "global_batch": B * world, "parallelism": f"image-parallel x{world}"}
 
 
 # ------------------------------------------------------------------------------------------- our arm
@@ -366,11 +373,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"4-step ControlLDM (SD-2.1 UNet + ControlNet, s4) + VAE decode, batch {B} per GPU, "
-                                   f"512x512 (64x64x4 latent), random-init weights", "batch_per_gpu": B,
-                       "global_batch": B * world, "parallelism": f"image-parallel x{world}",
-                       "l2": "per-step working set (2.5 GB weights + activations) exceeds the 126 MB L2; no flush needed",
-                       "unet_step_ms": None},
+            "config": dict(workload_config(B, world),
+                           l2="per-step working set (2.5 GB weights + activations) exceeds the 126 MB L2; no flush needed",
+                           unet_step_ms=None),
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(c_img_h.numel() * 4 + c_txt_h.numel() * 4 + x_T_h.numel() * 4),
                     "d2h_bytes_per_step": int(img_h.numel() * 4),
