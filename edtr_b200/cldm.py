@@ -136,11 +136,9 @@ class ControlLDM(nn.Module):
 
     @torch.no_grad()
     def vae_encode(self, image: torch.Tensor, sample: bool = True, tiled: bool = False, tile_size: int = -1):
-        """model/cldm.py:107-134 (untiled): posterior sample or mode, times the latent scale factor."""
-        if tiled:
-            raise NotImplementedError("tiled VAE *encode* (VAEHook with the encoder, pad 32) is not built yet; the "
-                                      "tiled decode is (vae_decode(tiled=True))")
-        posterior = self.vae.encode(image)
+        """model/cldm.py:107-134: posterior sample or mode, times the latent scale factor; tiled=True is the
+        reference's VAEHook encode (pad 32, pooled GroupNorm statistics)."""
+        posterior = self.vae.encode_tiled(image, tile_size) if tiled else self.vae.encode(image)
         z = posterior.sample() if sample else posterior.mode()
         return z * self.scale_factor
 

@@ -760,6 +760,77 @@ class _VaeBlocks:
         return ops.gemm(col, w[wk + "weight"], bias=w[wk + "bias"], **kw)
 
 
+    def _run_tiles(self, ws: Workspace, progs: Dict[int, object], wgt: Dict[int, float], B: int, n_sync: int,
+                   world: int, reduce_fn) -> Dict[int, torch.Tensor]:
+        """The tile loop of VAEHook.vae_tile_forward (utils/tilevae/tilevae.py:496-571) without its CPU<->GPU
+        shuffling: `progs` are this rank's tile programs (generators yielding (tensor, norm-key, silu) at every
+        GroupNorm), `wgt` their pixel weights over ALL tiles of all ranks.  Per synchronisation point the weighted
+        per-tile means / variances are accumulated on the device (edtr_groupnorm_pool), summed over ranks by
+        `reduce_fn`, and applied to every tile (edtr_groupnorm_apply_stats).  All ranks walk `n_sync` points."""
+        ops, w = self.ops, self.w
+        pending = {i: next(g) for i, g in progs.items()}
+        done: Dict[int, torch.Tensor] = {}
+        acc = torch.zeros((B, 32, 2), dtype=F32, device=self.device)
+        for _ in range(n_sync):
+            acc.zero_()
+            for i in progs:
+                x = pending[i][0]
+                ops.groupnorm_pool(x, 32, wgt[i], acc, stats=ws.gn_scratch(ops, x))
+            if world > 1:
+                reduce_fn(acc)
+            for i in progs:
+                x, key, silu = pending[i]
+                y = ops.groupnorm_apply_stats(x, acc, w[key + "weight"], w[key + "bias"], 32, 1e-6, silu)
+                try:
+                    pending[i] = progs[i].send(y)
+                except StopIteration as fin:
+                    done[i] = fin.value
+        if len(done) != len(progs):
+            raise RuntimeError("internal: tile programs did not finish after the last GroupNorm")
+        return done
+
+    def _tile_res(self, ws: Workspace, p: str, x: torch.Tensor):
+        """ResnetBlock as a tile-program fragment (yields at norm1 / norm2)."""
+        ops, w = self.ops, self.w
+        B, H, W, _ = x.shape
+        cout = w[p + "conv1.bias"].shape[0]
+        new = lambda shape: torch.empty(shape, dtype=BF16, device=x.device)
+        y = yield (x, p + "norm1.", True)
+        h = self._conv_any(ws, y, p + "conv1.", out=new((B, H, W, cout)))
+        y2 = yield (h, p + "norm2.", True)
+        if (p + "nin_shortcut.weight") in w:
+            skip = ops.gemm(x, w[p + "nin_shortcut.weight"], bias=w[p + "nin_shortcut.bias"], out=new((B, H, W, cout)))
+        else:
+            skip = x
+        return self._conv_any(ws, y2, p + "conv2.", residual=skip, out=new((B, H, W, cout)))
+
+    def _tile_attn(self, ws: Workspace, p: str, x: torch.Tensor):
+        """Tile-local single-head attention (utils/tilevae/attn.py:95-124) as a tile-program fragment; tokens are
+        padded to a multiple of 64 (zero probability columns, ignored rows) so that L = h*w may be anything."""
+        ops, w = self.ops, self.w
+        B, H, W, C = x.shape
+        L = H * W
+        Lp = _ceil(L, 64)
+        y = yield (x, p + "norm.", False)
+        o = torch.empty((B, L, C), dtype=BF16, device=x.device)
+        ypad = ws.get("ta_y", (Lp, C))
+        s = ws.get("ta_s", (Lp, Lp), F32)
+        pm = ws.get("ta_p", (Lp, Lp))
+        ypad[L:].zero_()        # padding tokens: zero features, zero probability columns
+        pm[:, L:].zero_()
+        for b in range(B):
+            ypad[:L].copy_(y[b].reshape(L, C))
+            qk = ops.gemm(ypad, w[p + "qk.weight"], bias=w[p + "qk.bias"], out=ws.get("ta_qk", (Lp, 2 * C)))
+            vt = ops.gemm(ypad, w[p + "v.weight"], bias=w[p + "v.bias"], out_mode=ops.OUT_NCHW_BF16, hw=Lp,
+                          out=ws.get("ta_vt", (1, C, Lp)))
+            ops.gemm(qk[:, :C], qk[:, C:], out_mode=ops.OUT_F32, out=s)
+            ops.softmax_rows(s[:, :L], float(C) ** -0.5, out=pm[:, :L])
+            ob = ops.gemm(pm, vt[0], out=ws.get("ta_o", (Lp, C)))
+            o[b].copy_(ob[:L])
+        return ops.gemm(o, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x.reshape(B, L, C),
+                        out=torch.empty((B, L, C), dtype=BF16, device=x.device)).view(B, H, W, C)
+
+
 class VaeDecoderEngine(_VaeBlocks):
     """ControlLDM.vae_decode (untiled): z / scale -> post_quant_conv -> Decoder.forward
     (model/cldm.py:136-156, model/vae.py:731-734, :527-560)."""
@@ -849,56 +920,17 @@ class VaeDecoderEngine(_VaeBlocks):
         """Decoder.forward of ONE tile as the task queue of build_task_queue (utils/tilevae/tilevae.py:72-165):
         a generator that yields (tensor, norm-key, silu) at every `pre_norm` task, is resumed with the tensor
         normalised by the pooled statistics, and returns the decoded tile [B, out_ch, 8h, 8w] fp32."""
-        ops, w = self.ops, self.w
+        ops = self.ops
         dev = x.device
         new = lambda shape: torch.empty(shape, dtype=BF16, device=dev)
-
-        def res(p, x):
-            B, H, W, cin = x.shape
-            cout = w[p + "conv1.bias"].shape[0]
-            y = yield (x, p + "norm1.", True)
-            h = self._conv_any(ws, y, p + "conv1.", out=new((B, H, W, cout)))
-            y2 = yield (h, p + "norm2.", True)
-            if (p + "nin_shortcut.weight") in w:
-                skip = ops.gemm(x, w[p + "nin_shortcut.weight"], bias=w[p + "nin_shortcut.bias"],
-                                out=new((B, H, W, cout)))
-            else:
-                skip = x
-            return self._conv_any(ws, y2, p + "conv2.", residual=skip, out=new((B, H, W, cout)))
-
-        def attn(p, x):
-            # tile-local single-head attention (utils/tilevae/attn.py:95-124); tokens padded to a multiple of 64
-            # (zero probability columns, ignored rows) so that L = h*w may be anything
-            B, H, W, C = x.shape
-            L = H * W
-            Lp = _ceil(L, 64)
-            y = yield (x, p + "norm.", False)
-            o = new((B, L, C))
-            ypad = ws.get("ta_y", (Lp, C))
-            s = ws.get("ta_s", (Lp, Lp), F32)
-            pm = ws.get("ta_p", (Lp, Lp))
-            ypad[L:].zero_()        # padding tokens: zero features, zero probability columns
-            pm[:, L:].zero_()
-            for b in range(B):
-                ypad[:L].copy_(y[b].reshape(L, C))
-                qk = ops.gemm(ypad, w[p + "qk.weight"], bias=w[p + "qk.bias"], out=ws.get("ta_qk", (Lp, 2 * C)))
-                vt = ops.gemm(ypad, w[p + "v.weight"], bias=w[p + "v.bias"], out_mode=ops.OUT_NCHW_BF16, hw=Lp,
-                              out=ws.get("ta_vt", (1, C, Lp)))
-                ops.gemm(qk[:, :C], qk[:, C:], out_mode=ops.OUT_F32, out=s)
-                ops.softmax_rows(s[:, :L], float(C) ** -0.5, out=pm[:, :L])
-                ob = ops.gemm(pm, vt[0], out=ws.get("ta_o", (Lp, C)))
-                o[b].copy_(ob[:L])
-            return ops.gemm(o, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x.reshape(B, L, C),
-                            out=new((B, L, C))).view(B, H, W, C)
-
         B, H, W, _ = x.shape
         h = self._conv_any(ws, x, "decoder.conv_in.", out=new((B, H, W, self.top)))
-        h = yield from res("decoder.mid.block_1.", h)
-        h = yield from attn("decoder.mid.attn_1.", h)
-        h = yield from res("decoder.mid.block_2.", h)
+        h = yield from self._tile_res(ws, "decoder.mid.block_1.", h)
+        h = yield from self._tile_attn(ws, "decoder.mid.attn_1.", h)
+        h = yield from self._tile_res(ws, "decoder.mid.block_2.", h)
         for level, blocks, has_up in self.levels:
             for i in range(len(blocks)):
-                h = yield from res(f"decoder.up.{level}.block.{i}.", h)
+                h = yield from self._tile_res(ws, f"decoder.up.{level}.block.{i}.", h)
             if has_up:
                 c = h.shape[-1]
                 u = ops.upsample2x(h, out=new((B, 2 * H, 2 * W, c)))
@@ -946,27 +978,9 @@ class VaeDecoderEngine(_VaeBlocks):
         wgt = {i: (in_boxes[i][1] - in_boxes[i][0]) * (in_boxes[i][3] - in_boxes[i][2]) / pix_total for i in mine}
         progs = {i: self._tile_program(ws, zin[:, in_boxes[i][2]:in_boxes[i][3], in_boxes[i][0]:in_boxes[i][1]].contiguous())
                  for i in mine}
-        pending = {i: next(g) for i, g in progs.items()}
-        done: Dict[int, torch.Tensor] = {}
-        acc = torch.zeros((B, 32, 2), dtype=F32, device=z.device)
         # every rank walks the same number of synchronisation points (one per GroupNorm of the decoder)
         n_sync = 2 * (2 + sum(len(b) for _, b, _ in self.levels)) + 2
-        for _ in range(n_sync):
-            acc.zero_()
-            for i in mine:
-                x = pending[i][0]
-                ops.groupnorm_pool(x, 32, wgt[i], acc, stats=ws.gn_scratch(ops, x))
-            if world > 1:
-                reduce_fn(acc)
-            for i in mine:
-                x, key, silu = pending[i]
-                y = ops.groupnorm_apply_stats(x, acc, w[key + "weight"], w[key + "bias"], 32, 1e-6, silu)
-                try:
-                    pending[i] = progs[i].send(y)
-                except StopIteration as fin:
-                    done[i] = fin.value
-        if len(done) != len(mine):
-            raise RuntimeError("internal: tile programs did not finish after the last GroupNorm")
+        done = self._run_tiles(ws, progs, wgt, B, n_sync, world, reduce_fn)
         out = torch.zeros((B, self.dd["out_ch"], H * 8, W * 8), dtype=F32, device=z.device)
         for i in mine:
             ib, ob, t = in_boxes[i], out_boxes[i], done[i]
@@ -1119,3 +1133,72 @@ class VaeEncoderEngine(_VaeBlocks):
         else:
             run()
         return mo.clone()
+
+    # ------------------------------------------------------------------ tiled encode (VAEHook)
+    def _tile_program(self, ws: Workspace, x: torch.Tensor):
+        """Encoder.forward of ONE image tile as a tile program (build_task_queue with is_decoder=False,
+        utils/tilevae/tilevae.py:144-165); returns the tile's moments [B, 2*embed_dim, h/8, w/8] fp32
+        (conv_out and the pointwise quant_conv folded: a 1x1 convolution commutes with the crop / paste)."""
+        ops, w = self.ops, self.w
+        dev = x.device
+        new = lambda shape: torch.empty(shape, dtype=BF16, device=dev)
+        B, H, W, _ = x.shape
+        h = self._conv_any(ws, x, "encoder.conv_in.", out=new((B, H, W, self.dd["ch"])))
+        for level, blocks, has_down in self.levels:
+            for i in range(len(blocks)):
+                h = yield from self._tile_res(ws, f"encoder.down.{level}.block.{i}.", h)
+            if has_down:
+                c = h.shape[-1]
+                Ho, Wo = (H - 2) // 2 + 1, (W - 2) // 2 + 1      # pad (0,1,0,1), 3x3, stride 2
+                q = f"encoder.down.{level}.downsample.conv."
+                col = ops.im2col(h, 3, 3, 2, 0, 0, Ho, Wo, out=ws.get("col", (B * Ho * Wo, 9 * c)))
+                h = ops.gemm(col, w[q + "weight"], bias=w[q + "bias"], out=new((B, Ho, Wo, c)))
+                H, W = Ho, Wo
+        h = yield from self._tile_res(ws, "encoder.mid.block_1.", h)
+        h = yield from self._tile_attn(ws, "encoder.mid.attn_1.", h)
+        h = yield from self._tile_res(ws, "encoder.mid.block_2.", h)
+        y = yield (h, "encoder.norm_out.", True)
+        mo = torch.empty((B, 2 * self.embed_dim, H, W), dtype=F32, device=dev)
+        self._conv_any(ws, y, "encoder.moments.", out=mo.view(B, 2 * self.embed_dim, H * W), out_mode=ops.OUT_NCHW_F32)
+        return mo
+
+    def encode_tiled(self, image: torch.Tensor, tile_size: int, rank: int = 0, world: int = 1, reduce_fn=None,
+                     use_graph: bool = True) -> torch.Tensor:
+        """ControlLDM.vae_encode(tiled=True) up to the moments (model/cldm.py:114-126): VAEHook on the encoder
+        (utils/tilevae/tilevae.py:307-323, :442-579; pad 32 image pixels, output boxes // 8), pooled GroupNorm
+        statistics at each of the encoder's GroupNorms, tiles spread over ranks like decode_tiled."""
+        from .tiling import VAE_TILE_PAD_ENCODER, vae_split_tiles
+
+        if image.dim() != 4 or image.shape[1] != self.dd["in_channels"]:
+            raise ValueError(f"image must be [B, {self.dd['in_channels']}, H, W], got {tuple(image.shape)}")
+        if getattr(self.ops, "REQUIRES_CUDA", True) and not image.is_cuda:
+            raise RuntimeError("edtr_b200 has no CPU path: image must be a CUDA tensor")
+        if len(self.levels) != 4:
+            raise NotImplementedError("the tiled VAE hook assumes the /8 encoder (4 resolution levels)")
+        if world > 1 and reduce_fn is None:
+            raise ValueError("reduce_fn (all-reduce SUM) is required when world > 1")
+        B, _, H, W = image.shape
+        pad = VAE_TILE_PAD_ENCODER
+        if max(H, W) <= pad * 2 + tile_size:
+            return self.encode(image, use_graph=use_graph)
+        in_boxes, out_boxes = vae_split_tiles(H, W, tile_size, pad, False)
+        ws = self._ws.get(("tiled", B))
+        if ws is None:
+            ws = self._ws[("tiled", B)] = Workspace(self.device)
+        xin = torch.zeros((B, H, W, 64), dtype=BF16, device=image.device)
+        self.ops.nchw_to_nhwc(image.contiguous().float(), xin, 0)
+        mine = list(range(rank, len(in_boxes), world))
+        pix_total = float(sum((b[1] - b[0]) * (b[3] - b[2]) for b in in_boxes))
+        wgt = {i: (in_boxes[i][1] - in_boxes[i][0]) * (in_boxes[i][3] - in_boxes[i][2]) / pix_total for i in mine}
+        progs = {i: self._tile_program(ws, xin[:, in_boxes[i][2]:in_boxes[i][3], in_boxes[i][0]:in_boxes[i][1]].contiguous())
+                 for i in mine}
+        n_sync = 2 * sum(len(b) for _, b, _ in self.levels) + 5 + 1
+        done = self._run_tiles(ws, progs, wgt, B, n_sync, world, reduce_fn)
+        out = torch.zeros((B, 2 * self.embed_dim, H // 8, W // 8), dtype=F32, device=image.device)
+        for i in mine:
+            ib, ob, t = in_boxes[i], out_boxes[i], done[i]
+            m = [ob[k] - ib[k] // 8 for k in range(4)]        # crop_valid_region, is_decoder=False
+            out[:, :, ob[2]:ob[3], ob[0]:ob[1]] = t[:, :, m[2]:t.shape[2] + m[3], m[0]:t.shape[3] + m[1]]
+        if world > 1:
+            reduce_fn(out)
+        return out

@@ -236,5 +236,18 @@ class AutoencoderKL(nn.Module):
         """Encoder.forward + quant_conv -> posterior (model/vae.py:725-729)."""
         return DiagonalGaussianDistribution(self._encoder_engine().encode(x.float().contiguous()))
 
+    @torch.no_grad()
+    def encode_tiled(self, x: torch.Tensor, tile_size: int) -> "DiagonalGaussianDistribution":
+        """The `encoder` closure of ControlLDM.vae_encode(tiled=True) (model/cldm.py:114-126): VAEHook + quant_conv;
+        tiles are spread over the ranks of the default process group when it has more than one rank."""
+        import torch.distributed as dist
+
+        rank, world, red = 0, 1, None
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            rank, world = dist.get_rank(), dist.get_world_size()
+            red = lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        return DiagonalGaussianDistribution(self._encoder_engine().encode_tiled(
+            x.float().contiguous(), int(tile_size), rank=rank, world=world, reduce_fn=red))
+
     def forward(self, input, sample_posterior=True):
         raise NotImplementedError("AutoencoderKL.forward (encode + decode) is a training-time call, out of scope")

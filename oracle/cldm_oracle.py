@@ -691,18 +691,10 @@ def _vae_decoder_program(sd: SD, cfg: dict, x: Tensor):
     return _conv(sd, "decoder.conv_out.", F.silu(h))
 
 
-def vae_decode_tiled(sd: SD, cfg: dict, z: Tensor, scale_factor: float, tile_size: int) -> Tensor:
-    """ControlLDM.vae_decode(tiled=True) (model/cldm.py:142-156) -> VAEHook.__call__ / vae_tile_forward in the
-    default (non-fast) mode (utils/tilevae/tilevae.py:317-323, :442-579): post_quant_conv on the whole latent,
-    overlapping latent tiles, every GroupNorm uses the pixel-weighted average of the per-tile mean AND of the
-    per-tile variance (GroupNormParam.summary, :263-278), attention is tile-local, valid regions are pasted."""
-    pad = VAE_TILE_PAD_DECODER
-    zq = _conv(sd, "post_quant_conv.", z / scale_factor, padding=0)
-    n, _, hh, ww = zq.shape
-    if max(hh, ww) <= pad * 2 + tile_size:          # "tiny and unnecessary to tile" (:319-321)
-        return vae_decode(sd, cfg, z, scale_factor)
-    in_boxes, out_boxes = vae_split_tiles(hh, ww, tile_size, pad, True)
-    progs = [_vae_decoder_program(sd, cfg, zq[:, :, b[2]:b[3], b[0]:b[1]]) for b in in_boxes]
+def _run_tile_programs(sd: SD, progs):
+    """The tile loop of VAEHook.vae_tile_forward (utils/tilevae/tilevae.py:496-571) without its CPU<->GPU
+    shuffling: all tiles advance to their next `pre_norm`, the statistics are pooled (GroupNormParam.summary,
+    :263-278: pixel-weighted average of per-tile means and per-tile variances), every tile is normalised with them."""
     pending = [next(g) for g in progs]
     done: List[Optional[Tensor]] = [None] * len(progs)
     while any(d is None for d in done):
@@ -720,6 +712,21 @@ def vae_decode_tiled(sd: SD, cfg: dict, z: Tensor, scale_factor: float, tile_siz
                 done[i] = fin.value
                 nxt.append(None)
         pending = nxt
+    return done
+
+
+def vae_decode_tiled(sd: SD, cfg: dict, z: Tensor, scale_factor: float, tile_size: int) -> Tensor:
+    """ControlLDM.vae_decode(tiled=True) (model/cldm.py:142-156) -> VAEHook.__call__ / vae_tile_forward in the
+    default (non-fast) mode (utils/tilevae/tilevae.py:317-323, :442-579): post_quant_conv on the whole latent,
+    overlapping latent tiles, every GroupNorm uses the pixel-weighted average of the per-tile mean AND of the
+    per-tile variance (GroupNormParam.summary, :263-278), attention is tile-local, valid regions are pasted."""
+    pad = VAE_TILE_PAD_DECODER
+    zq = _conv(sd, "post_quant_conv.", z / scale_factor, padding=0)
+    n, _, hh, ww = zq.shape
+    if max(hh, ww) <= pad * 2 + tile_size:          # "tiny and unnecessary to tile" (:319-321)
+        return vae_decode(sd, cfg, z, scale_factor)
+    in_boxes, out_boxes = vae_split_tiles(hh, ww, tile_size, pad, True)
+    done = _run_tile_programs(sd, [_vae_decoder_program(sd, cfg, zq[:, :, b[2]:b[3], b[0]:b[1]]) for b in in_boxes])
     out = torch.zeros((n, done[0].shape[1], hh * 8, ww * 8), dtype=done[0].dtype)
     for tile, ib, ob in zip(done, in_boxes, out_boxes):
         # crop_valid_region (:218-229)
@@ -727,6 +734,63 @@ def vae_decode_tiled(sd: SD, cfg: dict, z: Tensor, scale_factor: float, tile_siz
         out[:, :, ob[2]:ob[3], ob[0]:ob[1]] = tile[:, :, m[2]:tile.shape[2] + m[3], m[0]:tile.shape[3] + m[1]]
     return out
 
+
+VAE_TILE_PAD_ENCODER = 32   # utils/tilevae/tilevae.py:315 (image pixels)
+
+
+def _vae_encoder_program(sd: SD, cfg: dict, x: Tensor):
+    """Encoder.forward as the task queue of build_task_queue (is_decoder=False) for ONE tile; yields at `pre_norm`."""
+
+    def res(p, x):
+        h = yield (x, p + "norm1.")
+        h = _conv(sd, p + "conv1.", F.silu(h))
+        h = yield (h, p + "norm2.")
+        h = _conv(sd, p + "conv2.", F.silu(h))
+        if (p + "nin_shortcut.weight") in sd:
+            x = _conv(sd, p + "nin_shortcut.", x, padding=0)
+        return x + h
+
+    def attn(p, x):
+        b, c, hh, ww = x.shape
+        h = yield (x, p + "norm.")
+        q, k, v = (_conv(sd, p + n + ".", h, padding=0).reshape(b, c, hh * ww).permute(0, 2, 1) for n in "qkv")
+        w = torch.softmax(q @ k.transpose(1, 2) * (c ** -0.5), dim=-1)
+        o = (w @ v).permute(0, 2, 1).reshape(b, c, hh, ww)
+        return x + _conv(sd, p + "proj_out.", o, padding=0)
+
+    h = _conv(sd, "encoder.conv_in.", x)
+    plan, _ = vae_encoder_plan(cfg)
+    for level, blocks, has_down in plan:
+        for i in range(len(blocks)):
+            h = yield from res(f"encoder.down.{level}.block.{i}.", h)
+        if has_down:
+            h = _conv(sd, f"encoder.down.{level}.downsample.conv.", F.pad(h, (0, 1, 0, 1)), stride=2, padding=0)
+    h = yield from res("encoder.mid.block_1.", h)
+    h = yield from attn("encoder.mid.attn_1.", h)
+    h = yield from res("encoder.mid.block_2.", h)
+    h = yield (h, "encoder.norm_out.")
+    return _conv(sd, "encoder.conv_out.", F.silu(h))
+
+
+def vae_encode_tiled(sd: SD, cfg: dict, image: Tensor, scale_factor: float, tile_size: int,
+                     noise: Optional[Tensor] = None) -> Tensor:
+    """ControlLDM.vae_encode(tiled=True) (model/cldm.py:114-126): VAEHook on the encoder (pad 32 image pixels,
+    output boxes // 8), quant_conv on the assembled moments, then posterior mode / sample times the scale."""
+    pad = VAE_TILE_PAD_ENCODER
+    n, _, hh, ww = image.shape
+    if max(hh, ww) <= pad * 2 + tile_size:
+        return vae_encode(sd, cfg, image, scale_factor, noise)
+    in_boxes, out_boxes = vae_split_tiles(hh, ww, tile_size, pad, False)
+    done = _run_tile_programs(sd, [_vae_encoder_program(sd, cfg, image[:, :, b[2]:b[3], b[0]:b[1]]) for b in in_boxes])
+    h = torch.zeros((n, done[0].shape[1], hh // 8, ww // 8), dtype=done[0].dtype)
+    for tile, ib, ob in zip(done, in_boxes, out_boxes):
+        m = [ob[i] - ib[i] // 8 for i in range(4)]        # crop_valid_region with is_decoder=False
+        h[:, :, ob[2]:ob[3], ob[0]:ob[1]] = tile[:, :, m[2]:tile.shape[2] + m[3], m[0]:tile.shape[3] + m[1]]
+    mean, logvar = torch.chunk(_conv(sd, "quant_conv.", h, padding=0), 2, dim=1)
+    if noise is None:
+        return mean * scale_factor
+    std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+    return (mean + std * noise) * scale_factor
 
 def restore(w, cfg: dict, x_T: Tensor, cond, noise):
     """The unit of work of the headline metric: 4-step sample + VAE decode."""

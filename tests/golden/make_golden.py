@@ -15,6 +15,7 @@ four per-step noise draws are the seeded tensors the oracle receives explicitly.
 Outputs:  golden_tiny.npz  (TINY config, B=2, 16x16 latent; everything in fp32)
           golden_wavelet.npz    (utils.common.wavelet_reconstruction on two random [2,3,40,56] images)
           golden_vae_encode.npz (TINY VAE encoder, B=2, 64x64 image: vae_encode mode / sample, q_sample at t=200)
+          golden_vae_encode_tiled.npz (TINY_VAE8 encoder, B=2, 136x160 image (stored fp16), vae_encode(tiled=True, 64))
           golden_vae_tiled.npz  (TINY_VAE8 decoder, B=2, 40x48 latent, vae_decode(tiled=True, tile_size=16))
           golden_s4.npz    (s4 config, B=1, 64x64 latent; --full; image stored as fp16)
 """
@@ -203,6 +204,32 @@ def run_reference_vae_encode(vae_cfg, batch, hw):
     return image, z_mode, draw, z_sample, n2, x_T
 
 
+def run_reference_tiled_vae_encode(vae_cfg, batch, h, w, tile_size):
+    """ControlLDM.vae_encode(image, sample=False, tiled=True, tile_size) of the unmodified reference."""
+    from oracle import cldm_oracle as O
+
+    _stub_missing_packages()
+    from model.cldm import ControlLDM
+    from model.vae import AutoencoderKL
+
+    sd = O.make_weights(O.vae_encoder_param_shapes(vae_cfg), seed=3)
+    m = ControlLDM.__new__(ControlLDM)
+    torch.nn.Module.__init__(m)
+    m.vae = AutoencoderKL(ddconfig=dict(double_z=True, z_channels=vae_cfg["z_channels"], resolution=256,
+                                        in_channels=vae_cfg["in_channels"], out_ch=vae_cfg["out_ch"], ch=vae_cfg["ch"],
+                                        ch_mult=list(vae_cfg["ch_mult"]), num_res_blocks=vae_cfg["num_res_blocks"],
+                                        attn_resolutions=[], dropout=0.0), embed_dim=vae_cfg["embed_dim"])
+    res = m.vae.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys, res.unexpected_keys
+    m.scale_factor = 0.18215
+    m.eval()
+    g = torch.Generator().manual_seed(41)
+    image = (torch.rand(batch, 3, h, w, generator=g) * 2 - 1).half().float()   # fp16-exact: stored as fp16
+    with torch.no_grad():
+        z = m.vae_encode(image, sample=False, tiled=True, tile_size=tile_size)
+    return image, z
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also generate the s4 (full-size) fixture; ~2 min")
@@ -227,6 +254,10 @@ def main():
     np.savez_compressed(os.path.join(HERE, "golden_vae_encode.npz"), image=image.numpy(), z_mode=z_mode.numpy(),
                         draw=draw.numpy(), z_sample=z_sample.numpy(), q_noise=n2.numpy(), x_T=x_T.numpy())
     print("vae encode:", tuple(image.shape), "->", tuple(z_mode.shape))
+    timg, tz = run_reference_tiled_vae_encode(O.TINY_VAE8, batch=2, h=136, w=160, tile_size=64)
+    np.savez_compressed(os.path.join(HERE, "golden_vae_encode_tiled.npz"), image=timg.numpy().astype(np.float16),
+                        z=tz.numpy(), tile_size=np.int64(64))
+    print("tiled vae encode:", tuple(timg.shape), "->", tuple(tz.shape))
     print("tiled vae:", tuple(z.shape), tuple(img.shape), "tiled vs untiled max diff",
           float((img - img_u).abs().max()))
     if args.full:

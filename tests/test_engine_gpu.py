@@ -292,3 +292,18 @@ def test_dropin_pipeline_encode_sample_decode_colorfix():
     dec = model.vae_decode(zz)
     res = wavelet_reconstruction((dec + 1) / 2, pre_res.to(dev))
     assert O.psnr(res.cpu(), res_ref) >= PSNR_MIN
+
+
+def test_tiled_vae_encode_against_reference_fixture():
+    """ControlLDM.vae_encode(tiled=True) semantics (VAEHook on the encoder) on the CUDA kernels vs the fixture
+    recorded from the live reference."""
+    from edtr_b200.engine import VaeEncoderEngine
+
+    g = np.load(os.path.join(GOLD, "golden_vae_encode_tiled.npz"))
+    v = O.TINY_VAE8
+    sd = O.make_weights(O.vae_encoder_param_shapes(v), seed=3)
+    ve = VaeEncoderEngine(_dd(v), v["embed_dim"], sd, "cuda")
+    image = torch.from_numpy(g["image"].astype(np.float32)).cuda()
+    mo = ve.encode_tiled(image, int(g["tile_size"]))
+    z = (mo[:, :4] * 0.18215).cpu()
+    assert O.max_rel_err(z, torch.from_numpy(g["z"])) < STEP_TOL

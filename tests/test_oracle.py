@@ -107,3 +107,15 @@ def test_oracle_wavelet_matches_reference():
     g = np.load(os.path.join(GOLD, "golden_wavelet.npz"))
     out = O.wavelet_reconstruction(torch.from_numpy(g["content"]), torch.from_numpy(g["style"]))
     assert O.max_rel_err(out, torch.from_numpy(g["out"])) < 1e-6
+
+
+def test_oracle_tiled_vae_encode_matches_reference():
+    """vae_encode(tiled=True) of the live reference (VAEHook on the encoder, pad 32) vs the restatement."""
+    g = np.load(os.path.join(GOLD, "golden_vae_encode_tiled.npz"))
+    sd = O.make_weights(O.vae_encoder_param_shapes(O.TINY_VAE8), seed=3)
+    image = torch.from_numpy(g["image"].astype(np.float32))
+    with torch.no_grad():
+        z = O.vae_encode_tiled(sd, O.TINY_VAE8, image, 0.18215, int(g["tile_size"]))
+        z_untiled = O.vae_encode(sd, O.TINY_VAE8, image, 0.18215)
+    assert O.max_rel_err(z, torch.from_numpy(g["z"])) < 1e-5
+    assert O.max_rel_err(z, z_untiled) > 1e-3
