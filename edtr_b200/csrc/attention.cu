@@ -10,6 +10,8 @@
 // softmax warps of tile j+1 overlap the PV MMA of tile j, and the loop is bound by the exp2 rate.
 // Q/K/V are read in place from the projection GEMM outputs ([B, L, heads*64] rows): the head
 // split/merge permutes of the reference are TMA coordinates.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -22,7 +24,8 @@ constexpr int kD = 64;     // head dim
 constexpr int kKvStages = 3;
 constexpr int kTileBytes = kKT * kD * 2;   // 8 KB
 constexpr int kAttSmem = kQT * kD * 2 + kKvStages * 2 * kTileBytes + 2 * kQT * kKT * 2 + 1024 + 256;
-constexpr int kAttTmemCols = 256;  // S0 [0,64) S1 [64,128) O [128,192)
+constexpr int kAttTmemCols = 256;  // S0 [0,64) S1 [64,128) O [128,192); variant 2: P0 [192,224) P1 [224,256)
+constexpr int kPCol = 192;
 constexpr float kRescaleThreshold = 8.f;   // log2 units
 
 // ex2.approx: one MUFU op (exp2f() without -use_fast_math adds range handling around it)
@@ -35,6 +38,26 @@ __device__ __forceinline__ float fast_exp2(float x) {
 // Measured on B200 (L = 4096, 5 heads, B = 8): one or two threads per row, generic or STS stores all land at
 // 0.31-0.32 ms (~550 TFLOP/s); moving a share of the exp2 to an FMA-pipe polynomial (FA4-style) makes the loop
 // slower in proportion (25 % -> 0.40 ms, 50 % -> 0.48 ms), so the MUFU unit (53 % busy in ncu) is not the limiter.
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2): one FMA-pipe instruction per two keys.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 struct AttParams {
   void* O;
   int ldo;
@@ -42,6 +65,13 @@ struct AttParams {
   float scale_log2;
 };
 
+// kVariant 0: P through 128-byte-swizzled shared memory (STS + proxy fence), scalar fp32 math.
+// kVariant 1: same data flow; in-place tail masking (no register copies), packed f32x2 FMA / add for the exponent
+//             argument and the row sums (half the FMA-pipe instructions per key).
+// kVariant 2: variant 1 + P stays in tensor memory: the softmax threads write packed bf16 pairs with tcgen05.st
+//             (16 columns per 32 keys) and the PV MMA takes its A operand from TMEM -- no shared-memory round trip,
+//             no generic->async proxy fence (MEMBAR) in the loop.
+template <int kVariant>
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttParams p) {
@@ -146,12 +176,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       mbar_wait_u32(pfull_u32 + (j & 1) * 8, (j >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t pdesc = umma_smem_desc_sw128(sP_u32 + (j & 1) * (kQT * kKT * 2));
         const uint64_t vdesc = umma_smem_desc_sw128(sV_u32 + st * kTileBytes);
+        if constexpr (kVariant == 2) {
+          // A from TMEM: 16 keys = 8 packed 32-bit columns per MMA; B: +16 rows * 128 B (MN-major V)
 #pragma unroll
-        for (int k = 0; k < kKT / 16; ++k) {
-          // A: +32 B per 16 keys (K-major P); B: +16 rows * 128 B (MN-major V)
-          umma_ss(tmem_base + 128, pdesc + 2 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
+          for (int k = 0; k < kKT / 16; ++k)
+            umma_ts(tmem_base + 128, tmem_base + kPCol + (j & 1) * (kKT / 2) + 8 * k, vdesc + 128 * k, idesc_pv,
+                    (j | k) != 0);
+        } else {
+          const uint64_t pdesc = umma_smem_desc_sw128(sP_u32 + (j & 1) * (kQT * kKT * 2));
+#pragma unroll
+          for (int k = 0; k < kKT / 16; ++k) {
+            // A: +32 B per 16 keys (K-major P); B: +16 rows * 128 B (MN-major V)
+            umma_ss(tmem_base + 128, pdesc + 2 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
+          }
         }
         umma_commit_u32(pvdone_u32 + (j & 1) * 8);
         umma_commit_u32(empty_u32 + st * 8);
@@ -182,7 +220,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       tmem_ld_wait();
       const int valid = p.Lk - j * kKT - half * 32;  // key columns of this half that exist (may be <= 0)
       float mx;
-      if (valid >= 32) {
+      if constexpr (kVariant == 0) {
+        if (valid >= 32) {
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            m0 = fmaxf(m0, __uint_as_float(sr[i]));
+            m1 = fmaxf(m1, __uint_as_float(sr[i + 1]));
+            m2 = fmaxf(m2, __uint_as_float(sr[i + 2]));
+            m3 = fmaxf(m3, __uint_as_float(sr[i + 3]));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        } else {
+          mx = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = __uint_as_float(sr[i]);
+            if (i >= valid) v = -INFINITY;
+            sr[i] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+          }
+        }
+      } else {
+        if (valid < 32) {  // ragged last tile: mask in place
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= valid) sr[i] = 0xff800000u;
+        }
         float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -192,15 +256,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           m3 = fmaxf(m3, __uint_as_float(sr[i + 3]));
         }
         mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      } else {
-        mx = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float v = __uint_as_float(sr[i]);
-          if (i >= valid) v = -INFINITY;
-          sr[i] = __float_as_uint(v);
-          mx = fmaxf(mx, v);
-        }
       }
       // tile maximum of the whole row: exchange with the other half (double-buffered by tile parity)
       mx_ex[b][half][r] = mx;
@@ -229,25 +284,64 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       // P buffer b was last read by the PV MMA of tile j-2
       if (j >= 2) mbar_wait(&pv_done[b], ((j - 2) >> 1) & 1);
       const float mb = m_used * p.scale_log2;
-      const uint32_t prow = sP_base + b * (kQT * kKT * 2) + r * 128;   // shared-window address: plain STS
-      float sum = 0.f, sum1 = 0.f;
+      if constexpr (kVariant == 0) {
+        const uint32_t prow = sP_base + b * (kQT * kKT * 2) + r * 128;   // shared-window address: plain STS
+        float sum = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 keys = 16 B
-        float pv[8];
+        for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 keys = 16 B
+          float pv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(sr[c * 8 + i]), p.scale_log2, -mb));
-        sum += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-        sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
-        uint4 u;
-        u.x = pack_bf16(pv[0], pv[1]);
-        u.y = pack_bf16(pv[2], pv[3]);
-        u.z = pack_bf16(pv[4], pv[5]);
-        u.w = pack_bf16(pv[6], pv[7]);
-        st_shared_v4(prow + (((half * 4 + c) ^ (r & 7)) << 4), u);
+          for (int i = 0; i < 8; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(sr[c * 8 + i]), p.scale_log2, -mb));
+          sum += (pv[0] + pv[1]) + (pv[2] + pv[3]);
+          sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
+          uint4 u;
+          u.x = pack_bf16(pv[0], pv[1]);
+          u.y = pack_bf16(pv[2], pv[3]);
+          u.z = pack_bf16(pv[4], pv[5]);
+          u.w = pack_bf16(pv[6], pv[7]);
+          st_shared_v4(prow + (((half * 4 + c) ^ (r & 7)) << 4), u);
+        }
+        l += sum + sum1;
+        fence_proxy_async_smem();
+        tc_fence_before();
+      } else {
+        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+        const uint64_t nmb2 = pack_f32x2(-mb, -mb);
+        uint64_t acc0 = 0, acc1 = 0;   // two packed (even, odd) partial row sums
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float a0, a1, b0, b1;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sc2, nmb2),
+                       a0, a1);
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i + 2]), __uint_as_float(sr[2 * i + 3])), sc2, nmb2),
+                       b0, b1);
+          a0 = fast_exp2(a0);
+          a1 = fast_exp2(a1);
+          b0 = fast_exp2(b0);
+          b1 = fast_exp2(b1);
+          acc0 = add_f32x2(acc0, pack_f32x2(a0, a1));
+          acc1 = add_f32x2(acc1, pack_f32x2(b0, b1));
+          pk[i] = pack_bf16(a0, a1);
+          pk[i + 1] = pack_bf16(b0, b1);
+        }
+        float s0, s1;
+        unpack_f32x2(add_f32x2(acc0, acc1), s0, s1);
+        l += s0 + s1;
+        if constexpr (kVariant == 2) {
+          tmem_st16(trow + kPCol + b * (kKT / 2) + half * 16, pk);
+          tmem_st_wait();
+          tc_fence_before();
+        } else {
+          const uint32_t prow = sP_base + b * (kQT * kKT * 2) + r * 128;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            st_shared_v4(prow + (((half * 4 + c) ^ (r & 7)) << 4),
+                         make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
+          fence_proxy_async_smem();
+          tc_fence_before();
+        }
       }
-      l += sum + sum1;
-      fence_proxy_async_smem();
-      tc_fence_before();
       mbar_arrive(&p_full[b]);
     }
     // row sum of both halves
@@ -287,12 +381,25 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 int prime_attention_attributes() {
-  cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+  cudaError_t e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
     return EDTR_ERR_CUDA;
   }
   return EDTR_OK;
+}
+
+// Development switch (EDTR_ATT_VARIANT=0|1|2, read once); the default is the measured-fastest variant.
+static int attention_variant() {
+  static const int v = [] {
+    const char* e = getenv("EDTR_ATT_VARIANT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
 }
 
 static int make_head_tmap(CUtensorMap* tm, const void* base, int ld, int B, int heads, int L, int box_rows) {
@@ -330,6 +437,11 @@ extern "C" int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ld
   p.O = O; p.ldo = ldo; p.Lq = Lq; p.Lk = Lk;
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Lq + kQT - 1) / kQT, heads, B);
-  EDTR_LAUNCH(attention_kernel, grid, kAttThreads, kAttSmem, static_cast<cudaStream_t>(stream), tmQ, tmK, tmV, p);
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (attention_variant()) {
+    case 0: EDTR_LAUNCH(attention_kernel<0>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
+    case 1: EDTR_LAUNCH(attention_kernel<1>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
+    default: EDTR_LAUNCH(attention_kernel<2>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
+  }
   return check_launch("attention_kernel");
 }
