@@ -380,12 +380,315 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tile-split variant ("ts"): the two softmax warp sets do not share a tile.  Set A (warps 2-5) owns the even key
+// tiles, set B (warps 6-9) the odd ones; a thread owns one query row of its set's tile (all 64 keys), its own running
+// maximum / row sum and its own O accumulator in TMEM (O_A, O_B), so the loop has no cross-warp exchange at all: no
+// shared-memory maximum, no named barrier, no P-buffer hand-back.  P (bf16 pairs) overwrites the first 32 columns of
+// the S buffer it was computed from and the PV MMA reads it from TMEM; S(j+2) is issued right after PV(j) on the same
+// in-order tensor pipe, so the buffer is never overwritten early, and its completion (s_full) also tells the softmax
+// set that PV(j) has retired, i.e. that its O accumulator may be rescaled in place.  The two partial results are merged
+// once at the end:  O = (O_A 2^(m_A-m) + O_B 2^(m_B-m)) / (l_A 2^(m_A-m) + l_B 2^(m_B-m)).
+// kPolyPairs of every 8 key pairs take their exponential from a degree-3 polynomial on the FMA pipe (Cody-Waite range
+// reduction with packed f32x2 arithmetic) instead of MUFU.EX2, which is the scarce unit once the loop is this short.
+constexpr int kTsStages = 4;
+constexpr int kTsSmem = kQT * kD * 2 + kTsStages * 2 * kTileBytes + 1024 + 256;
+
+__device__ __forceinline__ uint64_t add_rm_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {   // a - b
+  uint64_t d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// 2^x for a pair, x <= ~2^7: n = floor(x) by the round-down magic add, 2^frac by a cubic (max rel. error 9e-5, below
+// bf16 resolution), exponent inserted with one integer multiply-add per element.
+__device__ __forceinline__ void exp2_poly_pair(float x0, float x1, float& y0, float& y1) {
+  const uint64_t magic = pack_f32x2(12582912.f, 12582912.f);
+  const uint64_t x = pack_f32x2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
+  const uint64_t xr = add_rm_f32x2(x, magic);              // low mantissa bits = floor(x)
+  const uint64_t fr = sub_f32x2(x, sub_f32x2(xr, magic));  // x - floor(x) in [0, 1)
+  uint64_t pl = fma_f32x2(pack_f32x2(0.077119089663028717f, 0.077119089663028717f), fr,
+                          pack_f32x2(0.227564394474029541f, 0.227564394474029541f));
+  pl = fma_f32x2(pl, fr, pack_f32x2(0.695146143436431885f, 0.695146143436431885f));
+  pl = fma_f32x2(pl, fr, pack_f32x2(1.f, 1.f));
+  float r0, r1, p0, p1;
+  unpack_f32x2(xr, r0, r1);
+  unpack_f32x2(pl, p0, p1);
+  y0 = __uint_as_float(__float_as_uint(r0) * 8388608u + __float_as_uint(p0));
+  y1 = __uint_as_float(__float_as_uint(r1) * 8388608u + __float_as_uint(p1));
+}
+
+template <int kPolyPairs>
+__global__ void __launch_bounds__(kAttThreads, 2)
+attention_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                              // 16 KB
+  uint8_t* sK = sQ + kQT * kD * 2;                 // stages x 8 KB
+  uint8_t* sV = sK + kTsStages * kTileBytes;       // stages x 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + kTsStages * kTileBytes);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;                    // [stages]
+  uint64_t* kv_empty = kv_full + kTsStages;        // [stages]
+  uint64_t* s_full = kv_empty + kTsStages;         // [2] S of an even / odd tile is in TMEM
+  uint64_t* p_full = s_full + 2;                   // [2] 128 arrivals: P of an even / odd tile is in TMEM
+  uint64_t* pv_done = p_full + 2;                  // [2] PV of an even / odd tile has retired
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
+  __shared__ float m_ex[2][kQT];
+  __shared__ float l_ex[2][kQT];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kQT;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int nkv = (p.Lk + kKT - 1) / kKT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kTsStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&p_full[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, kAttTmemCols);   // S_A|P_A [0,64) S_B|P_B [64,128) O_A [128,192) O_B [192,256)
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
+
+  if (warp == 0) {
+    const uint32_t sK_u32 = smem_u32(sK), sV_u32 = smem_u32(sV);
+    const uint32_t full_u32 = smem_u32(kv_full), empty_u32 = smem_u32(kv_empty);
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, kQT * kD * 2);
+      tma_load_4d(sQ, &tmQ, q_full, 0, q0, head, img);
+    }
+    __syncwarp();
+    uint32_t st = 0, ph = 0;
+    for (int j = 0; j < nkv; ++j) {
+      mbar_wait_u32(empty_u32 + st * 8, ph ^ 1);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_u32(full_u32 + st * 8, 2 * kTileBytes);
+        tma_load_4d_u32(sK_u32 + st * kTileBytes, &tmK, full_u32 + st * 8, 0, j * kKT, head, img);
+        tma_load_4d_u32(sV_u32 + st * kTileBytes, &tmV, full_u32 + st * 8, 0, j * kKT, head, img);
+      }
+      __syncwarp();
+      if (++st == kTsStages) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc_s = umma_idesc_bf16(kQT, kKT, false);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kD, true);
+    const uint32_t sQ_u32 = smem_u32(sQ), sK_u32 = smem_u32(sK), sV_u32 = smem_u32(sV);
+    const uint32_t full_u32 = smem_u32(kv_full), empty_u32 = smem_u32(kv_empty);
+    const uint32_t sfull_u32 = smem_u32(s_full), pfull_u32 = smem_u32(p_full), pvdone_u32 = smem_u32(pv_done);
+    uint32_t st_s = 0, ph_s = 0;   // K/V ring position of the next S = Q K^T
+    auto issue_s = [&](int j) {
+      mbar_wait_u32(full_u32 + st_s * 8, ph_s);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t qdesc = umma_smem_desc_sw128(sQ_u32);
+        const uint64_t kdesc = umma_smem_desc_sw128(sK_u32 + st_s * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_ss(tmem_base + (j & 1) * kKT, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
+        umma_commit_u32(sfull_u32 + (j & 1) * 8);
+      }
+      __syncwarp();
+      if (++st_s == kTsStages) { st_s = 0; ph_s ^= 1; }
+    };
+    mbar_wait(q_full, 0);
+    issue_s(0);
+    if (nkv > 1) issue_s(1);
+    uint32_t st = 0;
+    for (int j = 0; j < nkv; ++j) {
+      const int b = j & 1;
+      mbar_wait_u32(pfull_u32 + b * 8, (j >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t vdesc = umma_smem_desc_sw128(sV_u32 + st * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kKT / 16; ++k)   // A = P from TMEM: 16 keys = 8 packed columns; B: +16 rows * 128 B (MN-major V)
+          umma_ts(tmem_base + 128 + b * kD, tmem_base + b * kKT + 8 * k, vdesc + 128 * k, idesc_pv, (j >= 2) || (k != 0));
+        umma_commit_u32(pvdone_u32 + b * 8);
+        umma_commit_u32(empty_u32 + st * 8);
+      }
+      __syncwarp();
+      if (++st == kTsStages) st = 0;
+      if (j + 2 < nkv) issue_s(j + 2);   // overwrites S|P buffer b: ordered behind PV(j) on the tensor pipe
+    }
+  } else {
+    const int set = (warp - 2) >> 2;       // 0: even tiles, 1: odd tiles
+    const int lg = warp & 3;               // TMEM lane quadrant this warp may access
+    const int r = lg * 32 + lane;          // query row inside the tile == TMEM lane
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
+    const uint32_t s_col = trow + set * kKT;
+    const uint32_t o_col = trow + 128 + set * kD;
+    float m_used = -INFINITY, l = 0.f;
+    const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
+    int it = 0;
+    for (int j = set; j < nkv; j += 2, ++it) {
+      mbar_wait(&s_full[set], it & 1);
+      tc_fence_after();
+      uint32_t sr[64];
+      {
+        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[0]);
+        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[32]);
+        tmem_ld32(s_col, lo);
+        tmem_ld32(s_col + 32, hi);
+      }
+      tmem_ld_wait();
+      const int valid = p.Lk - j * kKT;
+      if (valid < kKT) {  // ragged last tile: mask in place
+#pragma unroll
+        for (int i = 0; i < kKT; ++i)
+          if (i >= valid) sr[i] = 0xff800000u;
+      }
+      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < kKT; i += 4) {
+        m0 = fmaxf(m0, __uint_as_float(sr[i]));
+        m1 = fmaxf(m1, __uint_as_float(sr[i + 1]));
+        m2 = fmaxf(m2, __uint_as_float(sr[i + 2]));
+        m3 = fmaxf(m3, __uint_as_float(sr[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      if (it == 0) {
+        m_used = mx;
+      } else {
+        const bool need = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // O of this set is quiescent: s_full of tile j was committed after PV(j-2)
+          const float f = need ? exp2f((m_used - mx) * p.scale_log2) : 1.f;
+          if (need) m_used = mx;
+          l *= f;
+#pragma unroll
+          for (int c = 0; c < kD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld16(o_col + 16 * c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+            tmem_st16(o_col + 16 * c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float mb = m_used * p.scale_log2;
+      const uint64_t nmb2 = pack_f32x2(-mb, -mb);
+      uint64_t acc0 = 0, acc1 = 0;   // packed (even, odd) partial row sums
+#pragma unroll
+      for (int c = 0; c < kKT / 16; ++c) {   // 16 keys -> 8 packed bf16 pairs -> 8 TMEM columns of P
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a0, a1;
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sr[16 * c + 2 * i]), __uint_as_float(sr[16 * c + 2 * i + 1])),
+                                 sc2, nmb2), a0, a1);
+          if (i < kPolyPairs) {
+            exp2_poly_pair(a0, a1, a0, a1);
+          } else {
+            a0 = fast_exp2(a0);
+            a1 = fast_exp2(a1);
+          }
+          if (i & 1) acc1 = add_f32x2(acc1, pack_f32x2(a0, a1));
+          else acc0 = add_f32x2(acc0, pack_f32x2(a0, a1));
+          pk[i] = pack_bf16(a0, a1);
+        }
+        tmem_st8(s_col + 8 * c, pk);
+      }
+      float s0, s1;
+      unpack_f32x2(add_f32x2(acc0, acc1), s0, s1);
+      l += s0 + s1;
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_full[set]);
+    }
+    // merge the two partial softmax states of the row (the partner thread lives in warp +-4: same lane quadrant)
+    const int n_mine = (nkv - set + 1) >> 1, n_other = (nkv - (set ^ 1) + 1) >> 1;
+    m_ex[set][r] = m_used;   // -inf when this set had no tile
+    l_ex[set][r] = l;
+    named_bar_sync(1 + lg, 64);
+    const float m_o = m_ex[set ^ 1][r], l_o = l_ex[set ^ 1][r];
+    const float m = fmaxf(m_used, m_o);
+    const float f_mine = n_mine > 0 ? exp2f((m_used - m) * p.scale_log2) : 0.f;
+    const float f_other = n_other > 0 ? exp2f((m_o - m) * p.scale_log2) : 0.f;
+    const float inv = 1.f / (l * f_mine + l_o * f_other);
+    const float fA = (set == 0 ? f_mine : f_other) * inv, fB = (set == 0 ? f_other : f_mine) * inv;
+    const int nA = (nkv + 1) >> 1, nB = nkv >> 1;
+    mbar_wait(&pv_done[0], (nA - 1) & 1);
+    if (nB > 0) mbar_wait(&pv_done[1], (nB - 1) & 1);
+    tc_fence_after();
+    // this thread writes output columns [set*32, set*32+32) of its row
+    uint32_t oa[32];
+    tmem_ld32(trow + 128 + set * 32, oa);
+    tmem_ld_wait();
+    float o[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(oa[i]) * fA;
+    if (nB > 0) {
+      tmem_ld32(trow + 128 + kD + set * 32, oa);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(oa[i]), fB, o[i]);
+    }
+    const int q = q0 + r;
+    if (q < p.Lq) {
+      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.O) +
+                          (static_cast<size_t>(img) * p.Lq + q) * p.ldo + head * kD + set * 32;
+      uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 u;
+        u.x = pack_bf16(o[8 * c + 0], o[8 * c + 1]);
+        u.y = pack_bf16(o[8 * c + 2], o[8 * c + 3]);
+        u.z = pack_bf16(o[8 * c + 4], o[8 * c + 5]);
+        u.w = pack_bf16(o[8 * c + 6], o[8 * c + 7]);
+        o4[c] = u;
+      }
+    }
+    tc_fence_before();
+  }
+  pdl_launch_dependents();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kAttTmemCols);
+  }
+}
+
 int prime_attention_attributes() {
   cudaError_t e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(attention_ts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
     return EDTR_ERR_CUDA;
@@ -397,7 +700,7 @@ int prime_attention_attributes() {
 static int attention_variant() {
   static const int v = [] {
     const char* e = getenv("EDTR_ATT_VARIANT");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : 4;
   }();
   return v;
 }
@@ -441,7 +744,10 @@ extern "C" int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ld
   switch (attention_variant()) {
     case 0: EDTR_LAUNCH(attention_kernel<0>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
     case 1: EDTR_LAUNCH(attention_kernel<1>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
-    default: EDTR_LAUNCH(attention_kernel<2>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
+    case 2: EDTR_LAUNCH(attention_kernel<2>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
+    case 3: EDTR_LAUNCH(attention_ts_kernel<0>, grid, kAttThreads, kTsSmem, st, tmQ, tmK, tmV, p); break;
+    case 4: EDTR_LAUNCH(attention_ts_kernel<2>, grid, kAttThreads, kTsSmem, st, tmQ, tmK, tmV, p); break;
+    default: EDTR_LAUNCH(attention_ts_kernel<3>, grid, kAttThreads, kTsSmem, st, tmQ, tmK, tmV, p); break;
   }
   return check_launch("attention_kernel");
 }

@@ -2,6 +2,8 @@
 // LayerNorm, row softmax.  All activations are bf16 channels-last; every global
 // access is a 16-byte vector of 8 channels, adjacent threads touch adjacent
 // vectors (coalesced), reductions use warp shuffles + shared memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -445,7 +447,15 @@ static GnFusedGeom gn_fused_geom(int B, int HW, int C, int groups) {
   const size_t bytes_per_image = static_cast<size_t>(HW) * C * 2;
   // Small L2-resident tensors only: measured on B200 the single launch wins up to ~1 MB per image (8x8 / 16x16
   // levels); above that the 8 CTAs per image cannot pull enough bandwidth and the two-pass kernels are faster.
-  if (bytes_per_image > (1u << 20) || static_cast<size_t>(B) * bytes_per_image > (64u << 20)) return g;
+  // With 16 CTAs per image (non-portable cluster size; one cluster per GPC, so 8 images run concurrently) the single
+  // launch also covers the 1 - 2.75 MB per image tensors (64x64x320, 32x32x640 ... 32x32x1280).  EDTR_GN_CS16=0
+  // restores the 1 MB limit.
+  static const bool cs16 = [] {
+    const char* e = getenv("EDTR_GN_CS16");
+    return e == nullptr || atoi(e) != 0;
+  }();
+  const size_t limit = cs16 ? (11u << 18) : (1u << 20);
+  if (bytes_per_image > limit || static_cast<size_t>(B) * bytes_per_image > (64u << 20)) return g;
   const int ppar = 512 / vpr;
   g.threads = vpr * ppar;
   if (g.threads % 32 != 0) {            // whole warps only (warp-per-group reduction, .aligned barriers)
@@ -456,7 +466,17 @@ static GnFusedGeom gn_fused_geom(int B, int HW, int C, int groups) {
   }
   g.smem = static_cast<size_t>(g.threads / vpr) * 2 * C * sizeof(float);
   g.cs = HW >= 64 ? 8 : (HW >= 8 ? 2 : 1);
+  if (bytes_per_image > (1u << 20)) g.cs = 16;
   return g;
+}
+
+int prime_norm_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(groupnorm_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(groupnorm_fused, non-portable cluster size): %s", cudaGetErrorString(e));
+    return EDTR_ERR_CUDA;
+  }
+  return EDTR_OK;
 }
 
 struct GnGeom {

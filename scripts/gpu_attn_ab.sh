@@ -1,9 +1,34 @@
-# A/B of the attention kernel variants: unit tests + microbench per variant, then the step profile with the best
+# A/B of the attention kernel variants: unit tests + microbench per variant, then engine parity + step profile with the
+# fastest variant that passed
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-for v in ${VARIANTS:-0 1 2}; do
-  EDTR_ATT_VARIANT=$v timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q --timeout 200 --tb=short -k attention > gpurun_out/attn_tests_v$v.log 2>&1
-  echo "== variant $v tests exit $?"; tail -n 3 gpurun_out/attn_tests_v$v.log
-  EDTR_ATT_VARIANT=$v timeout 300 python scripts/bench_attn.py > gpurun_out/bench_attn_v$v.txt 2>&1
-  echo "== variant $v bench exit $?"; cat gpurun_out/bench_attn_v$v.txt
+for v in ${VARIANTS:-0 1 2 3 4 5}; do
+  EDTR_ATT_VARIANT=$v timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q --timeout 120 --tb=short -k attention > gpurun_out/attn_tests_v$v.log 2>&1
+  echo "== variant $v tests exit $?" | tee gpurun_out/attn_tests_v$v.exit; tail -n 3 gpurun_out/attn_tests_v$v.log
+  EDTR_ATT_VARIANT=$v timeout 120 python scripts/bench_attn.py > gpurun_out/bench_attn_v$v.txt 2>&1
+  echo "== variant $v bench exit $?"; cat gpurun_out/bench_attn_v$v.txt | tail -n 9
 done
+best=$(python - <<'PY'
+import re, glob
+best, bt = 0, 1e9
+for f in glob.glob("gpurun_out/bench_attn_v*.txt"):
+    v = int(re.search(r"_v(\d+)\.txt", f).group(1))
+    if "exit 0" not in open(f"gpurun_out/attn_tests_v{v}.exit").read():
+        continue
+    t, ok = 0.0, True
+    for line in open(f):
+        m = re.search(r":\s+([\d.]+) us\s+([\d.]+) TFLOP/s\s+max-rel err ([\d.e+-]+|nan)", line)
+        if m:
+            t += float(m.group(1))
+            ok &= m.group(3) != "nan" and float(m.group(3)) < 2e-2
+    if ok and 0 < t < bt:
+        best, bt = v, t
+print(best)
+PY
+)
+echo "== fastest passing variant: $best"
+export EDTR_ATT_VARIANT=$best
+timeout 600 python -m pytest tests/test_engine_gpu.py -m gpu -x -q --timeout 400 --tb=short -k "s4 or tiny or batch8" > gpurun_out/engine_tests_best.log 2>&1
+echo "== engine tests (variant $best) exit $?"; tail -n 6 gpurun_out/engine_tests_best.log
+timeout 600 python scripts/profile_step.py --batch 8 --no-profile --out gpurun_out/profile_quick_best.txt > gpurun_out/profile_quick_best.log 2>&1
+echo "== profile exit $?"; grep -E "graph:|restore" gpurun_out/profile_quick_best.log | tail -n 3

@@ -197,7 +197,8 @@ def test_conv3x3_channel_slice_input(ops):
 
 
 @pytest.mark.parametrize("B,heads,Lq,Lk", [(2, 5, 256, 256), (1, 2, 4096, 4096), (2, 3, 128, 77), (1, 20, 64, 64),
-                                            (1, 1, 200, 130), (2, 2, 1024, 77)])
+                                            (1, 1, 200, 130), (2, 2, 1024, 77), (1, 2, 130, 192), (2, 1, 300, 290),
+                                            (1, 3, 64, 1), (1, 1, 128, 65)])
 def test_attention(ops, B, heads, Lq, Lk):
     C = heads * 64
     qkv = rnd(B, Lq, 3 * C, seed=1)
@@ -216,7 +217,7 @@ def test_attention(ops, B, heads, Lq, Lk):
     assert relerr(out, ref) < 2e-2
 
 
-@pytest.mark.parametrize("Lq,Lk", [(256, 1024), (384, 200), (128, 4096)])
+@pytest.mark.parametrize("Lq,Lk", [(256, 1024), (384, 200), (128, 4096), (128, 320)])
 def test_attention_growing_scores_exercise_lazy_rescale(ops, Lq, Lk):
     """Scores that keep growing along the key axis force the in-TMEM rescale of O many times per row."""
     B, heads = 2, 2
