@@ -447,14 +447,8 @@ static GnFusedGeom gn_fused_geom(int B, int HW, int C, int groups) {
   const size_t bytes_per_image = static_cast<size_t>(HW) * C * 2;
   // Small L2-resident tensors only: measured on B200 the single launch wins up to ~1 MB per image (8x8 / 16x16
   // levels); above that the 8 CTAs per image cannot pull enough bandwidth and the two-pass kernels are faster.
-  // With 16 CTAs per image (non-portable cluster size; one cluster per GPC, so 8 images run concurrently) the single
-  // launch also covers the 1 - 2.75 MB per image tensors (64x64x320, 32x32x640 ... 32x32x1280).  EDTR_GN_CS16=0
-  // restores the 1 MB limit.
-  static const bool cs16 = [] {
-    const char* e = getenv("EDTR_GN_CS16");
-    return e == nullptr || atoi(e) != 0;
-  }();
-  const size_t limit = cs16 ? (11u << 18) : (1u << 20);
+  // (16-CTA non-portable clusters for the 1 - 2.75 MB tensors were measured too: no gain, profiles/r01g.)
+  const size_t limit = 1u << 20;
   if (bytes_per_image > limit || static_cast<size_t>(B) * bytes_per_image > (64u << 20)) return g;
   const int ppar = 512 / vpr;
   g.threads = vpr * ppar;
@@ -466,17 +460,7 @@ static GnFusedGeom gn_fused_geom(int B, int HW, int C, int groups) {
   }
   g.smem = static_cast<size_t>(g.threads / vpr) * 2 * C * sizeof(float);
   g.cs = HW >= 64 ? 8 : (HW >= 8 ? 2 : 1);
-  if (bytes_per_image > (1u << 20)) g.cs = 16;
   return g;
-}
-
-int prime_norm_attributes() {
-  cudaError_t e = cudaFuncSetAttribute(groupnorm_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  if (e != cudaSuccess) {
-    set_error("cudaFuncSetAttribute(groupnorm_fused, non-portable cluster size): %s", cudaGetErrorString(e));
-    return EDTR_ERR_CUDA;
-  }
-  return EDTR_OK;
 }
 
 struct GnGeom {
