@@ -1,15 +1,13 @@
 // Flash-style attention for head dim 64 on tcgen05 / TMEM / TMA (sm_100a).
 //
-// One CTA owns 128 query rows of one (image, head) and streams the keys in tiles of 64 through a
-// 3-stage TMA ring:  S = Q K^T (UMMA, fp32 in TMEM, double-buffered) -> softmax numerators with one
-// thread per query row (a TMEM lane is a row: no shuffles) -> P (bf16) into one of two 128-byte-
-// swizzled shared buffers -> O += P V (UMMA accumulating in TMEM, V consumed MN-major straight from
-// the [keys, 64] TMA box).  O never leaves TMEM inside the loop: the running maximum used for the
-// exponent is only raised when the tile maximum exceeds it by more than 2^8 (lazy rescaling), and
-// only then are the 64 O columns of the affected rows rescaled in place (tcgen05.ld / st).  So the
-// softmax warps of tile j+1 overlap the PV MMA of tile j, and the loop is bound by the exp2 rate.
-// Q/K/V are read in place from the projection GEMM outputs ([B, L, heads*64] rows): the head
-// split/merge permutes of the reference are TMA coordinates.
+// One CTA owns 128 query rows of one (image, head) and streams the keys in tiles of 64 through a 4-stage TMA ring:
+// S = Q K^T (UMMA, fp32 in TMEM) -> softmax numerators with one thread per query row (a TMEM lane is a row: no
+// shuffles) -> P (packed bf16) back into TMEM -> O += P V (UMMA, A operand from TMEM, V consumed MN-major straight
+// from the [keys, 64] TMA box).  O never leaves TMEM inside the loop: the running maximum used for the exponent is
+// only raised when the tile maximum exceeds it by more than 2^8 (lazy rescaling), and only then are the O columns of
+// the affected rows rescaled in place (tcgen05.ld / st).  Q/K/V are read in place from the projection GEMM outputs
+// ([B, L, heads*64] rows): the head split/merge permutes of the reference (model/attention.py:176-203) are TMA
+// coordinates.  Kernel history and the measurements behind this structure: profiles/r01g_attention_variants.txt.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -21,11 +19,8 @@ constexpr int kAttThreads = 320;   // TMA warp, MMA warp, eight softmax warps
 constexpr int kQT = 128;   // query rows per CTA
 constexpr int kKT = 64;    // keys per tile
 constexpr int kD = 64;     // head dim
-constexpr int kKvStages = 3;
 constexpr int kTileBytes = kKT * kD * 2;   // 8 KB
-constexpr int kAttSmem = kQT * kD * 2 + kKvStages * 2 * kTileBytes + 2 * kQT * kKT * 2 + 1024 + 256;
-constexpr int kAttTmemCols = 256;  // S0 [0,64) S1 [64,128) O [128,192); variant 2: P0 [192,224) P1 [224,256)
-constexpr int kPCol = 192;
+constexpr int kAttTmemCols = 256;  // S_A|P_A [0,64) S_B|P_B [64,128) O_A [128,192) O_B [192,256)
 constexpr float kRescaleThreshold = 8.f;   // log2 units
 
 // ex2.approx: one MUFU op (exp2f() without -use_fast_math adds range handling around it)
@@ -35,9 +30,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// Measured on B200 (L = 4096, 5 heads, B = 8): one or two threads per row, generic or STS stores all land at
-// 0.31-0.32 ms (~550 TFLOP/s); moving a share of the exp2 to an FMA-pipe polynomial (FA4-style) makes the loop
-// slower in proportion (25 % -> 0.40 ms, 50 % -> 0.48 ms), so the MUFU unit (53 % busy in ncu) is not the limiter.
 // Packed fp32 pairs (sm_100 FFMA2 / FADD2): one FMA-pipe instruction per two keys.
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   uint64_t r;
@@ -65,324 +57,8 @@ struct AttParams {
   float scale_log2;
 };
 
-// kVariant 0: P through 128-byte-swizzled shared memory (STS + proxy fence), scalar fp32 math.
-// kVariant 1: same data flow; in-place tail masking (no register copies), packed f32x2 FMA / add for the exponent
-//             argument and the row sums (half the FMA-pipe instructions per key).
-// kVariant 2: variant 1 + P stays in tensor memory: the softmax threads write packed bf16 pairs with tcgen05.st
-//             (16 columns per 32 keys) and the PV MMA takes its A operand from TMEM -- no shared-memory round trip,
-//             no generic->async proxy fence (MEMBAR) in the loop.
-template <int kVariant>
-__global__ void __launch_bounds__(kAttThreads, 2)
-attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                 const __grid_constant__ CUtensorMap tmV, const AttParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                              // 16 KB
-  uint8_t* sK = sQ + kQT * kD * 2;                 // stages x 8 KB
-  uint8_t* sV = sK + kKvStages * kTileBytes;       // stages x 8 KB
-  uint8_t* sP = sV + kKvStages * kTileBytes;       // 2 x 16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kQT * kKT * 2);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;                    // [stages]
-  uint64_t* kv_empty = kv_full + kKvStages;        // [stages]
-  uint64_t* s_full = kv_empty + kKvStages;         // [2]
-  uint64_t* p_full = s_full + 2;                   // [2] 256 arrivals per tile; one barrier per P buffer, so a warp
-                                                   //     that runs one tile ahead cannot complete the wrong phase
-  uint64_t* pv_done = p_full + 2;                  // [2] PV of the tile that used P buffer b has retired
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
-  __shared__ float mx_ex[2][2][kQT];   // [tile parity][column half][row]: tile maxima of the two halves of a row
-  __shared__ float l_ex[2][kQT];
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kQT;
-  const int head = blockIdx.y;
-  const int img = blockIdx.z;
-  const int nkv = (p.Lk + kKT - 1) / kKT;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kKvStages; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&pv_done[i], 1);
-      mbar_init(&p_full[i], 256);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_holder, kAttTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
-  pdl_wait();  // PDL: everything above overlapped the previous kernel; global memory is touched only below
-
-  if (warp == 0) {
-    // TMA producer: warp-uniform loop state (uniform registers), one elected lane issues
-    const uint32_t sK_u32 = smem_u32(sK), sV_u32 = smem_u32(sV);
-    const uint32_t full_u32 = smem_u32(kv_full), empty_u32 = smem_u32(kv_empty);
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, kQT * kD * 2);
-      tma_load_4d(sQ, &tmQ, q_full, 0, q0, head, img);
-    }
-    __syncwarp();
-    uint32_t st = 0, ph = 0;
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait_u32(empty_u32 + st * 8, ph ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx_u32(full_u32 + st * 8, 2 * kTileBytes);
-        tma_load_4d_u32(sK_u32 + st * kTileBytes, &tmK, full_u32 + st * 8, 0, j * kKT, head, img);
-        tma_load_4d_u32(sV_u32 + st * kTileBytes, &tmV, full_u32 + st * 8, 0, j * kKT, head, img);
-      }
-      __syncwarp();
-      if (++st == kKvStages) { st = 0; ph ^= 1; }
-    }
-  } else if (warp == 1) {
-    // UMMA issuer: the whole warp waits on the barriers (uniform control flow), one elected lane issues
-    constexpr uint32_t idesc_s = umma_idesc_bf16(kQT, kKT, false);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kD, true);
-    const uint32_t sQ_u32 = smem_u32(sQ), sK_u32 = smem_u32(sK), sV_u32 = smem_u32(sV), sP_u32 = smem_u32(sP);
-    const uint32_t full_u32 = smem_u32(kv_full), empty_u32 = smem_u32(kv_empty);
-    const uint32_t sfull_u32 = smem_u32(s_full), pfull_u32 = smem_u32(p_full), pvdone_u32 = smem_u32(pv_done);
-    uint32_t st_s = 0, ph_s = 0;   // K/V ring position of the next S = Q K^T
-    auto issue_s = [&](int j) {
-      mbar_wait_u32(full_u32 + st_s * 8, ph_s);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t qdesc = umma_smem_desc_sw128(sQ_u32);
-        const uint64_t kdesc = umma_smem_desc_sw128(sK_u32 + st_s * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_ss(tmem_base + (j & 1) * kKT, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit_u32(sfull_u32 + (j & 1) * 8);
-      }
-      __syncwarp();
-      if (++st_s == kKvStages) { st_s = 0; ph_s ^= 1; }
-    };
-    mbar_wait(q_full, 0);
-    issue_s(0);
-    uint32_t st = 0;
-    for (int j = 0; j < nkv; ++j) {
-      if (j + 1 < nkv) issue_s(j + 1);
-      mbar_wait_u32(pfull_u32 + (j & 1) * 8, (j >> 1) & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t vdesc = umma_smem_desc_sw128(sV_u32 + st * kTileBytes);
-        if constexpr (kVariant == 2) {
-          // A from TMEM: 16 keys = 8 packed 32-bit columns per MMA; B: +16 rows * 128 B (MN-major V)
-#pragma unroll
-          for (int k = 0; k < kKT / 16; ++k)
-            umma_ts(tmem_base + 128, tmem_base + kPCol + (j & 1) * (kKT / 2) + 8 * k, vdesc + 128 * k, idesc_pv,
-                    (j | k) != 0);
-        } else {
-          const uint64_t pdesc = umma_smem_desc_sw128(sP_u32 + (j & 1) * (kQT * kKT * 2));
-#pragma unroll
-          for (int k = 0; k < kKT / 16; ++k) {
-            // A: +32 B per 16 keys (K-major P); B: +16 rows * 128 B (MN-major V)
-            umma_ss(tmem_base + 128, pdesc + 2 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
-          }
-        }
-        umma_commit_u32(pvdone_u32 + (j & 1) * 8);
-        umma_commit_u32(empty_u32 + st * 8);
-      }
-      __syncwarp();
-      if (++st == kKvStages) st = 0;
-    }
-  } else {
-    // Softmax: TWO threads per query row (warps w and w+4 share a TMEM lane quadrant and split the 64 key columns
-    // of a tile 32 / 32), i.e. eight softmax warps per CTA and four per SM sub-partition with two CTAs per SM:
-    // enough independent work to keep the exp2 unit busy while a warp waits on TMEM, a barrier or the fence.  The two
-    // halves of a row exchange their tile maximum through shared memory + a 64-thread named barrier; the row sums
-    // stay private until the end.
-    const int sw = warp - 2;               // 0..7
-    const int half = sw >> 2;              // which 32 of the 64 key columns
-    const int lg = warp & 3;               // TMEM lane quadrant this warp may access
-    const int r = lg * 32 + lane;          // query row inside the tile == TMEM lane
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    const int pair_bar = 1 + lg;           // named barrier of the two warps that share rows [lg*32, lg*32+32)
-    const uint32_t sP_base = smem_u32(sP);
-    float m_used = -INFINITY, l = 0.f;
-    for (int j = 0; j < nkv; ++j) {
-      const int b = j & 1;
-      mbar_wait(&s_full[b], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t sr[32];
-      tmem_ld32(trow + b * kKT + half * 32, sr);
-      tmem_ld_wait();
-      const int valid = p.Lk - j * kKT - half * 32;  // key columns of this half that exist (may be <= 0)
-      float mx;
-      if constexpr (kVariant == 0) {
-        if (valid >= 32) {
-          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            m0 = fmaxf(m0, __uint_as_float(sr[i]));
-            m1 = fmaxf(m1, __uint_as_float(sr[i + 1]));
-            m2 = fmaxf(m2, __uint_as_float(sr[i + 2]));
-            m3 = fmaxf(m3, __uint_as_float(sr[i + 3]));
-          }
-          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        } else {
-          mx = -INFINITY;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = __uint_as_float(sr[i]);
-            if (i >= valid) v = -INFINITY;
-            sr[i] = __float_as_uint(v);
-            mx = fmaxf(mx, v);
-          }
-        }
-      } else {
-        if (valid < 32) {  // ragged last tile: mask in place
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (i >= valid) sr[i] = 0xff800000u;
-        }
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          m0 = fmaxf(m0, __uint_as_float(sr[i]));
-          m1 = fmaxf(m1, __uint_as_float(sr[i + 1]));
-          m2 = fmaxf(m2, __uint_as_float(sr[i + 2]));
-          m3 = fmaxf(m3, __uint_as_float(sr[i + 3]));
-        }
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      }
-      // tile maximum of the whole row: exchange with the other half (double-buffered by tile parity)
-      mx_ex[b][half][r] = mx;
-      named_bar_sync(pair_bar, 64);
-      mx = fmaxf(mx, mx_ex[b][half ^ 1][r]);
-      if (j == 0) {
-        m_used = mx;
-      } else {
-        const bool need = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          // O must be quiescent: the PV MMA of tile j-1 is the last one issued
-          mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);
-          tc_fence_after();
-          const float f = need ? exp2f((m_used - mx) * p.scale_log2) : 1.f;
-          if (need) m_used = mx;
-          l *= f;
-          uint32_t o[32];
-          tmem_ld32(trow + 128 + half * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-          tmem_st32(trow + 128 + half * 32, o);
-          tmem_st_wait();
-        }
-      }
-      // P buffer b was last read by the PV MMA of tile j-2
-      if (j >= 2) mbar_wait(&pv_done[b], ((j - 2) >> 1) & 1);
-      const float mb = m_used * p.scale_log2;
-      if constexpr (kVariant == 0) {
-        const uint32_t prow = sP_base + b * (kQT * kKT * 2) + r * 128;   // shared-window address: plain STS
-        float sum = 0.f, sum1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {  // 4 chunks of 8 keys = 16 B
-          float pv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) pv[i] = fast_exp2(fmaf(__uint_as_float(sr[c * 8 + i]), p.scale_log2, -mb));
-          sum += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-          sum1 += (pv[4] + pv[5]) + (pv[6] + pv[7]);
-          uint4 u;
-          u.x = pack_bf16(pv[0], pv[1]);
-          u.y = pack_bf16(pv[2], pv[3]);
-          u.z = pack_bf16(pv[4], pv[5]);
-          u.w = pack_bf16(pv[6], pv[7]);
-          st_shared_v4(prow + (((half * 4 + c) ^ (r & 7)) << 4), u);
-        }
-        l += sum + sum1;
-        fence_proxy_async_smem();
-        tc_fence_before();
-      } else {
-        const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
-        const uint64_t nmb2 = pack_f32x2(-mb, -mb);
-        uint64_t acc0 = 0, acc1 = 0;   // two packed (even, odd) partial row sums
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          float a0, a1, b0, b1;
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sc2, nmb2),
-                       a0, a1);
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sr[2 * i + 2]), __uint_as_float(sr[2 * i + 3])), sc2, nmb2),
-                       b0, b1);
-          a0 = fast_exp2(a0);
-          a1 = fast_exp2(a1);
-          b0 = fast_exp2(b0);
-          b1 = fast_exp2(b1);
-          acc0 = add_f32x2(acc0, pack_f32x2(a0, a1));
-          acc1 = add_f32x2(acc1, pack_f32x2(b0, b1));
-          pk[i] = pack_bf16(a0, a1);
-          pk[i + 1] = pack_bf16(b0, b1);
-        }
-        float s0, s1;
-        unpack_f32x2(add_f32x2(acc0, acc1), s0, s1);
-        l += s0 + s1;
-        if constexpr (kVariant == 2) {
-          tmem_st16(trow + kPCol + b * (kKT / 2) + half * 16, pk);
-          tmem_st_wait();
-          tc_fence_before();
-        } else {
-          const uint32_t prow = sP_base + b * (kQT * kKT * 2) + r * 128;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            st_shared_v4(prow + (((half * 4 + c) ^ (r & 7)) << 4),
-                         make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]));
-          fence_proxy_async_smem();
-          tc_fence_before();
-        }
-      }
-      mbar_arrive(&p_full[b]);
-    }
-    // row sum of both halves
-    l_ex[half][r] = l;
-    named_bar_sync(pair_bar, 64);
-    l += l_ex[half ^ 1][r];
-    // last PV retired -> O complete
-    mbar_wait(&pv_done[(nkv - 1) & 1], ((nkv - 1) >> 1) & 1);
-    tc_fence_after();
-    uint32_t o0[32];
-    tmem_ld32(trow + 128 + half * 32, o0);
-    tmem_ld_wait();
-    const int q = q0 + r;
-    if (q < p.Lq) {
-      const float inv = 1.f / l;
-      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.O) +
-                          (static_cast<size_t>(img) * p.Lq + q) * p.ldo + head * kD + half * 32;
-      uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 u;
-        u.x = pack_bf16(__uint_as_float(o0[8 * c + 0]) * inv, __uint_as_float(o0[8 * c + 1]) * inv);
-        u.y = pack_bf16(__uint_as_float(o0[8 * c + 2]) * inv, __uint_as_float(o0[8 * c + 3]) * inv);
-        u.z = pack_bf16(__uint_as_float(o0[8 * c + 4]) * inv, __uint_as_float(o0[8 * c + 5]) * inv);
-        u.w = pack_bf16(__uint_as_float(o0[8 * c + 6]) * inv, __uint_as_float(o0[8 * c + 7]) * inv);
-        o4[c] = u;
-      }
-    }
-    tc_fence_before();
-  }
-  pdl_launch_dependents();  // late trigger (see gemm2.cu)
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kAttTmemCols);
-  }
-}
-
-
 // ------------------------------------------------------------------------------------------------------------------
-// Tile-split variant ("ts"): the two softmax warp sets do not share a tile.  Set A (warps 2-5) owns the even key
+// Tile-split softmax: the two softmax warp sets do not share a tile.  Set A (warps 2-5) owns the even key
 // tiles, set B (warps 6-9) the odd ones; a thread owns one query row of its set's tile (all 64 keys), its own running
 // maximum / row sum and its own O accumulator in TMEM (O_A, O_B), so the loop has no cross-warp exchange at all: no
 // shared-memory maximum, no named barrier, no P-buffer hand-back.  P (bf16 pairs) overwrites the first 32 columns of
@@ -678,317 +354,10 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 
-// ------------------------------------------------------------------------------------------------------------------
-// Early-S variant ("es") of the tile-split kernel.  In the ts kernel P overwrites its S buffer, so S(j+2) can only be
-// issued behind PV(j) and every softmax set idles for the PV + QK^T round trip of each tile (ncu: 26 % of all stall
-// samples sit on the s_full wait).  Here P goes through a 128-byte-swizzled shared-memory buffer per set instead, and
-// the set releases its S buffer as soon as the scores are in registers (s_free): the MMA warp issues S(j+2) at the
-// START of softmax(j), so the next tile's scores are waiting when the set comes back and the warps never idle.
-// K and V have separate rings (K is dead after S(j), V only after PV(j)): 3 x 8 KB + 4 x 8 KB, two CTAs per SM.
-constexpr int kEsKStages = 3;
-constexpr int kEsVStages = 4;
-constexpr int kEsSmem = kQT * kD * 2 + (kEsKStages + kEsVStages) * kTileBytes + 2 * kQT * kKT * 2 + 1024 + 256;
-
-template <int kPolyPairs>
-__global__ void __launch_bounds__(kAttThreads, 2)
-attention_es_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const AttParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                              // 16 KB
-  uint8_t* sK = sQ + kQT * kD * 2;                 // 3 x 8 KB
-  uint8_t* sV = sK + kEsKStages * kTileBytes;      // 4 x 8 KB
-  uint8_t* sP = sV + kEsVStages * kTileBytes;      // 2 x 16 KB (one per softmax set)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kQT * kKT * 2);
-  uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;                     // [3]
-  uint64_t* k_empty = k_full + kEsKStages;         // [3]
-  uint64_t* v_full = k_empty + kEsKStages;         // [4]
-  uint64_t* v_empty = v_full + kEsVStages;         // [4]
-  uint64_t* s_full = v_empty + kEsVStages;         // [2] S of an even / odd tile is in TMEM
-  uint64_t* s_free = s_full + 2;                   // [2] 128 arrivals: the set has its scores in registers
-  uint64_t* p_full = s_free + 2;                   // [2] 128 arrivals: P of an even / odd tile is in shared memory
-  uint64_t* pv_done = p_full + 2;                  // [2] PV of an even / odd tile has retired
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
-  __shared__ float m_ex[2][kQT];
-  __shared__ float l_ex[2][kQT];
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kQT;
-  const int head = blockIdx.y;
-  const int img = blockIdx.z;
-  const int nkv = (p.Lk + kKT - 1) / kKT;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < kEsKStages; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-    }
-    for (int i = 0; i < kEsVStages; ++i) {
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&pv_done[i], 1);
-      mbar_init(&s_free[i], 128);
-      mbar_init(&p_full[i], 128);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_holder, kAttTmemCols);   // S_A [0,64) S_B [64,128) O_A [128,192) O_B [192,256)
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_holder;
-  pdl_wait();
-
-  if (warp == 0) {
-    const uint32_t sK_u32 = smem_u32(sK), sV_u32 = smem_u32(sV);
-    const uint32_t kfull_u32 = smem_u32(k_full), kempty_u32 = smem_u32(k_empty);
-    const uint32_t vfull_u32 = smem_u32(v_full), vempty_u32 = smem_u32(v_empty);
-    if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, kQT * kD * 2);
-      tma_load_4d(sQ, &tmQ, q_full, 0, q0, head, img);
-    }
-    __syncwarp();
-    uint32_t ks = 0, kph = 0, vs = 0, vph = 0;
-    for (int j = 0; j < nkv; ++j) {
-      mbar_wait_u32(kempty_u32 + ks * 8, kph ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx_u32(kfull_u32 + ks * 8, kTileBytes);
-        tma_load_4d_u32(sK_u32 + ks * kTileBytes, &tmK, kfull_u32 + ks * 8, 0, j * kKT, head, img);
-      }
-      __syncwarp();
-      mbar_wait_u32(vempty_u32 + vs * 8, vph ^ 1);
-      if (elect_one()) {
-        mbar_arrive_expect_tx_u32(vfull_u32 + vs * 8, kTileBytes);
-        tma_load_4d_u32(sV_u32 + vs * kTileBytes, &tmV, vfull_u32 + vs * 8, 0, j * kKT, head, img);
-      }
-      __syncwarp();
-      if (++ks == kEsKStages) { ks = 0; kph ^= 1; }
-      if (++vs == kEsVStages) { vs = 0; vph ^= 1; }
-    }
-  } else if (warp == 1) {
-    constexpr uint32_t idesc_s = umma_idesc_bf16(kQT, kKT, false);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(kQT, kD, true);
-    const uint32_t sQ_u32 = smem_u32(sQ), sK_u32 = smem_u32(sK), sV_u32 = smem_u32(sV), sP_u32 = smem_u32(sP);
-    const uint32_t kfull_u32 = smem_u32(k_full), kempty_u32 = smem_u32(k_empty);
-    const uint32_t vfull_u32 = smem_u32(v_full), vempty_u32 = smem_u32(v_empty);
-    const uint32_t sfull_u32 = smem_u32(s_full), sfree_u32 = smem_u32(s_free);
-    const uint32_t pfull_u32 = smem_u32(p_full), pvdone_u32 = smem_u32(pv_done);
-    uint32_t ks = 0, kph = 0;
-    auto issue_s = [&](int j) {
-      mbar_wait_u32(kfull_u32 + ks * 8, kph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t qdesc = umma_smem_desc_sw128(sQ_u32);
-        const uint64_t kdesc = umma_smem_desc_sw128(sK_u32 + ks * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_ss(tmem_base + (j & 1) * kKT, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k != 0);
-        umma_commit_u32(sfull_u32 + (j & 1) * 8);
-        umma_commit_u32(kempty_u32 + ks * 8);
-      }
-      __syncwarp();
-      if (++ks == kEsKStages) { ks = 0; kph ^= 1; }
-    };
-    mbar_wait(q_full, 0);
-    issue_s(0);
-    if (nkv > 1) issue_s(1);
-    uint32_t vs = 0, vph = 0;
-    for (int j = 0; j < nkv; ++j) {
-      const int b = j & 1;
-      const uint32_t par = (j >> 1) & 1;
-      if (j + 2 < nkv) {   // the set has read S(j): its buffer may take the scores of the set's next tile
-        mbar_wait_u32(sfree_u32 + b * 8, par);
-        issue_s(j + 2);
-      }
-      mbar_wait_u32(pfull_u32 + b * 8, par);
-      mbar_wait_u32(vfull_u32 + vs * 8, vph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t pdesc = umma_smem_desc_sw128(sP_u32 + b * (kQT * kKT * 2));
-        const uint64_t vdesc = umma_smem_desc_sw128(sV_u32 + vs * kTileBytes);
-#pragma unroll
-        for (int k = 0; k < kKT / 16; ++k)   // A: +32 B per 16 keys (K-major P); B: +16 rows * 128 B (MN-major V)
-          umma_ss(tmem_base + 128 + b * kD, pdesc + 2 * k, vdesc + 128 * k, idesc_pv, (j >= 2) || (k != 0));
-        umma_commit_u32(pvdone_u32 + b * 8);
-        umma_commit_u32(vempty_u32 + vs * 8);
-      }
-      __syncwarp();
-      if (++vs == kEsVStages) { vs = 0; vph ^= 1; }
-    }
-  } else {
-    const int set = (warp - 2) >> 2;       // 0: even tiles, 1: odd tiles
-    const int lg = warp & 3;               // TMEM lane quadrant this warp may access
-    const int r = lg * 32 + lane;          // query row inside the tile == TMEM lane
-    const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
-    const uint32_t s_col = trow + set * kKT;
-    const uint32_t o_col = trow + 128 + set * kD;
-    const uint32_t prow = smem_u32(sP) + set * (kQT * kKT * 2) + r * 128;
-    const uint32_t rsw = static_cast<uint32_t>(r & 7);
-    float m_used = -INFINITY, l = 0.f;
-    const uint64_t sc2 = pack_f32x2(p.scale_log2, p.scale_log2);
-    int it = 0;
-    for (int j = set; j < nkv; j += 2, ++it) {
-      mbar_wait(&s_full[set], it & 1);
-      tc_fence_after();
-      uint32_t sr[64];
-      {
-        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[0]);
-        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sr[32]);
-        tmem_ld32(s_col, lo);
-        tmem_ld32(s_col + 32, hi);
-      }
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(&s_free[set]);   // scores are in registers
-      const int valid = p.Lk - j * kKT;
-      if (valid < kKT) {  // ragged last tile: mask in place
-#pragma unroll
-        for (int i = 0; i < kKT; ++i)
-          if (i >= valid) sr[i] = 0xff800000u;
-      }
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < kKT; i += 4) {
-        m0 = fmaxf(m0, __uint_as_float(sr[i]));
-        m1 = fmaxf(m1, __uint_as_float(sr[i + 1]));
-        m2 = fmaxf(m2, __uint_as_float(sr[i + 2]));
-        m3 = fmaxf(m3, __uint_as_float(sr[i + 3]));
-      }
-      const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-      if (it == 0) {
-        m_used = mx;
-      } else {
-        // PV of the set's previous tile has retired: its O accumulator is quiescent and the P buffer is free
-        mbar_wait(&pv_done[set], (it - 1) & 1);
-        const bool need = (mx - m_used) * p.scale_log2 > kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {
-          tc_fence_after();
-          const float f = need ? exp2f((m_used - mx) * p.scale_log2) : 1.f;
-          if (need) m_used = mx;
-          l *= f;
-#pragma unroll
-          for (int c = 0; c < kD / 16; ++c) {
-            uint32_t o[16];
-            tmem_ld16(o_col + 16 * c, o);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
-            tmem_st16(o_col + 16 * c, o);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-        }
-      }
-      const float mb = m_used * p.scale_log2;
-      const uint64_t nmb2 = pack_f32x2(-mb, -mb);
-      uint64_t acc0 = 0, acc1 = 0;   // packed (even, odd) partial row sums
-#pragma unroll
-      for (int c = 0; c < kKT / 8; ++c) {   // 8 keys -> one 16-byte chunk of the swizzled P row
-        uint32_t pk[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float a0, a1;
-          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sr[8 * c + 2 * i]), __uint_as_float(sr[8 * c + 2 * i + 1])),
-                                 sc2, nmb2), a0, a1);
-          if (((c & 1) * 4 + i) < kPolyPairs) {
-            exp2_poly_pair(a0, a1, a0, a1);
-          } else {
-            a0 = fast_exp2(a0);
-            a1 = fast_exp2(a1);
-          }
-          if (i & 1) acc1 = add_f32x2(acc1, pack_f32x2(a0, a1));
-          else acc0 = add_f32x2(acc0, pack_f32x2(a0, a1));
-          pk[i] = pack_bf16(a0, a1);
-        }
-        st_shared_v4(prow + ((static_cast<uint32_t>(c) ^ rsw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-      }
-      float s0, s1;
-      unpack_f32x2(add_f32x2(acc0, acc1), s0, s1);
-      l += s0 + s1;
-      fence_proxy_async_smem();
-      mbar_arrive(&p_full[set]);
-    }
-    // merge the two partial softmax states of the row (the partner thread lives in warp +-4: same lane quadrant)
-    const int n_mine = (nkv - set + 1) >> 1, n_other = (nkv - (set ^ 1) + 1) >> 1;
-    m_ex[set][r] = m_used;   // -inf when this set had no tile
-    l_ex[set][r] = l;
-    named_bar_sync(1 + lg, 64);
-    const float m_o = m_ex[set ^ 1][r], l_o = l_ex[set ^ 1][r];
-    const float m = fmaxf(m_used, m_o);
-    const float f_mine = n_mine > 0 ? exp2f((m_used - m) * p.scale_log2) : 0.f;
-    const float f_other = n_other > 0 ? exp2f((m_o - m) * p.scale_log2) : 0.f;
-    const float inv = 1.f / (l * f_mine + l_o * f_other);
-    const float fA = (set == 0 ? f_mine : f_other) * inv, fB = (set == 0 ? f_other : f_mine) * inv;
-    const int nA = (nkv + 1) >> 1, nB = nkv >> 1;
-    mbar_wait(&pv_done[0], (nA - 1) & 1);
-    if (nB > 0) mbar_wait(&pv_done[1], (nB - 1) & 1);
-    tc_fence_after();
-    // this thread writes output columns [set*32, set*32+32) of its row
-    uint32_t oa[32];
-    tmem_ld32(trow + 128 + set * 32, oa);
-    tmem_ld_wait();
-    float o[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(oa[i]) * fA;
-    if (nB > 0) {
-      tmem_ld32(trow + 128 + kD + set * 32, oa);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(oa[i]), fB, o[i]);
-    }
-    const int q = q0 + r;
-    if (q < p.Lq) {
-      __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.O) +
-                          (static_cast<size_t>(img) * p.Lq + q) * p.ldo + head * kD + set * 32;
-      uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 u;
-        u.x = pack_bf16(o[8 * c + 0], o[8 * c + 1]);
-        u.y = pack_bf16(o[8 * c + 2], o[8 * c + 3]);
-        u.z = pack_bf16(o[8 * c + 4], o[8 * c + 5]);
-        u.w = pack_bf16(o[8 * c + 6], o[8 * c + 7]);
-        o4[c] = u;
-      }
-    }
-    tc_fence_before();
-  }
-  pdl_launch_dependents();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, kAttTmemCols);
-  }
-}
-
 int prime_attention_attributes() {
-  cudaError_t e = cudaFuncSetAttribute(attention_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
+  cudaError_t e = cudaFuncSetAttribute(attention_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(attention_ts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_ts_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_es_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEsSmem);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(attention_es_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kEsSmem);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
     return EDTR_ERR_CUDA;
@@ -996,11 +365,12 @@ int prime_attention_attributes() {
   return EDTR_OK;
 }
 
-// Development switch (EDTR_ATT_VARIANT=0|1|2, read once); the default is the measured-fastest variant.
-static int attention_variant() {
-  static const int v = [] {
-    const char* e = getenv("EDTR_ATT_VARIANT");
-    return e ? atoi(e) : 4;
+// EDTR_ATT_POLY=0 computes every exponential on the MUFU unit; the default moves 2 of every 8 key pairs to the
+// FMA-pipe polynomial (measured 2.5 % faster on the L = 4096 self-attention).
+static bool attention_poly() {
+  static const bool v = [] {
+    const char* e = getenv("EDTR_ATT_POLY");
+    return e == nullptr || e[0] != '0';
   }();
   return v;
 }
@@ -1041,15 +411,9 @@ extern "C" int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ld
   p.scale_log2 = scale * 1.4426950408889634f;
   dim3 grid((Lq + kQT - 1) / kQT, heads, B);
   const cudaStream_t st = static_cast<cudaStream_t>(stream);
-  switch (attention_variant()) {
-    case 0: EDTR_LAUNCH(attention_kernel<0>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
-    case 1: EDTR_LAUNCH(attention_kernel<1>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
-    case 2: EDTR_LAUNCH(attention_kernel<2>, grid, kAttThreads, kAttSmem, st, tmQ, tmK, tmV, p); break;
-    case 3: EDTR_LAUNCH(attention_ts_kernel<0>, grid, kAttThreads, kTsSmem, st, tmQ, tmK, tmV, p); break;
-    case 4: EDTR_LAUNCH(attention_ts_kernel<2>, grid, kAttThreads, kTsSmem, st, tmQ, tmK, tmV, p); break;
-    case 5: EDTR_LAUNCH(attention_ts_kernel<3>, grid, kAttThreads, kTsSmem, st, tmQ, tmK, tmV, p); break;
-    case 6: EDTR_LAUNCH(attention_es_kernel<0>, grid, kAttThreads, kEsSmem, st, tmQ, tmK, tmV, p); break;
-    default: EDTR_LAUNCH(attention_es_kernel<2>, grid, kAttThreads, kEsSmem, st, tmQ, tmK, tmV, p); break;
-  }
-  return check_launch("attention_kernel");
+  if (attention_poly())
+    EDTR_LAUNCH(attention_ts_kernel<2>, grid, kAttThreads, kTsSmem, st, tmQ, tmK, tmV, p);
+  else
+    EDTR_LAUNCH(attention_ts_kernel<0>, grid, kAttThreads, kTsSmem, st, tmQ, tmK, tmV, p);
+  return check_launch("attention_ts_kernel");
 }

@@ -59,6 +59,8 @@ struct Gemm2Params {
   const float* rowvec;
   int rowvec_ld;
   int rows_per_group;
+  float* nchw_out;         // != NULL: N <= 8 output channels stored straight to an fp32 [B, N, hw] tensor (the eps /
+  int nchw_hw;             //          image / moments outputs of the path); one 64-column tile, bias only
 };
 
 __device__ __forceinline__ float gelu_fast(float x) {
@@ -307,6 +309,28 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
         continue;
       }
+      if (p.nchw_out != nullptr) {
+        // few-channel convolution (UNet eps, VAE image / moments): a lane owns one pixel, so for every channel the
+        // warp writes 32 consecutive floats of one NCHW plane
+        if (grp == 0) {
+          uint32_t r0[8];
+          tmem_ld8(tacc, r0);
+          tmem_ld_wait();
+          if (row < p.M) {
+            const int img = row / p.nchw_hw;
+            float* dst = p.nchw_out + static_cast<size_t>(img) * p.N * p.nchw_hw + (row - img * p.nchw_hw);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+              if (c < p.N)
+                dst[static_cast<size_t>(c) * p.nchw_hw] =
+                    fmaf(__uint_as_float(r0[c]), p.alpha, p.bias != nullptr ? __ldg(p.bias + c) : 0.f);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
+        continue;
+      }
       const int nchunks = tile_chunks(w);
       if (grp >= nchunks) {   // no chunk of this tile belongs to this warp: release the accumulator at once
         tc_fence_before();
@@ -545,6 +569,13 @@ bool gemm2_disabled();
 
 bool gemm2_eligible(int M, int N, const EdtrEpilogue* ep) {
   if (gemm2_disabled()) return false;
+  static const bool nchw_ok = [] {
+    const char* e = getenv("EDTR_GEMM2_NCHW");   // debugging switch: 0 sends the few-channel outputs to the single-CTA kernel
+    return e == nullptr || e[0] != '0';
+  }();
+  if (ep->out_mode == EDTR_OUT_NCHW_F32)
+    return nchw_ok && M >= 256 && N <= 8 && ep->hw > 0 && M % ep->hw == 0 && ep->residual == nullptr && ep->rowvec == nullptr &&
+           ep->act == EDTR_ACT_NONE;
   if (ep->out_mode != EDTR_OUT_BF16) return false;
   const int n_out = ep->act == EDTR_ACT_GEGLU ? N / 2 : N;
   if (ep->act == EDTR_ACT_GEGLU) return N % k2MaxBN == 0;  // any M: the weight interleave is tied to this kernel
@@ -574,7 +605,12 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   p.M = M; p.N = N; p.num_kblocks = K / k2BK; p.mode = mode; p.H = H; p.W = W; p.cblocks = cblocks;
   p.taps_x = taps_x; p.tap_dy0 = tap_dy0; p.tap_dx0 = tap_dx0; p.up2x = tmD_up != nullptr;
   p.geglu = ep->act == EDTR_ACT_GEGLU;
-  plan_tiles(M, N, p.num_kblocks, p.geglu, p.up2x ? 0 : g_ws_bytes, &p.tiles_n, &p.bn_base, &p.splits);
+  const bool nchw = ep->out_mode == EDTR_OUT_NCHW_F32;
+  plan_tiles(M, N, p.num_kblocks, p.geglu, (p.up2x || nchw) ? 0 : g_ws_bytes, &p.tiles_n, &p.bn_base, &p.splits);
+  if (nchw) {
+    p.nchw_out = static_cast<float*>(ep->out);
+    p.nchw_hw = ep->hw;
+  }
   p.kb_per_split = (p.num_kblocks + p.splits - 1) / p.splits;
   p.ws = g_ws;
   p.b_box_rows = p.bn_base / 2;
@@ -600,6 +636,8 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   }
   if (tmD_up != nullptr) {
     tmD = *tmD_up;
+  } else if (nchw) {
+    tmD = tmA;   // unused (plain stores); any valid descriptor will do for the prefetch
   } else {
     uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(M)};
     uint64_t strides[1] = {static_cast<uint64_t>(ep->ldc) * 2};

@@ -15,7 +15,7 @@ python scripts/summarize_launches.py gpurun_out/launches.csv gpurun_out/gemm2_tr
 EDTR_NCU=1 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off \
     -k regex:gemm2_kernel -s 300 -c 3 -o gpurun_out/prof_gemm -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 echo "== ncu full exit $?"
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 2 -c 1 -f \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:attention_ts_kernel -s 2 -c 1 -f \
     -o gpurun_out/prof_attn python scripts/ncu_attn.py > gpurun_out/ncu_attn.log 2>&1
 echo "== ncu attention exit $?"; ls -la gpurun_out/*.ncu-rep
 fi

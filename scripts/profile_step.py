@@ -111,7 +111,7 @@ def main():
         orig = {n: getattr(ops, n) for n in names}
         # kernels an op launches first ("primary", counted) — the rest (split-K reduce, GN apply) follow their primary
         PRIMARY = {"gemm": ("gemm2_kernel", "gemm_conv_kernel"), "conv3x3": ("gemm2_kernel", "gemm_conv_kernel"),
-                   "conv3x3_up2x": ("gemm2_kernel",), "attention": ("attention_kernel",),
+                   "conv3x3_up2x": ("gemm2_kernel",), "attention": ("attention_ts_kernel",),
                    "groupnorm": ("groupnorm_stats_kernel", "groupnorm_fused_kernel"), "layernorm": ("layernorm_kernel",),
                    "softmax_rows": ("softmax_rows_kernel",), "upsample2x": ("upsample2x_kernel",),
                    "im2col": ("im2col_kernel",), "nchw_to_nhwc": ("nchw_to_nhwc_kernel",),

@@ -147,14 +147,15 @@ def test_gemm_out_modes(ops):
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 64, 128), (1, 8, 8, 128, 64), (3, 8, 8, 64, 64),
                                              (2, 16, 16, 320, 320), (1, 32, 32, 640, 320), (1, 128, 128, 64, 64),
-                                             (1, 256, 256, 128, 3), (8, 8, 8, 1280, 1280), (1, 64, 64, 64, 4)])
+                                             (1, 256, 256, 128, 3), (8, 8, 8, 1280, 1280), (1, 64, 64, 64, 4),
+                                             (3, 32, 32, 320, 4), (2, 128, 128, 128, 3), (5, 16, 16, 512, 8)])
 def test_conv3x3(ops, B, H, W, Cin, Cout):
     x = rnd(B, H, W, Cin, seed=1)
     w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
     bias = torch.randn(Cout, device="cuda")
     emb = torch.randn(B, Cout, device="cuda")
     wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
-    if Cout % 8 == 0:
+    if Cout % 64 == 0:
         res = rnd(B, H, W, Cout, seed=3)
         out = ops.conv3x3(x, wp, bias=bias, rowvec=emb, residual=res.view(-1, Cout))
         ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + emb[:, :, None, None]
