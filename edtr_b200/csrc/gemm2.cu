@@ -59,8 +59,6 @@ struct Gemm2Params {
   const float* rowvec;
   int rowvec_ld;
   int rows_per_group;
-  int w_kb_rows;           // 0: weights row-major [N, K]; > 0: k-block-major [K/64][w_kb_rows][64] (each B box is one
-                           //    contiguous run in HBM); the B map is then 2-D over (64, k-block * rows + n)
   float* nchw_out;         // != NULL: N <= 8 output channels stored straight to an fp32 [B, N, hw] tensor (the eps /
   int nchw_hw;             //          image / moments outputs of the path); one 64-column tile, bias only
 };
@@ -168,8 +166,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           } else {
             tma_load_4d_pair_u32(sa, &tmA, fb, cb * k2BK, cx + tx, cy + ty, cn);
           }
-          if (p.w_kb_rows == 0) tma_load_2d_pair_u32(sa + k2ABytes, &tmB, fb, kb * k2BK, nrow0);
-          else tma_load_2d_pair_u32(sa + k2ABytes, &tmB, fb, 0, kb * p.w_kb_rows + nrow0);
+          tma_load_2d_pair_u32(sa + k2ABytes, &tmB, fb, kb * k2BK, nrow0);
         }
         __syncwarp();
         if (++cb == p.cblocks) {
@@ -600,44 +597,10 @@ bool gemm2_disabled() {
   return e != nullptr && e[0] == '1';
 }
 
-// B-operand (weight) tensor map for either weight layout (strides in elements):
-//   row-major       w_kb_stride == 64, w_row_stride >= K : element (n, k) at n * w_row_stride + k
-//   k-block-major   w_row_stride == 64, w_kb_stride = 64 * rows : element (n, k) at (k / 64) * w_kb_stride + n * 64 + k % 64
-// In the second layout the [box_rows x 64] box of one k-block is one contiguous run of box_rows * 128 bytes in HBM
-// instead of box_rows separate 128-byte pieces K * 2 bytes apart, which is what the weight-streaming GEMMs of the
-// 8x8 / 16x16 levels (few rows, every weight byte read once) are bound by.
-int make_weight_tmap(CUtensorMap* tm, const void* Wt, int64_t w_row_stride, int64_t w_kb_stride, int N, int K,
-                     int box_rows, int* w_kb_rows) {
-  if (w_kb_stride == 64) {
-    if (w_row_stride < K || w_row_stride % 8 != 0) {
-      set_error("row-major weights need a row stride >= K and a multiple of 8 (got %lld)", static_cast<long long>(w_row_stride));
-      return EDTR_ERR_INVALID;
-    }
-    *w_kb_rows = 0;
-    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
-    uint64_t strides[1] = {static_cast<uint64_t>(w_row_stride) * 2};
-    uint32_t box[2] = {64, static_cast<uint32_t>(box_rows)};
-    return make_tmap_bf16(tm, Wt, 2, dims, strides, box);
-  }
-  if (w_row_stride != 64 || w_kb_stride % 64 != 0 || w_kb_stride < static_cast<int64_t>(N) * 64 ||
-      w_kb_stride / 64 > (1 << 24)) {
-    set_error("weights must be row-major (k-block stride 64) or k-block-major (row stride 64, k-block stride = 64 * rows >= 64 * N); "
-              "got row stride %lld, k-block stride %lld", static_cast<long long>(w_row_stride),
-              static_cast<long long>(w_kb_stride));
-    return EDTR_ERR_INVALID;
-  }
-  const int rows = static_cast<int>(w_kb_stride / 64);
-  *w_kb_rows = rows;
-  uint64_t dims[2] = {64, static_cast<uint64_t>(K / 64 - 1) * rows + static_cast<uint64_t>(N)};
-  uint64_t strides[1] = {128};
-  uint32_t box[2] = {64, static_cast<uint32_t>(box_rows)};
-  return make_tmap_bf16(tm, Wt, 2, dims, strides, box);
-}
-
 // A/B tensor maps are built by the caller (gemm or conv geometry); C/D maps are built here.
-int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int64_t w_row_stride, int64_t w_kb_stride, int K, int M, int N,
-                 int mode, int H, int W, int cblocks, const EdtrEpilogue* ep, cudaStream_t stream, int taps_x,
-                 int tap_dy0, int tap_dx0, const CUtensorMap* tmD_up) {
+int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, int N, int mode, int H, int W,
+                 int cblocks, const EdtrEpilogue* ep, cudaStream_t stream, int taps_x, int tap_dy0, int tap_dx0,
+                 const CUtensorMap* tmD_up) {
   Gemm2Params p{};
   p.M = M; p.N = N; p.num_kblocks = K / k2BK; p.mode = mode; p.H = H; p.W = W; p.cblocks = cblocks;
   p.taps_x = taps_x; p.tap_dy0 = tap_dy0; p.tap_dx0 = tap_dx0; p.up2x = tmD_up != nullptr;
@@ -664,8 +627,13 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int64_t w_row_stride, i
   const int n_out = p.geglu ? N / 2 : N;
   CUtensorMap tmB, tmC, tmD;
   int rc;
-  rc = make_weight_tmap(&tmB, Wt, w_row_stride, w_kb_stride, N, K, p.b_box_rows, &p.w_kb_rows);
-  if (rc) return rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {k2BK, static_cast<uint32_t>(p.b_box_rows)};
+    rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
+    if (rc) return rc;
+  }
   if (tmD_up != nullptr) {
     tmD = *tmD_up;
   } else if (nchw) {

@@ -25,7 +25,6 @@ struct GemmKernelParams {
   int num_kblocks;
   int mode;             // 0 gemm, 1 conv3x3
   int H, W, cblocks;    // conv geometry (cblocks = Cin / 64)
-  int w_kb_rows;        // 0: row-major weights; > 0: k-block-major (see make_weight_tmap in gemm2.cu)
   EdtrEpilogue ep;
 };
 
@@ -196,8 +195,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else {
           tma_load_4d_u32(sA_u32 + s * Cfg::kABytes, &tmA, fb, cb * kBK, cx + tx, cy + ty, cn);
         }
-        if (p.w_kb_rows == 0) tma_load_2d_u32(sB_u32 + s * Cfg::kBBytes, &tmB, fb, kb * kBK, n0);
-        else tma_load_2d_u32(sB_u32 + s * Cfg::kBBytes, &tmB, fb, 0, kb * p.w_kb_rows + n0);
+        tma_load_2d_u32(sB_u32 + s * Cfg::kBBytes, &tmB, fb, kb * kBK, n0);
       }
       __syncwarp();
       if (++cb == p.cblocks) {
@@ -353,11 +351,9 @@ int prime_gemm_attributes() {
 bool gemm2_eligible(int M, int N, const EdtrEpilogue* ep);
 int gemm2_tile_n(int N, int geglu);
 bool gemm2_disabled();
-int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int64_t w_row_stride, int64_t w_kb_stride, int K, int M, int N,
-                 int mode, int H, int W, int cblocks, const EdtrEpilogue* ep, cudaStream_t stream, int taps_x = 3,
-                 int tap_dy0 = -1, int tap_dx0 = -1, const CUtensorMap* tmD_up = nullptr);
-int make_weight_tmap(CUtensorMap* tm, const void* Wt, int64_t w_row_stride, int64_t w_kb_stride, int N, int K,
-                     int box_rows, int* w_kb_rows);
+int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, int N, int mode, int H, int W,
+                 int cblocks, const EdtrEpilogue* ep, cudaStream_t stream, int taps_x = 3, int tap_dy0 = -1,
+                 int tap_dx0 = -1, const CUtensorMap* tmD_up = nullptr);
 
 static int check_epilogue(const EdtrEpilogue* ep, int M, int N) {
   EDTR_REQUIRE(ep != nullptr && ep->out != nullptr, "epilogue/out is NULL");
@@ -400,15 +396,10 @@ extern "C" int edtr_gemm_tile_n(int M, int N, int K, int act) {
 
 extern "C" int edtr_gemm_bf16(const void* A, int lda, const void* Wt, int ldw, int M, int N, int K,
                               const EdtrEpilogue* ep, void* stream) {
-  return edtr_gemm_bf16_w(A, lda, Wt, ldw, 64, M, N, K, ep, stream);
-}
-
-extern "C" int edtr_gemm_bf16_w(const void* A, int lda, const void* Wt, int64_t w_row_stride, int64_t w_kb_stride,
-                                int M, int N, int K, const EdtrEpilogue* ep, void* stream) {
   EDTR_REQUIRE(A && Wt, "A/Wt is NULL");
   EDTR_REQUIRE(M > 0 && N > 0 && K > 0, "bad GEMM shape %dx%dx%d", M, N, K);
   EDTR_REQUIRE(K % kBK == 0, "K (%d) must be a multiple of 64", K);
-  EDTR_REQUIRE(lda % 8 == 0 && lda >= K, "lda must be >= K and a multiple of 8");
+  EDTR_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K, "lda/ldw must be >= K and multiples of 8");
   EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(Wt)) & 15) == 0, "A/Wt must be 16-byte aligned");
   int rc = check_epilogue(ep, M, N);
   if (rc) return rc;
@@ -422,10 +413,15 @@ extern "C" int edtr_gemm_bf16_w(const void* A, int lda, const void* Wt, int64_t 
     if (rc) return rc;
   }
   if (gemm2_eligible(M, N, ep))
-    return launch_gemm2(tmA, Wt, w_row_stride, w_kb_stride, K, M, N, 0, 0, 0, 0, ep, static_cast<cudaStream_t>(stream));
+    return launch_gemm2(tmA, Wt, ldw, K, M, N, 0, 0, 0, 0, ep, static_cast<cudaStream_t>(stream));
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
+    rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
+    if (rc) return rc;
+  }
   GemmKernelParams p{};
-  rc = make_weight_tmap(&tmB, Wt, w_row_stride, w_kb_stride, N, K, bn, &p.w_kb_rows);
-  if (rc) return rc;
   p.M = M; p.N = N; p.num_kblocks = K / kBK; p.mode = 0;
   p.ep = *ep;
   return dispatch_gemm(bn, tmA, tmB, p, static_cast<cudaStream_t>(stream));
@@ -485,8 +481,8 @@ extern "C" int edtr_conv3x3_up2x_bf16(const void* X, int ldx, int B, int H, int 
       rc = make_tmap_bf16(&tmD, base, 4, dims, strides, box);
       if (rc) return rc;
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(Wt4) + static_cast<size_t>(py * 2 + px) * Cout * K;
-      rc = launch_gemm2(tmA, wp, K, 64, K, M, Cout, 1, H, W, Cin / kBK, ep, static_cast<cudaStream_t>(stream), 2,
-                        py - 1, px - 1, &tmD);
+      rc = launch_gemm2(tmA, wp, K, K, M, Cout, 1, H, W, Cin / kBK, ep, static_cast<cudaStream_t>(stream), 2, py - 1,
+                        px - 1, &tmD);
       if (rc) return rc;
     }
   return EDTR_OK;
@@ -494,12 +490,6 @@ extern "C" int edtr_conv3x3_up2x_bf16(const void* X, int ldx, int B, int H, int 
 
 extern "C" int edtr_conv3x3_bf16(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wt,
                                  int Cout, const EdtrEpilogue* ep, void* stream) {
-  return edtr_conv3x3_bf16_w(X, ldx, B, H, W, Cin, Wt, static_cast<int64_t>(9) * Cin, 64, Cout, ep, stream);
-}
-
-extern "C" int edtr_conv3x3_bf16_w(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wt,
-                                   int64_t w_row_stride, int64_t w_kb_stride, int Cout, const EdtrEpilogue* ep,
-                                   void* stream) {
   EDTR_REQUIRE(X && Wt, "X/Wt is NULL");
   EDTR_REQUIRE(B > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "bad conv shape");
   EDTR_REQUIRE(Cin % kBK == 0, "Cin (%d) must be a multiple of 64", Cin);
@@ -539,11 +529,15 @@ extern "C" int edtr_conv3x3_bf16_w(const void* X, int ldx, int B, int H, int W, 
   }
   const int K = 9 * Cin;
   if (gemm2_eligible(M, Cout, ep))
-    return launch_gemm2(tmA, Wt, w_row_stride, w_kb_stride, K, M, Cout, 1, H, W, Cin / kBK, ep,
-                        static_cast<cudaStream_t>(stream));
+    return launch_gemm2(tmA, Wt, K, K, M, Cout, 1, H, W, Cin / kBK, ep, static_cast<cudaStream_t>(stream));
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(Cout)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {kBK, static_cast<uint32_t>(bn)};
+    rc = make_tmap_bf16(&tmB, Wt, 2, dims, strides, box);
+    if (rc) return rc;
+  }
   GemmKernelParams p{};
-  rc = make_weight_tmap(&tmB, Wt, w_row_stride, w_kb_stride, Cout, K, bn, &p.w_kb_rows);
-  if (rc) return rc;
   p.M = M; p.N = Cout; p.num_kblocks = K / kBK; p.mode = 1;
   p.H = H; p.W = W; p.cblocks = Cin / kBK;
   p.ep = *ep;

@@ -24,7 +24,6 @@ other execution path in the product.
 from __future__ import annotations
 
 import math
-import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -46,17 +45,7 @@ def pack_conv3x3(w: torch.Tensor, device) -> torch.Tensor:
     cp = _ceil(cin, 64)
     wp = torch.zeros((cout, 3, 3, cp), dtype=F32)
     wp[..., :cin] = w.detach().float().cpu().permute(0, 2, 3, 1)
-    return _kblock_major(wp.reshape(cout, 9 * cp).to(BF16).contiguous().to(device))
-
-
-def _kblock_major(w: torch.Tensor) -> torch.Tensor:
-    """Weights live in HBM k-block-major ([K/64][N][64], viewed as [N, K/64, 64]): every operand tile a GEMM / conv
-    CTA fetches is then one contiguous run instead of N pieces of 128 bytes (ops.to_kblock_major; EDTR_W_KBM=0
-    keeps the row-major matrix, for A/B measurements)."""
-    if os.environ.get("EDTR_W_KBM", "1") == "0" or w.shape[1] % 64 != 0:
-        return w
-    N, K = w.shape
-    return w.view(N, K // 64, 64).permute(1, 0, 2).contiguous().permute(1, 0, 2)
+    return wp.reshape(cout, 9 * cp).to(BF16).contiguous().to(device)
 
 
 def pack_conv3x3_up2x(w: torch.Tensor, device) -> torch.Tensor:
@@ -81,7 +70,7 @@ def pack_conv3x3_up2x(w: torch.Tensor, device) -> torch.Tensor:
 def pack_matrix(w: torch.Tensor, device) -> torch.Tensor:
     """Linear [N, K] or 1x1 conv [N, K, 1, 1] -> bf16 [N, K]."""
     w = w.detach()
-    return _kblock_major(w.reshape(w.shape[0], -1).to(BF16).contiguous().to(device))
+    return w.reshape(w.shape[0], -1).to(BF16).contiguous().to(device)
 
 
 def vec(v: torch.Tensor, device) -> torch.Tensor:
@@ -880,7 +869,7 @@ class VaeDecoderEngine(_VaeBlocks):
             else:
                 w[k] = vec(v, dev)
         a = "decoder.mid.attn_1."
-        w[a + "qk.weight"] = _kblock_major(torch.cat([w[a + "q.weight"], w[a + "k.weight"]], 0).flatten(1).contiguous())
+        w[a + "qk.weight"] = torch.cat([w[a + "q.weight"], w[a + "k.weight"]], 0).contiguous()
         w[a + "qk.bias"] = torch.cat([w[a + "q.bias"], w[a + "k.bias"]], 0).contiguous()
         self.w = w
         self._ws: Dict[Tuple[int, int, int], Workspace] = {}
@@ -1076,7 +1065,7 @@ class VaeEncoderEngine(_VaeBlocks):
         w["encoder.moments.weight"] = pack_conv3x3(wf.float(), dev)
         w["encoder.moments.bias"] = vec(bf.float(), dev)
         a = "encoder.mid.attn_1."
-        w[a + "qk.weight"] = _kblock_major(torch.cat([w[a + "q.weight"], w[a + "k.weight"]], 0).flatten(1).contiguous())
+        w[a + "qk.weight"] = torch.cat([w[a + "q.weight"], w[a + "k.weight"]], 0).contiguous()
         w[a + "qk.bias"] = torch.cat([w[a + "q.bias"], w[a + "k.bias"]], 0).contiguous()
         self.w = w
         self._ws: Dict[Tuple[int, int, int], Workspace] = {}

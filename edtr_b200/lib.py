@@ -29,7 +29,7 @@ NVCC_FLAGS = [
 # every symbol include/edtr_b200.h declares
 EXPORTED = [
     "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_set_workspace", "edtr_gemm_tile_n", "edtr_gemm_bf16",
-    "edtr_gemm_bf16_w", "edtr_conv3x3_bf16", "edtr_conv3x3_bf16_w", "edtr_conv3x3_up2x_bf16", "edtr_attention_bf16", "edtr_groupnorm_partial_size", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
+    "edtr_conv3x3_bf16", "edtr_conv3x3_up2x_bf16", "edtr_attention_bf16", "edtr_groupnorm_partial_size", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
     "edtr_groupnorm_fused_supported", "edtr_groupnorm_fused", "edtr_groupnorm_pool", "edtr_groupnorm_apply_stats",
     "edtr_layernorm_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
     "edtr_nchw_f32_to_nhwc_bf16", "edtr_pointwise_nchw_f32_to_nhwc_bf16", "edtr_nhwc_bf16_to_nchw", "edtr_cast_f32_to_bf16",
@@ -113,10 +113,6 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_gemm_bf16.argtypes = [vp, ci, vp, ci, ci, ci, ci, ep, vp]
     lib.edtr_conv3x3_bf16.restype = ci
     lib.edtr_conv3x3_bf16.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, ep, vp]
-    lib.edtr_gemm_bf16_w.restype = ci
-    lib.edtr_gemm_bf16_w.argtypes = [vp, ci, vp, c_int64, c_int64, ci, ci, ci, ep, vp]
-    lib.edtr_conv3x3_bf16_w.restype = ci
-    lib.edtr_conv3x3_bf16_w.argtypes = [vp, ci, ci, ci, ci, ci, vp, c_int64, c_int64, ci, ep, vp]
     lib.edtr_conv3x3_up2x_bf16.restype = ci
     lib.edtr_conv3x3_up2x_bf16.argtypes = [vp, ci, ci, ci, ci, ci, vp, ci, ep, vp]
     lib.edtr_attention_bf16.restype = ci

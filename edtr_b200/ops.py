@@ -66,29 +66,6 @@ def rows_view(t: torch.Tensor, dtype=BF16) -> Tuple[int, int, int]:
     return rows, cols, ld
 
 
-def weight_view(w: torch.Tensor) -> Tuple[int, int, int, int]:
-    """(N, K, row stride, k-block stride) of a bf16 weight operand: a 2-D row-major ``[N, K]`` matrix, or a 3-D
-    ``[N, K/64, 64]`` view whose strides say where k-block ``kb`` of row ``n`` lives — ``to_kblock_major`` builds the
-    layout in which every operand tile is one contiguous run in HBM (include/edtr_b200.h: edtr_gemm_bf16_w)."""
-    if w.dtype != BF16:
-        raise ValueError(f"expected dtype {BF16}, got {w.dtype}")
-    if w.dim() == 2:
-        N, K, ldw = rows_view(w)
-        return N, K, ldw, 64
-    if w.dim() == 3 and w.shape[2] == 64 and w.stride(2) == 1:
-        return w.shape[0], w.shape[1] * 64, w.stride(0), w.stride(1)
-    raise ValueError(f"weights must be [N, K] or a [N, K/64, 64] view, got shape {tuple(w.shape)} strides {w.stride()}")
-
-
-def to_kblock_major(w: torch.Tensor) -> torch.Tensor:
-    """Repack a row-major bf16 ``[N, K]`` matrix (K % 64 == 0) as ``[K/64][N][64]`` and return the logical
-    ``[N, K/64, 64]`` view of it (strides (64, 64 N, 1)); ``w.reshape(N, K)`` gives the matrix back."""
-    N, K = w.shape
-    if K % 64 != 0:
-        raise ValueError(f"K ({K}) must be a multiple of 64")
-    return w.view(N, K // 64, 64).permute(1, 0, 2).contiguous().permute(1, 0, 2)
-
-
 def _f32(t: Optional[torch.Tensor], n: int, name: str) -> Optional[int]:
     if t is None:
         return None
@@ -149,10 +126,10 @@ def _alloc_out(M: int, n_out: int, out_mode: int, hw: int, device) -> torch.Tens
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, rows_per_group=0, residual=None,
          act=ACT_NONE, out=None, out_mode=OUT_BF16, hw=0, alpha=1.0) -> torch.Tensor:
-    """``epilogue(a @ w.T)`` — a [..., K] rows view, w [N, K] (bf16, row-major or a k-block-major view)."""
+    """``epilogue(a @ w.T)`` — a [..., K] rows view, w [N, K] (bf16)."""
     _require_cuda(a, w, bias, rowvec, residual, out)
     M, K, lda = rows_view(a)
-    N, Kw, w_rs, w_ks = weight_view(w)
+    N, Kw, ldw = rows_view(w)
     if Kw != K:
         raise ValueError(f"K mismatch: a has {K}, w has {Kw}")
     n_out = N // 2 if act == ACT_GEGLU else N
@@ -161,8 +138,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, rows_per_g
     ep = _epilogue(M, n_out, out, bias=bias, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual,
                    act=act, out_mode=out_mode, hw=hw, alpha=alpha)
     L = _lib.device_lib()
-    _lib.check(L.edtr_gemm_bf16_w(a.data_ptr(), lda, w.data_ptr(), w_rs, w_ks, M, N, K, ctypes.byref(ep), _stream()),
-               "edtr_gemm_bf16_w")
+    _lib.check(L.edtr_gemm_bf16(a.data_ptr(), lda, w.data_ptr(), ldw, M, N, K, ctypes.byref(ep), _stream()),
+               "edtr_gemm_bf16")
     return out
 
 
@@ -174,17 +151,17 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, residua
         raise ValueError("x must be [B, H, W, C]")
     B, H, W, Cin = x.shape
     M, _, ldx = rows_view(x)
-    Cout, Kw, w_rs, w_ks = weight_view(w)
-    if Kw != 9 * Cin:
-        raise ValueError(f"weight must be [Cout, 9*Cin={9 * Cin}], got {tuple(w.shape)}")
+    Cout, Kw, ldw = rows_view(w)
+    if Kw != 9 * Cin or ldw != Kw:
+        raise ValueError(f"weight must be contiguous [Cout, 9*Cin={9 * Cin}], got {tuple(w.shape)}")
     hw = H * W
     if out is None:
         out = _alloc_out(M, Cout, out_mode, hw, x.device)
     ep = _epilogue(M, Cout, out, bias=bias, rowvec=rowvec, rows_per_group=hw, residual=residual, act=act,
                    out_mode=out_mode, hw=hw, alpha=alpha)
     L = _lib.device_lib()
-    _lib.check(L.edtr_conv3x3_bf16_w(x.data_ptr(), ldx, B, H, W, Cin, w.data_ptr(), w_rs, w_ks, Cout, ctypes.byref(ep),
-                                     _stream()), "edtr_conv3x3_bf16_w")
+    _lib.check(L.edtr_conv3x3_bf16(x.data_ptr(), ldx, B, H, W, Cin, w.data_ptr(), Cout, ctypes.byref(ep), _stream()),
+               "edtr_conv3x3_bf16")
     return out
 
 

@@ -96,15 +96,6 @@ int edtr_gemm_tile_n(int M, int N, int K, int act);
  * 260-261; model/vae.py:97-101,265-284,689-690. */
 int edtr_gemm_bf16(const void* A, int lda, const void* Wt, int ldw, int M, int N, int K,
                    const EdtrEpilogue* ep, void* stream);
-/* Same, with an explicit weight layout (strides in elements):
- *   row-major      w_kb_stride == 64, w_row_stride = ldw:  Wt(n, k) at n * w_row_stride + k
- *   k-block-major  w_row_stride == 64, w_kb_stride = 64 * R (R >= N rows per k-block):
- *                  Wt(n, k) at (k / 64) * w_kb_stride + n * 64 + k % 64
- * The second layout makes every [rows x 64] operand tile one contiguous run in HBM; the engine
- * repacks all weights this way once (the weight-streaming GEMMs of the 8x8 / 16x16 levels read
- * every weight byte exactly once per step). */
-int edtr_gemm_bf16_w(const void* A, int lda, const void* Wt, int64_t w_row_stride, int64_t w_kb_stride,
-                     int M, int N, int K, const EdtrEpilogue* ep, void* stream);
 
 /* 3x3 / stride 1 / zero-pad 1 convolution as an implicit GEMM.  X is bf16
  * channels-last [B, H, W, Cin] with pixel stride ldx; Wt is bf16 [Cout, 3, 3, Cin]
@@ -114,10 +105,6 @@ int edtr_gemm_bf16_w(const void* A, int lda, const void* Wt, int64_t w_row_strid
  * 675-679; model/controlnet.py:137; model/vae.py:74-88,36-38,477-481,523-527. */
 int edtr_conv3x3_bf16(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wt,
                       int Cout, const EdtrEpilogue* ep, void* stream);
-/* Same, with an explicit layout of the [Cout, 9 * Cin] filter matrix (see edtr_gemm_bf16_w). */
-int edtr_conv3x3_bf16_w(const void* X, int ldx, int B, int H, int W, int Cin, const void* Wt,
-                        int64_t w_row_stride, int64_t w_kb_stride, int Cout, const EdtrEpilogue* ep,
-                        void* stream);
 
 /* Nearest 2x up-sampling followed by a 3x3 / pad-1 convolution, without materialising the up-sampled tensor:
  * four 2x2-tap implicit GEMMs on the low-resolution input, one per output phase (py, px).  X is bf16

@@ -72,7 +72,6 @@ def gemm(a, w, *, bias=None, rowvec=None, rows_per_group=0, residual=None, act=A
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     A = _rows(a)
     M, K = A.shape
-    w = w.reshape(w.shape[0], -1)      # a k-block-major [N, K/64, 64] view is the same matrix
     N, Kw = w.shape
     assert K == Kw and K % 64 == 0, (K, Kw)
     n_out = N // 2 if act == ACT_GEGLU else N
@@ -85,7 +84,6 @@ def conv3x3(x, w, *, bias=None, rowvec=None, residual=None, act=ACT_NONE, out=No
     B, H, W, Cin = x.shape
     assert Cin % 64 == 0
     Cout = w.shape[0]
-    w = w.reshape(Cout, -1)
     assert w.shape[1] == 9 * Cin
     wt = w.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)

@@ -131,38 +131,6 @@ def test_conv3x3_large_batch(ops):
     assert torch.equal(cat[..., :320], before[..., :320])
 
 
-@pytest.mark.parametrize("M,N,K", [(512, 1280, 2560), (2048, 1280, 1280), (8192, 640, 640), (8, 1280, 320), (300, 192, 128),
-                                   (512, 4, 320)])
-def test_gemm_kblock_major_weights(ops, M, N, K):
-    """The k-block-major weight layout (what the engine packs) gives the same result as the row-major matrix: CTA-pair
-    kernel with and without split-K, the single-CTA kernel (M < 256), a row slice of a taller packed matrix."""
-    a, w = rnd(M, K, seed=1), rnd(N + 64, K, scale=K ** -0.5, seed=2)
-    wk = ops.to_kblock_major(w)
-    assert wk.shape == (N + 64, K // 64, 64) and torch.equal(wk.reshape(N + 64, K), w)
-    bias = torch.randn(N, device="cuda")
-    if N % 8 == 0:
-        res = rnd(M, N, seed=3)
-        ref = ops.gemm(a, w[32:32 + N], bias=bias, residual=res)
-        out = ops.gemm(a, wk[32:32 + N], bias=bias, residual=res)
-        assert torch.equal(out, ref)
-        assert relerr(out, a.float() @ w[32:32 + N].float().t() + bias + res.float()) < 1e-2
-    else:
-        ref = ops.gemm(a, w[:N], bias=bias, out_mode=ops.OUT_NCHW_F32, hw=256)
-        out = ops.gemm(a, wk[:N], bias=bias, out_mode=ops.OUT_NCHW_F32, hw=256)
-        assert torch.equal(out, ref)
-
-
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(8, 8, 8, 1280, 1280), (2, 32, 32, 320, 640), (1, 8, 8, 128, 64),
-                                             (2, 64, 64, 128, 3)])
-def test_conv3x3_kblock_major_weights(ops, B, H, W, Cin, Cout):
-    x = rnd(B, H, W, Cin, seed=1)
-    wp = rnd(Cout, 9 * Cin, scale=(9 * Cin) ** -0.5, seed=2)
-    wk = ops.to_kblock_major(wp)
-    bias = torch.randn(Cout, device="cuda")
-    mode = ops.OUT_BF16 if Cout % 64 == 0 else ops.OUT_NCHW_F32
-    assert torch.equal(ops.conv3x3(x, wk, bias=bias, out_mode=mode), ops.conv3x3(x, wp, bias=bias, out_mode=mode))
-
-
 def test_gemm_out_modes(ops):
     M, N, K, hw = 512, 4, 320, 256
     a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
