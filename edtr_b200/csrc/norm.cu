@@ -33,11 +33,13 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------ GroupNorm stats
 // Deterministic two-level reduction, no atomics.  grid (pixel chunks, B, channel slabs);
 // block = vslab * ppar threads (vslab = 16-byte vectors per slab).  Thread (v, q) owns vector v
-// and walks pixels q, q+ppar, ... four at a time (four independent 16-byte loads in flight),
+// and walks pixels q, q+ppar, ... U at a time (U independent 16-byte loads in flight: 8 for the L2-resident tensors
+// of the UNet, whose launches are latency-bound, 4 for the HBM-streaming VAE tensors that run 8 CTAs per SM),
 // keeping its 8 per-channel sums in registers.  The CTA folds the ppar partial rows through
 // shared memory in a fixed order and writes per-(chunk, channel-group) partial sums to
 // partial[b][chunk][group][2]; slabs that split a group write their share into separate
 // slab slots: partial[b][chunk][slab][group][2].
+template <int U>
 __global__ void __launch_bounds__(256)
 groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int C, int groups,
                        int rows_per_cta, int vslab, float* __restrict__ partial) {
@@ -56,16 +58,16 @@ groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int
   for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
   if (q < ppar) {
     const __nv_bfloat16* base = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
-    for (int pidx = p0 + q; pidx < p1; pidx += 4 * ppar) {
-      uint4 u[4];
+    for (int pidx = p0 + q; pidx < p1; pidx += U * ppar) {
+      uint4 u[U];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < U; ++k) {
         u[k] = make_uint4(0u, 0u, 0u, 0u);   // bf16 zeros add nothing to either sum
         if (pidx + k * ppar < p1)
           u[k] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pidx + k * ppar) * ldx));
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < U; ++k) {
         float f[8];
         unpack8(u[k], f);
 #pragma unroll
@@ -97,12 +99,12 @@ groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int
 // ------------------------------------------------------------ GroupNorm apply
 // Same thread <-> channel-vector mapping, so the 8 scale/shift pairs of a thread live in
 // registers.  Every CTA first re-reduces the (tiny) partial-sum table in a fixed order.
+template <int U>
 __global__ void __launch_bounds__(256)
 groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y, int ldy,
                        int HW, int C, int groups, int rows_per_cta, int vslab, int nchunks_stats, int nslab_stats,
                        int cslab_stats, const float* __restrict__ partial, const float* __restrict__ gamma,
                        const float* __restrict__ beta, float eps, int silu, int direct) {
-  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   __shared__ float g_mean[64], g_rstd[64];  // groups intersecting this slab (<= 64)
   const int cslab = vslab * 8;
   const int ppar = blockDim.x / vslab;
@@ -114,6 +116,17 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
   const int g_first = c0 / cpg;
   const int g_last = (min(C, c0 + cslab) - 1) / cpg;
   const float inv_n = 1.f / (static_cast<float>(cpg) * static_cast<float>(HW));
+  // The affine parameters do not depend on the previous kernel: fetch them before the programmatic-dependent-launch
+  // wait, so their latency is hidden under the predecessor's tail.
+  const int cbase = c0 + v * 8;
+  float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga, ba = ga, bb = ga;
+  if (q < ppar) {
+    ga = __ldg(reinterpret_cast<const float4*>(gamma + cbase));
+    gb = __ldg(reinterpret_cast<const float4*>(gamma + cbase + 4));
+    ba = __ldg(reinterpret_cast<const float4*>(beta + cbase));
+    bb = __ldg(reinterpret_cast<const float4*>(beta + cbase + 4));
+  }
+  pdl_wait();
   if (direct) {
     // `partial` holds given statistics [B][groups][2] = (mean, biased variance): tiled VAE, pooled over tiles
     for (int g = g_first + threadIdx.x; g <= g_last; g += blockDim.x) {
@@ -122,72 +135,89 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
       g_rstd[g - g_first] = rsqrtf(mv.y + eps);
     }
   } else {
-    // one warp per group: lanes stride over the (chunk, slab) partial sums, then a fixed shuffle tree
-    // (only full warps take part: the block size need not be a multiple of 32)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int g = g_first + warp; warp < nwarps && g <= g_last; g += nwarps) {
-      const int s_lo = (g * cpg) / cslab_stats, s_hi = ((g + 1) * cpg - 1) / cslab_stats;
-      const int ns = s_hi - s_lo + 1;
-      float a = 0.f, a2 = 0.f;
-      for (int i = lane; i < nchunks_stats * ns; i += 32) {
-        const int ch = i / ns, sl = s_lo + (i - ch * ns);
-        const float2 pr = __ldg(reinterpret_cast<const float2*>(
-            partial + ((((static_cast<size_t>(b) * nchunks_stats + ch) * nslab_stats + sl) * groups + g) * 2)));
-        a += pr.x;
-        a2 += pr.y;
-      }
-      a = warp_sum(a);
-      a2 = warp_sum(a2);
-      if (lane == 0) {
-        const float mean = a * inv_n;
-        const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
-        g_mean[g - g_first] = mean;
-        g_rstd[g - g_first] = rsqrtf(var + eps);
+    // Four lanes per group stride over that group's (chunk, slab) partial sums with four loads in flight each, then a
+    // fixed two-step shuffle tree: every group of the slab is reduced at the same time, so the whole table costs about
+    // one memory round trip.  Only full warps take part (the block size need not be a multiple of 32).
+    const int nfull = static_cast<int>(blockDim.x) & ~31;
+    const int ng = g_last - g_first + 1;
+    const int sub = threadIdx.x & 3;
+    for (int gbase = 0; gbase < ng; gbase += nfull >> 2) {
+      const int gl = gbase + (static_cast<int>(threadIdx.x) >> 2);
+      if (static_cast<int>(threadIdx.x) < nfull) {
+        float a = 0.f, a2 = 0.f;
+        if (gl < ng) {
+          const int g = g_first + gl;
+          const int s_lo = (g * cpg) / cslab_stats, s_hi = ((g + 1) * cpg - 1) / cslab_stats;
+          const int ns = s_hi - s_lo + 1;
+          const int n = nchunks_stats * ns;
+          for (int i = sub; i < n; i += 16) {
+            float2 pr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int idx = i + 4 * k;
+              pr[k] = make_float2(0.f, 0.f);
+              if (idx < n) {
+                const int ch = idx / ns, sl = s_lo + (idx - ch * ns);
+                pr[k] = __ldg(reinterpret_cast<const float2*>(
+                    partial + ((((static_cast<size_t>(b) * nchunks_stats + ch) * nslab_stats + sl) * groups + g) * 2)));
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { a += pr[k].x; a2 += pr[k].y; }
+          }
+        }
+        a += __shfl_xor_sync(0xffffffffu, a, 1);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+        a += __shfl_xor_sync(0xffffffffu, a, 2);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+        if (sub == 0 && gl < ng) {
+          const float mean = a * inv_n;
+          const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
+          g_mean[gl] = mean;
+          g_rstd[gl] = rsqrtf(var + eps);
+        }
       }
     }
   }
   __syncthreads();
-  if (q >= ppar) return;
-  float sc[8], sf[8];
-  {
-    const int cbase = c0 + v * 8;
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + cbase));
-    const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + cbase + 4));
-    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + cbase));
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + cbase + 4));
-    const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-    const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+  if (q < ppar) {
+    float sc[8], sf[8];
+    {
+      const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+      const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = (cbase + i) / cpg - g_first;
-      sc[i] = g_rstd[g] * gg[i];
-      sf[i] = bt[i] - g_mean[g] * sc[i];
+      for (int i = 0; i < 8; ++i) {
+        const int g = (cbase + i) / cpg - g_first;
+        sc[i] = g_rstd[g] * gg[i];
+        sf[i] = bt[i] - g_mean[g] * sc[i];
+      }
     }
-  }
-  const int p0 = blockIdx.x * rows_per_cta;
-  const int p1 = min(HW, p0 + rows_per_cta);
-  const __nv_bfloat16* xb = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
-  __nv_bfloat16* yb = Y + (static_cast<size_t>(b) * HW) * ldy + c0 + v * 8;
-  for (int pidx = p0 + q; pidx < p1; pidx += 4 * ppar) {
-    uint4 u[4];
+    const int p0 = blockIdx.x * rows_per_cta;
+    const int p1 = min(HW, p0 + rows_per_cta);
+    const __nv_bfloat16* xb = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
+    __nv_bfloat16* yb = Y + (static_cast<size_t>(b) * HW) * ldy + c0 + v * 8;
+    for (int pidx = p0 + q; pidx < p1; pidx += U * ppar) {
+      uint4 u[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (pidx + k * ppar < p1)
-        u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+      for (int k = 0; k < U; ++k)
+        if (pidx + k * ppar < p1)
+          u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (pidx + k * ppar < p1) {
-        float f[8];
-        unpack8(u[k], f);
+      for (int k = 0; k < U; ++k) {
+        if (pidx + k * ppar < p1) {
+          float f[8];
+          unpack8(u[k], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float y = f[i] * sc[i] + sf[i];
-          f[i] = silu ? silu_f(y) : y;
+          for (int i = 0; i < 8; ++i) {
+            const float y = f[i] * sc[i] + sf[i];
+            f[i] = silu ? silu_f(y) : y;
+          }
+          *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
         }
-        *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
       }
     }
   }
+  pdl_launch_dependents();
 }
 
 // ------------------------------------------------- GroupNorm statistics pooling (tiled VAE)
@@ -305,8 +335,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ S, int lds, __nv_b
 // For tensors that stay in L2 (every GroupNorm of the UNet / ControlNet): a cluster of `CS` CTAs owns one
 // image.  Pass 1: each CTA sums its pixel range (thread <-> channel-vector mapping as above, eight 16-byte
 // loads in flight), folds them to per-group partials in shared memory; one cluster barrier; every CTA reads
-// the CS partial tables through distributed shared memory in rank order (deterministic), and pass 2 re-reads
-// the rows (L2 hits), normalises (+SiLU) and stores.  Replaces two launches and the partial-sum round trip.
+// the CS partial tables through distributed shared memory in rank order (deterministic), and pass 2 normalises
+// (+SiLU) the rows it kept in registers (or re-reads them: L2 hits) and stores.  Replaces two launches and the partial-sum round trip.
 __device__ __forceinline__ void cluster_arrive_release() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 }
@@ -323,7 +353,6 @@ __global__ void __launch_bounds__(512)
 groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y, int ldy,
                        int HW, int C, int groups, int cs, const float* __restrict__ gamma,
                        const float* __restrict__ beta, float eps, int silu) {
-  PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   extern __shared__ float sh[];            // [ppar][2][C] per-thread-row channel sums
   __shared__ float part[128];              // this CTA's per-group (sum, sumsq)
   __shared__ float g_mean[64], g_rstd[64];
@@ -336,24 +365,58 @@ groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
   const int rows = (HW + cs - 1) / cs;
   const int p0 = rank * rows, p1 = min(HW, p0 + rows);
   const __nv_bfloat16* xb = X + (static_cast<size_t>(b) * HW) * ldx + v * 8;
+  // the affine parameters do not depend on the previous kernel: fetched before the PDL wait
+  const int cbase = v * 8;
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + cbase));
+  const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + cbase + 4));
+  const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + cbase));
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + cbase + 4));
+  pdl_wait();
+  // Up to 16 vectors per thread (every shape the launch geometry admits today) stay in registers between the two
+  // passes, so the tensor is read once; larger slices fall back to re-reading their rows (L2 hits) in pass 2.
+  constexpr int kIt = 2;
+  const bool in_regs = rows <= kIt * 8 * ppar;
+  uint4 keep[kIt][8];
   {
     float s[8], ss[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
-    for (int pidx = p0 + q; pidx < p1; pidx += 8 * ppar) {
-      uint4 u[8];
+    if (in_regs) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        u[k] = make_uint4(0u, 0u, 0u, 0u);   // bf16 zeros add nothing to either sum
-        if (pidx + k * ppar < p1)
-          u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+      for (int it = 0; it < kIt; ++it) {
+        const int pidx = p0 + q + it * 8 * ppar;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          keep[it][k] = make_uint4(0u, 0u, 0u, 0u);   // bf16 zeros add nothing to either sum
+          if (pidx + k * ppar < p1)
+            keep[it][k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+        }
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float f[8];
-        unpack8(u[k], f);
+      for (int it = 0; it < kIt; ++it)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+        for (int k = 0; k < 8; ++k) {
+          float f[8];
+          unpack8(keep[it][k], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+        }
+    } else {
+      for (int pidx = p0 + q; pidx < p1; pidx += 8 * ppar) {
+        uint4 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          u[k] = make_uint4(0u, 0u, 0u, 0u);
+          if (pidx + k * ppar < p1)
+            u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float f[8];
+          unpack8(u[k], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+        }
       }
     }
     float* row = sh + static_cast<size_t>(q) * 2 * C;
@@ -396,11 +459,6 @@ groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
   cluster_arrive_release();   // this CTA is done reading its peers' tables (waited on before exit)
   float sc[8], sf[8];
   {
-    const int cbase = v * 8;
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + cbase));
-    const float4 gb = __ldg(reinterpret_cast<const float4*>(gamma + cbase + 4));
-    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + cbase));
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + cbase + 4));
     const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
     const float bt[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -411,27 +469,48 @@ groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
     }
   }
   __nv_bfloat16* yb = Y + (static_cast<size_t>(b) * HW) * ldy + v * 8;
-  for (int pidx = p0 + q; pidx < p1; pidx += 8 * ppar) {
-    uint4 u[8];
+  if (in_regs) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (pidx + k * ppar < p1)
-        u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+    for (int it = 0; it < kIt; ++it) {
+      const int pidx = p0 + q + it * 8 * ppar;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (pidx + k * ppar < p1) {
-        float f[8];
-        unpack8(u[k], f);
+      for (int k = 0; k < 8; ++k) {
+        if (pidx + k * ppar < p1) {
+          float f[8];
+          unpack8(keep[it][k], f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float y = f[i] * sc[i] + sf[i];
-          f[i] = silu ? silu_f(y) : y;
+          for (int i = 0; i < 8; ++i) {
+            const float y = f[i] * sc[i] + sf[i];
+            f[i] = silu ? silu_f(y) : y;
+          }
+          *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
         }
-        *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
+      }
+    }
+  } else {
+    for (int pidx = p0 + q; pidx < p1; pidx += 8 * ppar) {
+      uint4 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (pidx + k * ppar < p1)
+          u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (pidx + k * ppar < p1) {
+          float f[8];
+          unpack8(u[k], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float y = f[i] * sc[i] + sf[i];
+            f[i] = silu ? silu_f(y) : y;
+          }
+          *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
+        }
       }
     }
   }
   cluster_wait_acquire();     // no CTA may exit while a peer can still read its shared memory
+  pdl_launch_dependents();
 }
 
 // Launch geometry of the fused kernel; cs == 0: not eligible (use the two-pass kernels).
@@ -465,6 +544,7 @@ static GnFusedGeom gn_fused_geom(int B, int HW, int C, int groups) {
 
 struct GnGeom {
   int vslab, nslab, ppar, threads, rows, nchunks;
+  bool stream;   // HBM-streaming tensor (>= 64 MB): 8 CTAs per SM, four loads in flight per thread
 };
 
 // Launch geometry shared by the stats and apply kernels (and by edtr_groupnorm_partial_size).
@@ -480,14 +560,24 @@ static GnGeom gn_geom(int B, int HW, int C) {
   g.ppar = 256 / g.vslab;
   if (g.ppar < 1) g.ppar = 1;
   g.threads = g.vslab * g.ppar;
-  // aim for >= 2 CTAs per SM over the whole launch, at least 4 rows per thread-row; tensors that stream from HBM
-  // (VAE decoder, >= 64 MB; measured: 33 MB tensors are faster with 2) get 8 CTAs per SM so that enough 16-byte loads are in flight to cover the DRAM latency
+  // tensors that stream from HBM (VAE decoder, >= 64 MB) get 8 CTAs per SM so that enough 16-byte loads are in
+  // flight to cover the DRAM latency
   const size_t bytes = static_cast<size_t>(B) * HW * C * 2;
-  const int want_ctas = (bytes >= (64u << 20) ? 8 : 2) * 148;
-  int chunks = (want_ctas + B * g.nslab - 1) / (B * g.nslab);
-  int rows = (HW + chunks - 1) / chunks;
-  const int min_rows = 4 * g.ppar;
-  if (rows < min_rows) rows = min_rows;
+  g.stream = bytes >= (64u << 20);
+  int rows;
+  if (g.stream) {
+    const int want_ctas = 8 * 148;
+    const int chunks = (want_ctas + B * g.nslab - 1) / (B * g.nslab);
+    rows = (HW + chunks - 1) / chunks;
+    if (rows < 4 * g.ppar) rows = 4 * g.ppar;
+  } else {
+    // L2-resident tensors: the launches are bound by latency, not bandwidth.  One pass of eight 16-byte loads per
+    // thread when that needs no more than 64 chunks per image (the apply kernel re-reduces chunks x groups partial
+    // sums per CTA), else as few passes as 64 chunks allow.
+    rows = 8 * g.ppar;
+    const int cap_rows = (HW + 63) / 64;
+    if (rows < cap_rows) rows = cap_rows;
+  }
   if (rows > HW) rows = HW;
   g.rows = rows;
   g.nchunks = (HW + rows - 1) / rows;
@@ -523,8 +613,12 @@ extern "C" int edtr_groupnorm_stats(const void* X, int ldx, int B, int HW, int C
   dim3 grid(g.nchunks, B, g.nslab);
   const size_t sh = static_cast<size_t>(g.ppar) * 2 * g.vslab * 8 * sizeof(float);
   EDTR_REQUIRE(sh <= 48 * 1024, "GroupNorm stats shared memory too large");
-  EDTR_LAUNCH(groupnorm_stats_kernel, grid, g.threads, sh, static_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const __nv_bfloat16*>(X), ldx, HW, C, groups, g.rows, g.vslab, stats);
+  if (g.stream)
+    EDTR_LAUNCH(groupnorm_stats_kernel<4>, grid, g.threads, sh, static_cast<cudaStream_t>(stream),
+                reinterpret_cast<const __nv_bfloat16*>(X), ldx, HW, C, groups, g.rows, g.vslab, stats);
+  else
+    EDTR_LAUNCH(groupnorm_stats_kernel<8>, grid, g.threads, sh, static_cast<cudaStream_t>(stream),
+                reinterpret_cast<const __nv_bfloat16*>(X), ldx, HW, C, groups, g.rows, g.vslab, stats);
   return check_launch("groupnorm_stats_kernel");
 }
 
@@ -540,9 +634,14 @@ extern "C" int edtr_groupnorm_apply(const void* X, int ldx, void* Y, int ldy, in
   const GnGeom g = gn_geom(B, HW, C);
   EDTR_REQUIRE(g.vslab * 8 / (C / groups) + 2 <= 64, "too many groups per channel slab");
   dim3 grid(g.nchunks, B, g.nslab);
-  EDTR_LAUNCH(groupnorm_apply_kernel, grid, g.threads, 0, static_cast<cudaStream_t>(stream), 
-      reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
-      g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, stats, gamma, beta, eps, silu, 0);
+  if (g.stream)
+    EDTR_LAUNCH(groupnorm_apply_kernel<4>, grid, g.threads, 0, static_cast<cudaStream_t>(stream),
+                reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
+                g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, stats, gamma, beta, eps, silu, 0);
+  else
+    EDTR_LAUNCH(groupnorm_apply_kernel<8>, grid, g.threads, 0, static_cast<cudaStream_t>(stream),
+                reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
+                g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, stats, gamma, beta, eps, silu, 0);
   return check_launch("groupnorm_apply_kernel");
 }
 
@@ -559,9 +658,14 @@ extern "C" int edtr_groupnorm_apply_stats(const void* X, int ldx, void* Y, int l
   const GnGeom g = gn_geom(B, HW, C);
   EDTR_REQUIRE(g.vslab * 8 / (C / groups) + 2 <= 64, "too many groups per channel slab");
   dim3 grid(g.nchunks, B, g.nslab);
-  EDTR_LAUNCH(groupnorm_apply_kernel, grid, g.threads, 0, static_cast<cudaStream_t>(stream),
-      reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
-      g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, mean_var, gamma, beta, eps, silu, 1);
+  if (g.stream)
+    EDTR_LAUNCH(groupnorm_apply_kernel<4>, grid, g.threads, 0, static_cast<cudaStream_t>(stream),
+                reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
+                g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, mean_var, gamma, beta, eps, silu, 1);
+  else
+    EDTR_LAUNCH(groupnorm_apply_kernel<8>, grid, g.threads, 0, static_cast<cudaStream_t>(stream),
+                reinterpret_cast<const __nv_bfloat16*>(X), ldx, reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups,
+                g.rows, g.vslab, g.nchunks, g.nslab, g.vslab * 8, mean_var, gamma, beta, eps, silu, 1);
   return check_launch("groupnorm_apply_kernel");
 }
 

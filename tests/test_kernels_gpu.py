@@ -238,7 +238,10 @@ def test_attention_growing_scores_exercise_lazy_rescale(ops, Lq, Lk):
 
 @pytest.mark.parametrize("B,HW,C,silu,eps", [(2, 4096, 320, True, 1e-5), (2, 64, 2560, True, 1e-5),
                                               (1, 1024, 1920, False, 1e-6), (3, 256, 960, True, 1e-5),
-                                              (1, 65536, 128, True, 1e-6), (2, 4096, 512, True, 1e-6)])
+                                              (1, 65536, 128, True, 1e-6), (2, 4096, 512, True, 1e-6),
+                                              (8, 4096, 320, True, 1e-5), (8, 1024, 640, True, 1e-6), (3, 4096, 960, True, 1e-5),
+                                              (8, 256, 1280, True, 1e-5), (2, 1000, 64, False, 1e-5), (1, 77, 2560, True, 1e-5),
+                                              (8, 1024, 320, True, 1e-5), (5, 256, 1920, False, 1e-6), (2, 262144, 128, True, 1e-6)])
 @pytest.mark.parametrize("fused", [True, False])
 def test_groupnorm(ops, B, HW, C, silu, eps, fused):
     """fused=True: single-launch cluster kernel where eligible (L2-resident tensors); False: two-pass kernels."""
