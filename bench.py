@@ -144,7 +144,8 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         # the same workload as the CUDA arm's line; each reference step is a bounded sample of it (one image)
-        "config": dict(workload_config(args.batch, 1), sample="one 512x512 image per step (B=1), fp32 on the host CPU",
+        "config": dict(workload_config(args.batch, max(args.gpus, 1)),
+                       sample="one 512x512 image per step (B=1), fp32 on the host CPU (rank 0 only)",
                        steps_requested=args.steps),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{len(times)} x (1 image: 4 ControlLDM steps + VAE decode), oracle/cldm_oracle.py "

@@ -100,6 +100,7 @@ int prime_gemm_attributes();
 int prime_attention_attributes();
 int prime_gemm2_attributes();
 void set_gemm_workspace(void* ptr, size_t bytes);
+void set_gemm_max_clusters(int n);
 
 }  // namespace edtr
 
@@ -122,6 +123,15 @@ extern "C" int edtr_set_workspace(void* ptr, size_t bytes) {
     return EDTR_ERR_INVALID;
   }
   edtr::set_gemm_workspace(ptr, ptr == nullptr ? 0 : bytes);
+  return EDTR_OK;
+}
+
+extern "C" int edtr_set_gemm_max_clusters(int clusters) {
+  if (clusters < 1 || clusters > 74) {
+    edtr::set_error("clusters must be in [1, 74], got %d", clusters);
+    return EDTR_ERR_INVALID;
+  }
+  edtr::set_gemm_max_clusters(clusters);
   return EDTR_OK;
 }
 

@@ -506,8 +506,11 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, flo
   pdl_launch_dependents();
 }
 
+static int g_max_clusters = 74;    // CTA pairs a launch may occupy (edtr_set_gemm_max_clusters)
 static float* g_ws = nullptr;      // split-K workspace registered by the host (edtr_set_workspace)
 static size_t g_ws_bytes = 0;
+
+void set_gemm_max_clusters(int n) { g_max_clusters = n < 1 ? 1 : (n > 74 ? 74 : n); }
 
 void set_gemm_workspace(void* ptr, size_t bytes) {
   g_ws = static_cast<float*>(ptr);
@@ -550,7 +553,7 @@ static void plan_tiles(int M, int N, int nkb, int geglu, size_t ws_bytes, int* t
       if (sp > 1 && (sp > max_split_ws || nkb / sp < 8)) break;
       const int kbs = (nkb + sp - 1) / sp;
       if (sp > 1 && kbs * (sp - 1) >= nkb) continue;  // an empty split
-      const long waves = (static_cast<long>(tiles_m) * tn * sp + 73) / 74;
+      const long waves = (static_cast<long>(tiles_m) * tn * sp + g_max_clusters - 1) / g_max_clusters;
       const long cost = waves * (kbs * per_kb + 3000) + (sp > 1 ? 10000 : 0);
       if (best_cost < 0 || cost < best_cost) {
         best_cost = cost;
@@ -655,7 +658,7 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
     tmC = tmD;
   }
   const int work = p.tiles_m * p.tiles_n * p.splits;
-  const int clusters = work < 74 ? work : 74;
+  const int clusters = work < g_max_clusters ? work : g_max_clusters;
   if (p.splits > 1) p.has_residual = 0;  // the reduce kernel adds it
   if (p.up2x && p.splits > 1) {
     set_error("internal: split-K is not available for the up-sampling convolution");

@@ -24,6 +24,7 @@ other execution path in the product.
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -395,6 +396,9 @@ class CldmEngine:
         self._ws: Dict[Tuple[int, int, int], Workspace] = {}
         self._graphs: Dict[Tuple, "_Graph"] = {}
         self.overlap = True      # run the ControlNet concurrently with the UNet encoder on a second stream
+        # CTA pairs each branch's GEMM launches may use while both run (74 = no limit: the launches then only overlap
+        # in each other's tails); EDTR_OVERLAP_CLUSTERS overrides for measurements
+        self.overlap_clusters = int(os.environ.get("EDTR_OVERLAP_CLUSTERS", "74"))
         self._side = None
         # channel / resolution bookkeeping of the skip structure
         ins = self.unet.inputs
@@ -490,6 +494,9 @@ class CldmEngine:
             cn.block("middle_block.", self.cnet.middle, h, dst)
             couts.append(dst)
 
+        share = self.overlap_clusters if overlap else 74
+        if share < 74:   # both branches get a share of the SMs so that their persistent GEMMs run side by side
+            ops.set_gemm_max_clusters(share)
         if overlap:
             with torch.cuda.stream(side):
                 ops.use_workspace(1)
@@ -504,6 +511,8 @@ class CldmEngine:
         mid = cats[0][..., :self.cat_geom[0][1]]
         un.block("middle_block.", self.unet.middle, h, mid)
 
+        if share < 74:
+            ops.set_gemm_max_clusters(74)
         if overlap:
             main.wait_stream(side)
         else:

@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 
 # every symbol include/edtr_b200.h declares
 EXPORTED = [
-    "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_set_workspace", "edtr_gemm_tile_n", "edtr_gemm_bf16",
+    "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_set_workspace", "edtr_set_gemm_max_clusters", "edtr_gemm_tile_n", "edtr_gemm_bf16",
     "edtr_conv3x3_bf16", "edtr_conv3x3_up2x_bf16", "edtr_attention_bf16", "edtr_groupnorm_partial_size", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
     "edtr_groupnorm_fused_supported", "edtr_groupnorm_fused", "edtr_groupnorm_pool", "edtr_groupnorm_apply_stats",
     "edtr_layernorm_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
@@ -107,6 +107,8 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_set_workspace.restype = ci
     lib.edtr_set_workspace.argtypes = [vp, c_size_t]
     lib.edtr_init.argtypes = []
+    lib.edtr_set_gemm_max_clusters.restype = ci
+    lib.edtr_set_gemm_max_clusters.argtypes = [ci]
     lib.edtr_gemm_tile_n.restype = ci
     lib.edtr_gemm_tile_n.argtypes = [ci, ci, ci, ci]
     lib.edtr_gemm_bf16.restype = ci
@@ -176,6 +178,12 @@ def use_workspace(index: int) -> None:
     """Select which of the two split-K scratch buffers later launches use (one per concurrent stream)."""
     lib = device_lib()
     check(lib.edtr_set_workspace(_workspace[index].data_ptr(), WORKSPACE_BYTES), "edtr_set_workspace")
+    LAUNCHES[0] -= 1  # not a kernel launch
+
+
+def set_gemm_max_clusters(n: int) -> None:
+    """CTA pairs later GEMM / convolution launches may occupy (74 = the whole GPU)."""
+    check(device_lib().edtr_set_gemm_max_clusters(int(n)), "edtr_set_gemm_max_clusters")
     LAUNCHES[0] -= 1  # not a kernel launch
 
 

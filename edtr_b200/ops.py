@@ -36,6 +36,12 @@ def use_workspace(index: int) -> None:
     _lib.use_workspace(index)
 
 
+def set_gemm_max_clusters(n: int) -> None:
+    """Limit later GEMM / convolution launches to n CTA pairs (74 = whole GPU) so that launches on two streams can
+    run side by side."""
+    _lib.set_gemm_max_clusters(n)
+
+
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 

@@ -84,6 +84,11 @@ int edtr_init(void);
  * too few output tiles to fill the GPU (the 8x8 level of the UNet).  All calls that use it are ordered
  * on one stream.  ptr == NULL disables split-K.  The library never allocates. */
 int edtr_set_workspace(void* ptr, size_t bytes);
+/* Upper bound on the CTA pairs (2 SMs each, 74 on a B200) a GEMM / convolution launch issued from now on may occupy.
+ * The persistent kernel owns whole SMs (224 KB of shared memory per CTA), so two launches on different streams only
+ * run side by side when each is limited to a share of the GPU: the engine lowers the bound while the ControlNet and
+ * the UNet encoder run concurrently (model/controlnet.py:25-31 vs :263-277) and restores 74 afterwards. */
+int edtr_set_gemm_max_clusters(int clusters);
 /* N-tile width the GEMM will use for an N-column problem (for GEGLU weight
  * interleaving at plan time). */
 int edtr_gemm_tile_n(int M, int N, int K, int act);
