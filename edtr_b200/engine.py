@@ -399,7 +399,6 @@ class CldmEngine:
         # CTA pairs each branch's GEMM launches may use while both run (74 = no limit: the launches then only overlap
         # in each other's tails; measured 74 / 37 / 50: 47.94 / 47.39 / 47.34 ms per 4-step sample)
         self.overlap_clusters = int(os.environ.get("EDTR_OVERLAP_CLUSTERS", "50"))
-        self.overlap_zero_convs = os.environ.get("EDTR_OVERLAP_ZC", "1") != "0"
         self._side = None
         # channel / resolution bookkeeping of the skip structure
         ins = self.unet.inputs
@@ -518,26 +517,15 @@ class CldmEngine:
             main.wait_stream(side)
         else:
             run_controlnet()
-        # zero-conv epilogues accumulate into the UNet tensors (model/controlnet.py:270-275,31,37).  The decoder pops
-        # the skips deepest first, so the middle block and the three deepest skips are patched on the main stream and
-        # the (larger) shallow ones on the side stream, under the first decoder blocks.
-        n_out = len(self.unet.outputs)
-        n_deep = 3 if (overlap and self.overlap_zero_convs and n_in > 3 and n_out > 3) else n_in
-        self._zero_conv(w, "middle_block_out.0.", couts[n_in], mid, control_scales[n_in])
-        for s in range(n_in - 1, n_in - 1 - n_deep, -1):
+        # zero-conv epilogues accumulate into the UNet tensors (model/controlnet.py:270-275,31,37).  (Running the shallow
+        # ones on the side stream under the first decoder blocks was measured: no gain, profiles/r01g_overlap.txt.)
+        for s in range(n_in):
             self._zero_conv(w, f"zero_convs.{s}.0.", couts[s], hs_view(s), control_scales[s])
-        if n_deep < n_in:
-            side.wait_stream(main)     # the encoder has read every skip tensor; couts are complete
-            with torch.cuda.stream(side):
-                ops.use_workspace(1)
-                for s in range(n_in - 1 - n_deep, -1, -1):
-                    self._zero_conv(w, f"zero_convs.{s}.0.", couts[s], hs_view(s), control_scales[s])
-            ops.use_workspace(0)
+        self._zero_conv(w, "middle_block_out.0.", couts[n_in], mid, control_scales[n_in])
 
         # UNet decoder (model/controlnet.py:33-38)
+        n_out = len(self.unet.outputs)
         for j, blk in enumerate(self.unet.outputs):
-            if n_deep < n_in and j == n_deep:
-                main.wait_stream(side)
             if j + 1 < n_out:
                 out = cats[j + 1][..., :self.cat_geom[j + 1][1]]
             else:
