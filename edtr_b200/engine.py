@@ -397,8 +397,9 @@ class CldmEngine:
         self._graphs: Dict[Tuple, "_Graph"] = {}
         self.overlap = True      # run the ControlNet concurrently with the UNet encoder on a second stream
         # CTA pairs each branch's GEMM launches may use while both run (74 = no limit: the launches then only overlap
-        # in each other's tails; measured 74 / 37 / 50: 47.94 / 47.39 / 47.34 ms per 4-step sample)
-        self.overlap_clusters = int(os.environ.get("EDTR_OVERLAP_CLUSTERS", "50"))
+        # in each other's tails; measured 74 / 37 / 50: 47.94 / 47.39 / 47.34 ms per 4-step sample, i.e. within the
+        # box-to-box noise, so the limit stays off: profiles/r01g_overlap.txt); EDTR_OVERLAP_CLUSTERS overrides
+        self.overlap_clusters = int(os.environ.get("EDTR_OVERLAP_CLUSTERS", "74"))
         self._side = None
         # channel / resolution bookkeeping of the skip structure
         ins = self.unet.inputs
