@@ -18,6 +18,7 @@ Outputs:  golden_tiny.npz  (TINY config, B=2, 16x16 latent; everything in fp32)
           golden_vae_encode_tiled.npz (TINY_VAE8 encoder, B=2, 136x160 image (stored fp16), vae_encode(tiled=True, 64))
           golden_vae_tiled.npz  (TINY_VAE8 decoder, B=2, 40x48 latent, vae_decode(tiled=True, tile_size=16))
           golden_s4.npz    (s4 config, B=1, 64x64 latent; --full; image stored as fp16)
+          golden_swinir.npz (SWINIR_TINY: model.swinir.SwinIR on [2,3,128,128] and [1,3,64,192] images; --swinir alone)
 """
 import argparse
 import os
@@ -230,11 +231,50 @@ def run_reference_tiled_vae_encode(vae_cfg, batch, h, w, tile_size):
     return image, z
 
 
+def run_reference_swinir(cfg, shapes, seed=53):
+    """model.swinir.SwinIR (the pre-restoration network) built exactly as
+    configs/det/voc2012/test/007_edtr-s4.yaml:3-19 does (at the widths of `cfg`), with the oracle's synthetic
+    parameters; the relative_position_index / attn_mask buffers stay the reference's own."""
+    _stub_missing_packages()
+    from model.swinir import SwinIR
+    from oracle import swinir_oracle as S
+
+    m = SwinIR(img_size=cfg["img_size"], patch_size=1, in_chans=cfg["in_chans"], embed_dim=cfg["embed_dim"],
+               depths=list(cfg["depths"]), num_heads=list(cfg["num_heads"]), window_size=cfg["window_size"],
+               mlp_ratio=cfg["mlp_ratio"], sf=cfg["sf"], img_range=cfg["img_range"], upsampler="nearest+conv",
+               resi_connection="1conv", unshuffle=True, unshuffle_scale=cfg["sf"])
+    assert cfg["num_feat"] == 64   # hard-coded in the reference (model/swinir.py:686)
+    sd = S.make_swinir_weights(cfg)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith(("relative_position_index", "attn_mask")) for k in missing), missing
+    params = {k for k, _ in m.named_parameters()}
+    assert params == set(sd), (sorted(params - set(sd))[:5], sorted(set(sd) - params)[:5])
+    m.eval()
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for i, (b, h, w) in enumerate(shapes):
+        x = torch.rand(b, 3, h, w, generator=g)
+        with torch.no_grad():
+            y = m(x)
+        out[f"x{i}"], out[f"y{i}"] = x.numpy(), y.numpy()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="also generate the s4 (full-size) fixture; ~2 min")
+    ap.add_argument("--swinir", action="store_true", help="only (re)generate golden_swinir.npz")
     args = ap.parse_args()
     from oracle import cldm_oracle as O
+    from oracle import swinir_oracle as S
+
+    torch.set_num_threads(os.cpu_count())
+    sw = run_reference_swinir(S.SWINIR_TINY, [(2, 128, 128), (1, 64, 192)])
+    np.savez_compressed(os.path.join(HERE, "golden_swinir.npz"), **sw)
+    print("swinir:", {k: tuple(v.shape) for k, v in sw.items()})
+    if args.swinir:
+        return
 
     torch.set_num_threads(os.cpu_count())
     r = run_reference(O.TINY, batch=2, latent_hw=16)

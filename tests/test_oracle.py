@@ -119,3 +119,30 @@ def test_oracle_tiled_vae_encode_matches_reference():
         z_untiled = O.vae_encode(sd, O.TINY_VAE8, image, 0.18215)
     assert O.max_rel_err(z, torch.from_numpy(g["z"])) < 1e-5
     assert O.max_rel_err(z, z_untiled) > 1e-3
+
+
+def test_oracle_swinir_matches_reference():
+    """SwinIR pre-restoration network (model/swinir.py:856-894): the restatement against the
+    live-reference fixture (tests/golden/make_golden.py --swinir), square multi-window and rectangular one-window-high
+    inputs (plain and shifted window attention, relative position bias, nearest+conv x8 upsampler)."""
+    from oracle import swinir_oracle as S
+
+    d = np.load(os.path.join(GOLD, "golden_swinir.npz"))
+    sd = S.make_swinir_weights(S.SWINIR_TINY)
+    for i in range(2):
+        x, ref = torch.from_numpy(d[f"x{i}"]), torch.from_numpy(d[f"y{i}"])
+        with torch.no_grad():
+            y = S.swinir_forward(sd, S.SWINIR_TINY, x)
+        assert y.shape == ref.shape == x.shape
+        assert O.max_rel_err(y, ref) < 1e-5
+
+
+def test_swinir_parameter_enumeration_and_flops():
+    from oracle import swinir_oracle as S
+
+    n = sum(int(np.prod(s)) for _, s in S.swinir_param_shapes(S.SWINIR_EDTR))
+    assert 15.5e6 < n < 16.5e6          # 15.8 M parameters at the EDTR widths (embed 180, 8 x 6 blocks)
+    # 48 Swin blocks at 64x64 tokens (111 GF) + RSTB / body convs (21) + conv_first + the x8 nearest+conv upsampler (47)
+    assert abs(S.swinir_gflops(S.SWINIR_EDTR, 512, 512) - 181.5) < 1.0
+    assert S.block_geometry(S.SWINIR_EDTR, 0) == (8, 0) and S.block_geometry(S.SWINIR_EDTR, 1) == (8, 4)
+    assert S.block_geometry(dict(S.SWINIR_TINY, img_size=8), 1) == (8, 0)
