@@ -404,3 +404,43 @@ def test_tiled_vae_encode_dataflow_matches_reference_fixture():
     # decoder's gloo test (same driver, _VaeBlocks._run_tiles); here: an untiled-size input falls back to encode()
     small = image[:, :, :64, :64].contiguous()
     assert torch.equal(ve.encode_tiled(small, 64, use_graph=False), ve.encode(small, use_graph=False))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "model")), reason="reference tree not present")
+def test_dropin_signatures_match_reference():
+    """The drop-in boundary: every public callable a reference script uses keeps the reference's parameter
+    names, order and defaults — utils/sampler.py:75,185-194,207-224,268-285; model/cldm.py:19-27,107,136,162,166;
+    model/gaussian_diffusion.py:80; utils/common.py:136."""
+    import inspect
+
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_golden as MG
+
+    MG._stub_missing_packages()
+    from model.cldm import ControlLDM as RefCldm
+    from model.gaussian_diffusion import Diffusion as RefDiffusion
+    from utils.common import wavelet_reconstruction as ref_wavelet
+    from utils.sampler import SpacedSampler as RefSampler, space_timesteps as ref_space
+
+    from edtr_b200.cldm import ControlLDM
+    from edtr_b200.colorfix import wavelet_reconstruction
+    from edtr_b200.diffusion import Diffusion
+    from edtr_b200.sampler import SpacedSampler, space_timesteps
+
+    def params(fn):
+        return [(p.name, p.default if p.default is not inspect.Parameter.empty else "<required>")
+                for p in inspect.signature(fn).parameters.values() if p.kind != inspect.Parameter.VAR_KEYWORD]
+
+    for name in ("__init__", "make_schedule", "sample", "manual_sample_with_timesteps", "p_sample", "predict_noise",
+                 "q_posterior_mean_variance", "_predict_xstart_from_eps"):
+        assert params(getattr(SpacedSampler, name)) == params(getattr(RefSampler, name)), name
+    assert params(space_timesteps) == params(ref_space)
+    for name in ("forward", "vae_encode", "vae_decode", "prepare_condition", "load_pretrained_sd",
+                 "load_controlnet_from_ckpt", "load_controlnet_from_unet"):
+        assert params(getattr(ControlLDM, name)) == params(getattr(RefCldm, name)), name
+    # the constructor may take extra keyword arguments after the reference's six
+    ours, ref = params(ControlLDM.__init__), params(RefCldm.__init__)
+    assert ours[:len(ref)] == ref
+    assert params(Diffusion.q_sample) == params(RefDiffusion.q_sample)
+    assert params(Diffusion.__init__)[:len(params(RefDiffusion.__init__))] == params(RefDiffusion.__init__)
+    assert params(wavelet_reconstruction) == params(ref_wavelet)
