@@ -29,8 +29,9 @@ SD = Dict[str, Tensor]
 # configs/det/voc2012/test/007_edtr-s4.yaml:3-19 (swinir.params)
 SWINIR_EDTR = dict(img_size=64, in_chans=3, embed_dim=180, depths=(6,) * 8, num_heads=(6,) * 8, window_size=8, mlp_ratio=2,
                    sf=8, img_range=1.0, num_feat=64)
-# same topology rules at toy widths (two residual groups of two blocks: one plain and one shifted window block each)
-SWINIR_TINY = dict(img_size=16, in_chans=3, embed_dim=24, depths=(2, 2), num_heads=(2, 3), window_size=8, mlp_ratio=2,
+# same topology rules at toy widths (two residual groups of two blocks: one plain and one shifted window block each;
+# head dim 30 as in the EDTR configuration)
+SWINIR_TINY = dict(img_size=16, in_chans=3, embed_dim=60, depths=(2, 2), num_heads=(2, 2), window_size=8, mlp_ratio=2,
                    sf=8, img_range=1.0, num_feat=64)   # num_feat is hard-coded in the reference (model/swinir.py:686)
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # model/swinir.py:689-691
