@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
-from .engine import BF16, F32, Workspace, _ceil, pack_conv3x3, pack_conv3x3_up2x, vec
+from .engine import BF16, F32, Workspace, _ceil, _Graph, pack_conv3x3, pack_conv3x3_up2x, vec
 from .nets import _attach, state_version
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # model/swinir.py:689-691
@@ -250,6 +250,7 @@ class SwinIREngine:
         self.w = w
         self._ws: Dict[Tuple[int, int, int], Workspace] = {}
         self._masks: Dict[Tuple[int, int, int, int], torch.Tensor] = {}
+        self._graphs: Dict[Tuple[int, int, int], _Graph] = {}
 
     # ------------------------------------------------------------------------------------------ helpers
     def _conv(self, ws: Workspace, x: torch.Tensor, key: str, out: torch.Tensor, **kw) -> torch.Tensor:
@@ -284,9 +285,10 @@ class SwinIREngine:
         return self._masks[key]
 
     # ------------------------------------------------------------------------------------------ forward
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """[B, 3, H, W] fp32 in [0, 1] -> [B, 3, H, W] fp32 (model/swinir.py:856-894)."""
-        ops, w, cfg = self.ops, self.w, self.cfg
+    def forward(self, x: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
+        """[B, 3, H, W] fp32 in [0, 1] -> [B, 3, H, W] fp32 (model/swinir.py:856-894).  All buffers are static per
+        (B, H, W), so the ~600 launches replay as one CUDA graph."""
+        ops, cfg = self.ops, self.cfg
         if x.dim() != 4 or x.shape[1] != cfg["in_chans"]:
             raise ValueError(f"x must be [B, {cfg['in_chans']}, H, W], got {tuple(x.shape)}")
         if getattr(ops, "REQUIRES_CUDA", True) and not x.is_cuda:
@@ -297,12 +299,33 @@ class SwinIREngine:
             # the reference reflect-pads to a multiple of 8 pixels and then fails in window_partition unless the token
             # grid is a multiple of the window (model/swinir.py:834-839, :46): only multiples of 64 pixels ever work
             raise ValueError(f"H and W must be multiples of {sf * wsz} (got {H}x{W})")
+        ws = self._ws.setdefault((B, H, W), Workspace(self.device))
+        sx = ws.get("in_x", (B, cfg["in_chans"], H, W), F32)
+        out = ws.get("out_img", (B, cfg["in_chans"], H, W), F32)
+        sx.copy_(x)
+        h, w_ = H // sf, W // sf
+        for j in (0, 1):                     # masks are built (host -> device copy) outside any capture
+            wsj, shift = block_geometry(cfg, j)
+            self._mask(h, w_, wsj, shift)
+        run = lambda: self._forward(ws, sx, out)
+        if use_graph and x.is_cuda:
+            g = self._graphs.get((B, H, W))
+            if g is None:
+                g = self._graphs[(B, H, W)] = _Graph(run)
+            g.replay()
+        else:
+            run()
+        return out.clone()
+
+    def _forward(self, ws: Workspace, x: torch.Tensor, out: torch.Tensor) -> None:
+        ops, w, cfg = self.ops, self.w, self.cfg
+        B, _, H, W = x.shape
+        sf = cfg["sf"]
         h, w_ = H // sf, W // sf
         M = B * h * w_
         cp, hp, nf = self.cp, self.hid_p, self.nf
-        ws = self._ws.setdefault((B, H, W), Workspace(self.device))
         xin = ws.get("xin", (B, h, w_, cfg["in_chans"] * sf * sf))
-        ops.pixel_unshuffle(x.contiguous().float(), xin, RGB_MEAN, cfg["img_range"], sf)
+        ops.pixel_unshuffle(x, xin, RGB_MEAN, cfg["img_range"], sf)
         f0 = self._conv(ws, xin, "conv_first.1.", ws.get("f0", (B, h, w_, cp)))
         bufs = [ws.get(f"t{i}", (B, h, w_, cp)) for i in range(3)]
         nbuf = ws.get("n", (B, h, w_, cp))
@@ -341,6 +364,4 @@ class SwinIREngine:
         for k in (1, 2, 3):
             u = self._up(ws, u, k, ws.get(f"u{k}", (B, h << k, w_ << k, nf)))
         hr = self._conv(ws, u, "conv_hr.", ws.get("hr", (B, H, W, nf)), act=ops.ACT_LRELU_02)
-        out = torch.empty((B, cfg["in_chans"], H, W), dtype=F32, device=x.device)
         self._conv(ws, hr, "conv_last.", out.view(B, cfg["in_chans"], H * W), out_mode=ops.OUT_NCHW_F32, alpha=self.out_scale)
-        return out
