@@ -8,6 +8,9 @@ if [ -d .wip/attn ]; then
     echo "== EDTR_ATT_LAZYMAX=$v attention tests exit $?"; tail -n 3 $GRAFT_REPO_ROOT/gpurun_out/attn_lazy$v.log
     EDTR_ATT_LAZYMAX=$v timeout 120 python scripts/bench_attn.py 2>&1 | tee $GRAFT_REPO_ROOT/gpurun_out/bench_attn_lazy$v.txt | head -n 4
   done
+  EDTR_ATT_K128=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -x -q --timeout 120 --tb=short -k attention > $GRAFT_REPO_ROOT/gpurun_out/attn_k128.log 2>&1
+  echo "== EDTR_ATT_K128=1 attention tests exit $?"; tail -n 3 $GRAFT_REPO_ROOT/gpurun_out/attn_k128.log
+  EDTR_ATT_K128=1 timeout 120 python scripts/bench_attn.py 2>&1 | tee $GRAFT_REPO_ROOT/gpurun_out/bench_attn_k128.txt | head -n 4
   cd $GRAFT_REPO_ROOT
 fi
 if [ -d .wip/swinir ]; then
