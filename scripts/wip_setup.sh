@@ -3,6 +3,7 @@
 #   gpurun --timeout 900 -- 'bash scripts/gpu_wip.sh'
 set -e
 cd "$(dirname "$0")/.."
+git worktree prune
 for b in attn swinir; do
   if [ ! -d .wip/$b ]; then git worktree add .wip/$b $b-wip; fi
   (cd .wip/$b && git merge -q main -m "merge main" || echo "!! merge conflict in $b-wip: resolve by hand" && python -c "
