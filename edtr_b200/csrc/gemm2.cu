@@ -415,6 +415,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (p.act == EDTR_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          } else if (p.act >= EDTR_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_extra_f(v[j], p.act);
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -499,6 +502,9 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, flo
   if (act == EDTR_ACT_SILU) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = silu_f(v[i]);
+  } else if (act >= EDTR_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = act_extra_f(v[i], act);
   }
   uint4 o;
   o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);

@@ -38,7 +38,7 @@ struct GemmCfg {
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
-  return act == EDTR_ACT_SILU ? silu_f(v) : v;
+  return act == EDTR_ACT_SILU ? silu_f(v) : act_extra_f(v, act);
 }
 
 // Adds bias / rowvec / residual to 32 accumulator columns of one row.
@@ -252,6 +252,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (ep.act == EDTR_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          } else if (ep.act >= EDTR_ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_extra_f(v[j], ep.act);
           }
           epilogue_store(v, ep, row, col0, nv, p.N);
         }
@@ -357,7 +360,7 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
 
 static int check_epilogue(const EdtrEpilogue* ep, int M, int N) {
   EDTR_REQUIRE(ep != nullptr && ep->out != nullptr, "epilogue/out is NULL");
-  EDTR_REQUIRE(ep->act >= 0 && ep->act <= 2, "bad act %d", ep->act);
+  EDTR_REQUIRE(ep->act >= 0 && ep->act <= 5, "bad act %d", ep->act);
   EDTR_REQUIRE(ep->out_mode >= 0 && ep->out_mode <= 3, "bad out_mode %d", ep->out_mode);
   const int n_out = ep->act == EDTR_ACT_GEGLU ? N / 2 : N;
   if (ep->out_mode == EDTR_OUT_BF16) {
@@ -439,7 +442,7 @@ extern "C" int edtr_conv3x3_up2x_bf16(const void* X, int ldx, int B, int H, int 
   EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Wt4) | reinterpret_cast<uintptr_t>(ep->out)) & 15) == 0,
                "X/Wt4/out must be 16-byte aligned");
   EDTR_REQUIRE(ep->out_mode == EDTR_OUT_BF16 && ep->act != EDTR_ACT_GEGLU && ep->residual == nullptr && ep->rowvec == nullptr,
-               "the up-sampling convolution stores bf16 and supports bias / SiLU only");
+               "the up-sampling convolution stores bf16 and supports bias + a pointwise activation only");
   EDTR_REQUIRE(ep->ldc % 8 == 0 && ep->ldc >= Cout, "bad ldc");
   EDTR_REQUIRE(W >= 8 && (W & (W - 1)) == 0 && (W >= 128 || 128 % W == 0), "W (%d) must be a power of two >= 8", W);
   int bw, bh, bn_img;

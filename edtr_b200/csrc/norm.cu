@@ -252,8 +252,10 @@ __global__ void groupnorm_pool_kernel(const float* __restrict__ partial, int B, 
 // One warp per row, the row lives in registers (two exact passes).
 template <int MAXV>
 __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y,
-                                 int ldy, int M, int C, const float* __restrict__ gamma,
+                                 int ldy, int M, int C, int c_real, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float eps) {
+  // c_real <= C: the statistics run over the first c_real channels only; channels [c_real, C) are padding that holds
+  // zeros on input and (gamma = beta = 0 there) on output — SwinIR's 180 channels live in 192-wide rows.
   PdlScope pdl_scope;  // PDL: wait for the previous kernel on entry, trigger the next one on exit
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -271,17 +273,20 @@ __global__ void layernorm_kernel(const __nv_bfloat16* __restrict__ X, int ldx, _
       for (int i = 0; i < 8; ++i) s += f[k][i];
     }
   }
-  const float mean = warp_sum(s) / static_cast<float>(C);
+  const float mean = warp_sum(s) / static_cast<float>(c_real);
   float s2 = 0.f;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
     const int v = lane + 32 * k;
     if (v < vpr) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float d = f[k][i] - mean; s2 += d * d; }
+      for (int i = 0; i < 8; ++i) {
+        const float d = (v * 8 + i < c_real) ? f[k][i] - mean : 0.f;
+        s2 += d * d;
+      }
     }
   }
-  const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(C) + eps);
+  const float rstd = rsqrtf(warp_sum(s2) / static_cast<float>(c_real) + eps);
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
     const int v = lane + 32 * k;
@@ -716,8 +721,14 @@ extern "C" int edtr_groupnorm_fused(const void* X, int ldx, void* Y, int ldy, in
 
 extern "C" int edtr_layernorm_bf16(const void* X, int ldx, void* Y, int ldy, int M, int C, const float* gamma,
                                    const float* beta, float eps, void* stream) {
+  return edtr_layernorm_padded_bf16(X, ldx, Y, ldy, M, C, C, gamma, beta, eps, stream);
+}
+
+extern "C" int edtr_layernorm_padded_bf16(const void* X, int ldx, void* Y, int ldy, int M, int C, int C_real,
+                                          const float* gamma, const float* beta, float eps, void* stream) {
   EDTR_REQUIRE(X && Y && gamma && beta, "X/Y/gamma/beta is NULL");
   EDTR_REQUIRE(M > 0 && C > 0 && C % 8 == 0, "bad LayerNorm shape (C %% 8 == 0 required)");
+  EDTR_REQUIRE(C_real > 0 && C_real <= C, "C_real (%d) must be in [1, C = %d]", C_real, C);
   EDTR_REQUIRE(C <= 2048, "LayerNorm supports C <= 2048 (got %d)", C);
   EDTR_REQUIRE(ldx % 8 == 0 && ldy % 8 == 0 && ldx >= C && ldy >= C, "bad strides");
   EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y) |
@@ -729,9 +740,9 @@ extern "C" int edtr_layernorm_bf16(const void* X, int ldx, void* Y, int ldy, int
   const __nv_bfloat16* x = reinterpret_cast<const __nv_bfloat16*>(X);
   __nv_bfloat16* y = reinterpret_cast<__nv_bfloat16*>(Y);
   const int vpr = C / 8;
-  if (vpr <= 64) EDTR_LAUNCH((layernorm_kernel<2>), grid, warps * 32, 0, st, x, ldx, y, ldy, M, C, gamma, beta, eps);
-  else if (vpr <= 160) EDTR_LAUNCH((layernorm_kernel<5>), grid, warps * 32, 0, st, x, ldx, y, ldy, M, C, gamma, beta, eps);
-  else EDTR_LAUNCH((layernorm_kernel<8>), grid, warps * 32, 0, st, x, ldx, y, ldy, M, C, gamma, beta, eps);
+  if (vpr <= 64) EDTR_LAUNCH((layernorm_kernel<2>), grid, warps * 32, 0, st, x, ldx, y, ldy, M, C, C_real, gamma, beta, eps);
+  else if (vpr <= 160) EDTR_LAUNCH((layernorm_kernel<5>), grid, warps * 32, 0, st, x, ldx, y, ldy, M, C, C_real, gamma, beta, eps);
+  else EDTR_LAUNCH((layernorm_kernel<8>), grid, warps * 32, 0, st, x, ldx, y, ldy, M, C, C_real, gamma, beta, eps);
   return check_launch("layernorm_kernel");
 }
 

@@ -438,4 +438,13 @@ __device__ __forceinline__ float gelu_erf_f(float x) {
   return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
 }
 
+// Pointwise epilogue activations other than SiLU (EDTR_ACT_GELU / EDTR_ACT_LRELU_02 / EDTR_ACT_LRELU_001: SwinIR's
+// nn.GELU (erf form) and its two LeakyReLU slopes, model/swinir.py:24,768,803).  act is warp-uniform.
+__device__ __forceinline__ float act_extra_f(float v, int act) {
+  if (act == 3) return gelu_erf_f(v);
+  if (act == 4) return v > 0.f ? v : 0.2f * v;
+  if (act == 5) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+
 }  // namespace edtr

@@ -18,7 +18,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libedtr_b200.so")
-SOURCES = ["api.cu", "gemm_conv.cu", "gemm2.cu", "attention.cu", "norm.cu", "elementwise.cu"]
+SOURCES = ["api.cu", "gemm_conv.cu", "gemm2.cu", "attention.cu", "norm.cu", "elementwise.cu", "swin.cu"]
 HEADER = os.path.join(_REPO_DIR, "include", "edtr_b200.h")
 
 NVCC_FLAGS = [
@@ -31,7 +31,8 @@ EXPORTED = [
     "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_set_workspace", "edtr_set_gemm_max_clusters", "edtr_gemm_tile_n", "edtr_gemm_bf16",
     "edtr_conv3x3_bf16", "edtr_conv3x3_up2x_bf16", "edtr_attention_bf16", "edtr_groupnorm_partial_size", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
     "edtr_groupnorm_fused_supported", "edtr_groupnorm_fused", "edtr_groupnorm_pool", "edtr_groupnorm_apply_stats",
-    "edtr_layernorm_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
+    "edtr_layernorm_bf16", "edtr_layernorm_padded_bf16", "edtr_pixel_unshuffle_f32_to_nhwc_bf16",
+    "edtr_window_attention_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
     "edtr_nchw_f32_to_nhwc_bf16", "edtr_pointwise_nchw_f32_to_nhwc_bf16", "edtr_nhwc_bf16_to_nchw", "edtr_cast_f32_to_bf16",
     "edtr_tile_blend", "edtr_timestep_embedding", "edtr_sampler_update", "edtr_wavelet_level",
 ]
@@ -137,6 +138,12 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_groupnorm_apply.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, vp, vp, vp, c_float, ci, vp]
     lib.edtr_layernorm_bf16.restype = ci
     lib.edtr_layernorm_bf16.argtypes = [vp, ci, vp, ci, ci, ci, vp, vp, c_float, vp]
+    lib.edtr_layernorm_padded_bf16.restype = ci
+    lib.edtr_layernorm_padded_bf16.argtypes = [vp, ci, vp, ci, ci, ci, ci, vp, vp, c_float, vp]
+    lib.edtr_pixel_unshuffle_f32_to_nhwc_bf16.restype = ci
+    lib.edtr_pixel_unshuffle_f32_to_nhwc_bf16.argtypes = [vp, vp, ci, ci, ci, ci, ci, ci, vp, c_float, vp]
+    lib.edtr_window_attention_bf16.restype = ci
+    lib.edtr_window_attention_bf16.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, ci, c_float, vp, vp, vp]
     lib.edtr_softmax_rows.restype = ci
     lib.edtr_softmax_rows.argtypes = [vp, ci, vp, ci, ci, ci, c_float, vp]
     lib.edtr_upsample2x_bf16.restype = ci

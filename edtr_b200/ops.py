@@ -12,14 +12,14 @@ channel slice ``buf[..., :320]`` of a wider concat buffer.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
 from . import lib as _lib
 from .lib import EdtrEpilogue
 
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU, ACT_LRELU_02, ACT_LRELU_001 = 0, 1, 2, 3, 4, 5
 OUT_BF16, OUT_F32, OUT_NCHW_F32, OUT_NCHW_BF16 = 0, 1, 2, 3
 
 BF16 = torch.bfloat16
@@ -336,15 +336,62 @@ def groupnorm_apply_stats(x: torch.Tensor, mean_var: torch.Tensor, gamma: torch.
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, c_real: Optional[int] = None) -> torch.Tensor:
+    """Row LayerNorm.  c_real < C: rows are padded to C channels, the statistics use the first c_real channels and the
+    pads (zeros on input; gamma = beta = 0 there) stay zero."""
     _require_cuda(x, gamma, beta, out)
     M, C, ldx = rows_view(x)
     if out is None:
         out = torch.empty(x.shape, dtype=BF16, device=x.device)
     _, _, ldy = rows_view(out)
     L = _lib.device_lib()
-    _lib.check(L.edtr_layernorm_bf16(x.data_ptr(), ldx, out.data_ptr(), ldy, M, C, _f32(gamma, C, "gamma"),
-                                     _f32(beta, C, "beta"), eps, _stream()), "edtr_layernorm_bf16")
+    _lib.check(L.edtr_layernorm_padded_bf16(x.data_ptr(), ldx, out.data_ptr(), ldy, M, C, C if c_real is None else c_real,
+                                            _f32(gamma, C, "gamma"), _f32(beta, C, "beta"), eps, _stream()),
+               "edtr_layernorm_padded_bf16")
+    return out
+
+
+def pixel_unshuffle(x: torch.Tensor, out: torch.Tensor, mean: Sequence[float], scale: float, r: int = 8) -> torch.Tensor:
+    """fp32 NCHW image -> bf16 channels-last [B, H/r, W/r, >= C r^2] with the per-channel mean removed
+    (nn.PixelUnshuffle channel order)."""
+    _require_cuda(x, out)
+    if x.dtype != torch.float32 or x.dim() != 4 or not x.is_contiguous():
+        raise ValueError("x must be a contiguous fp32 [B, C, H, W] tensor")
+    B, C, H, W = x.shape
+    if out.dtype != BF16 or out.dim() != 4 or tuple(out.shape[:3]) != (B, H // r, W // r) or out.shape[3] < C * r * r:
+        raise ValueError(f"out must be bf16 [B, H/{r}, W/{r}, >= {C * r * r}], got {tuple(out.shape)}")
+    _, _, ldy = rows_view(out)
+    m = (ctypes.c_float * 3)(*([float(v) for v in mean] + [0.0] * 3)[:3])
+    L = _lib.device_lib()
+    _lib.check(L.edtr_pixel_unshuffle_f32_to_nhwc_bf16(x.data_ptr(), out.data_ptr(), ldy, B, C, H, W, r,
+                                                       ctypes.cast(m, ctypes.c_void_p), float(scale), _stream()),
+               "edtr_pixel_unshuffle_f32_to_nhwc_bf16")
+    return out
+
+
+def window_attention(qkv: torch.Tensor, heads: int, shift: int, scale: float, bias: torch.Tensor,
+                     mask: Optional[torch.Tensor], out: torch.Tensor) -> torch.Tensor:
+    """Swin window attention (8x8 windows) on a [B, H, W, 3*heads*32] fused projection; out [B, H, W, heads*32]."""
+    _require_cuda(qkv, bias, mask, out)
+    if qkv.dim() != 4 or out.dim() != 4 or qkv.shape[:3] != out.shape[:3]:
+        raise ValueError("qkv / out must be [B, H, W, C] tensors over the same token grid")
+    B, H, W, C3 = qkv.shape
+    _, _, ld = rows_view(qkv)
+    _, _, ldo = rows_view(out)
+    if C3 < 3 * heads * 32 or out.shape[3] < heads * 32:
+        raise ValueError("qkv / out are too narrow for heads * 32 columns")
+    nb = heads * 64 * 64
+    if bias.dtype != torch.float32 or not bias.is_contiguous() or bias.numel() != nb:
+        raise ValueError(f"bias must be a contiguous fp32 [heads, 64, 64] tensor ({nb} elements)")
+    mp = None
+    if mask is not None:
+        nm = (H // 8) * (W // 8) * 64 * 64
+        if mask.dtype != torch.float32 or not mask.is_contiguous() or mask.numel() != nm:
+            raise ValueError(f"mask must be a contiguous fp32 [windows, 64, 64] tensor ({nm} elements)")
+        mp = mask.data_ptr()
+    L = _lib.device_lib()
+    _lib.check(L.edtr_window_attention_bf16(qkv.data_ptr(), ld, out.data_ptr(), ldo, B, H, W, heads, shift, float(scale),
+                                            bias.data_ptr(), mp, _stream()), "edtr_window_attention_bf16")
     return out
 
 

@@ -1,0 +1,367 @@
+"""Drop-in for the reference's SwinIR pre-restoration network (``model/swinir.py:624-905``).
+
+``SwinIR`` keeps the reference constructor signature and state-dict keys (parameters and the
+``relative_position_index`` / ``attn_mask`` buffers), so ``swinir.load_state_dict(torch.load(...), strict=True)`` of
+``main/det/test_edtr.py:42-45`` works unchanged; ``forward`` runs on the CUDA kernels through ``SwinIREngine``.
+
+Layout: tokens and feature maps share one channels-last bf16 buffer ``[B, h, w, 192]`` (the 180 channels padded to
+192: pad channels are kept exactly zero by zero weight rows / biases / norm gains); attention heads are stored 32
+wide (30 + 2 zero columns), the MLP hidden width 360 as 384.  The cyclic shift, window partition / reverse and patch
+embed / unembed of the reference are index arithmetic inside ``edtr_window_attention_bf16`` — no permute passes.
+
+UNVERIFIED ON HARDWARE (branch swinir-wip): the dataflow is checked on CPU against the live-reference fixture
+through the torch stand-in for the kernels (tests/test_host_cpu.py); the CUDA kernels it calls are compile-checked only.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from .engine import BF16, F32, Workspace, _ceil, _Graph, pack_conv3x3, pack_conv3x3_up2x, vec
+from .nets import _attach, state_version
+
+RGB_MEAN = (0.4488, 0.4371, 0.4040)   # model/swinir.py:689-691
+HEAD_PAD = 32
+
+
+def _relative_position_index(ws: int) -> torch.Tensor:
+    """model/swinir.py:97-108."""
+    coords = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")).flatten(1)
+    rel = (coords[:, :, None] - coords[:, None, :]).permute(1, 2, 0).contiguous()
+    rel[:, :, 0] += ws - 1
+    rel[:, :, 1] += ws - 1
+    rel[:, :, 0] *= 2 * ws - 1
+    return rel.sum(-1)
+
+
+def shifted_window_mask(H: int, W: int, ws: int, shift: int) -> torch.Tensor:
+    """[nW, ws*ws, ws*ws] additive 0 / -100 mask of SW-MSA (model/swinir.py:222-243)."""
+    img = torch.zeros((1, H, W, 1))
+    cnt = 0
+    for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+        for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
+            img[:, hs, wsl, :] = cnt
+            cnt += 1
+    mw = img.view(1, H // ws, ws, W // ws, ws, 1).permute(0, 1, 3, 2, 4, 5).reshape(-1, ws * ws)
+    m = mw.unsqueeze(1) - mw.unsqueeze(2)
+    return m.masked_fill(m != 0, -100.0).masked_fill(m == 0, 0.0)
+
+
+class SwinIR(nn.Module):
+    """Same constructor as ``model.swinir.SwinIR`` (model/swinir.py:652-681); only the configuration EDTR uses is
+    implemented (configs/*/007_edtr-s4.yaml:3-19): patch_size 1, window 8, 'nearest+conv' upsampler, '1conv' residual
+    connection, PixelUnshuffle(8) in front, no absolute position embedding."""
+
+    def __init__(self, img_size=64, patch_size=1, in_chans=3, embed_dim=96, depths=(6, 6, 6, 6), num_heads=(6, 6, 6, 6),
+                 window_size=7, mlp_ratio=4., qkv_bias=True, qk_scale=None, drop_rate=0., attn_drop_rate=0.,
+                 drop_path_rate=0.1, norm_layer=nn.LayerNorm, ape=False, patch_norm=True, use_checkpoint=False, sf=4,
+                 img_range=1., upsampler="", resi_connection="1conv", unshuffle=False, unshuffle_scale=None,
+                 hq_key: str = "jpg", lq_key: str = "hint", learning_rate: float = None, weight_decay: float = None):
+        super().__init__()
+        unsupported = []
+        if patch_size != 1: unsupported.append("patch_size != 1")
+        if window_size != 8: unsupported.append("window_size != 8")
+        if upsampler != "nearest+conv": unsupported.append(f"upsampler {upsampler!r}")
+        if resi_connection != "1conv": unsupported.append(f"resi_connection {resi_connection!r}")
+        if not unshuffle or sf != 8 or (unshuffle_scale not in (None, 8)): unsupported.append("unshuffle / sf != 8")
+        if ape or not patch_norm or not qkv_bias or qk_scale is not None: unsupported.append("ape / patch_norm / qkv options")
+        if in_chans != 3: unsupported.append("in_chans != 3")
+        if any(embed_dim % h for h in num_heads) or any(embed_dim // h > HEAD_PAD for h in num_heads):
+            unsupported.append("head dim > 32")
+        if unsupported:
+            raise NotImplementedError("edtr_b200.SwinIR covers the EDTR configuration only: " + ", ".join(unsupported))
+        self.cfg = dict(img_size=int(img_size), in_chans=in_chans, embed_dim=embed_dim, depths=tuple(depths),
+                        num_heads=tuple(num_heads), window_size=window_size, mlp_ratio=mlp_ratio, sf=sf,
+                        img_range=float(img_range), num_feat=64)
+        self.upscale, self.window_size, self.img_range = sf, window_size, img_range
+        for key, shape in swinir_param_shapes(self.cfg):
+            _attach(self, key, shape)
+        self._init_like_reference()
+        # buffers of the reference state-dict (model/swinir.py:108, :220): kept so that strict loading works
+        idx = _relative_position_index(window_size)
+        res = self.cfg["img_size"]
+        for i, depth in enumerate(self.cfg["depths"]):
+            for j in range(depth):
+                blk = self._modules["layers"]._modules[str(i)]._modules["residual_group"]._modules["blocks"]._modules[str(j)]
+                blk._modules["attn"].register_buffer("relative_position_index", idx.clone())
+                ws, shift = block_geometry(self.cfg, j)
+                blk.register_buffer("attn_mask", shifted_window_mask(res, res, ws, shift) if shift > 0 else None)
+        self._engine: Optional["SwinIREngine"] = None
+        self._engine_version = -1
+
+    @torch.no_grad()
+    def _init_like_reference(self) -> None:
+        """model/swinir.py:816-825: trunc_normal(0.02) Linear weights, zero biases, LayerNorm (1, 0); convolutions keep
+        torch's default init; bias tables trunc_normal(0.02) (:116)."""
+        for k, p in self.named_parameters():
+            if k.endswith("relative_position_bias_table"):
+                nn.init.trunc_normal_(p, std=0.02)
+            elif k.endswith("weight") and p.dim() == 2:
+                nn.init.trunc_normal_(p, std=0.02)
+            elif k.endswith("weight") and p.dim() == 4:
+                nn.init.kaiming_uniform_(p, a=math.sqrt(5))
+            elif k.endswith("weight"):
+                p.fill_(1.0)
+            else:
+                p.zero_()
+
+    def engine(self) -> "SwinIREngine":
+        dev = next(self.parameters()).device
+        v = state_version(self)
+        if self._engine is None or self._engine_version != v or self._engine.device != dev:
+            sd = {k: p.detach() for k, p in self.named_parameters()}
+            self._engine = SwinIREngine(self.cfg, sd, dev)
+            self._engine_version = v
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.engine().forward(x)
+
+
+def swinir_param_shapes(cfg: Dict) -> List[Tuple[str, Tuple[int, ...]]]:
+    """Learnable tensors of the reference module in the supported configuration (model/swinir.py:682-814)."""
+    c, nf, ws = cfg["embed_dim"], cfg["num_feat"], cfg["window_size"]
+    cin = cfg["in_chans"] * cfg["sf"] ** 2
+    hid = int(c * cfg["mlp_ratio"])
+    out: List[Tuple[str, Tuple[int, ...]]] = [("conv_first.1.weight", (c, cin, 3, 3)), ("conv_first.1.bias", (c,)),
+                                              ("patch_embed.norm.weight", (c,)), ("patch_embed.norm.bias", (c,))]
+    for i, (depth, heads) in enumerate(zip(cfg["depths"], cfg["num_heads"])):
+        for j in range(depth):
+            p = f"layers.{i}.residual_group.blocks.{j}."
+            out += [(p + "norm1.weight", (c,)), (p + "norm1.bias", (c,)),
+                    (p + "attn.relative_position_bias_table", ((2 * ws - 1) ** 2, heads)),
+                    (p + "attn.qkv.weight", (3 * c, c)), (p + "attn.qkv.bias", (3 * c,)),
+                    (p + "attn.proj.weight", (c, c)), (p + "attn.proj.bias", (c,)),
+                    (p + "norm2.weight", (c,)), (p + "norm2.bias", (c,)),
+                    (p + "mlp.fc1.weight", (hid, c)), (p + "mlp.fc1.bias", (hid,)),
+                    (p + "mlp.fc2.weight", (c, hid)), (p + "mlp.fc2.bias", (c,))]
+        out += [(f"layers.{i}.conv.weight", (c, c, 3, 3)), (f"layers.{i}.conv.bias", (c,))]
+    out += [("norm.weight", (c,)), ("norm.bias", (c,)),
+            ("conv_after_body.weight", (c, c, 3, 3)), ("conv_after_body.bias", (c,)),
+            ("conv_before_upsample.0.weight", (nf, c, 3, 3)), ("conv_before_upsample.0.bias", (nf,))]
+    for k in (1, 2, 3):
+        out += [(f"conv_up{k}.weight", (nf, nf, 3, 3)), (f"conv_up{k}.bias", (nf,))]
+    out += [("conv_hr.weight", (nf, nf, 3, 3)), ("conv_hr.bias", (nf,)),
+            ("conv_last.weight", (cfg["in_chans"], nf, 3, 3)), ("conv_last.bias", (cfg["in_chans"],))]
+    return out
+
+
+def block_geometry(cfg: Dict, j: int) -> Tuple[int, int]:
+    """(window, shift) of block j of a residual group, resolved against the constructor resolution as the reference
+    does (model/swinir.py:199-202, :391-393)."""
+    ws = cfg["window_size"]
+    if cfg["img_size"] <= ws:
+        return cfg["img_size"], 0
+    return ws, (0 if j % 2 == 0 else ws // 2)
+
+
+def _pad_rows(w: torch.Tensor, rows: int) -> torch.Tensor:
+    out = torch.zeros((rows,) + tuple(w.shape[1:]), dtype=w.dtype)
+    out[:w.shape[0]] = w
+    return out
+
+
+def _pad_mat(w: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    out = torch.zeros((rows, cols), dtype=torch.float32)
+    out[:w.shape[0], :w.shape[1]] = w
+    return out
+
+
+class SwinIREngine:
+    """Packed weights + the block walk of SwinIR.forward (model/swinir.py:856-894) on the C-ABI kernels."""
+
+    def __init__(self, cfg: Dict, sd: Dict[str, torch.Tensor], device, ops=None):
+        if ops is None:
+            from . import ops as _ops
+            ops = _ops
+        self.ops, self.cfg, self.device = ops, cfg, torch.device(device)
+        c = cfg["embed_dim"]
+        self.c, self.cp = c, _ceil(c, 64)
+        self.hid_p = _ceil(int(c * cfg["mlp_ratio"]), 64)
+        self.nf = cfg["num_feat"]
+        dev = self.device
+        f = {k: v.detach().float().cpu() for k, v in sd.items()}
+        missing = [k for k, _ in swinir_param_shapes(cfg) if k not in f]
+        if missing:
+            raise KeyError(f"state-dict is missing {missing[:3]} ...")
+        w: Dict[str, torch.Tensor] = {}
+        cp, hp = self.cp, self.hid_p
+
+        def conv_to_cp(key: str, rows: int) -> None:    # [Cout, Cin, 3, 3] -> [rows, 9 * Cin_pad] bf16 (+ bias padded)
+            m = pack_conv3x3(f[key + "weight"], "cpu")
+            w[key + "weight"] = _pad_rows(m, rows).to(dev)
+            w[key + "bias"] = _pad_rows(f[key + "bias"], rows).contiguous().to(dev)
+
+        def norm(key: str) -> None:
+            w[key + "weight"] = _pad_rows(f[key + "weight"], cp).contiguous().to(dev)
+            w[key + "bias"] = _pad_rows(f[key + "bias"], cp).contiguous().to(dev)
+
+        conv_to_cp("conv_first.1.", cp)
+        norm("patch_embed.norm.")
+        idx = _relative_position_index(cfg["window_size"]).view(-1)
+        for i, (depth, heads) in enumerate(zip(cfg["depths"], cfg["num_heads"])):
+            d = c // heads
+            if heads * HEAD_PAD > cp:
+                raise NotImplementedError("heads * 32 must fit the padded embedding width")
+            for j in range(depth):
+                p = f"layers.{i}.residual_group.blocks.{j}."
+                norm(p + "norm1.")
+                norm(p + "norm2.")
+                # fused projection rows [3][heads][d] -> [3][cp] with head h at [32 h, 32 h + d)
+                qw, qb = f[p + "attn.qkv.weight"].view(3, heads, d, c), f[p + "attn.qkv.bias"].view(3, heads, d)
+                W3 = torch.zeros((3, cp, cp))
+                b3 = torch.zeros((3, cp))
+                for h in range(heads):
+                    W3[:, h * HEAD_PAD:h * HEAD_PAD + d, :c] = qw[:, h]
+                    b3[:, h * HEAD_PAD:h * HEAD_PAD + d] = qb[:, h]
+                w[p + "attn.qkv.weight"] = W3.view(3 * cp, cp).to(BF16).contiguous().to(dev)
+                w[p + "attn.qkv.bias"] = b3.view(-1).contiguous().to(dev)
+                # output projection: its input columns follow the padded head layout
+                pw = f[p + "attn.proj.weight"].view(c, heads, d)
+                Wp = torch.zeros((cp, cp))
+                for h in range(heads):
+                    Wp[:c, h * HEAD_PAD:h * HEAD_PAD + d] = pw[:, h]
+                w[p + "attn.proj.weight"] = Wp.to(BF16).contiguous().to(dev)
+                w[p + "attn.proj.bias"] = _pad_rows(f[p + "attn.proj.bias"], cp).contiguous().to(dev)
+                w[p + "mlp.fc1.weight"] = _pad_mat(f[p + "mlp.fc1.weight"], hp, cp).to(BF16).contiguous().to(dev)
+                w[p + "mlp.fc1.bias"] = _pad_rows(f[p + "mlp.fc1.bias"], hp).contiguous().to(dev)
+                w[p + "mlp.fc2.weight"] = _pad_mat(f[p + "mlp.fc2.weight"], cp, hp).to(BF16).contiguous().to(dev)
+                w[p + "mlp.fc2.bias"] = _pad_rows(f[p + "mlp.fc2.bias"], cp).contiguous().to(dev)
+                tab = f[p + "attn.relative_position_bias_table"]
+                w[p + "attn.bias"] = tab[idx].view(64, 64, heads).permute(2, 0, 1).contiguous().to(dev)   # [heads, 64, 64]
+            conv_to_cp(f"layers.{i}.conv.", cp)
+        norm("norm.")
+        conv_to_cp("conv_after_body.", cp)
+        conv_to_cp("conv_before_upsample.0.", self.nf)
+        for k in (1, 2, 3):
+            w[f"conv_up{k}.weight_up2x"] = pack_conv3x3_up2x(f[f"conv_up{k}.weight"], dev)
+            w[f"conv_up{k}.weight"] = pack_conv3x3(f[f"conv_up{k}.weight"], dev)
+            w[f"conv_up{k}.bias"] = vec(f[f"conv_up{k}.bias"], dev)
+        conv_to_cp("conv_hr.", self.nf)
+        w["conv_last.weight"] = pack_conv3x3(f["conv_last.weight"], dev)
+        # x / img_range + mean (model/swinir.py:892) folded into the bias
+        mean = torch.tensor(RGB_MEAN[:cfg["in_chans"]])
+        self.out_scale = 1.0 / cfg["img_range"]
+        w["conv_last.bias"] = (f["conv_last.bias"] * self.out_scale + mean).contiguous().to(dev)
+        self.w = w
+        self._ws: Dict[Tuple[int, int, int], Workspace] = {}
+        self._masks: Dict[Tuple[int, int, int, int], torch.Tensor] = {}
+        self._graphs: Dict[Tuple[int, int, int], _Graph] = {}
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _conv(self, ws: Workspace, x: torch.Tensor, key: str, out: torch.Tensor, **kw) -> torch.Tensor:
+        ops, w = self.ops, self.w
+        B, H, W, C = x.shape
+        if ops.conv3x3_supported(H, W, C):
+            return ops.conv3x3(x, w[key + "weight"], bias=w[key + "bias"], out=out, **kw)
+        col = ops.im2col(x, 3, 3, 1, 1, 1, H, W, out=ws.get("col", (B * H * W, 9 * C)))
+        if kw.get("out_mode", ops.OUT_BF16) in (ops.OUT_NCHW_F32, ops.OUT_NCHW_BF16):
+            kw["hw"] = H * W
+        if kw.get("residual") is not None:
+            kw["residual"] = kw["residual"].reshape(B * H * W, -1)
+        o2 = out if out.dim() != 4 else out.view(B * H * W, -1)
+        ops.gemm(col, w[key + "weight"], bias=w[key + "bias"], out=o2, **kw)
+        return out
+
+    def _up(self, ws: Workspace, x: torch.Tensor, k: int, out: torch.Tensor) -> torch.Tensor:
+        """lrelu(conv_up_k(nearest-2x(x))) (model/swinir.py:876-880)."""
+        ops, w = self.ops, self.w
+        B, H, W, C = x.shape
+        if ops.conv3x3_up2x_supported(B, H, W, C, out.shape[-1]):
+            return ops.conv3x3_up2x(x, w[f"conv_up{k}.weight_up2x"], bias=w[f"conv_up{k}.bias"], act=ops.ACT_LRELU_02, out=out)
+        u = ops.upsample2x(x, out=ws.get("up", (B, 2 * H, 2 * W, C)))
+        return self._conv(ws, u, f"conv_up{k}.", out, act=ops.ACT_LRELU_02)
+
+    def _mask(self, h: int, w_: int, ws: int, shift: int) -> Optional[torch.Tensor]:
+        if shift == 0:
+            return None
+        key = (h, w_, ws, shift)
+        if key not in self._masks:
+            self._masks[key] = shifted_window_mask(h, w_, ws, shift).contiguous().to(self.device)
+        return self._masks[key]
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, x: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
+        """[B, 3, H, W] fp32 in [0, 1] -> [B, 3, H, W] fp32 (model/swinir.py:856-894).  All buffers are static per
+        (B, H, W), so the ~600 launches replay as one CUDA graph."""
+        ops, cfg = self.ops, self.cfg
+        if x.dim() != 4 or x.shape[1] != cfg["in_chans"]:
+            raise ValueError(f"x must be [B, {cfg['in_chans']}, H, W], got {tuple(x.shape)}")
+        if getattr(ops, "REQUIRES_CUDA", True) and not x.is_cuda:
+            raise RuntimeError("edtr_b200 has no CPU path: x must be a CUDA tensor")
+        B, _, H, W = x.shape
+        sf, wsz = cfg["sf"], cfg["window_size"]
+        if H % (sf * wsz) or W % (sf * wsz):
+            # the reference reflect-pads to a multiple of 8 pixels and then fails in window_partition unless the token
+            # grid is a multiple of the window (model/swinir.py:834-839, :46): only multiples of 64 pixels ever work
+            raise ValueError(f"H and W must be multiples of {sf * wsz} (got {H}x{W})")
+        ws = self._ws.setdefault((B, H, W), Workspace(self.device))
+        sx = ws.get("in_x", (B, cfg["in_chans"], H, W), F32)
+        out = ws.get("out_img", (B, cfg["in_chans"], H, W), F32)
+        sx.copy_(x)
+        h, w_ = H // sf, W // sf
+        for j in (0, 1):                     # masks are built (host -> device copy) outside any capture
+            wsj, shift = block_geometry(cfg, j)
+            self._mask(h, w_, wsj, shift)
+        run = lambda: self._forward(ws, sx, out)
+        if use_graph and x.is_cuda:
+            g = self._graphs.get((B, H, W))
+            if g is None:
+                g = self._graphs[(B, H, W)] = _Graph(run)
+            g.replay()
+        else:
+            run()
+        return out.clone()
+
+    def _forward(self, ws: Workspace, x: torch.Tensor, out: torch.Tensor) -> None:
+        ops, w, cfg = self.ops, self.w, self.cfg
+        B, _, H, W = x.shape
+        sf = cfg["sf"]
+        h, w_ = H // sf, W // sf
+        M = B * h * w_
+        cp, hp, nf = self.cp, self.hid_p, self.nf
+        xin = ws.get("xin", (B, h, w_, cfg["in_chans"] * sf * sf))
+        ops.pixel_unshuffle(x, xin, RGB_MEAN, cfg["img_range"], sf)
+        f0 = self._conv(ws, xin, "conv_first.1.", ws.get("f0", (B, h, w_, cp)))
+        bufs = [ws.get(f"t{i}", (B, h, w_, cp)) for i in range(3)]
+        nbuf = ws.get("n", (B, h, w_, cp))
+        qkv = ws.get("qkv", (B, h, w_, 3 * cp))
+        ao = ws.get("ao", (B, h, w_, cp))
+        hid = ws.get("hid", (M, hp))
+        cur = ops.layernorm(f0, w["patch_embed.norm.weight"], w["patch_embed.norm.bias"], 1e-5, out=bufs[0], c_real=self.c)
+        ci = 0                                       # bufs[ci] holds the input of the residual group
+        for i, (depth, heads) in enumerate(zip(cfg["depths"], cfg["num_heads"])):
+            scale = (self.c // heads) ** -0.5
+            work = bufs[(ci + 1) % 3]
+            src = cur
+            for j in range(depth):
+                p = f"layers.{i}.residual_group.blocks.{j}."
+                wsj, shift = block_geometry(cfg, j)
+                if wsj != 8:
+                    raise NotImplementedError("feature maps smaller than the 8x8 window are not supported")
+                ops.layernorm(src, w[p + "norm1.weight"], w[p + "norm1.bias"], 1e-5, out=nbuf, c_real=self.c)
+                ops.gemm(nbuf, w[p + "attn.qkv.weight"], bias=w[p + "attn.qkv.bias"], out=qkv.view(M, 3 * cp))
+                ops.window_attention(qkv, heads, shift, scale, w[p + "attn.bias"], self._mask(h, w_, wsj, shift), ao)
+                # x = shortcut + attn (model/swinir.py:283): the first block of a group writes the working buffer
+                ops.gemm(ao, w[p + "attn.proj.weight"], bias=w[p + "attn.proj.bias"], residual=src.view(M, cp),
+                         out=work.view(M, cp))
+                ops.layernorm(work, w[p + "norm2.weight"], w[p + "norm2.bias"], 1e-5, out=nbuf, c_real=self.c)
+                ops.gemm(nbuf, w[p + "mlp.fc1.weight"], bias=w[p + "mlp.fc1.bias"], act=ops.ACT_GELU, out=hid)
+                ops.gemm(hid, w[p + "mlp.fc2.weight"], bias=w[p + "mlp.fc2.bias"], residual=work.view(M, cp),
+                         out=work.view(M, cp))
+                src = work
+            # RSTB: conv(blocks(x)) + x (model/swinir.py:487-488)
+            nxt = bufs[(ci + 2) % 3]
+            self._conv(ws, work, f"layers.{i}.conv.", nxt, residual=cur.view(M, cp))
+            cur, ci = nxt, (ci + 2) % 3
+        ops.layernorm(cur, w["norm.weight"], w["norm.bias"], 1e-5, out=nbuf, c_real=self.c)
+        body = self._conv(ws, nbuf, "conv_after_body.", bufs[(ci + 1) % 3], residual=f0.view(M, cp))
+        u = self._conv(ws, body, "conv_before_upsample.0.", ws.get("u0", (B, h, w_, nf)), act=ops.ACT_LRELU_001)
+        for k in (1, 2, 3):
+            u = self._up(ws, u, k, ws.get(f"u{k}", (B, h << k, w_ << k, nf)))
+        hr = self._conv(ws, u, "conv_hr.", ws.get("hr", (B, H, W, nf)), act=ops.ACT_LRELU_02)
+        self._conv(ws, hr, "conv_last.", out.view(B, cfg["in_chans"], H * W), out_mode=ops.OUT_NCHW_F32, alpha=self.out_scale)

@@ -35,6 +35,9 @@ extern "C" {
 #define EDTR_ACT_NONE 0
 #define EDTR_ACT_SILU 1  /* x * sigmoid(x)            replaces: model/unet.py:166-172 (emb SiLU) */
 #define EDTR_ACT_GEGLU 2 /* x * gelu_erf(gate)         replaces: model/attention.py:20-27 */
+#define EDTR_ACT_GELU 3      /* gelu_erf(x)            replaces: nn.GELU, model/swinir.py:19-31 */
+#define EDTR_ACT_LRELU_02 4  /* LeakyReLU(0.2)         replaces: model/swinir.py:803, 874-880 */
+#define EDTR_ACT_LRELU_001 5 /* LeakyReLU(0.01)        replaces: model/swinir.py:766-769 (nn.LeakyReLU default) */
 
 /* Output addressing of the GEMM epilogue. */
 #define EDTR_OUT_BF16 0      /* out[row*ldc + col], bf16                         */
@@ -170,6 +173,26 @@ int edtr_groupnorm_fused(const void* X, int ldx, void* Y, int ldy, int B, int HW
  * replaces: nn.LayerNorm — model/attention.py:222-224. */
 int edtr_layernorm_bf16(const void* X, int ldx, void* Y, int ldy, int M, int C,
                         const float* gamma, const float* beta, float eps, void* stream);
+/* Same over rows that are padded to C channels: statistics over the first C_real channels, the pad channels hold
+ * zeros on input and (gamma = beta = 0 there) on output.  replaces: nn.LayerNorm(180) in 192-wide rows —
+ * model/swinir.py:205,212,531-533,760. */
+int edtr_layernorm_padded_bf16(const void* X, int ldx, void* Y, int ldy, int M, int C, int C_real,
+                               const float* gamma, const float* beta, float eps, void* stream);
+
+/* ---- SwinIR pre-restoration network (model/swinir.py) --------------------- */
+/* Y[b, y, x, (c*r + dy)*r + dx] = (X[b, c, y*r + dy, x*r + dx] - mean3[c]) * scale: nn.PixelUnshuffle(8) of the
+ * mean-shifted fp32 NCHW image into a bf16 channels-last tensor with pixel stride ldy.  mean3 is a HOST pointer to
+ * C floats (or NULL).  replaces: model/swinir.py:859-860 + conv_first[0] (:700-704). */
+int edtr_pixel_unshuffle_f32_to_nhwc_bf16(const float* X, void* Y, int ldy, int B, int C, int H, int W, int r,
+                                          const float* mean3, float scale, void* stream);
+/* Window attention of one SwinTransformerBlock on a [B, H, W] token grid (H, W multiples of 8): QKV is the fused
+ * projection output, rows = tokens in (b, y, x) order with stride ld, columns q | k | v each heads*32 wide (head h at
+ * [32h, 32h+32), the reference's 30 channels + 2 zero pads); O likewise heads*32 wide with stride ldo.  `shift` is the
+ * cyclic shift (0 or 4), `bias` fp32 [heads, 64, 64] the gathered relative-position bias, `mask` fp32
+ * [(H/8)*(W/8), 64, 64] the 0 / -100 SW-MSA mask (NULL when shift == 0).  The roll, the window partition and their
+ * inverses are index arithmetic.  replaces: model/swinir.py:120-151, 253-281. */
+int edtr_window_attention_bf16(const void* QKV, int ld, void* O, int ldo, int B, int H, int W, int heads,
+                               int shift, float scale, const float* bias, const float* mask, void* stream);
 /* Row softmax of fp32 S[M, N] (stride lds) scaled by `scale`, bf16 output P.
  * replaces: the softmax inside SDPA for the single-head d=512 VAE attention —
  * model/vae.py:298. */

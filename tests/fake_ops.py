@@ -12,7 +12,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU, ACT_GELU, ACT_LRELU_02, ACT_LRELU_001 = 0, 1, 2, 3, 4, 5
 OUT_BF16, OUT_F32, OUT_NCHW_F32, OUT_NCHW_BF16 = 0, 1, 2, 3
 REQUIRES_CUDA = False
 GEGLU_TILE = 128
@@ -56,6 +56,12 @@ def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, ou
         v = v + _rows(residual)
     if act == ACT_SILU:
         v = F.silu(v)
+    elif act == ACT_GELU:
+        v = F.gelu(v)
+    elif act == ACT_LRELU_02:
+        v = F.leaky_relu(v, 0.2)
+    elif act == ACT_LRELU_001:
+        v = F.leaky_relu(v, 0.01)
     if out_mode in (OUT_BF16, OUT_F32):
         want = torch.bfloat16 if out_mode == OUT_BF16 else torch.float32
         if out is None:
@@ -124,6 +130,8 @@ def conv3x3_up2x(x, w4, *, bias=None, act=ACT_NONE, out=None):
         y = y + bias.float()
     if act == ACT_SILU:
         y = F.silu(y)
+    elif act == ACT_LRELU_02:
+        y = F.leaky_relu(y, 0.2)
     if out is None:
         out = torch.empty((B, 2 * H, 2 * W, Cout), dtype=torch.bfloat16)
     out.copy_(y)
@@ -195,9 +203,14 @@ def conv3x3_supported(H, W, Cin):
     return H % rows == 0 if H >= rows else rows % H == 0
 
 
-def layernorm(x, gamma, beta, eps, out=None):
+def layernorm(x, gamma, beta, eps, out=None, c_real=None):
     LAUNCHES[0] += 1
-    y = F.layer_norm(x.float(), (x.shape[-1],), gamma, beta, eps)
+    C = x.shape[-1]
+    if c_real is None or c_real == C:
+        y = F.layer_norm(x.float(), (C,), gamma, beta, eps)
+    else:
+        y = torch.zeros(x.shape, dtype=torch.float32)
+        y[..., :c_real] = F.layer_norm(x.float()[..., :c_real], (c_real,), gamma[:c_real], beta[:c_real], eps)
     if out is None:
         out = torch.empty(x.shape, dtype=torch.bfloat16)
     out.copy_(y.view(out.shape))
@@ -300,3 +313,33 @@ def sampler_update(x, eps, noise, index, tables, want_pred_x0=True, x_prev=None,
     if pred_x0 is not None:
         pred_x0.copy_(x0)
     return x_prev, pred_x0
+
+
+def pixel_unshuffle(x, out, mean, scale, r=8):
+    LAUNCHES[0] += 1
+    B, C, H, W = x.shape
+    m = torch.tensor(list(mean)[:C], dtype=torch.float32).view(1, C, 1, 1)
+    y = F.pixel_unshuffle((x - m) * scale, r).permute(0, 2, 3, 1)
+    out[..., :C * r * r].copy_(y)
+    return out
+
+
+def window_attention(qkv, heads, shift, scale, bias, mask, out):
+    """Swin W-MSA / SW-MSA on 32-wide (padded) heads, evaluated literally: roll, partition, attention, reverse."""
+    LAUNCHES[0] += 1
+    B, H, W, _ = qkv.shape
+    C = heads * 32
+    x = qkv.float()
+    if shift:
+        x = torch.roll(x, shifts=(-shift, -shift), dims=(1, 2))
+    win = x.view(B, H // 8, 8, W // 8, 8, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(-1, 64, 3, heads, 32).permute(2, 0, 3, 1, 4)
+    q, k, v = win[0], win[1], win[2]                                   # [B*nW, heads, 64, 32]
+    attn = (q @ k.transpose(-2, -1)) * scale + bias.view(1, heads, 64, 64)
+    if mask is not None:
+        nW = (H // 8) * (W // 8)
+        attn = (attn.view(B, nW, heads, 64, 64) + mask.view(1, nW, 1, 64, 64)).view(-1, heads, 64, 64)
+    o = (attn.softmax(-1) @ v).transpose(1, 2).reshape(B, H // 8, W // 8, 8, 8, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)
+    if shift:
+        o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
+    out[..., :C].copy_(o)
+    return out

@@ -307,3 +307,39 @@ def test_tiled_vae_encode_against_reference_fixture():
     mo = ve.encode_tiled(image, int(g["tile_size"]))
     z = (mo[:, :4] * 0.18215).cpu()
     assert O.max_rel_err(z, torch.from_numpy(g["z"])) < STEP_TOL
+
+
+def test_swinir_against_reference_fixture():
+    """SwinIR pre-restoration drop-in on the CUDA kernels vs the live-reference fixture (toy widths, head dim 30)."""
+    from oracle import swinir_oracle as S
+
+    from edtr_b200.swinir import SwinIREngine
+
+    cfg = S.SWINIR_TINY
+    d = np.load(os.path.join(GOLD, "golden_swinir.npz"))
+    eng = SwinIREngine(cfg, S.make_swinir_weights(cfg), "cuda")
+    for i in range(2):
+        x, ref = torch.from_numpy(d[f"x{i}"]).cuda(), torch.from_numpy(d[f"y{i}"])
+        y = eng.forward(x)
+        assert O.psnr(y.cpu().clamp(0, 1), ref.clamp(0, 1)) >= 40.0
+
+
+def test_swinir_edtr_widths_against_oracle():
+    """The EDTR configuration (embed 180, 8 x 6 blocks, 6 heads) on one 128x128 image vs the fp32 oracle."""
+    from oracle import swinir_oracle as S
+
+    from edtr_b200.swinir import SwinIR
+
+    cfg = S.SWINIR_EDTR
+    sd = S.make_swinir_weights(cfg)
+    m = SwinIR(img_size=64, patch_size=1, in_chans=3, embed_dim=180, depths=[6] * 8, num_heads=[6] * 8, window_size=8,
+               mlp_ratio=2, sf=8, img_range=1.0, upsampler="nearest+conv", resi_connection="1conv", unshuffle=True,
+               unshuffle_scale=8)
+    m.load_state_dict(sd, strict=False)
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(1, 3, 128, 128, generator=g)
+    with torch.no_grad():
+        ref = S.swinir_forward(sd, cfg, x)
+        y = m(x.cuda())
+    assert O.psnr(y.cpu().clamp(0, 1), ref.clamp(0, 1)) >= 40.0

@@ -388,3 +388,81 @@ def test_wavelet_reconstruction_against_reference_fixture(ops):
     gen = torch.Generator().manual_seed(3)
     c, s = torch.rand(2, 3, 512, 512, generator=gen), torch.rand(2, 3, 512, 512, generator=gen)
     assert relerr(ops.wavelet_reconstruction(c.cuda(), s.cuda()).cpu(), O.wavelet_reconstruction(c, s)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ SwinIR kernels (swin.cu)
+def _fake():
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import fake_ops
+
+    return fake_ops
+
+
+@pytest.mark.parametrize("B,H,W,heads,shift", [(2, 16, 16, 6, 0), (2, 16, 16, 6, 4), (1, 8, 24, 2, 4), (3, 64, 64, 6, 4),
+                                               (1, 8, 8, 2, 0)])
+def test_window_attention(ops, B, H, W, heads, shift):
+    """W-MSA / SW-MSA on 32-wide padded heads (two zero columns per head) against the literal roll / partition /
+    softmax / reverse evaluation."""
+    from edtr_b200.swinir import shifted_window_mask
+
+    C = heads * 32
+    qkv = rnd(B, H, W, 3 * C, seed=1)
+    qkv.view(B, H, W, 3, heads, 32)[..., 30:] = 0
+    bias = torch.randn(heads, 64, 64, device="cuda") * 0.5
+    mask = shifted_window_mask(H, W, 8, shift).contiguous().cuda() if shift else None
+    out = torch.zeros(B, H, W, C, dtype=BF, device="cuda")
+    ops.window_attention(qkv, heads, shift, 30 ** -0.5, bias, mask, out)
+    ref = torch.zeros(B, H, W, C, dtype=BF)
+    _fake().window_attention(qkv.cpu(), heads, shift, 30 ** -0.5, bias.cpu(), None if mask is None else mask.cpu(), ref)
+    assert relerr(out.cpu(), ref) < 2e-2
+    assert float(out.view(B, H, W, heads, 32)[..., 30:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,C,c_real", [(1000, 192, 180), (512, 64, 60), (300, 320, 320)])
+def test_layernorm_padded(ops, M, C, c_real):
+    x = rnd(M, C, seed=1)
+    x[:, c_real:] = 0
+    gamma, beta = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    gamma[c_real:] = 0
+    beta[c_real:] = 0
+    out = ops.layernorm(x, gamma, beta, 1e-5, c_real=c_real)
+    ref = F.layer_norm(x.float()[:, :c_real], (c_real,), gamma[:c_real], beta[:c_real], 1e-5)
+    assert relerr(out[:, :c_real], ref) < 1e-2
+    assert float(out[:, c_real:].abs().max()) == 0.0 if c_real < C else True
+
+
+def test_pixel_unshuffle(ops):
+    x = torch.rand(2, 3, 128, 192, device="cuda")
+    mean = (0.4488, 0.4371, 0.4040)
+    out = torch.empty(2, 16, 24, 192, dtype=BF, device="cuda")
+    ops.pixel_unshuffle(x, out, mean, 1.0, 8)
+    m = torch.tensor(mean, device="cuda").view(1, 3, 1, 1)
+    ref = F.pixel_unshuffle(x - m, 8).permute(0, 2, 3, 1)
+    assert relerr(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("act", [3, 4, 5])
+@pytest.mark.parametrize("M,N,K", [(2048, 384, 192), (64, 128, 64)])
+def test_gemm_pointwise_activations(ops, act, M, N, K):
+    """GELU (erf) / LeakyReLU(0.2) / LeakyReLU(0.01) epilogues on both tensor-core kernels."""
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    v = a.float() @ w.float().t() + bias
+    ref = F.gelu(v) if act == 3 else F.leaky_relu(v, 0.2 if act == 4 else 0.01)
+    assert relerr(ops.gemm(a, w, bias=bias, act=act), ref) < 1e-2
+
+
+def test_conv3x3_up2x_leaky_relu(ops):
+    B, H, W, Cin, Cout = 2, 16, 16, 64, 64
+    from edtr_b200.engine import pack_conv3x3_up2x
+
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = torch.randn(Cout, device="cuda")
+    out = ops.conv3x3_up2x(x, pack_conv3x3_up2x(w.float(), "cuda"), bias=bias, act=ops.ACT_LRELU_02)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.leaky_relu(F.conv2d(up, w.float(), bias, padding=1), 0.2).permute(0, 2, 3, 1)
+    assert relerr(out, ref) < 1e-2
