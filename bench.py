@@ -170,6 +170,119 @@ def cpu_baseline_sample():
                       f"{cores} torch CPU threads, no warm-up"}
 
 
+def reference_gpu_measure(dev, B, steps, warmup, variants=("autocast", "bf16_channels_last", "bf16_channels_last_graph")):
+    """The reference's own GPU path on this box ("the bar on the same box is the reference Python
+    path under bf16 autocast, i.e. cuDNN / cuBLAS / SDPA"): the oracle port issues the reference's torch ops one for
+    one (pinned to the live reference by tests/golden), here on `dev` with F.scaled_dot_product_attention as the
+    reference's default attention mode does, same workload as our arm (B images: 4 ControlLDM steps + VAE decode).
+      autocast                  fp32 weights under torch.autocast(bf16) — how the reference's scripts run it
+      bf16_channels_last        weights pre-cast to bf16, activations channels_last (no per-call weight casts)
+      bf16_channels_last_graph  the same captured into one CUDA graph (removes the Python / launch overhead that
+                                dominates eager PyTorch at this size): best case for stock cuDNN / cuBLAS / SDPA kernels
+    Returns {variant: {images_per_s, ms_per_step, unet_step_ms}}."""
+    import torch
+
+    from oracle import cldm_oracle as O
+
+    O.USE_SDPA = True
+    cfg = O.S4
+    w32 = {k: {n: v.to(dev) for n, v in sd.items()} for k, sd in O.make_cldm_weights(cfg, seed=0).items()}
+    x_T, cond, _ = O.make_inputs(cfg, B, 64, seed=1)
+    x_T = x_T.to(dev)
+    cond = {k: v.to(dev) for k, v in cond.items()}
+    t200 = torch.full((B,), 200, dtype=torch.long, device=dev)
+    out = {}
+
+    def timed(fn, n, wu):
+        for _ in range(wu):
+            fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / n
+
+    for variant in variants:
+        cl = variant.startswith("bf16_channels_last")
+        if cl:
+            def prep(v):
+                v = v.to(torch.bfloat16) if v.dim() >= 2 else v      # norm gains / biases stay fp32
+                return v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v
+            w = {k: {n: prep(v) for n, v in sd.items()} for k, sd in w32.items()}
+            xin = x_T.contiguous(memory_format=torch.channels_last)
+            cnd = {"c_txt": cond["c_txt"], "c_img": cond["c_img"].contiguous(memory_format=torch.channels_last)}
+        else:
+            w, xin, cnd = w32, x_T, cond
+
+        def restore():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                noise = [torch.randn_like(xin) for _ in range(4)]
+                z, _, _ = O.sample(w, cfg, xin, cnd, noise)
+                return O.vae_decode(w["vae"], cfg["vae"], z.float(), cfg["latent_scale_factor"])
+
+        def fwd():
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                return O.cldm_forward(w, cfg, xin, t200, cnd)
+
+        try:
+            if variant.endswith("_graph"):
+                restore(); fwd()
+                torch.cuda.synchronize()
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    restore()
+                with torch.cuda.graph(g2):
+                    fwd()
+                ms = timed(g1.replay, steps, warmup)
+                ms_f = timed(g2.replay, 5, 2)
+            else:
+                ms = timed(restore, steps, warmup)
+                ms_f = timed(fwd, 5, 2)
+            out[variant] = {"images_per_s": B / (ms / 1e3), "ms_per_step": ms, "unet_step_ms": ms_f}
+        except Exception as exc:  # keep the other variants
+            out[variant] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        if cl:
+            del w
+            torch.cuda.empty_cache()
+    O.USE_SDPA = False
+    del w32
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_reference_gpu(args):
+    """`--impl reference-gpu`: the reference algorithm through stock PyTorch GPU kernels (cuDNN / cuBLAS / SDPA, bf16
+    autocast) on one B200 — none of this repo's kernels on the path.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"impl": "reference-gpu", "unavailable": "no CUDA device"}), flush=True)
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B = args.batch
+    res = reference_gpu_measure(dev, B, args.steps, max(args.warmup, 3))
+    ok = {k: v for k, v in res.items() if "images_per_s" in v}
+    best = max(ok, key=lambda k: ok[k]["images_per_s"]) if ok else None
+    eager = res.get("autocast", {})
+    val = eager.get("images_per_s")
+    line = {
+        "impl": "reference-gpu", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": eager.get("ms_per_step"), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16 autocast", "data": "synthetic",
+        "config": dict(workload_config(B, 1), what="oracle port of the reference on cuDNN / cuBLAS / SDPA kernels; "
+                       "`value` is the eager bf16-autocast run (how the reference's scripts execute)",
+                       torch=torch.__version__, cudnn=torch.backends.cudnn.version()),
+        "variants": res, "best_variant": best,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def workload_config(B, world):
     return {"workload": f"4-step ControlLDM (SD-2.1 UNet + ControlNet, s4) + VAE decode, batch {B} per GPU, "
                         f"512x512 (64x64x4 latent), random-init weights", "batch_per_gpu": B,
@@ -398,12 +511,14 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         run_ours(args)
 
