@@ -37,6 +37,11 @@ class ControlLDM(nn.Module):
         self.controlnet = ControlNet(**controlnet_cfg)
         self.scale_factor = latent_scale_factor
         self.control_scales = [1.0] * 13
+        # Tile-parallel execution of the tiled paths (cldm-tiled sampling, VAEHook encode / decode; config C4) is an
+        # explicit opt-in: None (default) = every rank works alone, exactly like the reference; True / a ProcessGroup =
+        # the tiles of ONE image, identical on every rank of the group, are spread over its ranks (parallel.tile_sharding).
+        self.tile_group = None
+        self.tile_group_check = True   # verify (one tiny collective per call) that the ranks really hold the same input
         self._engine = None
         self._engine_version = None
 
@@ -103,6 +108,15 @@ class ControlLDM(nn.Module):
         return with_new_zero, with_scratch
 
     # ----------------------------------------------------------------- engine plumbing
+    def invalidate_engine(self) -> None:
+        """Drop the packed bf16 weight copies (and captured graphs): call after writing parameters through `.data`
+        (EMA updates, hand-written loaders) — such writes do not bump the version counters `engine()` watches."""
+        self._engine = None
+        self._engine_version = None
+        self.vae.invalidate_engine()
+
+    refresh_weights = invalidate_engine
+
     def engine(self):
         from .engine import CldmEngine
 
@@ -120,14 +134,13 @@ class ControlLDM(nn.Module):
     @torch.no_grad()
     def forward_tiled(self, x_noisy, t, cond, tile_size: int, tile_stride: int) -> torch.Tensor:
         """Batched equivalent of the sampler's tiled wrapper (utils/sampler.py:288-303): all latent tiles of the step
-        in one forward, gaussian-blended on the device; tiles are spread over the ranks of the default process
-        group when torch.distributed is initialised with more than one rank (config C4)."""
-        import torch.distributed as dist
+        in one forward, gaussian-blended on the device.  With `self.tile_group` set (opt-in, same latent on every
+        rank) the tiles are spread over the ranks of that group: one all-reduce of the partial blend per call."""
+        from .parallel import check_same_across_ranks, tile_sharding
 
-        rank, world, red = 0, 1, None
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            rank, world = dist.get_rank(), dist.get_world_size()
-            red = lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        rank, world, red = tile_sharding(self.tile_group)
+        if world > 1 and self.tile_group_check:
+            check_same_across_ranks(x_noisy, self.tile_group, "latent")
         eps = self.engine().forward_tiled(x_noisy.float().contiguous(), t.long().contiguous(),
                                           cond["c_img"].float().contiguous(), cond["c_txt"].float().contiguous(),
                                           tile_size, tile_stride, control_scales=self.control_scales, rank=rank,
@@ -138,24 +151,25 @@ class ControlLDM(nn.Module):
     def vae_encode(self, image: torch.Tensor, sample: bool = True, tiled: bool = False, tile_size: int = -1):
         """model/cldm.py:107-134: posterior sample or mode, times the latent scale factor; tiled=True is the
         reference's VAEHook encode (pad 32, pooled GroupNorm statistics)."""
-        posterior = self.vae.encode_tiled(image, tile_size) if tiled else self.vae.encode(image)
+        posterior = (self.vae.encode_tiled(image, tile_size, tile_group=self.tile_group,
+                                           tile_group_check=self.tile_group_check)
+                     if tiled else self.vae.encode(image))
         z = posterior.sample() if sample else posterior.mode()
         return z * self.scale_factor
 
     @torch.no_grad()
     def vae_decode(self, z: torch.Tensor, tiled: bool = False, tile_size: int = -1) -> torch.Tensor:
         """model/cldm.py:136-156.  Returns fp32 NCHW in [-1, 1].  tiled=True is the reference's VAEHook decode
-        (utils/tilevae/tilevae.py:307-579, pooled GroupNorm statistics); its tiles are spread over the ranks of the
-        default process group when torch.distributed is initialised with more than one rank (config C4)."""
+        (utils/tilevae/tilevae.py:307-579, pooled GroupNorm statistics); with `self.tile_group` set (opt-in, same
+        latent on every rank) its tiles are spread over the ranks of that group (config C4)."""
         eng = self.vae._decoder_engine()
         if not tiled:
             return eng.decode(z.float().contiguous(), float(self.scale_factor))
-        import torch.distributed as dist
+        from .parallel import check_same_across_ranks, tile_sharding
 
-        rank, world, red = 0, 1, None
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            rank, world = dist.get_rank(), dist.get_world_size()
-            red = lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        rank, world, red = tile_sharding(self.tile_group)
+        if world > 1 and self.tile_group_check:
+            check_same_across_ranks(z, self.tile_group, "latent")
         return eng.decode_tiled(z.float().contiguous(), float(self.scale_factor), int(tile_size), rank=rank,
                                 world=world, reduce_fn=red)
 

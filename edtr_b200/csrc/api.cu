@@ -99,8 +99,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int prime_gemm_attributes();
 int prime_attention_attributes();
 int prime_gemm2_attributes();
-void set_gemm_workspace(void* ptr, size_t bytes);
-void set_gemm_max_clusters(int n);
+size_t gemm2_workspace_size(int M, int N, int K);
 
 }  // namespace edtr
 
@@ -117,22 +116,9 @@ extern "C" int edtr_set_device(int device) {
   return EDTR_OK;
 }
 
-extern "C" int edtr_set_workspace(void* ptr, size_t bytes) {
-  if ((reinterpret_cast<uintptr_t>(ptr) & 255) != 0) {
-    edtr::set_error("workspace must be 256-byte aligned");
-    return EDTR_ERR_INVALID;
-  }
-  edtr::set_gemm_workspace(ptr, ptr == nullptr ? 0 : bytes);
-  return EDTR_OK;
-}
-
-extern "C" int edtr_set_gemm_max_clusters(int clusters) {
-  if (clusters < 1 || clusters > 74) {
-    edtr::set_error("clusters must be in [1, 74], got %d", clusters);
-    return EDTR_ERR_INVALID;
-  }
-  edtr::set_gemm_max_clusters(clusters);
-  return EDTR_OK;
+extern "C" size_t edtr_gemm_workspace_size(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return edtr::gemm2_workspace_size(M, N, K);
 }
 
 extern "C" int edtr_init(void) {

@@ -48,6 +48,13 @@ struct Gemm2Params {
   int splits;              // split-K factor (1 = none); partial tiles go to `ws` as fp32 [splits][M][N]
   int kb_per_split;
   float* ws;
+  // LayerNorm folded into the GEMM (see EdtrEpilogue): acc' = rstd * (acc - mean * colsum[n])
+  const float* ln_stats;
+  int ln_parts;
+  float ln_inv_c, ln_eps;
+  const float* ln_colsum;
+  float* row_stats;        // [M][row_parts][2] sums / sums of squares of the stored values (NULL: not wanted);
+  int row_parts;           // row_parts = 2 * tiles_n: one pair per (column tile, epilogue warp group)
   int ring;                // epilogue staging buffers per warp: 4 when the epilogue is the bottleneck (short K), else 2
   int stages;              // pipeline depth: (k2DataBytes - staging) / stage_bytes, <= k2MaxStages
   int stage_bytes;         // 16 KB of A + b_box_rows * 128 B of B
@@ -286,6 +293,43 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int bn = tile_bn(w);
       const uint32_t a = ti & 1, aph = (ti >> 1) & 1;
       const uint32_t tacc = trow + a * k2MaxBN;
+      // LayerNorm folded into the GEMM: per-row mean / rstd from the producer's partial sums (one lane = one row).
+      // The loads are issued before the accumulator wait, four at a time, so their latency hides under the main loop.
+      float ln_a = p.alpha, ln_b = 0.f;   // v = acc * ln_a + ln_b * colsum[n] + bias[n]
+      if (p.ln_stats != nullptr) {
+        // The epilogue is the critical path of these short-K GEMMs, so an L2 round trip per tile would be fully exposed:
+        // the statistics of the NEXT tile's row are pulled into L1 now (fire and forget) and are L1 hits one tile later.
+        {
+          const int wn = w + num_clusters;
+          if (wn < num_work) {
+            const int rown = tile_m0(wn) + rl;
+            if (rown < p.M) {
+              const char* pf = reinterpret_cast<const char*>(p.ln_stats) + static_cast<size_t>(rown) * p.ln_parts * 8;
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + p.ln_parts * 8 - 8));
+            }
+          }
+        }
+        float s1 = 0.f, s2 = 0.f;
+        if (row < p.M) {
+          const float2* st = reinterpret_cast<const float2*>(p.ln_stats) + static_cast<size_t>(row) * p.ln_parts;
+          int q = 0;
+          for (; q + 4 <= p.ln_parts; q += 4) {
+            const float2 t0 = __ldg(st + q), t1 = __ldg(st + q + 1), t2 = __ldg(st + q + 2), t3 = __ldg(st + q + 3);
+            s1 += (t0.x + t1.x) + (t2.x + t3.x);
+            s2 += (t0.y + t1.y) + (t2.y + t3.y);
+          }
+          for (; q < p.ln_parts; ++q) {
+            const float2 t = __ldg(st + q);
+            s1 += t.x;
+            s2 += t.y;
+          }
+        }
+        const float mu = s1 * p.ln_inv_c;
+        const float rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - mu * mu, 0.f) + p.ln_eps);
+        ln_a = p.alpha * rstd;
+        ln_b = -ln_a * mu;
+      }
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
       if (p.splits > 1) {
@@ -336,6 +380,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_leader + a * 8);
+        if (p.row_stats != nullptr && row < p.M)
+          reinterpret_cast<float2*>(p.row_stats)[static_cast<size_t>(row) * p.row_parts + 2 * (n_tile0 / p.bn_base) + grp] =
+              make_float2(0.f, 0.f);
         continue;
       }
       const int out_col_tile0 = tile_outcol0(w);
@@ -343,6 +390,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const float* rowvec_row = (p.rowvec != nullptr && row < p.M)
                                     ? p.rowvec + static_cast<size_t>(row / p.rows_per_group) * p.rowvec_ld
                                     : nullptr;
+      float rs1 = 0.f, rs2 = 0.f;   // producer side of the folded LayerNorm: this row's sums over the warp's chunks
 #pragma unroll 1
       for (int c = grp; c < nchunks; c += 2, ++g) {
         const int out_col0 = out_col_tile0 + c * 64;
@@ -359,57 +407,98 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int h = 0; h < 2; ++h) {            // 32 columns per TMEM load; rolled to keep the code in the I-cache
           float v[32];
           const int cb = c * 64 + h * 32;        // accumulator / bias column inside the tile
-          {
+          if (!p.geglu) {
+            // The epilogue is the critical path of the short-K GEMMs and only two warps per scheduler hide latency, so
+            // everything that does not depend on the accumulator is gathered FIRST, straight into v[] (no extra
+            // registers), while the asynchronous TMEM load is in flight: bias, the folded-LayerNorm column term, the
+            // time-embedding row vector and the residual chunk.  After the wait one FMA per element remains.
             uint32_t rv[32];
             tmem_ld32(tacc + cb, rv);
-            if (!p.geglu) {
-              tmem_ld_wait();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rv[j]) * p.alpha;
-              if (p.bias != nullptr) {
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_tile0 + cb);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 b = __ldg(b4 + j);
-                  v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-                }
-              }
-            } else {
-              uint32_t rg[32];
-              tmem_ld32(tacc + half + cb, rg);   // gate columns
-              tmem_ld_wait();
-              const float4* bx = reinterpret_cast<const float4*>(p.bias + n_tile0 + cb);
-              const float4* bg = reinterpret_cast<const float4*>(p.bias + n_tile0 + half + cb);
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + n_tile0 + cb);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = x4;
-                if (p.bias != nullptr) { x4 = __ldg(bx + j); g4 = __ldg(bg + j); }
-                v[4 * j] = fmaf(__uint_as_float(rv[4 * j]), p.alpha, x4.x) *
-                           gelu_fast(fmaf(__uint_as_float(rg[4 * j]), p.alpha, g4.x));
-                v[4 * j + 1] = fmaf(__uint_as_float(rv[4 * j + 1]), p.alpha, x4.y) *
-                               gelu_fast(fmaf(__uint_as_float(rg[4 * j + 1]), p.alpha, g4.y));
-                v[4 * j + 2] = fmaf(__uint_as_float(rv[4 * j + 2]), p.alpha, x4.z) *
-                               gelu_fast(fmaf(__uint_as_float(rg[4 * j + 2]), p.alpha, g4.z));
-                v[4 * j + 3] = fmaf(__uint_as_float(rv[4 * j + 3]), p.alpha, x4.w) *
-                               gelu_fast(fmaf(__uint_as_float(rg[4 * j + 3]), p.alpha, g4.w));
+                const float4 b = __ldg(b4 + j);
+                v[4 * j] = b.x; v[4 * j + 1] = b.y; v[4 * j + 2] = b.z; v[4 * j + 3] = b.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if (p.ln_stats != nullptr) {
+              const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + n_tile0 + cb);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 t = __ldg(c4 + j);
+                v[4 * j] = fmaf(ln_b, t.x, v[4 * j]); v[4 * j + 1] = fmaf(ln_b, t.y, v[4 * j + 1]);
+                v[4 * j + 2] = fmaf(ln_b, t.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(ln_b, t.w, v[4 * j + 3]);
               }
             }
-          }
-          if (rowvec_row != nullptr) {
-            const float4* r4 = reinterpret_cast<const float4*>(rowvec_row + out_col0 + h * 32);
+            if (rowvec_row != nullptr) {
+              const float4* r4 = reinterpret_cast<const float4*>(rowvec_row + out_col0 + h * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(r4 + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+            if (p.has_residual) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = *reinterpret_cast<const uint4*>(my_row + (((h * 4 + q) ^ (rl & 7)) << 4));
+                const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+                v[8 * q] += f0.x; v[8 * q + 1] += f0.y; v[8 * q + 2] += f1.x; v[8 * q + 3] += f1.y;
+                v[8 * q + 4] += f2.x; v[8 * q + 5] += f2.y; v[8 * q + 6] += f3.x; v[8 * q + 7] += f3.y;
+              }
+            }
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(rv[j]), ln_a, v[j]);
+          } else {
+            uint32_t rv[32], rg[32];
+            tmem_ld32(tacc + cb, rv);
+            tmem_ld32(tacc + half + cb, rg);   // gate columns
+            tmem_ld_wait();
+            const float4* bx = reinterpret_cast<const float4*>(p.bias + n_tile0 + cb);
+            const float4* bg = reinterpret_cast<const float4*>(p.bias + n_tile0 + half + cb);
+            const float4* cx = reinterpret_cast<const float4*>(p.ln_colsum + n_tile0 + cb);
+            const float4* cg = reinterpret_cast<const float4*>(p.ln_colsum + n_tile0 + half + cb);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(r4 + j);
-              v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = x4;
+              if (p.bias != nullptr) { x4 = __ldg(bx + j); g4 = __ldg(bg + j); }
+              if (p.ln_stats != nullptr) {
+                const float4 sx = __ldg(cx + j), sg = __ldg(cg + j);
+                x4.x = fmaf(ln_b, sx.x, x4.x); x4.y = fmaf(ln_b, sx.y, x4.y);
+                x4.z = fmaf(ln_b, sx.z, x4.z); x4.w = fmaf(ln_b, sx.w, x4.w);
+                g4.x = fmaf(ln_b, sg.x, g4.x); g4.y = fmaf(ln_b, sg.y, g4.y);
+                g4.z = fmaf(ln_b, sg.z, g4.z); g4.w = fmaf(ln_b, sg.w, g4.w);
+              }
+              v[4 * j] = fmaf(__uint_as_float(rv[4 * j]), ln_a, x4.x) *
+                         gelu_fast(fmaf(__uint_as_float(rg[4 * j]), ln_a, g4.x));
+              v[4 * j + 1] = fmaf(__uint_as_float(rv[4 * j + 1]), ln_a, x4.y) *
+                             gelu_fast(fmaf(__uint_as_float(rg[4 * j + 1]), ln_a, g4.y));
+              v[4 * j + 2] = fmaf(__uint_as_float(rv[4 * j + 2]), ln_a, x4.z) *
+                             gelu_fast(fmaf(__uint_as_float(rg[4 * j + 2]), ln_a, g4.z));
+              v[4 * j + 3] = fmaf(__uint_as_float(rv[4 * j + 3]), ln_a, x4.w) *
+                             gelu_fast(fmaf(__uint_as_float(rg[4 * j + 3]), ln_a, g4.w));
             }
-          }
-          if (p.has_residual) {
+            if (rowvec_row != nullptr) {
+              const float4* r4 = reinterpret_cast<const float4*>(rowvec_row + out_col0 + h * 32);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const uint4 u = *reinterpret_cast<const uint4*>(my_row + (((h * 4 + q) ^ (rl & 7)) << 4));
-              const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
-              v[8 * q] += f0.x; v[8 * q + 1] += f0.y; v[8 * q + 2] += f1.x; v[8 * q + 3] += f1.y;
-              v[8 * q + 4] += f2.x; v[8 * q + 5] += f2.y; v[8 * q + 6] += f3.x; v[8 * q + 7] += f3.y;
+              for (int j = 0; j < 8; ++j) {
+                const float4 b = __ldg(r4 + j);
+                v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+              }
+            }
+            if (p.has_residual) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const uint4 u = *reinterpret_cast<const uint4*>(my_row + (((h * 4 + q) ^ (rl & 7)) << 4));
+                const float2 f0 = unpack_bf16(u.x), f1 = unpack_bf16(u.y), f2 = unpack_bf16(u.z), f3 = unpack_bf16(u.w);
+                v[8 * q] += f0.x; v[8 * q + 1] += f0.y; v[8 * q + 2] += f1.x; v[8 * q + 3] += f1.y;
+                v[8 * q + 4] += f2.x; v[8 * q + 5] += f2.y; v[8 * q + 6] += f3.x; v[8 * q + 7] += f3.y;
+              }
             }
           }
           if (p.act == EDTR_ACT_SILU) {
@@ -418,6 +507,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           } else if (p.act >= EDTR_ACT_GELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = act_extra_f(v[j], p.act);
+          }
+          if (p.row_stats != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { rs1 += v[j]; rs2 = fmaf(v[j], v[j], rs2); }
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -445,6 +538,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           bulk_commit_group();
         }
       }
+      if (p.row_stats != nullptr && row < p.M)   // one pair per (row, column tile, warp group): 2 * tiles_n per row
+        reinterpret_cast<float2*>(p.row_stats)[static_cast<size_t>(row) * p.row_parts + 2 * (n_tile0 / p.bn_base) + grp] =
+            make_float2(rs1, rs2);
     }
     if (lane == 0) bulk_wait_group<0>();
     (void)n_out;
@@ -512,17 +608,6 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, flo
   pdl_launch_dependents();
 }
 
-static int g_max_clusters = 74;    // CTA pairs a launch may occupy (edtr_set_gemm_max_clusters)
-static float* g_ws = nullptr;      // split-K workspace registered by the host (edtr_set_workspace)
-static size_t g_ws_bytes = 0;
-
-void set_gemm_max_clusters(int n) { g_max_clusters = n < 1 ? 1 : (n > 74 ? 74 : n); }
-
-void set_gemm_workspace(void* ptr, size_t bytes) {
-  g_ws = static_cast<float*>(ptr);
-  g_ws_bytes = bytes;
-}
-
 int prime_gemm2_attributes() {
   cudaError_t e = cudaFuncSetAttribute(gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
   if (e != cudaSuccess) {
@@ -538,7 +623,8 @@ int prime_gemm2_attributes() {
 // pair tile costs max(2*bn, 300) cycles (narrow tiles are bound by operand fetch, not by the tensor
 // pipe) and splitting pays for the fp32 round trip + reduce launch.  GEGLU is pinned to 256 columns,
 // unsplit, because its weight interleave is done at pack time.
-static void plan_tiles(int M, int N, int nkb, int geglu, size_t ws_bytes, int* tiles_n, int* bn_base, int* splits) {
+static void plan_tiles(int M, int N, int nkb, int geglu, size_t ws_bytes, int max_clusters, int* tiles_n, int* bn_base,
+                       int* splits) {
   *splits = 1;
   if (geglu) {
     *tiles_n = N / k2MaxBN;
@@ -548,7 +634,8 @@ static void plan_tiles(int M, int N, int nkb, int geglu, size_t ws_bytes, int* t
   const int tiles_m = (M + 2 * k2BM - 1) / (2 * k2BM);
   long best_cost = -1;
   int best_t = 1, best_b = 64, best_s = 1;
-  const int max_split_ws = static_cast<int>(ws_bytes / (static_cast<size_t>(M) * N * sizeof(float)));
+  const size_t split_max = ws_bytes / (static_cast<size_t>(M) * N * sizeof(float));
+  const int max_split_ws = split_max > 16 ? 16 : static_cast<int>(split_max);
   for (int cap = k2MaxBN; cap >= 64; cap -= 64) {
     const int t = (N + cap - 1) / cap;
     int base = ((N + t - 1) / t + 63) & ~63;
@@ -559,7 +646,7 @@ static void plan_tiles(int M, int N, int nkb, int geglu, size_t ws_bytes, int* t
       if (sp > 1 && (sp > max_split_ws || nkb / sp < 8)) break;
       const int kbs = (nkb + sp - 1) / sp;
       if (sp > 1 && kbs * (sp - 1) >= nkb) continue;  // an empty split
-      const long waves = (static_cast<long>(tiles_m) * tn * sp + g_max_clusters - 1) / g_max_clusters;
+      const long waves = (static_cast<long>(tiles_m) * tn * sp + max_clusters - 1) / max_clusters;
       const long cost = waves * (kbs * per_kb + 3000) + (sp > 1 ? 10000 : 0);
       if (best_cost < 0 || cost < best_cost) {
         best_cost = cost;
@@ -597,8 +684,24 @@ bool gemm2_eligible(int M, int N, const EdtrEpilogue* ep) {
 
 int gemm2_tile_n(int N, int geglu) {
   int t, b, sp;
-  plan_tiles(1 << 20, N, 64, geglu, 0, &t, &b, &sp);
+  plan_tiles(1 << 20, N, 64, geglu, 0, 74, &t, &b, &sp);
   return b;
+}
+
+int gemm2_row_stats_parts(int M, int N, int K, const EdtrEpilogue* ep) {
+  int max_clusters = ep->max_clusters > 0 ? ep->max_clusters : 74;
+  if (max_clusters > 74) max_clusters = 74;
+  int t, b, sp;
+  plan_tiles(M, N, K / k2BK, 0, 0, max_clusters, &t, &b, &sp);   // launches that write row statistics never split
+  return 2 * t;
+}
+
+size_t gemm2_workspace_size(int M, int N, int K) {
+  if (M < 256 || N % 64 != 0 || K % k2BK != 0) return 0;
+  int t, b, sp;
+  plan_tiles(M, N, K / k2BK, 0, static_cast<size_t>(-1), 74, &t, &b, &sp);
+  if (sp <= 1) return 0;
+  return static_cast<size_t>(sp) * M * N * sizeof(float);
 }
 
 bool gemm2_disabled() {
@@ -615,13 +718,32 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   p.taps_x = taps_x; p.tap_dy0 = tap_dy0; p.tap_dx0 = tap_dx0; p.up2x = tmD_up != nullptr;
   p.geglu = ep->act == EDTR_ACT_GEGLU;
   const bool nchw = ep->out_mode == EDTR_OUT_NCHW_F32;
-  plan_tiles(M, N, p.num_kblocks, p.geglu, (p.up2x || nchw) ? 0 : g_ws_bytes, &p.tiles_n, &p.bn_base, &p.splits);
+  int max_clusters = ep->max_clusters > 0 ? ep->max_clusters : 74;
+  if (max_clusters > 74) max_clusters = 74;
+  // split-K scratch (fp32 partial tiles).  The folded LayerNorm and the row statistics live in the tile epilogue only,
+  // so launches that use them do not split (they are N = C GEMMs with K <= 4C: the planner would not split them anyway)
+  size_t ws_partial_bytes = 0;
+  if (ep->workspace != nullptr && !p.up2x && !nchw && ep->ln_stats == nullptr && ep->row_stats == nullptr)
+    ws_partial_bytes = static_cast<size_t>(ep->workspace_bytes);
+  plan_tiles(M, N, p.num_kblocks, p.geglu, ws_partial_bytes, max_clusters, &p.tiles_n, &p.bn_base, &p.splits);
   if (nchw) {
     p.nchw_out = static_cast<float*>(ep->out);
     p.nchw_hw = ep->hw;
   }
   p.kb_per_split = (p.num_kblocks + p.splits - 1) / p.splits;
-  p.ws = g_ws;
+  p.ws = static_cast<float*>(ep->workspace);
+  p.ln_stats = ep->ln_stats;
+  p.ln_parts = ep->ln_parts;
+  p.ln_inv_c = ep->ln_c > 0 ? 1.f / static_cast<float>(ep->ln_c) : 0.f;
+  p.ln_eps = ep->ln_eps;
+  p.ln_colsum = ep->ln_colsum;
+  p.row_stats = ep->row_stats;
+  p.row_parts = 2 * p.tiles_n;
+  if (ep->row_stats != nullptr && ep->row_stats_cap < p.row_parts) {
+    set_error("row_stats_cap %d < %d pairs per row this launch writes (edtr_gemm_row_stats_parts)", ep->row_stats_cap,
+              p.row_parts);
+    return EDTR_ERR_INVALID;
+  }
   p.b_box_rows = p.bn_base / 2;
   p.stage_bytes = k2ABytes + p.b_box_rows * k2BK * 2;
   // two staging buffers per epilogue warp; a ring of four (residual requested two chunks ahead) was measured on
@@ -664,7 +786,7 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
     tmC = tmD;
   }
   const int work = p.tiles_m * p.tiles_n * p.splits;
-  const int clusters = work < g_max_clusters ? work : g_max_clusters;
+  const int clusters = work < max_clusters ? work : max_clusters;
   if (p.splits > 1) p.has_residual = 0;  // the reduce kernel adds it
   if (p.up2x && p.splits > 1) {
     set_error("internal: split-K is not available for the up-sampling convolution");
@@ -674,7 +796,7 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   rc = check_launch("gemm2_kernel");
   if (rc || p.splits == 1) return rc;
   const size_t nvec = static_cast<size_t>(M) * (N / 8);
-  EDTR_LAUNCH(splitk_reduce_kernel, static_cast<unsigned>((nvec + 255) / 256), 256, 0, stream, 
+  EDTR_LAUNCH(splitk_reduce_kernel, static_cast<unsigned>((nvec + 255) / 256), 256, 0, stream,
       p.ws, p.splits, M, N, ep->alpha, ep->bias, ep->rowvec, ep->rowvec_ld, p.rows_per_group,
       reinterpret_cast<const __nv_bfloat16*>(ep->residual), ep->ldr, reinterpret_cast<__nv_bfloat16*>(ep->out),
       ep->ldc, ep->act);

@@ -235,7 +235,23 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(lg * 32) << 16);
     const EdtrEpilogue& ep = p.ep;
+    float ln_a = ep.alpha, ln_b = 0.f;   // folded LayerNorm: v = acc * ln_a + ln_b * colsum[n] (+ bias ...)
+    if (ep.ln_stats != nullptr && row < p.M) {
+      const float2* st = reinterpret_cast<const float2*>(ep.ln_stats) + static_cast<size_t>(row) * ep.ln_parts;
+      float s1 = 0.f, s2 = 0.f;
+      for (int q = 0; q < ep.ln_parts; ++q) {
+        const float2 t = __ldg(st + q);
+        s1 += t.x;
+        s2 += t.y;
+      }
+      const float inv_c = 1.f / static_cast<float>(ep.ln_c);
+      const float mu = s1 * inv_c;
+      const float rstd = rsqrtf(fmaxf(s2 * inv_c - mu * mu, 0.f) + ep.ln_eps);
+      ln_a = ep.alpha * rstd;
+      ln_b = -ln_a * mu;
+    }
     if (ep.act != EDTR_ACT_GEGLU) {
+      float rs1 = 0.f, rs2 = 0.f;   // row statistics of the stored values: one pair per (row, column tile)
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int col0 = n0 + c * 32;
@@ -247,7 +263,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int nv = min(32, p.N - col0);
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ep.alpha;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * ln_a;
+          if (ep.ln_stats != nullptr) {   // folded LayerNorm (see EdtrEpilogue): N % 32 == 0 is checked on the host
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(ln_b, __ldg(ep.ln_colsum + col0 + j), v[j]);
+          }
           epilogue_addends(v, ep, row, col0, nv);
           if (ep.act == EDTR_ACT_SILU) {
 #pragma unroll
@@ -256,9 +276,16 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = act_extra_f(v[j], ep.act);
           }
+          if (ep.row_stats != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < nv) { rs1 += v[j]; rs2 = fmaf(v[j], v[j], rs2); }
+          }
           epilogue_store(v, ep, row, col0, nv, p.N);
         }
       }
+      if (ep.row_stats != nullptr && row < p.M)
+        reinterpret_cast<float2*>(ep.row_stats)[static_cast<size_t>(row) * gridDim.x + blockIdx.x] = make_float2(rs1, rs2);
     } else {
       // value columns [0, BN/2) and gate columns [BN/2, BN) of this tile
       constexpr int HALF = BN / 2;
@@ -353,6 +380,7 @@ int prime_gemm_attributes() {
 
 bool gemm2_eligible(int M, int N, const EdtrEpilogue* ep);
 int gemm2_tile_n(int N, int geglu);
+int gemm2_row_stats_parts(int M, int N, int K, const EdtrEpilogue* ep);
 bool gemm2_disabled();
 int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, int N, int mode, int H, int W,
                  int cblocks, const EdtrEpilogue* ep, cudaStream_t stream, int taps_x = 3, int tap_dy0 = -1,
@@ -375,6 +403,21 @@ static int check_epilogue(const EdtrEpilogue* ep, int M, int N) {
   if (ep->residual != nullptr)
     EDTR_REQUIRE(ep->ldr % 8 == 0 && (reinterpret_cast<uintptr_t>(ep->residual) & 15) == 0,
                  "residual must be 16-byte aligned (ldr %% 8 == 0)");
+  if (ep->workspace != nullptr)
+    EDTR_REQUIRE((reinterpret_cast<uintptr_t>(ep->workspace) & 255) == 0, "workspace must be 256-byte aligned");
+  EDTR_REQUIRE(ep->max_clusters >= 0, "max_clusters must be >= 0");
+  if (ep->ln_stats != nullptr) {
+    EDTR_REQUIRE(ep->ln_colsum != nullptr && ep->ln_parts > 0 && ep->ln_c > 0, "folded LayerNorm needs ln_colsum / ln_parts / ln_c");
+    EDTR_REQUIRE(N % 32 == 0 && ((reinterpret_cast<uintptr_t>(ep->ln_stats) & 7) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(ep->ln_colsum) & 15) == 0),
+                 "folded LayerNorm needs N %% 32 == 0, 8-byte aligned ln_stats and 16-byte aligned ln_colsum");
+    EDTR_REQUIRE(ep->act != EDTR_ACT_GEGLU || (N % 256 == 0 && !gemm2_disabled()),
+                 "folded LayerNorm + GEGLU runs on the CTA-pair kernel only (N %% 256 == 0)");
+  }
+  if (ep->row_stats != nullptr)
+    EDTR_REQUIRE(ep->out_mode == EDTR_OUT_BF16 && ep->act != EDTR_ACT_GEGLU &&
+                     (reinterpret_cast<uintptr_t>(ep->row_stats) & 7) == 0,
+                 "row_stats needs a bf16 output, act != GEGLU and an 8-byte aligned buffer");
   if (ep->rowvec != nullptr)
     EDTR_REQUIRE(ep->rows_per_group > 0 && ep->rowvec_ld >= n_out, "bad rowvec geometry");
   if (ep->bias != nullptr)
@@ -395,6 +438,13 @@ extern "C" int edtr_gemm_tile_n(int M, int N, int K, int act) {
   (void)K;
   if (act == EDTR_ACT_GEGLU && N % 256 == 0 && !gemm2_disabled()) return gemm2_tile_n(N, 1);
   return pick_bn(M, N, act);
+}
+
+extern "C" int edtr_gemm_row_stats_parts(int M, int N, int K, const EdtrEpilogue* ep) {
+  if (ep == nullptr || M <= 0 || N <= 0 || K <= 0 || K % kBK != 0) return 0;
+  if (gemm2_eligible(M, N, ep)) return gemm2_row_stats_parts(M, N, K, ep);
+  const int bn = pick_bn(M, N, ep->act);
+  return (N + bn - 1) / bn;
 }
 
 extern "C" int edtr_gemm_bf16(const void* A, int lda, const void* Wt, int ldw, int M, int N, int K,
@@ -427,6 +477,8 @@ extern "C" int edtr_gemm_bf16(const void* A, int lda, const void* Wt, int ldw, i
   GemmKernelParams p{};
   p.M = M; p.N = N; p.num_kblocks = K / kBK; p.mode = 0;
   p.ep = *ep;
+  EDTR_REQUIRE(ep->row_stats == nullptr || ep->row_stats_cap >= (N + bn - 1) / bn,
+               "row_stats_cap %d < %d pairs per row this launch writes", ep->row_stats_cap, (N + bn - 1) / bn);
   return dispatch_gemm(bn, tmA, tmB, p, static_cast<cudaStream_t>(stream));
 }
 

@@ -39,6 +39,22 @@ def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+def _on_device(fn):
+    """Engine entry points run with the engine's device current: launches go to that device's current stream and use
+    its split-K scratch even when the caller's current device is another GPU (a model moved with .to('cuda:1'))."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        guard = getattr(self.ops, "device_guard", None)
+        if guard is None:
+            return fn(self, *args, **kwargs)
+        with guard(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 # --------------------------------------------------------------------------- packing
 def pack_conv3x3(w: torch.Tensor, device) -> torch.Tensor:
     """[Cout, Cin, 3, 3] -> bf16 [Cout, 9 * Cin_pad] tap-major / channel-minor (Cin padded to 64)."""
@@ -78,6 +94,20 @@ def vec(v: torch.Tensor, device) -> torch.Tensor:
     return v.detach().float().contiguous().to(device)
 
 
+def fold_layernorm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, device):
+    """LayerNorm folded into the Linear that consumes it (include/edtr_b200.h, EdtrEpilogue.ln_*):
+        LN(x) W^T + b = rstd * (x (W*gamma)^T - mean * colsum) + (W beta + b),   colsum[n] = sum_k (W*gamma)[n, k].
+    Returns (bf16 W*gamma, fp32 colsum of the bf16-ROUNDED matrix — so that `mean * colsum` cancels the mean part of
+    the accumulator exactly — and the fp32 bias W beta + b)."""
+    wf = w.detach().double().cpu()
+    wg = (wf * gamma.detach().double().cpu()[None, :]).float().to(BF16)
+    colsum = wg.double().sum(1).float()
+    b = wf @ beta.detach().double().cpu()
+    if bias is not None:
+        b = b + bias.detach().double().cpu()
+    return wg.contiguous().to(device), colsum.contiguous().to(device), b.float().contiguous().to(device)
+
+
 def geglu_permutation(n_half: int, tile_n: int) -> torch.Tensor:
     """Row order that puts, inside every N-tile of the GEGLU projection, the value columns in the
     first half and the matching gate columns in the second half (see EDTR_ACT_GEGLU)."""
@@ -89,11 +119,17 @@ def geglu_permutation(n_half: int, tile_n: int) -> torch.Tensor:
 
 
 class Workspace:
-    """Named, lazily grown device buffers: a name is one live tensor at a time."""
+    """Named, lazily grown device buffers: a name is one live tensor at a time.
+
+    `generation` counts (re)allocations.  A captured CUDA graph has the device pointers of the buffers it used baked
+    in, so a graph is only replayed while the workspace generation is the one it was captured at (`_Graph.valid`):
+    growing any buffer (a longer step count or text length at the same B, H, W) drops the graphs that could point at
+    the freed storage and they are re-captured on their next use."""
 
     def __init__(self, device):
         self.device = device
         self._bufs: Dict[Tuple[str, torch.dtype], torch.Tensor] = {}
+        self.generation = 0
 
     def get(self, name: str, shape: Sequence[int], dtype=BF16) -> torch.Tensor:
         n = int(math.prod(shape))
@@ -102,6 +138,7 @@ class Workspace:
         if t is None or t.numel() < n:
             t = torch.empty(n, dtype=dtype, device=self.device)
             self._bufs[key] = t
+            self.generation += 1
         return t[:n].view(*shape)
 
     def zeros(self, name: str, shape: Sequence[int], dtype=BF16) -> torch.Tensor:
@@ -112,6 +149,7 @@ class Workspace:
         if t is None or t.numel() != n:
             t = torch.zeros(n, dtype=dtype, device=self.device)
             self._bufs[key] = t
+            self.generation += 1
         return t.view(*shape)
 
     def gn_scratch(self, ops, x: torch.Tensor, groups: int = 32) -> torch.Tensor:
@@ -132,6 +170,10 @@ class Workspace:
 class _ScopedWorkspace:
     def __init__(self, base: Workspace, prefix: str):
         self.base, self.prefix, self.device = base, prefix, base.device
+
+    @property
+    def generation(self) -> int:
+        return self.base.generation
 
     def get(self, name, shape, dtype=BF16):
         return self.base.get(self.prefix + name, shape, dtype)
@@ -203,15 +245,22 @@ class _PackedNet:
                 for n in (p + "proj_in.", p + "proj_out.", t + "attn1.to_out.0.", t + "attn2.to_out.0.", t + "ff.net.2."):
                     w[n + "weight"] = pack_matrix(sd[n + "weight"], dev)
                     w[n + "bias"] = vec(sd[n + "bias"], dev)
-                w[t + "attn1.qkv"] = pack_matrix(
-                    torch.cat([sd[t + "attn1.to_q.weight"], sd[t + "attn1.to_k.weight"], sd[t + "attn1.to_v.weight"]], 0), dev)
+                qkv = torch.cat([sd[t + "attn1.to_q.weight"], sd[t + "attn1.to_k.weight"], sd[t + "attn1.to_v.weight"]], 0)
+                w[t + "attn1.qkv"] = pack_matrix(qkv, dev)
                 w[t + "attn2.to_q.weight"] = pack_matrix(sd[t + "attn2.to_q.weight"], dev)
+                # the three LayerNorms folded into the GEMMs that consume them (engine.fold_layernorm)
+                w[t + "attn1.qkv.ln"] = fold_layernorm(qkv, None, sd[t + "norm1.weight"], sd[t + "norm1.bias"], dev)
+                w[t + "attn2.to_q.ln"] = fold_layernorm(sd[t + "attn2.to_q.weight"], None, sd[t + "norm2.weight"],
+                                                        sd[t + "norm2.bias"], dev)
                 ctx_w.append(torch.cat([sd[t + "attn2.to_k.weight"], sd[t + "attn2.to_v.weight"]], 0).detach().float().cpu())
                 self.ctx_off[p] = (co, ch)
                 co += 2 * ch
                 perm = geglu_permutation(4 * ch, geglu_tile)
                 w[t + "ff.net.0.proj.weight"] = pack_matrix(sd[t + "ff.net.0.proj.weight"].detach().cpu()[perm], dev)
                 w[t + "ff.net.0.proj.bias"] = vec(sd[t + "ff.net.0.proj.bias"].detach().cpu()[perm], dev)
+                w[t + "ff.net.0.proj.ln"] = fold_layernorm(sd[t + "ff.net.0.proj.weight"].detach().cpu()[perm],
+                                                           sd[t + "ff.net.0.proj.bias"].detach().cpu()[perm],
+                                                           sd[t + "norm3.weight"], sd[t + "norm3.bias"], dev)
 
         for j, block in enumerate(self.inputs):
             for k, layer in enumerate(block):
@@ -242,14 +291,19 @@ class _PackedNet:
             w["out.2.bias"] = vec(sd["out.2.bias"], dev)
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in self.w.values())
+        n = 0
+        for t in self.w.values():
+            for u in (t if isinstance(t, tuple) else (t,)):
+                n += u.numel() * u.element_size()
+        return n
 
 
 class _NetRunner:
     """Launch sequences of the reference leaf blocks on one packed net."""
 
-    def __init__(self, net: _PackedNet, ws: Workspace, ops, tag: str):
+    def __init__(self, net: _PackedNet, ws: Workspace, ops, tag: str, fold_ln: bool = True):
         self.net, self.ws, self.ops, self.tag = net, ws.scoped(tag), ops, ""
+        self.fold_ln = fold_ln
         self.emb: Optional[torch.Tensor] = None   # [B, emb_total] fp32: Linear(SiLU(emb)) of every ResBlock
         self.ctx: Optional[torch.Tensor] = None   # [B, 77, ctx_total] bf16: cross-attention K|V of every block
 
@@ -300,6 +354,32 @@ class _NetRunner:
         t = p + "transformer_blocks.0."
         y = ops.groupnorm(x, w[p + "norm.weight"], w[p + "norm.bias"], 32, 1e-6, False,
                           stats=ws.gn_scratch(ops, x), out=ws.get("gn", (B, L, C)))
+        co, _ = self.net.ctx_off[p]
+        if self.fold_ln:
+            # LayerNorm never runs as a kernel: the GEMM that produces each residual-stream tensor emits per-row partial
+            # (sum, sum of squares) in its epilogue, the GEMM that consumes LN(t) applies mean / rstd in its own
+            parts = ops.row_stats_parts(B * L, C, C, x.device)
+            rs = [ws.get(f"st_rs{i}", (B * L, parts, 2), F32) for i in range(3)]
+            t0 = ops.gemm(y, w[p + "proj_in.weight"], bias=w[p + "proj_in.bias"], row_stats=rs[0],
+                          out=ws.get("st_t0", (B, L, C)))
+            wq, cs, bq = w[t + "attn1.qkv.ln"]
+            qkv = ops.gemm(t0, wq, bias=bq, ln=(rs[0], C, 1e-5, cs), out=ws.get("st_qkv", (B, L, 3 * C)))
+            a = ops.attention(qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:], heads, 0.125,
+                              out=ws.get("st_att", (B, L, C)))
+            t1 = ops.gemm(a, w[t + "attn1.to_out.0.weight"], bias=w[t + "attn1.to_out.0.bias"], residual=t0,
+                          row_stats=rs[1], out=ws.get("st_t1", (B, L, C)))
+            wq, cs, bq = w[t + "attn2.to_q.ln"]
+            q = ops.gemm(t1, wq, bias=bq, ln=(rs[1], C, 1e-5, cs), out=ws.get("st_q", (B, L, C)))
+            a = ops.attention(q, self.ctx[..., co:co + C], self.ctx[..., co + C:co + 2 * C], heads, 0.125,
+                              out=ws.get("st_att", (B, L, C)))
+            t2 = ops.gemm(a, w[t + "attn2.to_out.0.weight"], bias=w[t + "attn2.to_out.0.bias"], residual=t1,
+                          row_stats=rs[2], out=ws.get("st_t0", (B, L, C)))
+            wq, cs, bq = w[t + "ff.net.0.proj.ln"]
+            g = ops.gemm(t2, wq, bias=bq, ln=(rs[2], C, 1e-5, cs), act=ops.ACT_GEGLU, out=ws.get("st_ff", (B, L, 4 * C)))
+            t3 = ops.gemm(g, w[t + "ff.net.2.weight"], bias=w[t + "ff.net.2.bias"], residual=t2,
+                          out=ws.get("st_t1", (B, L, C)))
+            ops.gemm(t3, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out)
+            return
         t0 = ops.gemm(y, w[p + "proj_in.weight"], bias=w[p + "proj_in.bias"], out=ws.get("st_t0", (B, L, C)))
         # self-attention
         n = ops.layernorm(t0, w[t + "norm1.weight"], w[t + "norm1.bias"], 1e-5, out=ws.get("st_ln", (B, L, C)))
@@ -311,7 +391,6 @@ class _NetRunner:
         # cross-attention against the hoisted K/V
         n = ops.layernorm(t1, w[t + "norm2.weight"], w[t + "norm2.bias"], 1e-5, out=ws.get("st_ln", (B, L, C)))
         q = ops.gemm(n, w[t + "attn2.to_q.weight"], out=ws.get("st_q", (B, L, C)))
-        co, _ = self.net.ctx_off[p]
         a = ops.attention(q, self.ctx[..., co:co + C], self.ctx[..., co + C:co + 2 * C], heads, 0.125,
                           out=ws.get("st_att", (B, L, C)))
         t2 = ops.gemm(a, w[t + "attn2.to_out.0.weight"], bias=w[t + "attn2.to_out.0.bias"], residual=t1,
@@ -395,6 +474,9 @@ class CldmEngine:
         self.out_c = unet_cfg["out_channels"]
         self._ws: Dict[Tuple[int, int, int], Workspace] = {}
         self._graphs: Dict[Tuple, "_Graph"] = {}
+        # LayerNorm folded into the producing / consuming GEMM epilogues (no LayerNorm launches); EDTR_LN_FOLD=0 runs the
+        # standalone kernel instead (A/B measurements, and the reference for the fold's parity test)
+        self.fold_ln = os.environ.get("EDTR_LN_FOLD", "1") != "0"
         self.overlap = True      # run the ControlNet concurrently with the UNet encoder on a second stream
         # CTA pairs each branch's GEMM launches may use while both run (74 = no limit: the launches then only overlap
         # in each other's tails; measured 74 / 37 / 50: 47.94 / 47.39 / 47.34 ms per 4-step sample, i.e. within the
@@ -446,8 +528,8 @@ class CldmEngine:
         """x, c_img: fp32 NCHW; t int64 [B]; eps_out fp32 [B, out_c, H, W] (written)."""
         ops = self.ops
         B, _, H, W = x.shape
-        un = _NetRunner(self.unet, ws, ops, "u_")
-        cn = _NetRunner(self.cnet, ws, ops, "c_")
+        un = _NetRunner(self.unet, ws, ops, "u_", self.fold_ln)
+        cn = _NetRunner(self.cnet, ws, ops, "c_", self.fold_ln)
         if ctx_ready:
             un.ctx = un.ws.get("ctx", (B, c_txt.shape[1], self.unet.ctx_total))
             cn.ctx = cn.ws.get("ctx", (B, c_txt.shape[1], self.cnet.ctx_total))
@@ -570,6 +652,7 @@ class CldmEngine:
                 if not a.is_cuda:
                     raise RuntimeError("edtr_b200 has no CPU path: inputs must be CUDA tensors")
 
+    @_on_device
     def forward(self, x_noisy, t, c_img, c_txt, control_scales=None, use_graph: bool = True) -> torch.Tensor:
         """eps = ControlLDM.forward(x_noisy, t, {c_txt, c_img}) (model/cldm.py:166-194)."""
         self._check_inputs(x_noisy, t, c_img, c_txt)
@@ -587,11 +670,12 @@ class CldmEngine:
         sc.copy_(c_txt)
         run = lambda: self._forward(ws, sx, st, si, eps, scales, c_txt=sc)
         if use_graph:
-            self._graph(("fwd", B, H, W, c_txt.shape[1], scales), run).replay()
+            self._graph(("fwd", B, H, W, c_txt.shape[1], scales), run, ws).replay()
         else:
             run()
         return eps.clone()
 
+    @_on_device
     def forward_tiled(self, x_noisy, t, c_img, c_txt, tile_size: int, tile_stride: int, control_scales=None,
                       rank: int = 0, world: int = 1, reduce_fn=None, use_graph: bool = True) -> torch.Tensor:
         """cldm-tiled evaluation (utils/sampler.py:288-303 + make_tiled_fn, utils/common.py:367-427): the latent is cut
@@ -632,6 +716,7 @@ class CldmEngine:
             reduce_fn(out)
         return out * inv_count
 
+    @_on_device
     def sample(self, x_T, timesteps: Sequence[int], tables: Dict[str, torch.Tensor], c_img, c_txt,
                noise: Sequence[torch.Tensor], control_scales=None, use_graph: bool = True,
                return_intermediates: bool = False):
@@ -668,8 +753,8 @@ class CldmEngine:
         idx.copy_(torch.tensor([[n - i - 1] * B for i in range(n)], dtype=torch.int64))
 
         def run():
-            un = _NetRunner(self.unet, ws, self.ops, "u_")
-            cn = _NetRunner(self.cnet, ws, self.ops, "c_")
+            un = _NetRunner(self.unet, ws, self.ops, "u_", self.fold_ln)
+            cn = _NetRunner(self.cnet, ws, self.ops, "c_", self.fold_ln)
             self._context(ws, un, cn, sc)  # c_txt is step-invariant: project K/V once
             cur = sx
             for i in range(n):
@@ -679,35 +764,44 @@ class CldmEngine:
                 cur = xs[i]
 
         if use_graph:
-            self._graph(("sample", B, H, W, c_txt.shape[1], n, scales), run).replay()
+            self._graph(("sample", B, H, W, c_txt.shape[1], n, scales), run, ws).replay()
         else:
             run()
         if return_intermediates:
             return xs[n - 1].clone(), [x0s[i].clone() for i in range(n)], [xs[i].clone() for i in range(n)]
         return xs[n - 1].clone()
 
-    def _graph(self, key, fn) -> "_Graph":
+    def _graph(self, key, fn, ws: Workspace) -> "_Graph":
         g = self._graphs.get(key)
-        if g is None:
-            g = _Graph(fn)
+        if g is None or not g.valid():
+            g = _Graph(fn, ws)
             self._graphs[key] = g
         return g
 
 
 class _Graph:
-    """Warm up twice eagerly (sizes every workspace buffer), then capture into a CUDA graph."""
+    """Warm up twice eagerly (sizes every workspace buffer), then capture into a CUDA graph.  The graph remembers the
+    generation of the workspace it was captured on; `valid()` is False once any buffer of that workspace has been
+    reallocated since (the baked-in pointers may dangle), and the owner then captures a new graph."""
 
-    def __init__(self, fn):
+    def __init__(self, fn, ws: Optional[Workspace] = None):
         from . import lib as _lib
 
         fn()
         fn()
         torch.cuda.synchronize()
+        self.ws = ws
+        self.generation = ws.generation if ws is not None else 0
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.LAUNCHES[0]
         with torch.cuda.graph(self.graph):
             fn()
         self.launches = _lib.LAUNCHES[0] - n0  # kernels per replay
+        if not self.valid():
+            raise RuntimeError("internal: a workspace buffer was reallocated during CUDA-graph capture")
+
+    def valid(self) -> bool:
+        return self.ws is None or self.ws.generation == self.generation
 
     def replay(self) -> None:
         from . import lib as _lib
@@ -952,6 +1046,7 @@ class VaeDecoderEngine(_VaeBlocks):
         self._conv_any(ws, y, "decoder.conv_out.", out=img.view(B, self.dd["out_ch"], H * W), out_mode=ops.OUT_NCHW_F32)
         return img
 
+    @_on_device
     def decode_tiled(self, z: torch.Tensor, scale_factor: float, tile_size: int, rank: int = 0, world: int = 1,
                      reduce_fn=None, use_graph: bool = True) -> torch.Tensor:
         """ControlLDM.vae_decode(tiled=True) (model/cldm.py:142-156): VAEHook in its default (non-fast) mode
@@ -1001,6 +1096,7 @@ class VaeDecoderEngine(_VaeBlocks):
             reduce_fn(out)      # valid regions are disjoint: the sum assembles the image on every rank
         return out
 
+    @_on_device
     def decode(self, z: torch.Tensor, scale_factor: float, use_graph: bool = True) -> torch.Tensor:
         if z.dim() != 4 or z.shape[1] != self.embed_dim:
             raise ValueError(f"z must be [B, {self.embed_dim}, H, W], got {tuple(z.shape)}")
@@ -1019,8 +1115,8 @@ class VaeDecoderEngine(_VaeBlocks):
         if use_graph:
             gk = (B, H, W, float(scale_factor))
             g = self._graphs.get(gk)
-            if g is None:
-                g = self._graphs[gk] = _Graph(run)
+            if g is None or not g.valid():
+                g = self._graphs[gk] = _Graph(run, ws)
             g.replay()
         else:
             run()
@@ -1117,6 +1213,7 @@ class VaeEncoderEngine(_VaeBlocks):
         self._conv_any(ws, y, "encoder.moments.", out=moments.view(B, 2 * self.embed_dim, H * W),
                        out_mode=ops.OUT_NCHW_F32)
 
+    @_on_device
     def encode(self, image: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
         """image [B, in_channels, H, W] fp32 in [-1, 1] -> posterior moments [B, 2*embed_dim, H/f, W/f] fp32
         (mean | logvar), f = 2^(levels-1)."""
@@ -1138,8 +1235,8 @@ class VaeEncoderEngine(_VaeBlocks):
         run = lambda: self._encode(ws, si, mo)
         if use_graph:
             g = self._graphs.get(key)
-            if g is None:
-                g = self._graphs[key] = _Graph(run)
+            if g is None or not g.valid():
+                g = self._graphs[key] = _Graph(run, ws)
             g.replay()
         else:
             run()
@@ -1173,6 +1270,7 @@ class VaeEncoderEngine(_VaeBlocks):
         self._conv_any(ws, y, "encoder.moments.", out=mo.view(B, 2 * self.embed_dim, H * W), out_mode=ops.OUT_NCHW_F32)
         return mo
 
+    @_on_device
     def encode_tiled(self, image: torch.Tensor, tile_size: int, rank: int = 0, world: int = 1, reduce_fn=None,
                      use_graph: bool = True) -> torch.Tensor:
         """ControlLDM.vae_encode(tiled=True) up to the moments (model/cldm.py:114-126): VAEHook on the encoder

@@ -12,7 +12,7 @@ import os
 import shutil
 import subprocess
 import threading
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 
 # every symbol include/edtr_b200.h declares
 EXPORTED = [
-    "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_set_workspace", "edtr_set_gemm_max_clusters", "edtr_gemm_tile_n", "edtr_gemm_bf16",
+    "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_gemm_workspace_size", "edtr_gemm_row_stats_parts", "edtr_gemm_tile_n", "edtr_gemm_bf16",
     "edtr_conv3x3_bf16", "edtr_conv3x3_up2x_bf16", "edtr_attention_bf16", "edtr_groupnorm_partial_size", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
     "edtr_groupnorm_fused_supported", "edtr_groupnorm_fused", "edtr_groupnorm_pool", "edtr_groupnorm_apply_stats",
     "edtr_layernorm_bf16", "edtr_layernorm_padded_bf16", "edtr_pixel_unshuffle_f32_to_nhwc_bf16",
@@ -54,6 +54,16 @@ class EdtrEpilogue(Structure):
         ("out_mode", c_int32),
         ("hw", c_int32),
         ("alpha", c_float),
+        ("workspace", c_void_p),
+        ("workspace_bytes", c_uint64),
+        ("max_clusters", c_int32),
+        ("ln_stats", c_void_p),
+        ("ln_parts", c_int32),
+        ("ln_c", c_int32),
+        ("ln_eps", c_float),
+        ("ln_colsum", c_void_p),
+        ("row_stats", c_void_p),
+        ("row_stats_cap", c_int32),
     ]
 
 
@@ -89,10 +99,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 _lock = threading.Lock()
-WORKSPACE_BYTES = 64 << 20
-_workspace = None
+WORKSPACE_BYTES = 64 << 20      # split-K scratch (fp32 partial tiles) per (device, slot)
 _lib = None
-_initialised = False
+_devices = {}                   # device index -> {"workspaces": {slot: tensor}}: per-device init, no global device state
+_tls = threading.local()        # per host thread: workspace slot and CTA-pair share of the launches issued from it
 
 
 def _bind(lib: ctypes.CDLL) -> None:
@@ -105,11 +115,11 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_set_device.restype = ci
     lib.edtr_set_device.argtypes = [ci]
     lib.edtr_init.restype = ci
-    lib.edtr_set_workspace.restype = ci
-    lib.edtr_set_workspace.argtypes = [vp, c_size_t]
     lib.edtr_init.argtypes = []
-    lib.edtr_set_gemm_max_clusters.restype = ci
-    lib.edtr_set_gemm_max_clusters.argtypes = [ci]
+    lib.edtr_gemm_workspace_size.restype = c_size_t
+    lib.edtr_gemm_workspace_size.argtypes = [ci, ci, ci]
+    lib.edtr_gemm_row_stats_parts.restype = ci
+    lib.edtr_gemm_row_stats_parts.argtypes = [ci, ci, ci, ep]
     lib.edtr_gemm_tile_n.restype = ci
     lib.edtr_gemm_tile_n.argtypes = [ci, ci, ci, ci]
     lib.edtr_gemm_bf16.restype = ci
@@ -182,16 +192,31 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
 
 
 def use_workspace(index: int) -> None:
-    """Select which of the two split-K scratch buffers later launches use (one per concurrent stream)."""
-    lib = device_lib()
-    check(lib.edtr_set_workspace(_workspace[index].data_ptr(), WORKSPACE_BYTES), "edtr_set_workspace")
-    LAUNCHES[0] -= 1  # not a kernel launch
+    """Which split-K scratch slot launches issued by THIS host thread use from now on (one slot per stream that may
+    run concurrently: 0 main stream, 1 the ControlNet side stream).  Python-side selection only: the buffer is passed
+    to the library with every call (EdtrEpilogue.workspace); the library itself keeps no state."""
+    _tls.slot = int(index)
 
 
 def set_gemm_max_clusters(n: int) -> None:
-    """CTA pairs later GEMM / convolution launches may occupy (74 = the whole GPU)."""
-    check(device_lib().edtr_set_gemm_max_clusters(int(n)), "edtr_set_gemm_max_clusters")
-    LAUNCHES[0] -= 1  # not a kernel launch
+    """CTA pairs later GEMM / convolution launches of this host thread may occupy (74 = the whole GPU); passed per
+    call (EdtrEpilogue.max_clusters)."""
+    n = int(n)
+    if not 1 <= n <= 74:
+        raise ValueError(f"clusters must be in [1, 74], got {n}")
+    _tls.max_clusters = n
+
+
+def gemm_scratch(device_index: int):
+    """(pointer, bytes, max_clusters) of the current thread's split-K workspace on `device_index`."""
+    st = _devices[device_index]
+    slot = getattr(_tls, "slot", 0)
+    ws = st["workspaces"].get(slot)
+    if ws is None:
+        import torch
+
+        ws = st["workspaces"][slot] = torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device=f"cuda:{device_index}")
+    return ws.data_ptr(), WORKSPACE_BYTES, getattr(_tls, "max_clusters", 74)
 
 
 def last_error() -> str:
@@ -211,20 +236,24 @@ def check(rc: int, what: str) -> None:
     raise RuntimeError(msg)
 
 
-def device_lib() -> ctypes.CDLL:
-    """Library handle for compute calls: requires a CUDA sm_100-class device."""
-    global _initialised
+def device_lib(device_index=None) -> ctypes.CDLL:
+    """Library handle for compute calls on `device_index` (default: torch's current device): requires a CUDA
+    sm_100-class device; kernel attributes are primed once per device.  The caller must have made the device current
+    (ops does so with torch.cuda.device(...) around every launch sequence)."""
     lib = load()
-    if not _initialised:
-        import torch
+    import torch
 
-        if not torch.cuda.is_available():
-            raise RuntimeError("edtr_b200 has no CPU fallback: a CUDA (sm_100a) device is required")
-        check(lib.edtr_set_device(torch.cuda.current_device()), "edtr_set_device")
-        check(lib.edtr_init(), "edtr_init")
-        # split-K scratch (stream-ordered use on the current stream; kept alive for the process lifetime)
-        global _workspace
-        _workspace = [torch.empty(WORKSPACE_BYTES, dtype=torch.uint8, device="cuda") for _ in range(2)]
-        check(lib.edtr_set_workspace(_workspace[0].data_ptr(), WORKSPACE_BYTES), "edtr_set_workspace")
-        _initialised = True
+    if not torch.cuda.is_available():
+        raise RuntimeError("edtr_b200 has no CPU fallback: a CUDA (sm_100a) device is required")
+    if device_index is None:
+        device_index = torch.cuda.current_device()
+    if device_index not in _devices:
+        with _lock:
+            if device_index not in _devices:
+                with torch.cuda.device(device_index):
+                    check(lib.edtr_set_device(device_index), "edtr_set_device")
+                    LAUNCHES[0] -= 1
+                    check(lib.edtr_init(), "edtr_init")
+                    LAUNCHES[0] -= 1
+                _devices[device_index] = {"workspaces": {}}
     return lib

@@ -202,6 +202,13 @@ class AutoencoderKL(nn.Module):
         self._engine = None
         self._engine_version = None
 
+    def invalidate_engine(self) -> None:
+        """Drop the packed weights / graphs of both engines (needed after `.data` writes, see ControlLDM)."""
+        self._engine = None
+        self._engine_version = None
+        self._enc_engine = None
+        self._enc_engine_version = None
+
     def _decoder_engine(self):
         from .engine import VaeDecoderEngine
 
@@ -237,15 +244,16 @@ class AutoencoderKL(nn.Module):
         return DiagonalGaussianDistribution(self._encoder_engine().encode(x.float().contiguous()))
 
     @torch.no_grad()
-    def encode_tiled(self, x: torch.Tensor, tile_size: int) -> "DiagonalGaussianDistribution":
-        """The `encoder` closure of ControlLDM.vae_encode(tiled=True) (model/cldm.py:114-126): VAEHook + quant_conv;
-        tiles are spread over the ranks of the default process group when it has more than one rank."""
-        import torch.distributed as dist
+    def encode_tiled(self, x: torch.Tensor, tile_size: int, tile_group=None,
+                     tile_group_check: bool = True) -> "DiagonalGaussianDistribution":
+        """The `encoder` closure of ControlLDM.vae_encode(tiled=True) (model/cldm.py:114-126): VAEHook + quant_conv.
+        `tile_group` (opt-in, see parallel.tile_sharding) spreads the tiles of one image — the SAME image on every
+        rank — over the ranks of a process group; None (default) never communicates."""
+        from .parallel import check_same_across_ranks, tile_sharding
 
-        rank, world, red = 0, 1, None
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            rank, world = dist.get_rank(), dist.get_world_size()
-            red = lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        rank, world, red = tile_sharding(tile_group)
+        if world > 1 and tile_group_check:
+            check_same_across_ranks(x, tile_group, "image")
         return DiagonalGaussianDistribution(self._encoder_engine().encode_tiled(
             x.float().contiguous(), int(tile_size), rank=rank, world=world, reduce_fn=red))
 

@@ -32,18 +32,61 @@ def geglu_tile_n() -> int:
 
 
 def use_workspace(index: int) -> None:
-    """Split-K scratch selection for launches issued from now on (0: main stream, 1: side stream)."""
+    """Split-K scratch slot for launches issued by this host thread from now on (0: main stream, 1: side stream);
+    the buffer travels with every call (EdtrEpilogue.workspace) — the library keeps no state."""
     _lib.use_workspace(index)
 
 
 def set_gemm_max_clusters(n: int) -> None:
-    """Limit later GEMM / convolution launches to n CTA pairs (74 = whole GPU) so that launches on two streams can
-    run side by side."""
+    """Limit later GEMM / convolution launches of this host thread to n CTA pairs (74 = whole GPU) so that launches on
+    two streams can run side by side (passed per call as EdtrEpilogue.max_clusters)."""
     _lib.set_gemm_max_clusters(n)
+
+
+def gemm_workspace_size(M: int, N: int, K: int) -> int:
+    """Bytes of split-K scratch with which the planner may pick any split factor for an M x N x K problem."""
+    return int(_lib.load().edtr_gemm_workspace_size(M, N, K))
 
 
 def _stream() -> ctypes.c_void_p:
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _NullGuard:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_GUARD = _NullGuard()
+
+
+def device_guard(device):
+    """Context that makes `device` (a tensor's or an engine's) the current CUDA device for the launches inside: kernels
+    are issued on that device's current stream with that device's scratch (a model moved to cuda:1 works while the
+    current device is cuda:0, as it does in the reference).  Free when the device is already current."""
+    if isinstance(device, torch.Tensor):
+        device = device.device
+    device = torch.device(device)
+    if device.type != "cuda":
+        return _NULL_GUARD
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx == torch.cuda.current_device():
+        return _NULL_GUARD
+    return torch.cuda.device(idx)
+
+
+def row_stats_parts(M: int, N: int, K: int, device=None) -> int:
+    """(sum, sum of squares) pairs per row that `gemm(a [M, K], w [N, K], ..., row_stats=...)` writes with the current
+    thread's split-K scratch / CTA-pair share: one per column tile and epilogue warp group of the launch's tile plan."""
+    dev = torch.cuda.current_device() if device is None or torch.device(device).index is None else torch.device(device).index
+    L = _lib.device_lib(dev)
+    ep = EdtrEpilogue()
+    ep.workspace, ep.workspace_bytes, ep.max_clusters = _lib.gemm_scratch(dev)
+    ep.out_mode, ep.act = OUT_BF16, ACT_NONE
+    return int(L.edtr_gemm_row_stats_parts(M, N, K, ctypes.byref(ep)))
 
 
 def _require_cuda(*ts: Optional[torch.Tensor]) -> None:
@@ -81,8 +124,30 @@ def _f32(t: Optional[torch.Tensor], n: int, name: str) -> Optional[int]:
 
 
 def _epilogue(M: int, n_out: int, out: torch.Tensor, *, bias, rowvec, rows_per_group, residual, act, out_mode, hw,
-              alpha) -> EdtrEpilogue:
+              alpha, ln=None, row_stats=None) -> EdtrEpilogue:
     ep = EdtrEpilogue()
+    dev = out.device.index if out.device.index is not None else torch.cuda.current_device()
+    _lib.device_lib(dev)
+    ep.workspace, ep.workspace_bytes, ep.max_clusters = _lib.gemm_scratch(dev)
+    if ln is not None:
+        stats, c, eps, colsum = ln
+        n_w = 2 * n_out if act == ACT_GEGLU else n_out
+        if stats.dtype != torch.float32 or stats.dim() != 3 or stats.shape[0] != M or stats.shape[2] != 2 \
+                or not stats.is_contiguous():
+            raise ValueError(f"ln stats must be a contiguous fp32 [M={M}, parts, 2] tensor, got {tuple(stats.shape)}")
+        ep.ln_stats = stats.data_ptr()
+        ep.ln_parts = stats.shape[1]
+        ep.ln_c = int(c)
+        ep.ln_eps = float(eps)
+        ep.ln_colsum = _f32(colsum, n_w, "ln colsum")
+    if row_stats is not None:
+        if act == ACT_GEGLU or out_mode != OUT_BF16:
+            raise ValueError("row_stats needs a bf16 output and act != GEGLU")
+        if row_stats.dtype != torch.float32 or row_stats.dim() != 3 or row_stats.shape[0] != M \
+                or row_stats.shape[2] != 2 or not row_stats.is_contiguous():
+            raise ValueError(f"row_stats must be a contiguous fp32 [{M}, row_stats_parts(M, N, K), 2] tensor")
+        ep.row_stats = row_stats.data_ptr()
+        ep.row_stats_cap = row_stats.shape[1]
     ep.bias = _f32(bias, n_out if act != ACT_GEGLU else 2 * n_out, "bias")
     if rowvec is not None:
         if rowvec.dtype != torch.float32 or rowvec.dim() != 2 or rowvec.stride(1) != 1:
@@ -131,8 +196,13 @@ def _alloc_out(M: int, n_out: int, out_mode: int, hw: int, device) -> torch.Tens
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, rows_per_group=0, residual=None,
-         act=ACT_NONE, out=None, out_mode=OUT_BF16, hw=0, alpha=1.0) -> torch.Tensor:
-    """``epilogue(a @ w.T)`` — a [..., K] rows view, w [N, K] (bf16)."""
+         act=ACT_NONE, out=None, out_mode=OUT_BF16, hw=0, alpha=1.0, ln=None, row_stats=None) -> torch.Tensor:
+    """``epilogue(a @ w.T)`` — a [..., K] rows view, w [N, K] (bf16).
+
+    ln = (stats [M, parts, 2], C, eps, colsum [N]): LayerNorm over the K = C channels of `a` folded into the GEMM — `a`
+    holds the un-normalised rows, `w` is pre-scaled by the LayerNorm gain, `bias` already contains W @ beta, `stats`
+    are the (sum, sum of squares) partials a producer wrote through `row_stats` (engine.fold_layernorm packs these).
+    row_stats = fp32 [M, N/32, 2]: receives per-row partial (sum, sum of squares) of the stored matrix."""
     _require_cuda(a, w, bias, rowvec, residual, out)
     M, K, lda = rows_view(a)
     N, Kw, ldw = rows_view(w)
@@ -141,9 +211,14 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, rows_per_g
     n_out = N // 2 if act == ACT_GEGLU else N
     if out is None:
         out = _alloc_out(M, n_out, out_mode, hw, a.device)
+    if ln is not None and ln[1] != K:
+        raise ValueError(f"folded LayerNorm width {ln[1]} != K {K}")
     ep = _epilogue(M, n_out, out, bias=bias, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual,
-                   act=act, out_mode=out_mode, hw=hw, alpha=alpha)
+                   act=act, out_mode=out_mode, hw=hw, alpha=alpha, ln=ln, row_stats=row_stats)
     L = _lib.device_lib()
+    if row_stats is not None and row_stats.shape[1] != L.edtr_gemm_row_stats_parts(M, N, K, ctypes.byref(ep)):
+        raise ValueError(f"row_stats must hold exactly row_stats_parts(M, N, K) = "
+                         f"{L.edtr_gemm_row_stats_parts(M, N, K, ctypes.byref(ep))} pairs per row, got {row_stats.shape[1]}")
     _lib.check(L.edtr_gemm_bf16(a.data_ptr(), lda, w.data_ptr(), ldw, M, N, K, ctypes.byref(ep), _stream()),
                "edtr_gemm_bf16")
     return out
@@ -548,11 +623,12 @@ def sampler_update(x, eps, noise, index, tables, want_pred_x0: bool = True, x_pr
     if x_prev is None:
         x_prev = torch.empty_like(x)
     pred = pred_x0 if pred_x0 is not None else (torch.empty_like(x) if want_pred_x0 else None)
-    L = _lib.device_lib()
-    _lib.check(L.edtr_sampler_update(x.data_ptr(), eps.data_ptr(), noise.data_ptr(), index.data_ptr(),
-                                     *[t.data_ptr() for t in tables], x_prev.data_ptr(),
-                                     pred.data_ptr() if pred is not None else None, B, n, _stream()),
-               "edtr_sampler_update")
+    with device_guard(x):
+        L = _lib.device_lib()
+        _lib.check(L.edtr_sampler_update(x.data_ptr(), eps.data_ptr(), noise.data_ptr(), index.data_ptr(),
+                                         *[t.data_ptr() for t in tables], x_prev.data_ptr(),
+                                         pred.data_ptr() if pred is not None else None, B, n, _stream()),
+                   "edtr_sampler_update")
     return x_prev, pred
 
 
@@ -566,6 +642,11 @@ def wavelet_reconstruction(content: torch.Tensor, style: torch.Tensor, levels: i
         raise ValueError("the colour fix runs in fp32")
     content, style = content.contiguous(), style.contiguous()
     B, C, H, W = content.shape
+    with device_guard(content):
+        return _wavelet_reconstruction(content, style, levels, B, C, H, W)
+
+
+def _wavelet_reconstruction(content, style, levels, B, C, H, W):
     L = _lib.device_lib()
     st = _stream()
     high = torch.empty_like(content)

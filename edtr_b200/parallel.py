@@ -10,6 +10,41 @@ import torch
 import torch.distributed as dist
 
 
+def tile_sharding(tile_group):
+    """(rank, world, reduce_fn) of the OPT-IN tile-parallel mode of the tiled paths (config C4).
+
+    `tile_group` is None (default: no sharding, no communication — what the reference does, and the only valid choice
+    when ranks hold different images, as in the image-parallel evaluation loops), True (the default process group) or a
+    ``torch.distributed`` ProcessGroup.  Tile-parallelism requires that EVERY rank of the group calls with the SAME
+    image / latent: rank r then evaluates tiles r, r+world, ... and the partial results are summed over the group."""
+    if tile_group is None or tile_group is False:
+        return 0, 1, None
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("tile_group is set but torch.distributed is not initialised")
+    group = None if tile_group is True else tile_group
+    world = dist.get_world_size(group)
+    if world == 1:
+        return 0, 1, None
+    return dist.get_rank(group), world, (lambda buf: dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group))
+
+
+def check_same_across_ranks(t: torch.Tensor, tile_group, what: str) -> None:
+    """Debug guard for the tile-parallel mode: raises when the ranks of `tile_group` do not hold the same tensor
+    (a 3-number fingerprint is max-/min-reduced; one tiny collective)."""
+    rank, world, _ = tile_sharding(tile_group)
+    if world == 1:
+        return
+    group = None if tile_group is True else tile_group
+    tf = t.detach().float()
+    fp = torch.stack([tf.sum(), tf.abs().sum(), tf.reshape(-1)[:: max(1, tf.numel() // 97)].sum()]).to(torch.float64)
+    lo, hi = fp.clone(), fp.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if not torch.equal(lo, hi):
+        raise RuntimeError(f"tile-parallel mode needs the same {what} on every rank of tile_group (they differ); "
+                           "leave tile_group=None for image-parallel runs")
+
+
 def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous [lo, hi) slice of `total` images for `rank`; the first total % world ranks take one extra."""
     if world <= 0 or not (0 <= rank < world):

@@ -172,6 +172,8 @@ class SpacedSampler(nn.Module):
             from .tiling import make_tiled_fn
 
             forward = model.forward
+            had_own_forward = "forward" in getattr(model, "__dict__", {})
+            own_forward = model.__dict__.get("forward") if had_own_forward else None
             model.forward = make_tiled_fn(
                 lambda x_tile, t, cond, hi, hi_end, wi, wi_end: forward(
                     x_tile, t, {"c_txt": cond["c_txt"], "c_img": cond["c_img"][..., hi:hi_end, wi:wi_end]}),
@@ -187,8 +189,12 @@ class SpacedSampler(nn.Module):
         finally:
             if tiled:
                 # the reference leaves the wrapper installed and nests it on the next call
-                # (utils/sampler.py:289-303); restoring is numerically identical
-                model.forward = forward
+                # (utils/sampler.py:289-303); restoring is numerically identical.  Restore the
+                # instance dict exactly: leaving a bound method behind would switch the fused paths off for good
+                if had_own_forward:
+                    model.__dict__["forward"] = own_forward
+                else:
+                    model.__dict__.pop("forward", None)
         if return_intermediates:
             return img, intermediates
         return img

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 import torch.nn as nn
 
-from .engine import BF16, F32, Workspace, _ceil, _Graph, pack_conv3x3, pack_conv3x3_up2x, vec
+from .engine import BF16, F32, Workspace, _ceil, _Graph, _on_device, pack_conv3x3, pack_conv3x3_up2x, vec
 from .nets import _attach, state_version
 
 RGB_MEAN = (0.4488, 0.4371, 0.4040)   # model/swinir.py:689-691
@@ -285,6 +285,7 @@ class SwinIREngine:
         return self._masks[key]
 
     # ------------------------------------------------------------------------------------------ forward
+    @_on_device
     def forward(self, x: torch.Tensor, use_graph: bool = True) -> torch.Tensor:
         """[B, 3, H, W] fp32 in [0, 1] -> [B, 3, H, W] fp32 (model/swinir.py:856-894).  All buffers are static per
         (B, H, W), so the ~600 launches replay as one CUDA graph."""
@@ -310,8 +311,8 @@ class SwinIREngine:
         run = lambda: self._forward(ws, sx, out)
         if use_graph and x.is_cuda:
             g = self._graphs.get((B, H, W))
-            if g is None:
-                g = self._graphs[(B, H, W)] = _Graph(run)
+            if g is None or not g.valid():
+                g = self._graphs[(B, H, W)] = _Graph(run, ws)
             g.replay()
         else:
             run()

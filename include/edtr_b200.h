@@ -72,7 +72,35 @@ typedef struct EdtrEpilogue {
   int32_t out_mode;
   int32_t hw; /* rows per image, for the NCHW output modes */
   float alpha;
+  /* ---- per-call scratch: the library keeps NO state between calls (re-entrant per device / stream) ----
+   * workspace: device scratch for split-K partial tiles (256-byte aligned, >= edtr_gemm_workspace_size(...) bytes to
+   * enable every split the planner may pick; smaller buffers just limit the split factor; NULL disables split-K).
+   * One workspace must not be used by two launches that may run concurrently (one per stream).
+   * max_clusters: CTA pairs this launch may occupy (0 = the whole GPU, 74 pairs on a B200). */
+  void* workspace;
+  uint64_t workspace_bytes;
+  int32_t max_clusters;
+  /* ---- LayerNorm folded into this GEMM (replaces nn.LayerNorm in front of to_q/k/v and the GEGLU projection,
+   * model/attention.py:222-224,231-233): A holds the UN-normalised rows x, Wt must be pre-scaled by the LayerNorm
+   * gain (Wt[n,k] * gamma[k], rounded to bf16), and the epilogue evaluates
+   *     acc' = rstd[row] * (acc - mean[row] * ln_colsum[n]),      ln_colsum[n] = sum_k Wt[n,k] (of the bf16 values)
+   * before alpha / bias (the bias must already contain sum_k beta[k] * W[n,k]).  mean / rstd come from
+   * ln_stats = fp32 [M][ln_parts][2] partial (sum, sum of squares) pairs as written by a producer's row_stats
+   * (below), over ln_c = K channels, eps inside the sqrt.  NULL = no LayerNorm. */
+  const float* ln_stats;
+  int32_t ln_parts;
+  int32_t ln_c;
+  float ln_eps;
+  const float* ln_colsum;
+  /* ---- row statistics of the STORED matrix (the producer side of the fold above): row_stats = fp32
+   * [M][row_stats_cap][2]; for every row the launch writes P = edtr_gemm_row_stats_parts(...) <= row_stats_cap
+   * (sum, sum of squares) pairs — one per column tile and epilogue warp group, in-lane sums of the fp32 values before
+   * bf16 rounding — into entries [m][0..P); a consumer passes ln_parts = P with a row stride of P pairs, so allocate
+   * exactly [M][P][2].  EDTR_OUT_BF16, act != GEGLU.  NULL = not wanted. */
+  float* row_stats;
+  int32_t row_stats_cap;
 } EdtrEpilogue;
+
 
 /* ---- library ------------------------------------------------------------ */
 const char* edtr_last_error(void);
@@ -82,16 +110,14 @@ int edtr_version(void);
 int edtr_set_device(int device);
 /* Verifies the current device is sm_100-class and primes kernel attributes. */
 int edtr_init(void);
-/* Registers a device scratch buffer (256-byte aligned, owned by the caller, must outlive every later
- * call) that the GEMM / convolution entry points may use for split-K partial sums when a problem has
- * too few output tiles to fill the GPU (the 8x8 level of the UNet).  All calls that use it are ordered
- * on one stream.  ptr == NULL disables split-K.  The library never allocates. */
-int edtr_set_workspace(void* ptr, size_t bytes);
-/* Upper bound on the CTA pairs (2 SMs each, 74 on a B200) a GEMM / convolution launch issued from now on may occupy.
- * The persistent kernel owns whole SMs (224 KB of shared memory per CTA), so two launches on different streams only
- * run side by side when each is limited to a share of the GPU: the engine lowers the bound while the ControlNet and
- * the UNet encoder run concurrently (model/controlnet.py:25-31 vs :263-277) and restores 74 afterwards. */
-int edtr_set_gemm_max_clusters(int clusters);
+/* Bytes of EdtrEpilogue.workspace with which the GEMM / convolution planner is free to pick any split-K factor for an
+ * M x N x K problem (fp32 partial tiles); a smaller workspace only limits the split.  There is no
+ * library-global scratch: the workspace (and the share of the GPU a launch may take, EdtrEpilogue.max_clusters) are
+ * per-call arguments, so calls on different devices / streams / host threads do not interact. */
+size_t edtr_gemm_workspace_size(int M, int N, int K);
+/* Pairs per row that edtr_gemm_bf16(M, N, K, ep) writes to ep->row_stats (depends on the tile plan, i.e. on the shape
+ * and on ep->workspace_bytes / ep->max_clusters / ep->act; ep->row_stats itself may still be NULL). */
+int edtr_gemm_row_stats_parts(int M, int N, int K, const EdtrEpilogue* ep);
 /* N-tile width the GEMM will use for an N-column problem (for GEGLU weight
  * interleaving at plan time). */
 int edtr_gemm_tile_n(int M, int N, int K, int act);

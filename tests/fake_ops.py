@@ -39,8 +39,27 @@ def _rows(t):
     return t.reshape(-1, t.shape[-1]).float()
 
 
-def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, out_mode, hw, alpha, geglu_bias=None):
+def row_stats_parts(M, N, K, device=None):
+    return 3     # any split of the columns works for the consumer: it only sums the parts
+
+
+def device_guard(device):
+    import contextlib
+
+    return contextlib.nullcontext()
+
+
+def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, out_mode, hw, alpha, geglu_bias=None,
+            ln=None, row_stats=None):
     LAUNCHES[0] += 1
+    if ln is not None:
+        # folded LayerNorm (EdtrEpilogue.ln_*): acc' = rstd * (acc - mean * colsum[n]) from the producer's partial sums
+        stats, c, eps, colsum = ln
+        assert stats.dtype == torch.float32 and stats.shape[0] == M and stats.shape[2] == 2
+        s1, s2 = stats[:, :, 0].sum(1), stats[:, :, 1].sum(1)
+        mu = s1 / c
+        rstd = torch.rsqrt(torch.clamp(s2 / c - mu * mu, min=0.0) + eps)
+        v = rstd[:, None] * (v - mu[:, None] * colsum.float()[None, :])
     v = v * alpha
     if act == ACT_GEGLU:
         if bias is not None:
@@ -62,6 +81,11 @@ def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, ou
         v = F.leaky_relu(v, 0.2)
     elif act == ACT_LRELU_001:
         v = F.leaky_relu(v, 0.01)
+    if row_stats is not None:
+        assert act != ACT_GEGLU and out_mode == OUT_BF16 and row_stats.shape[0] == M and row_stats.shape[2] == 2
+        for j, vv in enumerate(torch.tensor_split(v, row_stats.shape[1], dim=1)):
+            row_stats[:, j, 0] = vv.sum(-1)
+            row_stats[:, j, 1] = (vv * vv).sum(-1)
     if out_mode in (OUT_BF16, OUT_F32):
         want = torch.bfloat16 if out_mode == OUT_BF16 else torch.float32
         if out is None:
@@ -78,7 +102,7 @@ def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, ou
 
 
 def gemm(a, w, *, bias=None, rowvec=None, rows_per_group=0, residual=None, act=ACT_NONE, out=None,
-         out_mode=OUT_BF16, hw=0, alpha=1.0):
+         out_mode=OUT_BF16, hw=0, alpha=1.0, ln=None, row_stats=None):
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     A = _rows(a)
     M, K = A.shape
@@ -86,7 +110,8 @@ def gemm(a, w, *, bias=None, rowvec=None, rows_per_group=0, residual=None, act=A
     assert K == Kw and K % 64 == 0, (K, Kw)
     n_out = N // 2 if act == ACT_GEGLU else N
     return _finish(A @ w.float().t(), M, n_out, bias=bias, rowvec=rowvec, rows_per_group=rows_per_group,
-                   residual=residual, act=act, out=out, out_mode=out_mode, hw=hw, alpha=alpha)
+                   residual=residual, act=act, out=out, out_mode=out_mode, hw=hw, alpha=alpha, ln=ln,
+                   row_stats=row_stats)
 
 
 def conv3x3(x, w, *, bias=None, rowvec=None, residual=None, act=ACT_NONE, out=None, out_mode=OUT_BF16, alpha=1.0):

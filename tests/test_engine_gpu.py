@@ -343,3 +343,68 @@ def test_swinir_edtr_widths_against_oracle():
         ref = S.swinir_forward(sd, cfg, x)
         y = m(x.cuda())
     assert O.psnr(y.cpu().clamp(0, 1), ref.clamp(0, 1)) >= 40.0
+
+
+# ----------------------------------------------------------------------------- round 2 regressions
+def test_graphs_survive_workspace_growth(tiny):
+    """sample(4 steps) -> sample(8 steps) -> sample(4 steps) at the same B/H/W.  The 8-step call grows
+    the staging buffers; the 4-step graph captured before must not be replayed against the freed storage."""
+    w, x_T, cond, noise, g, (eng, vd) = tiny
+    tabs4, ts4 = _tables(O.TINY)
+    used8 = (25, 50, 75, 100, 125, 150, 175, 200)
+    s8 = O.make_schedule(O.make_betas(**O.TINY["diffusion"]), 8, used8)
+    tabs8 = {k: torch.from_numpy(v).cuda() for k, v in s8.items() if k != "timesteps"}
+    ts8 = list(s8["timesteps"][::-1])
+    gen = torch.Generator().manual_seed(11)
+    noise8 = [torch.randn(x_T.shape, generator=gen) for _ in range(8)]
+    args = (cond["c_img"].cuda(), cond["c_txt"].cuda())
+    z4a = eng.sample(x_T.cuda(), ts4, tabs4, *args, [n.cuda() for n in noise])
+    z8 = eng.sample(x_T.cuda(), ts8, tabs8, *args, [n.cuda() for n in noise8])
+    z4b = eng.sample(x_T.cuda(), ts4, tabs4, *args, [n.cuda() for n in noise])
+    assert torch.equal(z4a, z4b)
+    assert O.max_rel_err(z4b.cpu(), torch.from_numpy(g["xs"][3])) < STEP_TOL
+    with torch.no_grad():
+        z8_ref, _, _ = O.sample(w, O.TINY, x_T, cond, noise8, used_timesteps=used8)
+    assert O.max_rel_err(z8.cpu(), z8_ref) < STEP_TOL
+    # a longer text (more context tokens) at the same B/H/W grows the context buffers as well
+    g2 = torch.Generator().manual_seed(12)
+    c_long = torch.randn(2, 100, 128, generator=g2)
+    with torch.no_grad():
+        z_long_ref, _, _ = O.sample(w, O.TINY, x_T, dict(c_img=cond["c_img"], c_txt=c_long), noise)
+    z_long = eng.sample(x_T.cuda(), ts4, tabs4, cond["c_img"].cuda(), c_long.cuda(), [n.cuda() for n in noise])
+    assert O.max_rel_err(z_long.cpu(), z_long_ref) < STEP_TOL
+    z4c = eng.sample(x_T.cuda(), ts4, tabs4, *args, [n.cuda() for n in noise])
+    assert torch.equal(z4a, z4c)
+
+
+def test_layernorm_fold_matches_standalone_layernorm(tiny):
+    """The folded LayerNorm (statistics in the producer epilogue, mean / rstd applied in the consumer epilogue) against
+    the same engine running the standalone LayerNorm kernel, and both against the reference fixture."""
+    from edtr_b200.engine import CldmEngine
+
+    w, x_T, cond, noise, g, (eng, vd) = tiny
+    t = torch.full((2,), 200, dtype=torch.long, device="cuda")
+    ref = torch.from_numpy(g["eps0"])
+    outs = {}
+    for fold in (True, False):
+        e = CldmEngine(O.TINY["unet"], O.TINY["controlnet"], w["unet"], w["controlnet"], "cuda")
+        e.fold_ln = fold
+        outs[fold] = e.forward(x_T.cuda(), t, cond["c_img"].cuda(), cond["c_txt"].cuda(), use_graph=False).cpu()
+        assert O.max_rel_err(outs[fold], ref) < 3e-2, fold
+    assert O.max_rel_err(outs[True], outs[False]) < STEP_TOL   # two bf16 evaluations of the same graph
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_engine_on_non_current_device(tiny):
+    """an engine built on cuda:1 runs there (its stream, its split-K scratch) while the current
+    device is cuda:0, and a second engine on cuda:0 is undisturbed."""
+    from edtr_b200.engine import CldmEngine
+
+    w, x_T, cond, noise, g, (eng0, _) = tiny
+    torch.cuda.set_device(0)
+    eng1 = CldmEngine(O.TINY["unet"], O.TINY["controlnet"], w["unet"], w["controlnet"], "cuda:1")
+    t = torch.full((2,), 200, dtype=torch.long)
+    e1 = eng1.forward(x_T.to("cuda:1"), t.to("cuda:1"), cond["c_img"].to("cuda:1"), cond["c_txt"].to("cuda:1"))
+    e0 = eng0.forward(x_T.cuda(), t.cuda(), cond["c_img"].cuda(), cond["c_txt"].cuda())
+    assert e1.device.index == 1 and torch.cuda.current_device() == 0
+    assert torch.equal(e0.cpu(), e1.cpu())

@@ -280,6 +280,53 @@ def _gloo_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _gloo_tile_group_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    from edtr_b200.parallel import check_same_across_ranks, tile_sharding
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    # default: NO sharding and no collective although a process group exists (image-parallel runs hold different
+    # images per rank; ADVICE r1: never infer tile-parallelism from dist.is_initialized())
+    r0 = tile_sharding(None)
+    # opt-in: the default group, or an explicit ProcessGroup
+    r1, w1, red1 = tile_sharding(True)
+    grp = dist.new_group(ranks=list(range(world)))
+    r2, w2, red2 = tile_sharding(grp)
+    buf = torch.full((3,), float(rank + 1))
+    red2(buf)
+    same = torch.arange(12.0).view(3, 4)
+    check_same_across_ranks(same, True, "latent")          # identical tensors: passes
+    differs = False
+    try:
+        check_same_across_ranks(same + rank, True, "latent")   # per-rank tensors: must raise on every rank
+    except RuntimeError:
+        differs = True
+    q.put((rank, r0 == (0, 1, None), (r1, w1) == (rank, world), (r2, w2) == (rank, world),
+           bool(torch.equal(buf, torch.full((3,), 3.0))), differs))
+    dist.destroy_process_group()
+
+
+def test_tile_parallel_mode_is_opt_in_gloo():
+    import torch.multiprocessing as mp
+
+    from edtr_b200.parallel import tile_sharding
+
+    assert tile_sharding(None) == (0, 1, None)
+    with pytest.raises(RuntimeError):
+        tile_sharding(True)                                 # opt-in without an initialised process group
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_tile_group_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True, True, True, True, True), (1, True, True, True, True, True)]
+
+
 def test_two_rank_sharding_and_gather_gloo():
     import torch.multiprocessing as mp
 

@@ -466,3 +466,104 @@ def test_conv3x3_up2x_leaky_relu(ops):
     up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
     ref = F.leaky_relu(F.conv2d(up, w.float(), bias, padding=1), 0.2).permute(0, 2, 3, 1)
     assert relerr(out, ref) < 1e-2
+
+
+# ------------------------------------------------------------------ round 2: epilogue statistics / folded LayerNorm / in-kernel split-K
+@pytest.mark.parametrize("M,N,K,res", [(32768, 320, 320, True), (2048, 1280, 1280, True), (512, 1280, 1280, False),
+                                        (128, 640, 640, True), (300, 320, 320, False)])
+def test_gemm_row_stats(ops, M, N, K, res):
+    """EdtrEpilogue.row_stats: per-row partial (sum, sum of squares) of the stored matrix, one pair per column tile and
+    epilogue warp group, on the CTA-pair kernel (M >= 256) and on the single-CTA kernel (M < 256); the parts of a row
+    add up to the row's totals."""
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    r = rnd(M, N, seed=3) if res else None
+    parts = ops.row_stats_parts(M, N, K)
+    assert 1 <= parts <= 2 * ((N + 63) // 64)
+    rs = torch.full((M, parts, 2), float("nan"), device="cuda")
+    out = ops.gemm(a, w, bias=bias, residual=r, row_stats=rs)
+    ref = a.float() @ w.float().t() + bias + (r.float() if res else 0)
+    assert relerr(out, ref) < 1e-2
+    assert not torch.isnan(rs).any()
+    assert relerr(rs[..., 0].sum(1), ref.sum(-1)) < 2e-3
+    assert relerr(rs[..., 1].sum(1), (ref * ref).sum(-1)) < 2e-3
+    with pytest.raises(ValueError):
+        ops.gemm(a, w, row_stats=torch.empty((M, parts + 1, 2), device="cuda"))
+
+
+@pytest.mark.parametrize("M,C,N", [(32768, 320, 960), (2048, 1280, 1280), (512, 1280, 3840), (128, 640, 640), (64, 1280, 1280)])
+def test_gemm_folded_layernorm(ops, M, C, N):
+    """LayerNorm folded into the consuming GEMM (engine.fold_layernorm + EdtrEpilogue.ln_*) vs F.layer_norm + matmul;
+    rows get a large common offset so that the mean-cancellation term matters."""
+    from edtr_b200.engine import fold_layernorm
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = (torch.randn(M, C, generator=g, device="cuda") * 1.5 + 3.0 * torch.randn(M, 1, generator=g, device="cuda")).to(BF)
+    w = torch.randn(N, C, generator=g, device="cuda") * C ** -0.5
+    b = torch.randn(N, generator=g, device="cuda") * 0.1
+    gamma = 1 + 0.3 * torch.randn(C, generator=g, device="cuda")
+    beta = 0.2 * torch.randn(C, generator=g, device="cuda")
+    wg, cs, bf = fold_layernorm(w, b, gamma, beta, "cuda")
+    xf = x.float().view(M, C // 32, 32)
+    stats = torch.stack([xf.sum(-1), (xf * xf).sum(-1)], -1).contiguous()
+    out = ops.gemm(x, wg, bias=bf, ln=(stats, C, 1e-5, cs))
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.t() + b
+    assert relerr(out, ref) < 1.5e-2
+
+
+def test_gemm_folded_layernorm_geglu_and_producer_chain(ops):
+    """Producer GEMM (+residual) emits the row statistics, the GEGLU projection consumes them: the dataflow of
+    BasicTransformerBlock's `ff(norm3(x)) + x` (model/attention.py:233) without a LayerNorm kernel."""
+    from edtr_b200.engine import fold_layernorm, geglu_permutation
+
+    M, C = 4096, 320
+    g = torch.Generator(device="cuda").manual_seed(6)
+    a = rnd(M, C, seed=1)
+    w0 = rnd(C, C, scale=C ** -0.5, seed=2)
+    res = rnd(M, C, seed=3)
+    rs = torch.empty((M, ops.row_stats_parts(M, C, C), 2), device="cuda")
+    t = ops.gemm(a, w0, residual=res, row_stats=rs)          # stored bf16 residual stream + its statistics
+    w = torch.randn(8 * C, C, generator=g, device="cuda") * C ** -0.5
+    b = torch.randn(8 * C, generator=g, device="cuda") * 0.1
+    gamma = 1 + 0.3 * torch.randn(C, generator=g, device="cuda")
+    beta = 0.2 * torch.randn(C, generator=g, device="cuda")
+    perm = geglu_permutation(4 * C, ops.geglu_tile_n()).cuda()
+    wg, cs, bf = fold_layernorm(w[perm], b[perm], gamma, beta, "cuda")
+    out = ops.gemm(t, wg, bias=bf, ln=(rs, C, 1e-5, cs), act=ops.ACT_GEGLU)
+    y = F.layer_norm(t.float(), (C,), gamma, beta, 1e-5) @ w.t() + b
+    xh, gate = y.chunk(2, dim=-1)
+    assert relerr(out, xh * F.gelu(gate)) < 1.5e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 1280, 11520), (512, 1280, 5120), (2048, 1280, 11520), (256, 640, 5760)])
+def test_gemm_split_k(ops, M, N, K):
+    """Under-filled problems split K into the per-call workspace (EdtrEpilogue.workspace); the partial tiles are summed
+    in split order (bit-reproducible) with bias / rowvec / residual / SiLU applied by the reduce pass."""
+    if M <= 512:
+        assert ops.gemm_workspace_size(M, N, K) > 0      # the planner does split these
+    a, w = rnd(M, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    res = rnd(M, N, seed=3)
+    rowvec = torch.randn(M // 64, N, device="cuda")
+    ref = a.float() @ w.float().t() + bias + res.float() + rowvec.repeat_interleave(64, 0)
+    outs = [ops.gemm(a, w, bias=bias, residual=res, rowvec=rowvec, rows_per_group=64) for _ in range(3)]
+    assert relerr(outs[0], ref) < 1e-2
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    out = ops.gemm(a, w, bias=bias, act=ops.ACT_SILU)
+    assert relerr(out, F.silu(a.float() @ w.float().t() + bias)) < 1e-2
+    # in-place accumulation (zero-conv into the skip tensor) through the split path
+    acc = res.clone()
+    ops.gemm(a, w, bias=bias, residual=acc, out=acc, alpha=0.5)
+    assert relerr(acc, 0.5 * (a.float() @ w.float().t()) + bias + res.float()) < 1e-2
+
+
+def test_conv3x3_split_k(ops):
+    B, H, W, Cin, Cout = 8, 8, 8, 1280, 1280
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    bias = torch.randn(Cout, device="cuda")
+    emb = torch.randn(B, Cout, device="cuda")
+    out = ops.conv3x3(x, wp, bias=bias, rowvec=emb)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + emb[:, :, None, None]
+    assert relerr(out.view(B, H, W, Cout), ref.permute(0, 2, 3, 1)) < 1e-2
