@@ -18,6 +18,7 @@ on the host cores, bounded sample), `clocks`, `gpu_launches`.
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -310,19 +311,37 @@ def build_model(device):
     return model.to(device).eval()
 
 
-class TensorCoreTimer:
-    """Brackets every tensor-core launch (gemm / conv3x3 / attention) of one eager pass with CUDA events on the
-    launching stream; used after the timed region to attribute time to the dominant kernel family."""
+class KernelTimer:
+    """Brackets every tensor-core launch (gemm / conv3x3 / conv3x3_up2x / attention) and every normalisation launch
+    (groupnorm / layernorm) of one eager pass with CUDA events on the launching stream; used after the timed region to
+    attribute time to kernel families and to count their algorithmic bytes."""
+
+    NAMES = ("gemm", "conv3x3", "conv3x3_up2x", "attention", "groupnorm", "layernorm")
 
     def __init__(self, ops):
         import torch
 
         self.ops, self.torch = ops, torch
-        self.events = {"gemm": [], "conv3x3": [], "attention": []}
+        self.events = {n: [] for n in self.NAMES}
+        self.bytes = {n: 0 for n in self.NAMES}
         self.orig = {}
 
+    @staticmethod
+    def _algorithmic_bytes(name, a, k, r):
+        """Bytes a launch must move at least once (operands + result, bf16 unless noted)."""
+        n = lambda t: t.numel() * t.element_size()
+        if name in ("gemm", "conv3x3", "conv3x3_up2x"):
+            b = n(a[0]) + n(a[1]) + n(r)
+            for key in ("residual", "bias", "rowvec"):
+                if k.get(key) is not None:
+                    b += n(k[key])
+            return b
+        if name == "attention":
+            return n(a[0]) + n(a[1]) + n(a[2]) + n(r)
+        return n(a[0]) + n(r)          # norms: read x, write y (4 B / element, SURVEY §8d)
+
     def __enter__(self):
-        for name in self.events:
+        for name in self.NAMES:
             fn = getattr(self.ops, name)
             self.orig[name] = fn
 
@@ -332,6 +351,7 @@ class TensorCoreTimer:
                 r = _fn(*a, **k)
                 e.record()
                 self.events[_name].append((s, e))
+                self.bytes[_name] += self._algorithmic_bytes(_name, a, k, r)
                 return r
 
             setattr(self.ops, name, wrapped)
@@ -343,7 +363,7 @@ class TensorCoreTimer:
 
     def totals(self):
         self.torch.cuda.synchronize()
-        return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in self.events.items()}
+        return {k: (len(v), sum(s.elapsed_time(e) for s, e in v), self.bytes[k]) for k, v in self.events.items()}
 
 
 def run_ours(args):
@@ -358,9 +378,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("EDTR_NCCL_LOG", "0") == "1":     # keep the algorithm / channel lines of the communicator
+            # (opt-in: NCCL_DEBUG prints its version banner on stdout, which must carry the one JSON line only)
+            os.environ.setdefault("NCCL_DEBUG", "INFO")
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
+            os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", f"nccl_n{world}.%h.%p.log"))
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         dist.init_process_group("nccl", device_id=dev)
+    if args.config == "c4":
+        return run_c4(args, rank, world, dev)
     from edtr_b200 import lib as elib
     from edtr_b200 import ops
+    from edtr_b200.parallel import ImageGatherer
     from edtr_b200.sampler import SpacedSampler
 
     B = args.batch
@@ -382,14 +411,16 @@ def run_ours(args):
     tables = {k: getattr(sampler, k) for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
                                                "posterior_mean_coef1", "posterior_mean_coef2", "posterior_variance")}
     ts = [200, 150, 100, 50]
-    gather = [torch.empty(B, 3, 512, 512, device=dev) for _ in range(world)] if world > 1 else None
+    # end-of-batch exchange (configs[2]): one all_gather_into_tensor of bf16 images on a side stream, overlapped with
+    # the next batch (edtr_b200.parallel.ImageGatherer); the last one is waited for inside the timed region
+    gather = ImageGatherer((B, 3, 512, 512), dev, torch.bfloat16) if world > 1 else None
 
     def step_resident():
         noise = [torch.randn_like(x_T) for _ in range(4)]
         z = eng.sample(x_T, ts, tables, c_img, c_txt, noise, control_scales=model.control_scales)
         img = vae_eng.decode(z, model.scale_factor)
         if gather is not None:
-            dist.all_gather(gather, img)
+            gather.submit(img)
         return img
 
     def step_e2e():
@@ -398,7 +429,7 @@ def run_ours(args):
         z = sampler.manual_sample_with_timesteps(model, dev, x, 4, USED_TIMESTEPS, B, cond, None, 1.0, progress=False)
         img = model.vae_decode(z)
         if gather is not None:
-            dist.all_gather(gather, img)
+            gather.submit(img)
         img_h.copy_(img, non_blocking=True)
         return img
 
@@ -407,9 +438,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, sample_clocks=False):
+    def timed(fn, steps, warmup, sample_clocks=False, finish=None):
         for _ in range(warmup):
             fn()
+        if finish is not None:
+            finish()
         barrier()
         clk = ClockSampler(local) if sample_clocks else None
         if clk:
@@ -421,6 +454,8 @@ def run_ours(args):
         s.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()          # the last batch's gather completes inside the timed region
         e.record()
         barrier()
         if sample_clocks and os.environ.get("EDTR_NCU"):
@@ -433,11 +468,26 @@ def run_ours(args):
             ms = float(t.item())
         return ms, elib.LAUNCHES[0] - n0, clocks
 
+    fin = gather.result if gather is not None else None
     W = max(args.warmup, 3)
-    ms, launches, clocks = timed(step_resident, args.steps, W, sample_clocks=True)
+    ms, launches, clocks = timed(step_resident, args.steps, W, sample_clocks=True, finish=fin)
     value = world * B * args.steps / (ms / 1e3)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, W)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, W, finish=fin)
     e2e = world * B * args.steps / (ms_e2e / 1e3)
+    # the contract times exactly K steps; a sustained figure over >= 5 s of the same loop is reported beside it
+    sustained = None
+    if args.sustain_seconds > 0:
+        n_sus = max(args.steps, int(math.ceil(args.sustain_seconds * 1e3 / (ms / args.steps))))
+        ms_sus, _, clk_sus = timed(step_resident, n_sus, 1, sample_clocks=True, finish=fin)
+        sustained = {"value": world * B * n_sus / (ms_sus / 1e3), "unit": UNIT, "steps": n_sus, "seconds": ms_sus / 1e3,
+                     "sm_mhz": clk_sus.get("sm_mhz") if clk_sus else None,
+                     "reasons": clk_sus.get("reasons") if clk_sus else None}
+
+    # multi-GPU output check: rank r restores its slice of a common 2*world-image batch with the slice of
+    # the common noise; the gathered result must be the 1-GPU restore of the whole batch, which rank 0 recomputes
+    gather_check = None
+    if world > 1:
+        gather_check = multi_gpu_output_check(model, eng, vae_eng, tables, ts, rank, world, dev)
 
     # secondary metric of BASELINE.json: one ControlLDM evaluation (ControlNet + UNet) at batch B
     t200 = torch.full((B,), 200, dtype=torch.long, device=dev)
@@ -450,15 +500,20 @@ def run_ours(args):
     ms_enc, _, _ = timed(lambda: model.vae_encode(img_dev * 2 - 1, sample=False), 5, 3)
     ms_fix, _, _ = timed(lambda: wavelet_reconstruction(img_dev, img_dev), 5, 3)
 
-    # dominant kernel family, measured live: one eager (non-graph) restore with every tensor-core launch bracketed
+    # kernel families, measured live: one eager (non-graph) restore with every launch of the families bracketed
     pk = peaks()
-    with TensorCoreTimer(ops) as tc:
+    with KernelTimer(ops) as tc:
         noise = [torch.randn_like(x_T) for _ in range(4)]
+        # a short device-side delay lets the host run ahead, so the events bracket back-to-back GPU work and not the
+        # host's launch path (the pass below is eager: ~2500 Python-issued launches)
+        torch.cuda._sleep(int(0.25 * 1.9e9))
         z = eng.sample(x_T, ts, tables, c_img, c_txt, noise, use_graph=False)
         vae_eng.decode(z, model.scale_factor, use_graph=False)
     tot = tc.totals()
-    gemm_ms = tot["gemm"][1] + tot["conv3x3"][1]
-    gemm_n = tot["gemm"][0] + tot["conv3x3"][0]
+    fam = ("gemm", "conv3x3", "conv3x3_up2x")
+    gemm_ms = sum(tot[k][1] for k in fam)
+    gemm_n = sum(tot[k][0] for k in fam)      # an up2x call is four phase launches of the same kernel
+    gemm_bytes = sum(tot[k][2] for k in fam)
     achieved = GF_GEMM_PER_IMAGE * B / gemm_ms  # GF / ms = TFLOP/s
     # DRAM bytes per launch of the dominant kernel, from the committed ncu launch list of this same command
     # (profiles/gemm2_traffic.json, written by scripts/summarize_launches.py); null when no capture is committed
@@ -469,18 +524,41 @@ def run_ours(args):
             traffic = json.load(open(tpath))["dram_bytes_per_launch"]
         except (OSError, ValueError, KeyError):
             traffic = None
+
+    def mem_entry(name, kernel):
+        n, t_ms, nbytes = tot[name]
+        gbs = nbytes / 1e9 / (t_ms / 1e3) if t_ms > 0 else 0.0
+        return {"kernel": kernel, "launches_per_step": n, "ms_per_step": t_ms, "algorithmic_bytes_per_step": nbytes,
+                "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"]}
+
     roofline = {
         "bound": "tensor", "kernel": "edtr::gemm2_kernel (CTA-pair tcgen05 implicit-GEMM: all conv3x3 / 1x1 / Linear launches)",
         "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-        "traffic": traffic, "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
+        "traffic": traffic, "algorithmic_bytes_per_launch": gemm_bytes / max(gemm_n, 1),
+        "peak_source": pk["source"] + " sustained bf16 (kernel timed inside a long step)",
         "launches_per_step": gemm_n, "avg_launch_us": 1e3 * gemm_ms / max(gemm_n, 1),
         "algorithmic_gflop_per_step": GF_GEMM_PER_IMAGE * B,
+        "note": "effective throughput against the reference graph's FLOPs (SURVEY §8d); the sub-pixel up-convolutions "
+                "execute 2.25x fewer MACs than the reference's upsample+conv (about 9.6 % of the family's FLOPs)",
         "attention": {"launches_per_step": tot["attention"][0], "ms_per_step": tot["attention"][1],
-                      "achieved": GF_ATTN_PER_IMAGE * B / max(tot["attention"][1], 1e-9)},
+                      "achieved": GF_ATTN_PER_IMAGE * B / max(tot["attention"][1], 1e-9),
+                      "frac": GF_ATTN_PER_IMAGE * B / max(tot["attention"][1], 1e-9) / pk["tf_sustained"]},
+        "memory_bound": [mem_entry("groupnorm", "edtr::groupnorm_* (GroupNorm + SiLU, 4 B / element)"),
+                         mem_entry("layernorm", "edtr::layernorm_kernel (standalone LayerNorm launches; 0 when folded "
+                                                "into the GEMM epilogues)")],
         "whole_step": {"achieved": value / world * GF_PER_IMAGE / 1e3, "frac": value / world * GF_PER_IMAGE / 1e3 / pk["tf_sustained"]},
     }
     if rank == 0:
         cpu = None
+        ref_gpu = None
+        if world == 1 and not args.no_reference_gpu:
+            try:
+                ref_gpu = reference_gpu_measure(dev, B, 2, 2)
+                ref_gpu["note"] = ("the reference algorithm (oracle port) on stock cuDNN / cuBLAS / SDPA kernels under bf16 "
+                                   "autocast on this same GPU: eager as the reference runs it, channels_last + bf16 "
+                                   "weights, and the same captured in one CUDA graph (best case for library kernels)")
+            except Exception as exc:  # a reported baseline must not take the bench down
+                ref_gpu = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_baseline_sample()
         line = {
@@ -496,11 +574,162 @@ def run_ours(args):
                     "api": "edtr_b200.SpacedSampler.manual_sample_with_timesteps + ControlLDM.vae_decode"},
             "gpu_launches": launches, "roofline": roofline, "clocks": clocks,
         }
+        if sustained is not None:
+            line["sustained"] = sustained
+        if gather is not None:
+            line["comm"] = {"op": "all_gather_into_tensor (bf16 images, side stream, overlapped with the next batch)",
+                            "bytes_per_rank_per_step": gather.bytes_per_rank, "output_check": gather_check,
+                            "nccl_log": nccl_log_tail(world)}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if ref_gpu is not None:
+            line["reference_gpu"] = ref_gpu
         line["config"]["unet_step_ms"] = unet_step_ms
         line["config"]["vae_encode_ms"] = ms_enc / 5
         line["config"]["colorfix_ms"] = ms_fix / 5
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def nccl_log_tail(world, keep=6):
+    """A few algorithm / channel lines of the NCCL_DEBUG=INFO log of this run (kept in gpurun_out/)."""
+    import glob
+
+    out = []
+    for f in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"nccl_n{world}.*.log")))[:1]:
+        try:
+            for ln in open(f, errors="replace"):
+                if any(k in ln for k in ("NVLS", "Channel", "AllGather", "Connected all", "comm 0x", "nranks")):
+                    out.append(ln.strip()[:200])
+        except OSError:
+            pass
+    return out[:keep] + (["..."] + out[-keep:] if len(out) > 2 * keep else out[keep:])
+
+
+def multi_gpu_output_check(model, eng, vae_eng, tables, ts, rank, world, dev):
+    """N-GPU vs 1-GPU parity on hardware: image-parallel shards with sliced common noise must reproduce the single-GPU
+    restore image by image (bit for bit: the kernels are batch-invariant per image and deterministic)."""
+    import torch
+
+    from edtr_b200.parallel import ImageGatherer, shard_range, sliced_noise
+
+    per = 2
+    total = per * world
+    g = torch.Generator().manual_seed(4242)
+    c_img = 0.8 * torch.randn(total, 4, 64, 64, generator=g)
+    c_txt = torch.randn(total, 77, 1024, generator=g)
+    x_T = 0.9 * c_img + 0.45 * torch.randn(total, 4, 64, 64, generator=g)
+    lo, hi = shard_range(total, rank, world)
+
+    def restore(a, b):
+        noise = sliced_noise((total, 4, 64, 64), 99, 4, a, b, dev)
+        z = eng.sample(x_T[a:b].to(dev), ts, tables, c_img[a:b].to(dev), c_txt[a:b].to(dev), noise,
+                       control_scales=model.control_scales)
+        return vae_eng.decode(z, model.scale_factor)
+
+    ga = ImageGatherer((per, 3, 512, 512), dev, torch.float32)
+    ga.submit(restore(lo, hi))
+    full = ga.result().clone()
+    res = None
+    if rank == 0:
+        worst, exact = 0.0, True
+        for r in range(world):      # the single-GPU restore, two images at a time (same batch size as the shards)
+            a, b = shard_range(total, r, world)
+            one = restore(a, b)
+            exact = exact and bool(torch.equal(one, full[a:b]))
+            worst = max(worst, float((one - full[a:b]).abs().max()))
+        res = {"images": total, "bit_exact_vs_1gpu": exact, "max_abs_diff": worst}
+    return res
+
+
+def run_c4(args, rank, world, dev):
+    """BASELINE configs[3]: cldm-tiled + vae-tiled restore of ONE 2048x2048 image (latent 256x256; 49 latent tiles of
+    64 with stride 32 per step, utils/common.py:351-427; 16 VAE decoder tiles of 64 + pad 11, utils/tilevae/) with the
+    tiles spread over the ranks (tile_group opt-in): one all-reduce of the blended eps (1 MB) per step, one [B,32,2]
+    all-reduce at each of the decoder's 30 GroupNorms, one of the output image.  Strong scaling: the work is fixed."""
+    import torch
+    import torch.distributed as dist
+
+    from edtr_b200 import lib as elib
+    from edtr_b200.sampler import SpacedSampler
+
+    model = build_model(dev)
+    if world > 1:
+        model.tile_group = True
+        model.tile_group_check = False     # identical inputs by construction below (same seed on every rank)
+    betas = (torch.linspace(0.00085 ** 0.5, 0.0120 ** 0.5, 1000, dtype=torch.float64) ** 2).numpy()
+    sampler = SpacedSampler(betas)
+    Hl = args.c4_latent
+    g = torch.Generator().manual_seed(7)
+    c_img = (0.8 * torch.randn(1, 4, Hl, Hl, generator=g)).to(dev)
+    c_txt = torch.randn(1, 77, 1024, generator=g).to(dev)
+    x_T = (0.9 * c_img.cpu() + 0.45 * torch.randn(1, 4, Hl, Hl, generator=g)).to(dev)
+    cond = {"c_txt": c_txt, "c_img": c_img}
+
+    def step():
+        torch.manual_seed(11)            # identical noise on every rank (SURVEY §8e)
+        z = sampler.manual_sample_with_timesteps(model, dev, x_T, 4, USED_TIMESTEPS, 1, cond, None, 1.0, tiled=True,
+                                                 tile_size=64, tile_stride=32, progress=False)
+        return model.vae_decode(z, tiled=True, tile_size=64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        img = step()
+    barrier()
+    clk = ClockSampler(dev.index)
+    clk.start()
+    n0 = elib.LAUNCHES[0]
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        img = step()
+    e.record()
+    barrier()
+    clocks = clk.stop()
+    ms = s.elapsed_time(e)
+    check = None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # every rank must hold the same assembled image; rank 0 also recomputes it alone (tile_group off)
+        ref = img.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([float(torch.equal(ref, img))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        check = {"identical_on_all_ranks": bool(same.item() == 1.0)}
+        if rank == 0:
+            model.tile_group = None
+            alone = step()
+            mse = torch.mean((alone.double() - img.double()) ** 2) / 4.0     # [-1, 1] -> [0, 1]
+            check["psnr_vs_single_rank_db"] = float(10.0 * torch.log10(1.0 / (mse + 1e-8)))
+    pk = peaks()
+    tiles = 49 if Hl == 256 else None
+    gf = 4 * 49 * 1073.38 + 16 * (86 / 64) ** 2 * 2514.52 if Hl == 256 else None   # SURVEY §8(d) C4 figures
+    if rank == 0:
+        val = args.steps / (ms / 1e3)
+        line = {
+            "metric": "2048x2048 restored images/sec (cldm-tiled 4-step ControlLDM + vae-tiled decode)", "value": val,
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"cldm-tiled + vae-tiled restore of one {Hl * 8}x{Hl * 8} image (latent {Hl}x{Hl}, tile 64 / "
+                                   f"stride 32 -> {tiles} latent tiles per step; VAE decoder tile 64 + pad 11), latent tiles "
+                                   f"spread over {world} rank(s)", "parallelism": f"tile-parallel x{world}",
+                       "l2": "per-step working set exceeds the 126 MB L2; no flush needed"},
+            "gpu_launches": elib.LAUNCHES[0] - n0, "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": (val * gf / 1e3 / world) if gf else None, "peak": pk["tf_sustained"],
+                         "unit": "TFLOP/s", "frac": (val * gf / 1e3 / world / pk["tf_sustained"]) if gf else None,
+                         "traffic": None, "note": "per GPU; algorithmic GF per image = 4 x 49 x 1073.38 + 16 x (86/64)^2 x 2514.52"},
+            "comm": {"per_step": "1 all-reduce of the blended eps (1 MB fp32) per sampling step; per decode 30 x [B,32,2] "
+                                 "GroupNorm statistics + 1 output image", "output_check": check,
+                     "nccl_log": nccl_log_tail(world) if world > 1 else None},
+        }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -514,6 +743,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the stock-PyTorch GPU arm in our line")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"],
+                    help="c2/c3: batch of 512^2 images per GPU (default); c4: one 2048^2 image, tiles over the ranks")
+    ap.add_argument("--c4-latent", type=int, default=256, help="latent side of the c4 image (256 = 2048^2 pixels)")
+    ap.add_argument("--sustain-seconds", type=float, default=5.0,
+                    help="also report throughput over a region of at least this many seconds (0 = off)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

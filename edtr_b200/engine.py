@@ -779,6 +779,9 @@ class CldmEngine:
         return g
 
 
+_CAPTURE_STREAMS: Dict[int, "torch.cuda.Stream"] = {}
+
+
 class _Graph:
     """Warm up twice eagerly (sizes every workspace buffer), then capture into a CUDA graph.  The graph remembers the
     generation of the workspace it was captured on; `valid()` is False once any buffer of that workspace has been
@@ -794,7 +797,13 @@ class _Graph:
         self.generation = ws.generation if ws is not None else 0
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.LAUNCHES[0]
-        with torch.cuda.graph(self.graph):
+        # capture on a stream of the CURRENT device (the engine's, see _on_device): torch's default capture stream is a
+        # process-wide singleton living on whichever device captured first, and entering it would switch devices
+        dev = torch.cuda.current_device()
+        cs = _CAPTURE_STREAMS.get(dev)
+        if cs is None:
+            cs = _CAPTURE_STREAMS[dev] = torch.cuda.Stream(device=dev)
+        with torch.cuda.graph(self.graph, stream=cs):
             fn()
         self.launches = _lib.LAUNCHES[0] - n0  # kernels per replay
         if not self.valid():

@@ -101,6 +101,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 _lock = threading.Lock()
 WORKSPACE_BYTES = 64 << 20      # split-K scratch (fp32 partial tiles) per (device, slot)
 _lib = None
+_torch = None
 _devices = {}                   # device index -> {"workspaces": {slot: tensor}}: per-device init, no global device state
 _tls = threading.local()        # per host thread: workspace slot and CTA-pair share of the launches issued from it
 
@@ -240,9 +241,24 @@ def device_lib(device_index=None) -> ctypes.CDLL:
     """Library handle for compute calls on `device_index` (default: torch's current device): requires a CUDA
     sm_100-class device; kernel attributes are primed once per device.  The caller must have made the device current
     (ops does so with torch.cuda.device(...) around every launch sequence)."""
-    lib = load()
-    import torch
+    global _torch
+    if _torch is None:
+        import torch as _t
 
+        _torch = _t
+    torch = _torch
+    if device_index is None:
+        device_index = torch.cuda.current_device() if torch.cuda.is_initialized() else None
+    if device_index is not None and device_index in _devices:      # hot path: a few lookups per launch
+        if getattr(_tls, "device", None) != device_index:
+            # The library links its own (static) CUDA runtime, whose per-thread current device is independent of
+            # torch's: keep it on the device the launches are meant for (a NULL / default stream handle is valid on
+            # every device, so a mismatch would silently run the kernel on the wrong GPU).
+            check(_lib.edtr_set_device(device_index), "edtr_set_device")
+            LAUNCHES[0] -= 1
+            _tls.device = device_index
+        return _lib
+    lib = load()
     if not torch.cuda.is_available():
         raise RuntimeError("edtr_b200 has no CPU fallback: a CUDA (sm_100a) device is required")
     if device_index is None:
@@ -256,4 +272,8 @@ def device_lib(device_index=None) -> ctypes.CDLL:
                     check(lib.edtr_init(), "edtr_init")
                     LAUNCHES[0] -= 1
                 _devices[device_index] = {"workspaces": {}}
+    if getattr(_tls, "device", None) != device_index:
+        check(lib.edtr_set_device(device_index), "edtr_set_device")
+        LAUNCHES[0] -= 1
+        _tls.device = device_index
     return lib

@@ -215,7 +215,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, rows_per_g
         raise ValueError(f"folded LayerNorm width {ln[1]} != K {K}")
     ep = _epilogue(M, n_out, out, bias=bias, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual,
                    act=act, out_mode=out_mode, hw=hw, alpha=alpha, ln=ln, row_stats=row_stats)
-    L = _lib.device_lib()
+    L = _lib.load()
     if row_stats is not None and row_stats.shape[1] != L.edtr_gemm_row_stats_parts(M, N, K, ctypes.byref(ep)):
         raise ValueError(f"row_stats must hold exactly row_stats_parts(M, N, K) = "
                          f"{L.edtr_gemm_row_stats_parts(M, N, K, ctypes.byref(ep))} pairs per row, got {row_stats.shape[1]}")

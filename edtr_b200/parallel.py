@@ -73,3 +73,47 @@ def gather_images(local: torch.Tensor, counts: List[int]) -> torch.Tensor:
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad.contiguous())
     return torch.cat([b[:n] for b, n in zip(bufs, counts)], 0)
+
+
+class ImageGatherer:
+    """The end-of-batch exchange of the image-parallel mode: ONE ``all_gather_into_tensor`` of the
+    rank's restored images on a side stream, so that the NVLink transfer of batch i runs under the sampling of batch
+    i+1 (the reference's ``accelerator.gather_for_metrics`` blocks the compute stream, main/cls/test_edtr.py:134-138).
+
+    ``dtype``: wire / result dtype (bf16 halves the bytes; a [0, 1] image rounded to bf16 keeps > 55 dB PSNR against
+    the fp32 image, far above any metric's resolution).  ``submit(img)`` returns at once; ``result()`` waits for the
+    last submitted gather and returns the [world * B, C, H, W] tensor (valid until the next ``submit``)."""
+
+    def __init__(self, shape, device, dtype=torch.bfloat16, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device(device)
+        self.dtype = dtype
+        self.stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.local = torch.empty(tuple(shape), dtype=dtype, device=self.device)
+        self.out = torch.empty((self.world * shape[0],) + tuple(shape[1:]), dtype=dtype, device=self.device)
+        self.bytes_per_rank = self.local.numel() * self.local.element_size()
+        self._work = None
+
+    def submit(self, img: torch.Tensor) -> None:
+        if self.world == 1:
+            self.out.copy_(img)
+            return
+        if self.stream is None:           # CPU / gloo (tests)
+            self.local.copy_(img)
+            dist.all_gather_into_tensor(self.out, self.local, group=self.group)
+            return
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)       # the images are ready; also orders after the previous gather's readers
+        with torch.cuda.stream(self.stream):
+            self.local.copy_(img)          # cast to the wire dtype into a buffer the compute stream never touches
+            self._work = dist.all_gather_into_tensor(self.out, self.local, group=self.group, async_op=True)
+        img.record_stream(self.stream)
+
+    def result(self) -> torch.Tensor:
+        if self._work is not None:
+            self._work.wait()
+            self._work = None
+        if self.stream is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return self.out

@@ -408,3 +408,172 @@ def test_engine_on_non_current_device(tiny):
     e0 = eng0.forward(x_T.cuda(), t.cuda(), cond["c_img"].cuda(), cond["c_txt"].cuda())
     assert e1.device.index == 1 and torch.cuda.current_device() == 0
     assert torch.equal(e0.cpu(), e1.cpu())
+
+
+# ----------------------------------------------------------------------------- multi-GPU parity on hardware (C3 / C4)
+def _c3_worker(rank, world, port, q):
+    """Image-parallel shard of a common batch with the slice of the common noise (parallel.sliced_noise)."""
+    import torch.distributed as dist
+
+    from edtr_b200.engine import CldmEngine, VaeDecoderEngine
+    from edtr_b200.parallel import ImageGatherer, shard_range, sliced_noise
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
+    cfg = O.TINY
+    w = O.make_cldm_weights(cfg, seed=0)
+    eng = CldmEngine(cfg["unet"], cfg["controlnet"], w["unet"], w["controlnet"], dev)
+    vd = VaeDecoderEngine(_dd(cfg["vae"]), cfg["vae"]["embed_dim"], w["vae"], dev)
+    total, steps = 2 * world, 4
+    x_T, cond, _ = O.make_inputs(cfg, total, 16, seed=21)
+    s = O.make_schedule(O.make_betas(**cfg["diffusion"]), steps, cfg["used_timesteps"])
+    tabs = {k: torch.from_numpy(v).to(dev) for k, v in s.items() if k != "timesteps"}
+    ts = list(s["timesteps"][::-1])
+
+    def restore(a, b):
+        noise = sliced_noise((total, 4, 16, 16), 5, steps, a, b, dev)
+        z = eng.sample(x_T[a:b].to(dev), ts, tabs, cond["c_img"][a:b].to(dev), cond["c_txt"][a:b].to(dev), noise)
+        return vd.decode(z, cfg["latent_scale_factor"])
+
+    lo, hi = shard_range(total, rank, world)
+    mine = restore(lo, hi)
+    ga = ImageGatherer(tuple(mine.shape), dev, torch.float32)
+    ga.submit(mine)
+    full = ga.result().clone()
+    ok = True
+    if rank == 0:
+        for r in range(world):      # the 1-GPU result of every shard, on this one GPU
+            a, b = shard_range(total, r, world)
+            ok = ok and bool(torch.equal(restore(a, b), full[a:b]))
+        # and against the oracle (fp32 CPU) with the same sliced noise
+        noise = sliced_noise((total, 4, 16, 16), 5, steps, 0, total, "cpu")
+        with torch.no_grad():
+            z_ref, _, _ = O.sample(w, cfg, x_T, cond, noise)
+            img_ref = O.vae_decode(w["vae"], cfg["vae"], z_ref, cfg["latent_scale_factor"])
+        ok = ok and O.psnr((full.cpu() + 1) / 2, (img_ref + 1) / 2) >= PSNR_MIN
+    q.put((rank, bool(ok)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _c4_worker(rank, world, port, q):
+    """Tile-parallel (tile_group opt-in) cldm-tiled sampling + tiled VAE decode of one image vs the same on one rank."""
+    import torch.distributed as dist
+
+    from edtr_b200.cldm import ControlLDM
+    from edtr_b200.sampler import SpacedSampler
+
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=dev)
+    torch.manual_seed(0)
+    net = dict(image_size=32, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[2, 1],
+               num_res_blocks=1, channel_mult=[1, 2], num_head_channels=64, use_spatial_transformer=True,
+               use_linear_in_transformer=True, transformer_depth=1, context_dim=128, legacy=False)
+    cn = dict(net, hint_channels=4)
+    cn.pop("out_channels")
+    vae = dict(embed_dim=4, ddconfig=dict(double_z=True, z_channels=4, resolution=64, in_channels=3, out_ch=3, ch=64,
+                                          ch_mult=[1, 1, 2, 2], num_res_blocks=1, attn_resolutions=[], dropout=0.0))
+    model = ControlLDM(net, vae, None, cn, 0.18215)
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() >= 2 and float(p.abs().max()) == 0.0:
+                p.uniform_(-p[0].numel() ** -0.5, p[0].numel() ** -0.5, generator=gen)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(8)
+    c_img = (0.8 * torch.randn(1, 4, 48, 48, generator=g)).to(dev)
+    cond = {"c_txt": torch.randn(1, 77, 128, generator=g).to(dev), "c_img": c_img}
+    x_T = torch.randn(1, 4, 48, 48, generator=g).to(dev)
+    betas = (torch.linspace(0.00085 ** 0.5, 0.0120 ** 0.5, 1000, dtype=torch.float64) ** 2).numpy()
+    sampler = SpacedSampler(betas)
+
+    def run():
+        torch.manual_seed(31)
+        z = sampler.manual_sample_with_timesteps(model, dev, x_T, 4, [50, 100, 150, 200], 1, cond, None, 1.0, tiled=True,
+                                                 tile_size=16, tile_stride=8, progress=False)
+        return z, model.vae_decode(z, tiled=True, tile_size=16)
+
+    model.tile_group = True
+    z_par, img_par = run()
+    model.tile_group = None
+    z_one, img_one = run()
+    ok = O.max_rel_err(z_par, z_one) < 1e-2 and O.psnr((img_par + 1) / 2, (img_one + 1) / 2) > 45.0
+    # image-parallel calls must NOT communicate: with tile_group unset every rank may hold a different image
+    z_other, _ = sampler.manual_sample_with_timesteps(model, dev, x_T + rank, 4, [50, 100, 150, 200], 1, cond, None, 1.0,
+                                                      tiled=True, tile_size=16, tile_stride=8, progress=False), None
+    q.put((rank, bool(ok), bool(torch.isfinite(z_other).all())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _spawn(worker, world, base_port):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = base_port + os.getpid() % 2000
+    procs = [ctx.Process(target=worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    import queue
+    import time
+
+    res, t0 = [], time.time()
+    while len(res) < world:
+        try:
+            res.append(q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > 300:      # a crashed rank must fail the test at once, not after a long wait
+                for p in procs:
+                    if p.is_alive():
+                        p.kill()
+                raise AssertionError(f"worker exit codes {[p.exitcode for p in procs]} after {time.time() - t0:.0f} s")
+    for p in procs:
+        p.join(60)
+    return sorted(res)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_c3_image_parallel_equals_single_gpu_nccl():
+    """the N-GPU restore (image shards, sliced common noise, NCCL all-gather) is the 1-GPU restore
+    image by image — bit for bit — and matches the oracle."""
+    world = min(torch.cuda.device_count(), 8)
+    res = _spawn(_c3_worker, world, 35500)
+    assert res == [(r, True) for r in range(world)]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_c4_tile_parallel_equals_single_rank_nccl():
+    world = min(torch.cuda.device_count(), 8)
+    res = _spawn(_c4_worker, world, 37500)
+    assert res == [(r, True, True) for r in range(world)]
+
+
+def test_c4_full_size_step_against_oracle(s4):
+    """Config C4 at its real size: one cldm-tiled ControlLDM evaluation of a 2048x2048 image (latent 256x256, 49 tiles of
+    64 with stride 32, all batched into one forward and blended on the device) against the reference's tiling semantics
+    (make_tiled_fn, utils/common.py:367-427) evaluated tile by tile with the fp32 oracle on the GPU."""
+    from edtr_b200.tiling import make_tiled_fn, sliding_windows
+
+    w, (eng, vd) = s4
+    assert len(sliding_windows(256, 256, 64, 32)) == 49
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(1, 4, 256, 256, generator=g).cuda()
+    cond = dict(c_img=(0.8 * torch.randn(1, 4, 256, 256, generator=g)).cuda(), c_txt=torch.randn(1, 77, 1024, generator=g).cuda())
+    t = torch.full((1,), 150, dtype=torch.long, device="cuda")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    wd = {k: {n: v.cuda() for n, v in sd.items()} for k, sd in w.items() if k != "vae"}
+    with torch.no_grad():
+        fn = make_tiled_fn(lambda xt, tt, c, hi, hi_end, wi, wi_end: O.cldm_forward(
+            wd, O.S4, xt, tt, {"c_txt": c["c_txt"], "c_img": c["c_img"][..., hi:hi_end, wi:wi_end]}), 64, 32)
+        ref = fn(x, t, cond)
+    out = eng.forward_tiled(x, t, cond["c_img"], cond["c_txt"], 64, 32)
+    err = O.max_rel_err(out, ref)
+    print("c4 full-size step rel err", err)
+    assert err < 3e-2
+    del wd
+    torch.cuda.empty_cache()
