@@ -291,7 +291,7 @@ def workload_config(B, world):
 
 
 # ------------------------------------------------------------------------------------------- our arm
-def build_model(device):
+def build_model(device, clip_cfg=None):
     """Random-init weights of the s4 architecture through the drop-in classes (zero modules re-randomised)."""
     import torch
 
@@ -301,7 +301,7 @@ def build_model(device):
     cn = dict(S4_NET)
     cn.pop("out_channels")
     cn["hint_channels"] = 4
-    model = ControlLDM(S4_NET, S4_VAE, None, cn, 0.18215)
+    model = ControlLDM(S4_NET, S4_VAE, clip_cfg, cn, 0.18215)
     g = torch.Generator().manual_seed(123)
     with torch.no_grad():
         for p in model.parameters():
@@ -387,6 +387,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     if args.config == "c4":
         return run_c4(args, rank, world, dev)
+    if args.config == "c5":
+        return run_c5(args, rank, world, dev)
     from edtr_b200 import lib as elib
     from edtr_b200 import ops
     from edtr_b200.parallel import ImageGatherer
@@ -643,6 +645,119 @@ def multi_gpu_output_check(model, eng, vae_eng, tables, ts, rank, world, dev):
     return res
 
 
+S4_SWINIR = dict(img_size=64, patch_size=1, in_chans=3, embed_dim=180, depths=[6] * 8, num_heads=[6] * 8, window_size=8,
+                 mlp_ratio=2, sf=8, img_range=1.0, upsampler="nearest+conv", resi_connection="1conv", unshuffle=True,
+                 unshuffle_scale=8)                      # configs/det/voc2012/test/007_edtr-s4.yaml:3-19
+S4_CLIP = dict(embed_dim=1024, vision_cfg=dict(image_size=224, layers=32, width=1280, head_width=80, patch_size=14),
+               text_cfg=dict(context_length=77, vocab_size=49408, width=1024, heads=16, layers=24), layer="penultimate")
+
+
+def run_c5(args, rank, world, dev):
+    """BASELINE configs[4]: the end-to-end EDTR detection pipeline of main/det/test_edtr.py:115-139 on a synthetic
+    VOC-shaped batch, every stage through the drop-in classes: SwinIR pre-restoration -> VAE encode -> c_txt of the
+    constant "" prompt (text tower, cached) -> q_sample(t=200) -> 4-step ControlLDM sampling -> VAE decode -> wavelet
+    colour fix -> Faster R-CNN forward.  The detector is the downstream CONSUMER of the path (out of scope,
+    "run unmodified"): torchvision's fasterrcnn_mobilenet_v3_large_fpn (the network the reference vendors in
+    model/faster_rcnn.py), random-init, 21 classes, stock torchvision CUDA ops.  Image-parallel over the ranks."""
+    import torch
+    import torch.distributed as dist
+    from torchvision.models.detection import fasterrcnn_mobilenet_v3_large_fpn
+
+    from edtr_b200 import lib as elib
+    from edtr_b200.colorfix import wavelet_reconstruction
+    from edtr_b200.diffusion import Diffusion
+    from edtr_b200.sampler import SpacedSampler
+    from edtr_b200.swinir import SwinIR
+
+    B = args.batch
+    torch.manual_seed(0)
+    model = build_model(dev, clip_cfg=S4_CLIP)
+    swinir = SwinIR(**S4_SWINIR).to(dev).eval()
+    detnet = fasterrcnn_mobilenet_v3_large_fpn(weights=None, weights_backbone=None, num_classes=21).to(dev).eval()
+    diffusion = Diffusion(linear_start=0.00085, linear_end=0.0120, timesteps=1000).to(dev)
+    sampler = SpacedSampler(diffusion.betas)
+    g = torch.Generator().manual_seed(5 + rank)
+    lq_h = torch.rand(B, 3, 512, 512, generator=g).pin_memory()
+    prompt = [""] * B
+    t200 = torch.full((B,), 200, dtype=torch.int64, device=dev)
+    stage_ev = {}
+
+    def step(profile=False):
+        def mark(name):
+            if profile:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                stage_ev.setdefault(name, []).append(e)
+
+        with torch.no_grad():
+            lq = lq_h.to(dev, non_blocking=True)
+            mark("start")
+            pre = swinir(lq)
+            mark("swinir")
+            z0 = model.vae_encode(pre * 2 - 1, sample=False)
+            cond = dict(c_txt=model.clip.encode(prompt), c_img=z0)
+            mark("vae_encode+clip")
+            x_T = diffusion.q_sample(x_start=z0, t=t200, noise=torch.randn_like(z0))
+            z = sampler.manual_sample_with_timesteps(model=model, device=dev, x_T=x_T, steps=4,
+                                                     used_timesteps=USED_TIMESTEPS, batch_size=B, cond=cond, uncond=None,
+                                                     cfg_scale=1.0, progress=False)
+            mark("sample")
+            res = wavelet_reconstruction((model.vae_decode(z) + 1) / 2, pre)
+            mark("decode+colorfix")
+            preds = detnet(list(res.clamp(0, 1)))
+            mark("detector")
+            n = torch.stack([p["scores"].numel() * torch.ones((), device=dev) for p in preds]).sum()
+            return float(n.item())          # device -> host read of the step's result (number of detections)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W = max(args.warmup, 3)
+    for _ in range(W):
+        step()
+    barrier()
+    clk = ClockSampler(dev.index)
+    clk.start()
+    n0 = elib.LAUNCHES[0]
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(args.steps):
+        step()
+    e.record()
+    barrier()
+    clocks = clk.stop()
+    ms = s.elapsed_time(e)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    for _ in range(3):
+        step(profile=True)
+    torch.cuda.synchronize()
+    names = ["swinir", "vae_encode+clip", "sample", "decode+colorfix", "detector"]
+    stages = {}
+    for i, nme in enumerate(names):
+        prev = "start" if i == 0 else names[i - 1]
+        stages[nme + "_ms"] = sum(a.elapsed_time(b) for a, b in zip(stage_ev[prev], stage_ev[nme])) / len(stage_ev[nme])
+    if rank == 0:
+        line = {
+            "metric": "512x512 images/sec through the EDTR detection pipeline (SwinIR, VAE encode, 4-step ControlLDM, "
+                      "VAE decode, colour fix, Faster R-CNN forward)", "value": world * B * args.steps / (ms / 1e3),
+            "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (detector fp32)",
+            "data": "synthetic",
+            "config": dict(workload_config(B, world), pipeline="main/det/test_edtr.py:115-139", stages_ms=stages,
+                           detector="torchvision fasterrcnn_mobilenet_v3_large_fpn, random init, unmodified (consumer of the path)",
+                           h2d_bytes_per_step=int(lq_h.numel() * 4)),
+            "gpu_launches": elib.LAUNCHES[0] - n0, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_c4(args, rank, world, dev):
     """BASELINE configs[3]: cldm-tiled + vae-tiled restore of ONE 2048x2048 image (latent 256x256; 49 latent tiles of
     64 with stride 32 per step, utils/common.py:351-427; 16 VAE decoder tiles of 64 + pad 11, utils/tilevae/) with the
@@ -744,8 +859,9 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the stock-PyTorch GPU arm in our line")
-    ap.add_argument("--config", default="c2", choices=["c2", "c4"],
-                    help="c2/c3: batch of 512^2 images per GPU (default); c4: one 2048^2 image, tiles over the ranks")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2/c3: batch of 512^2 images per GPU (default); c4: one 2048^2 image, tiles over the ranks; "
+                         "c5: the end-to-end detection pipeline (SwinIR .. Faster R-CNN)")
     ap.add_argument("--c4-latent", type=int, default=256, help="latent side of the c4 image (256 = 2048^2 pixels)")
     ap.add_argument("--sustain-seconds", type=float, default=5.0,
                     help="also report throughput over a region of at least this many seconds (0 = off)")

@@ -29,9 +29,14 @@ class ControlLDM(nn.Module):
             raise NotImplementedError("tail_block / woSD is not used by any EDTR config or script (SURVEY §8 a4)")
         self.unet = ControlledUnetModel(**unet_cfg)
         self.vae = AutoencoderKL(**vae_cfg)
-        # The OpenCLIP text tower produces an INPUT of the path (c_txt for the constant "" prompt,
-        # model/clip.py:41-63); it is not re-implemented here.  Pass a ready embedder (e.g. the
-        # reference's FrozenOpenCLIPEmbedder) as `clip`, or supply cond["c_txt"] directly.
+        # The OpenCLIP text tower produces an INPUT of the path (c_txt for the constant "" prompt, model/clip.py:41-63):
+        # `self.clip` is built from clip_cfg exactly as the reference does (model/cldm.py:31) — edtr_b200.clip keeps the
+        # constructor, state-dict keys and encode() of FrozenOpenCLIPEmbedder and caches the embedding of the constant
+        # prompt.  clip_cfg=None (synthetic c_txt, as in the benchmarks) leaves it out; a ready embedder may be passed.
+        if clip is None and clip_cfg is not None:
+            from .clip import FrozenOpenCLIPEmbedder
+
+            clip = FrozenOpenCLIPEmbedder(**clip_cfg)
         self.clip = clip
         self.clip_cfg = clip_cfg
         self.controlnet = ControlNet(**controlnet_cfg)
@@ -118,12 +123,12 @@ class ControlLDM(nn.Module):
     refresh_weights = invalidate_engine
 
     def engine(self):
-        from .engine import CldmEngine
+        from .engine import CldmEngine, resolve_ops
 
         dev = next(self.unet.parameters()).device
         ver = (state_version(self.unet), state_version(self.controlnet), dev)
         if self._engine is None or self._engine_version != ver:
-            if dev.type != "cuda":
+            if dev.type != "cuda" and getattr(resolve_ops(), "REQUIRES_CUDA", True):
                 raise RuntimeError("edtr_b200 has no CPU path: move the model to a CUDA device first")
             self._engine = CldmEngine(self.unet.cfg, self.controlnet.cfg, self.unet.state_dict(),
                                       self.controlnet.state_dict(), dev)
@@ -173,8 +178,16 @@ class ControlLDM(nn.Module):
         return eng.decode_tiled(z.float().contiguous(), float(self.scale_factor), int(tile_size), rank=rank,
                                 world=world, reduce_fn=red)
 
+    @torch.no_grad()
     def prepare_condition(self, clean: torch.Tensor, prompt: List[str]) -> Dict[str, torch.Tensor]:
-        raise NotImplementedError("prepare_condition = CLIP text tower + VAE encoder, both inputs of the path")
+        """model/cldm.py:158-164: c_txt from the text tower (cached for the constant prompt), c_img = the posterior
+        mode of the VAE encoder on the [-1, 1] image times the latent scale."""
+        if prompt is None:
+            prompt = [""] * clean.size(0)
+        if self.clip is None:
+            raise RuntimeError("this ControlLDM was built with clip_cfg=None: supply cond['c_txt'] yourself or construct "
+                               "it with the reference's clip_cfg")
+        return dict(c_txt=self.clip.encode(prompt), c_img=self.vae_encode(clean * 2 - 1, sample=False))
 
     @torch.no_grad()
     def forward(self, x_noisy, t, cond, woSD=False):

@@ -4,10 +4,10 @@ from __future__ import annotations
 
 import torch
 
-from . import ops
+from .engine import resolve_ops
 
 
 @torch.no_grad()
 def wavelet_reconstruction(content_feat: torch.Tensor, style_feat: torch.Tensor) -> torch.Tensor:
     """content_feat's high frequencies + style_feat's low frequencies (5-level dilated binomial decomposition)."""
-    return ops.wavelet_reconstruction(content_feat.float(), style_feat.float()).to(content_feat.dtype)
+    return resolve_ops().wavelet_reconstruction(content_feat.float(), style_feat.float()).to(content_feat.dtype)

@@ -39,6 +39,22 @@ def _ceil(a: int, b: int) -> int:
     return (a + b - 1) // b * b
 
 
+# The kernel namespace every engine launches through.  None = ``edtr_b200.ops`` (the C-ABI CUDA kernels, the only
+# execution path of the product).  The CPU test-suite points this at a torch stand-in (tests/fake_ops.py) to check the
+# host-side dataflow of the drop-in classes without a GPU; nothing in the package ever sets it.
+DEFAULT_OPS = None
+
+
+def resolve_ops(ops=None):
+    if ops is not None:
+        return ops
+    if DEFAULT_OPS is not None:
+        return DEFAULT_OPS
+    from . import ops as _ops
+
+    return _ops
+
+
 def _on_device(fn):
     """Engine entry points run with the engine's device current: launches go to that device's current stream and use
     its split-K scratch even when the caller's current device is another GPU (a model moved with .to('cuda:1'))."""
@@ -455,9 +471,7 @@ class CldmEngine:
     """ControlNet + ControlledUnetModel evaluation and the spaced sampler loop."""
 
     def __init__(self, unet_cfg: Dict, controlnet_cfg: Dict, unet_sd, controlnet_sd, device, ops=None):
-        if ops is None:
-            from . import ops as _ops
-            ops = _ops
+        ops = resolve_ops(ops)
         self.ops = ops
         self.device = torch.device(device)
         for cfg in (unet_cfg, controlnet_cfg):
@@ -668,8 +682,9 @@ class CldmEngine:
         st.copy_(t)
         si.copy_(c_img)
         sc.copy_(c_txt)
+        ws.ctx_key = None     # this call projects its own context into the workspace
         run = lambda: self._forward(ws, sx, st, si, eps, scales, c_txt=sc)
-        if use_graph:
+        if use_graph and self.device.type == "cuda":   # (the CPU stand-in of the test-suite has no graphs)
             self._graph(("fwd", B, H, W, c_txt.shape[1], scales), run, ws).replay()
         else:
             run()
@@ -719,7 +734,7 @@ class CldmEngine:
     @_on_device
     def sample(self, x_T, timesteps: Sequence[int], tables: Dict[str, torch.Tensor], c_img, c_txt,
                noise: Sequence[torch.Tensor], control_scales=None, use_graph: bool = True,
-               return_intermediates: bool = False):
+               return_intermediates: bool = False, ctx_key=None):
         """The loop of SpacedSampler.sample / manual_sample_with_timesteps (utils/sampler.py:304-323) with
         cfg_scale == 1: `timesteps` descending model timesteps, `tables` the five fp32 coefficient
         vectors of make_schedule, `noise[i]` the i-th torch.randn_like draw."""
@@ -752,10 +767,14 @@ class CldmEngine:
         ts.copy_(torch.tensor([[int(s)] * B for s in timesteps], dtype=torch.int64))
         idx.copy_(torch.tensor([[n - i - 1] * B for i in range(n)], dtype=torch.int64))
 
+        # K/V cache: valid while nothing else projected a context into this workspace and no buffer moved
+        reuse_ctx = ctx_key is not None and getattr(ws, "ctx_key", None) == (ctx_key, ws.generation, c_txt.shape[1])
+
         def run():
             un = _NetRunner(self.unet, ws, self.ops, "u_", self.fold_ln)
             cn = _NetRunner(self.cnet, ws, self.ops, "c_", self.fold_ln)
-            self._context(ws, un, cn, sc)  # c_txt is step-invariant: project K/V once
+            if not reuse_ctx:
+                self._context(ws, un, cn, sc)  # c_txt is step-invariant: project K/V once
             cur = sx
             for i in range(n):
                 self._forward(ws, cur, ts[i], si, eps, scales, ctx_ready=True, c_txt=sc)
@@ -763,10 +782,11 @@ class CldmEngine:
                                         x_prev=xs[i], pred_x0=x0s[i])
                 cur = xs[i]
 
-        if use_graph:
-            self._graph(("sample", B, H, W, c_txt.shape[1], n, scales), run, ws).replay()
+        if use_graph and self.device.type == "cuda":   # (the CPU stand-in of the test-suite has no graphs)
+            self._graph(("sample", B, H, W, c_txt.shape[1], n, scales, reuse_ctx), run, ws).replay()
         else:
             run()
+        ws.ctx_key = (ctx_key, ws.generation, c_txt.shape[1]) if ctx_key is not None else None
         if return_intermediates:
             return xs[n - 1].clone(), [x0s[i].clone() for i in range(n)], [xs[i].clone() for i in range(n)]
         return xs[n - 1].clone()
@@ -950,9 +970,7 @@ class VaeDecoderEngine(_VaeBlocks):
     (model/cldm.py:136-156, model/vae.py:731-734, :527-560)."""
 
     def __init__(self, ddconfig: Dict, embed_dim: int, sd: Dict[str, torch.Tensor], device, ops=None):
-        if ops is None:
-            from . import ops as _ops
-            ops = _ops
+        ops = resolve_ops(ops)
         self.ops = ops
         self.device = torch.device(device)
         self.dd = ddconfig
@@ -1121,7 +1139,7 @@ class VaeDecoderEngine(_VaeBlocks):
         img = ws.get("out_img", (B, self.dd["out_ch"], H * up, W * up), F32)
         sz.copy_(z)
         run = lambda: self._decode(ws, sz, float(scale_factor), img)
-        if use_graph:
+        if use_graph and self.device.type == "cuda":   # (the CPU stand-in of the test-suite has no graphs)
             gk = (B, H, W, float(scale_factor))
             g = self._graphs.get(gk)
             if g is None or not g.valid():
@@ -1141,9 +1159,7 @@ class VaeEncoderEngine(_VaeBlocks):
     linear with nothing in between, so they are folded into one 3x3 convolution at pack time (fp32)."""
 
     def __init__(self, ddconfig: Dict, embed_dim: int, sd: Dict[str, torch.Tensor], device, ops=None):
-        if ops is None:
-            from . import ops as _ops
-            ops = _ops
+        ops = resolve_ops(ops)
         self.ops = ops
         self.device = torch.device(device)
         self.dd = ddconfig
@@ -1242,7 +1258,7 @@ class VaeEncoderEngine(_VaeBlocks):
         mo = ws.get("out_moments", (B, 2 * self.embed_dim, H // f, W // f), F32)
         si.copy_(image)
         run = lambda: self._encode(ws, si, mo)
-        if use_graph:
+        if use_graph and self.device.type == "cuda":   # (the CPU stand-in of the test-suite has no graphs)
             g = self._graphs.get(key)
             if g is None or not g.valid():
                 g = self._graphs[key] = _Graph(run, ws)

@@ -210,12 +210,12 @@ class AutoencoderKL(nn.Module):
         self._enc_engine_version = None
 
     def _decoder_engine(self):
-        from .engine import VaeDecoderEngine
+        from .engine import VaeDecoderEngine, resolve_ops
 
         ver = state_version(self)
         dev = next(self.parameters()).device
         if self._engine is None or self._engine_version != (ver, dev):
-            if dev.type != "cuda":
+            if dev.type != "cuda" and getattr(resolve_ops(), "REQUIRES_CUDA", True):
                 raise RuntimeError("edtr_b200 has no CPU path: move the model to a CUDA device first")
             self._engine = VaeDecoderEngine(self.ddconfig, self.embed_dim, self.state_dict(), dev)
             self._engine_version = (ver, dev)
@@ -227,12 +227,12 @@ class AutoencoderKL(nn.Module):
         return self._decoder_engine().decode(z.float().contiguous(), 1.0)
 
     def _encoder_engine(self):
-        from .engine import VaeEncoderEngine
+        from .engine import VaeEncoderEngine, resolve_ops
 
         ver = state_version(self)
         dev = next(self.parameters()).device
         if getattr(self, "_enc_engine", None) is None or self._enc_engine_version != (ver, dev):
-            if dev.type != "cuda":
+            if dev.type != "cuda" and getattr(resolve_ops(), "REQUIRES_CUDA", True):
                 raise RuntimeError("edtr_b200 has no CPU path: move the model to a CUDA device first")
             self._enc_engine = VaeEncoderEngine(self.ddconfig, self.embed_dim, self.state_dict(), dev)
             self._enc_engine_version = (ver, dev)

@@ -125,8 +125,9 @@ class SpacedSampler(nn.Module):
     @torch.no_grad()
     def p_sample(self, model, x, t, index, cond, uncond, cfg_scale):
         """utils/sampler.py:184-204 -> (x_prev, pred_x0)."""
-        from . import ops
+        from .engine import resolve_ops
 
+        ops = resolve_ops()
         eps = self.predict_noise(model, x, t, cond, uncond, cfg_scale)
         noise = torch.randn_like(x)
         return ops.sampler_update(x.float().contiguous(), eps.float().contiguous(), noise.float().contiguous(),
@@ -145,10 +146,13 @@ class SpacedSampler(nn.Module):
             x = img.float().contiguous()
             noise = [torch.randn_like(x) for _ in range(total)]
             tables = {k: getattr(self, k) for k in _TABLES}
+            c_txt = cond["c_txt"]
+            ck = getattr(c_txt, "_edtr_ctx_key", None)          # set by edtr_b200.clip.encode (constant-prompt cache)
+            ck = ck[0] if ck is not None and ck[1] == c_txt._version else None
             out = model.engine().sample(x, [int(s) for s in timesteps], tables, cond["c_img"].float().contiguous(),
-                                        cond["c_txt"].float().contiguous(), noise,
+                                        c_txt.float().contiguous(), noise,
                                         control_scales=model.control_scales,
-                                        return_intermediates=return_intermediates)
+                                        return_intermediates=return_intermediates, ctx_key=ck)
             if return_intermediates:
                 return out[0], out[1]
             return out
@@ -161,9 +165,9 @@ class SpacedSampler(nn.Module):
                 index = torch.full_like(ts, fill_value=total - i - 1)
                 eps = model.forward_tiled(img, ts, cond, tile_size, tile_stride)
                 noise = torch.randn_like(img)
-                from . import ops
+                from .engine import resolve_ops
 
-                img, pred_x0 = ops.sampler_update(img.float().contiguous(), eps.float().contiguous(),
+                img, pred_x0 = resolve_ops().sampler_update(img.float().contiguous(), eps.float().contiguous(),
                                                   noise.float().contiguous(), index, self._tables_for_kernel())
                 if return_intermediates:
                     intermediates.append(pred_x0)

@@ -175,9 +175,9 @@ class SwinIREngine:
     """Packed weights + the block walk of SwinIR.forward (model/swinir.py:856-894) on the C-ABI kernels."""
 
     def __init__(self, cfg: Dict, sd: Dict[str, torch.Tensor], device, ops=None):
-        if ops is None:
-            from . import ops as _ops
-            ops = _ops
+        from .engine import resolve_ops
+
+        ops = resolve_ops(ops)
         self.ops, self.cfg, self.device = ops, cfg, torch.device(device)
         c = cfg["embed_dim"]
         self.c, self.cp = c, _ceil(c, 64)

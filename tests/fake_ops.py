@@ -368,3 +368,23 @@ def window_attention(qkv, heads, shift, scale, bias, mask, out):
         o = torch.roll(o, shifts=(shift, shift), dims=(1, 2))
     out[..., :C].copy_(o)
     return out
+
+
+def wavelet_reconstruction(content, style, levels=5):
+    """utils/common.py:99-147 with plain torch ops (dilated 3x3 binomial blur, replicate padding)."""
+    def blur(img, r):
+        c = img.shape[1]
+        k = torch.tensor([[0.0625, 0.125, 0.0625], [0.125, 0.25, 0.125], [0.0625, 0.125, 0.0625]], dtype=img.dtype)
+        k = k[None, None].repeat(c, 1, 1, 1)
+        return F.conv2d(F.pad(img, (r, r, r, r), mode="replicate"), k, groups=c, dilation=r)
+
+    def decompose(img):
+        high = torch.zeros_like(img)
+        for i in range(levels):
+            low = blur(img, 2 ** i)
+            high = high + (img - low)
+            img = low
+        return high, img
+
+    LAUNCHES[0] += 2 * levels
+    return decompose(content)[0] + decompose(style)[1]

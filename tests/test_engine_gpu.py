@@ -577,3 +577,90 @@ def test_c4_full_size_step_against_oracle(s4):
     assert err < 3e-2
     del wd
     torch.cuda.empty_cache()
+
+
+def test_c5_detection_pipeline_against_oracle():
+    """BASELINE configs[4] at toy widths: SwinIR -> vae_encode -> q_sample -> 4-step sample -> vae_decode -> colour fix
+    through the drop-in classes, then the detector forward (torchvision Faster R-CNN, the downstream consumer, run
+    unmodified).  A random-init detector returns no boxes, so parity is judged on the restored image
+    (PSNR vs the oracle pipeline) and on the detector's backbone features computed from both restorations."""
+    torchvision = pytest.importorskip("torchvision")
+    from torchvision.models.detection import fasterrcnn_mobilenet_v3_large_fpn
+
+    from oracle import swinir_oracle as SO
+    from edtr_b200.cldm import ControlLDM
+    from edtr_b200.colorfix import wavelet_reconstruction
+    from edtr_b200.diffusion import Diffusion
+    from edtr_b200.sampler import SpacedSampler
+    from edtr_b200.swinir import SwinIR
+
+    cfg = O.TINY
+    v = O.TINY_VAE8            # /8 VAE: 64x64 images <-> 8x8 latents ... use 128x128 images, 16x16 latents
+
+    def kw(c, controlnet):
+        d = dict(image_size=32, in_channels=c["in_channels"], model_channels=c["model_channels"],
+                 attention_resolutions=list(c["attention_resolutions"]), num_res_blocks=c["num_res_blocks"],
+                 channel_mult=list(c["channel_mult"]), num_head_channels=c["num_head_channels"],
+                 use_spatial_transformer=True, use_linear_in_transformer=True, transformer_depth=1,
+                 context_dim=c["context_dim"], legacy=False, use_checkpoint=True)
+        d["hint_channels" if controlnet else "out_channels"] = c["hint_channels" if controlnet else "out_channels"]
+        return d
+
+    model = ControlLDM(kw(cfg["unet"], False), dict(ddconfig=dict(_dd(v), double_z=True), embed_dim=v["embed_dim"]),
+                       None, kw(cfg["controlnet"], True), cfg["latent_scale_factor"])
+    w = O.make_cldm_weights(cfg, seed=0)
+    vae_sd = O.make_weights(O.vae_decoder_param_shapes(v), seed=2)
+    vae_sd.update(O.make_weights(O.vae_encoder_param_shapes(v), seed=3))
+    model.unet.load_state_dict(w["unet"], strict=True)
+    model.controlnet.load_state_dict(w["controlnet"], strict=True)
+    model.vae.load_state_dict(vae_sd, strict=True)
+    model = model.cuda().eval()
+    scfg = SO.SWINIR_TINY
+    ssd = SO.make_swinir_weights(scfg, seed=4)
+    swinir = SwinIR(img_size=scfg["img_size"], patch_size=1, in_chans=3, embed_dim=scfg["embed_dim"], depths=list(scfg["depths"]),
+                    num_heads=list(scfg["num_heads"]), window_size=8, mlp_ratio=scfg["mlp_ratio"], sf=8, img_range=1.0,
+                    upsampler="nearest+conv", resi_connection="1conv", unshuffle=True, unshuffle_scale=8)
+    swinir.load_state_dict(ssd, strict=False)
+    swinir = swinir.cuda().eval()
+    torch.manual_seed(0)
+    detnet = fasterrcnn_mobilenet_v3_large_fpn(weights=None, weights_backbone=None, num_classes=21).cuda().eval()
+
+    B = 2
+    g = torch.Generator().manual_seed(19)
+    lq = torch.rand(B, 3, 128, 128, generator=g)
+    c_txt = torch.randn(B, 77, cfg["unet"]["context_dim"], generator=g)
+    q_noise = torch.randn(B, 4, 16, 16, generator=g)
+    step_noise = [torch.randn(B, 4, 16, 16, generator=g) for _ in range(4)]
+    betas = O.make_betas(**cfg["diffusion"])
+    with torch.no_grad():       # the oracle pipeline (CPU fp32)
+        pre_ref = SO.swinir_forward(ssd, scfg, lq)
+        z0 = O.vae_encode(vae_sd, v, pre_ref * 2 - 1, cfg["latent_scale_factor"])
+        x_T = O.q_sample(betas, z0, torch.full((B,), 200, dtype=torch.long), q_noise)
+        z_ref, _, _ = O.sample(w, cfg, x_T, dict(c_txt=c_txt, c_img=z0), step_noise)
+        dec_ref = O.vae_decode(vae_sd, v, z_ref, cfg["latent_scale_factor"])
+        res_ref = O.wavelet_reconstruction((dec_ref + 1) / 2, pre_ref)
+
+    dev = torch.device("cuda")
+    diffusion = Diffusion(timesteps=1000, beta_schedule="linear", linear_start=0.00085, linear_end=0.0120).to(dev)
+    sampler = SpacedSampler(diffusion.betas)
+    with torch.no_grad():
+        pre = swinir(lq.to(dev))
+        assert O.psnr(pre.cpu(), pre_ref) >= PSNR_MIN
+        z = model.vae_encode(pre * 2 - 1, sample=False)
+        x = diffusion.q_sample(x_start=z, t=torch.full((B,), 200, dtype=torch.long, device=dev), noise=q_noise.to(dev))
+        draws = [n.to(dev) for n in step_noise]
+        real = torch.randn_like
+        torch.randn_like = lambda t, *a, **k: draws.pop(0)
+        try:
+            zz = sampler.manual_sample_with_timesteps(model, dev, x, 4, list(cfg["used_timesteps"]), B,
+                                                      dict(c_txt=c_txt.to(dev), c_img=z), None, 1.0, progress=False)
+        finally:
+            torch.randn_like = real
+        res = wavelet_reconstruction((model.vae_decode(zz) + 1) / 2, pre)
+        assert O.psnr(res.cpu(), res_ref) >= PSNR_MIN
+        preds = detnet(list(res.clamp(0, 1)))
+        assert len(preds) == B and all(set(p) >= {"boxes", "labels", "scores"} for p in preds)
+        f_new = detnet.backbone(res.clamp(0, 1))
+        f_ref = detnet.backbone(res_ref.clamp(0, 1).to(dev))
+        for k in f_ref:
+            assert O.max_rel_err(f_new[k], f_ref[k]) < 5e-2, k
