@@ -55,6 +55,17 @@ def resolve_ops(ops=None):
     return _ops
 
 
+def stream_key(device) -> int:
+    """Identity of the CUDA stream the caller is on.  Every engine keeps ONE set of static buffers / captured graphs /
+    split-K scratch per (shape, calling stream): calls issued on different streams never share scratch, so two batches
+    may be in flight at the same time (a serving loop alternating two streams overlaps the VAE decode of batch i with
+    the sampling of batch i + 1).  Calls on one stream are ordered by the stream, as usual."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        return 0
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
 def _on_device(fn):
     """Engine entry points run with the engine's device current: launches go to that device's current stream and use
     its split-K scratch even when the caller's current device is another GPU (a model moved with .to('cuda:1'))."""
@@ -142,10 +153,14 @@ class Workspace:
     growing any buffer (a longer step count or text length at the same B, H, W) drops the graphs that could point at
     the freed storage and they are re-captured on their next use."""
 
+    _next_uid = [0]
+
     def __init__(self, device):
         self.device = device
         self._bufs: Dict[Tuple[str, torch.dtype], torch.Tensor] = {}
         self.generation = 0
+        Workspace._next_uid[0] += 1
+        self.uid = Workspace._next_uid[0]      # names this workspace's split-K scratch slots (ops.use_workspace)
 
     def get(self, name: str, shape: Sequence[int], dtype=BF16) -> torch.Tensor:
         n = int(math.prod(shape))
@@ -523,7 +538,7 @@ class CldmEngine:
 
     # ------------------------------------------------------------------ workspace
     def workspace(self, B: int, H: int, W: int) -> Workspace:
-        key = (B, H, W)
+        key = (B, H, W, stream_key(self.device))
         ws = self._ws.get(key)
         if ws is None:
             ws = Workspace(self.device)
@@ -542,6 +557,7 @@ class CldmEngine:
         """x, c_img: fp32 NCHW; t int64 [B]; eps_out fp32 [B, out_c, H, W] (written)."""
         ops = self.ops
         B, _, H, W = x.shape
+        ops.use_workspace((ws.uid, 0))
         un = _NetRunner(self.unet, ws, ops, "u_", self.fold_ln)
         cn = _NetRunner(self.cnet, ws, ops, "c_", self.fold_ln)
         if ctx_ready:
@@ -596,9 +612,9 @@ class CldmEngine:
             ops.set_gemm_max_clusters(share)
         if overlap:
             with torch.cuda.stream(side):
-                ops.use_workspace(1)
+                ops.use_workspace((ws.uid, 1))
                 run_controlnet()
-            ops.use_workspace(0)
+            ops.use_workspace((ws.uid, 0))
 
         # UNet encoder + middle (model/controlnet.py:25-28)
         h = xu
@@ -685,7 +701,7 @@ class CldmEngine:
         ws.ctx_key = None     # this call projects its own context into the workspace
         run = lambda: self._forward(ws, sx, st, si, eps, scales, c_txt=sc)
         if use_graph and self.device.type == "cuda":   # (the CPU stand-in of the test-suite has no graphs)
-            self._graph(("fwd", B, H, W, c_txt.shape[1], scales), run, ws).replay()
+            self._graph(("fwd", B, H, W, c_txt.shape[1], scales, stream_key(self.device)), run, ws).replay()
         else:
             run()
         return eps.clone()
@@ -771,6 +787,7 @@ class CldmEngine:
         reuse_ctx = ctx_key is not None and getattr(ws, "ctx_key", None) == (ctx_key, ws.generation, c_txt.shape[1])
 
         def run():
+            self.ops.use_workspace((ws.uid, 0))
             un = _NetRunner(self.unet, ws, self.ops, "u_", self.fold_ln)
             cn = _NetRunner(self.cnet, ws, self.ops, "c_", self.fold_ln)
             if not reuse_ctx:
@@ -783,7 +800,7 @@ class CldmEngine:
                 cur = xs[i]
 
         if use_graph and self.device.type == "cuda":   # (the CPU stand-in of the test-suite has no graphs)
-            self._graph(("sample", B, H, W, c_txt.shape[1], n, scales, reuse_ctx), run, ws).replay()
+            self._graph(("sample", B, H, W, c_txt.shape[1], n, scales, reuse_ctx, stream_key(self.device)), run, ws).replay()
         else:
             run()
         ws.ctx_key = (ctx_key, ws.generation, c_txt.shape[1]) if ctx_key is not None else None
@@ -1100,9 +1117,11 @@ class VaeDecoderEngine(_VaeBlocks):
         if max(H, W) <= pad * 2 + tile_size:      # "tiny and unnecessary to tile" (utils/tilevae/tilevae.py:319-321)
             return self.decode(z, scale_factor, use_graph=use_graph)
         in_boxes, out_boxes = vae_split_tiles(H, W, tile_size, pad, True)
-        ws = self._ws.get(("tiled", B))
+        tkey = ("tiled", B, stream_key(self.device))
+        ws = self._ws.get(tkey)
         if ws is None:
-            ws = self._ws[("tiled", B)] = Workspace(self.device)
+            ws = self._ws[tkey] = Workspace(self.device)
+        self.ops.use_workspace((ws.uid, 0))
         zin = torch.zeros((B, H, W, 64), dtype=BF16, device=z.device)
         ops.pointwise_nchw_to_nhwc(z.contiguous().float(), w["post_quant_conv.weight"], w["post_quant_conv.bias"],
                                    1.0 / scale_factor, zin, 0)
@@ -1131,16 +1150,17 @@ class VaeDecoderEngine(_VaeBlocks):
             raise RuntimeError("edtr_b200 has no CPU path: z must be a CUDA tensor")
         B, _, H, W = z.shape
         up = 2 ** (len(self.levels) - 1)
-        key = (B, H, W)
+        key = (B, H, W, stream_key(self.device))
         ws = self._ws.get(key)
         if ws is None:
             ws = self._ws[key] = Workspace(self.device)
+        self.ops.use_workspace((ws.uid, 0))
         sz = ws.get("in_z", tuple(z.shape), F32)
         img = ws.get("out_img", (B, self.dd["out_ch"], H * up, W * up), F32)
         sz.copy_(z)
         run = lambda: self._decode(ws, sz, float(scale_factor), img)
         if use_graph and self.device.type == "cuda":   # (the CPU stand-in of the test-suite has no graphs)
-            gk = (B, H, W, float(scale_factor))
+            gk = key + (float(scale_factor),)
             g = self._graphs.get(gk)
             if g is None or not g.valid():
                 g = self._graphs[gk] = _Graph(run, ws)
@@ -1250,10 +1270,11 @@ class VaeEncoderEngine(_VaeBlocks):
         f = 2 ** (len(self.levels) - 1)
         if H % f or W % f:
             raise ValueError(f"image size {H}x{W} must be a multiple of {f}")
-        key = (B, H, W)
+        key = (B, H, W, stream_key(self.device))
         ws = self._ws.get(key)
         if ws is None:
             ws = self._ws[key] = Workspace(self.device)
+        self.ops.use_workspace((ws.uid, 0))
         si = ws.get("in_img", tuple(image.shape), F32)
         mo = ws.get("out_moments", (B, 2 * self.embed_dim, H // f, W // f), F32)
         si.copy_(image)
@@ -1316,9 +1337,11 @@ class VaeEncoderEngine(_VaeBlocks):
         if max(H, W) <= pad * 2 + tile_size:
             return self.encode(image, use_graph=use_graph)
         in_boxes, out_boxes = vae_split_tiles(H, W, tile_size, pad, False)
-        ws = self._ws.get(("tiled", B))
+        tkey = ("tiled", B, stream_key(self.device))
+        ws = self._ws.get(tkey)
         if ws is None:
-            ws = self._ws[("tiled", B)] = Workspace(self.device)
+            ws = self._ws[tkey] = Workspace(self.device)
+        self.ops.use_workspace((ws.uid, 0))
         xin = torch.zeros((B, H, W, 64), dtype=BF16, device=image.device)
         self.ops.nchw_to_nhwc(image.contiguous().float(), xin, 0)
         mine = list(range(rank, len(in_boxes), world))

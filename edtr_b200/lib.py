@@ -192,11 +192,13 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
         return _lib
 
 
-def use_workspace(index: int) -> None:
-    """Which split-K scratch slot launches issued by THIS host thread use from now on (one slot per stream that may
-    run concurrently: 0 main stream, 1 the ControlNet side stream).  Python-side selection only: the buffer is passed
-    to the library with every call (EdtrEpilogue.workspace); the library itself keeps no state."""
-    _tls.slot = int(index)
+def use_workspace(index) -> None:
+    """Which split-K scratch slot launches issued by THIS host thread use from now on.  A slot is any hashable name; the
+    engines use (workspace uid, 0 | 1): one slot per set of static buffers and per branch that may run concurrently
+    (0 main stream, 1 the ControlNet side stream), so batches in flight on different streams never share scratch.
+    Python-side selection only: the buffer is passed to the library with every call (EdtrEpilogue.workspace); the
+    library itself keeps no state."""
+    _tls.slot = index
 
 
 def set_gemm_max_clusters(n: int) -> None:

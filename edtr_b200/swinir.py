@@ -300,7 +300,13 @@ class SwinIREngine:
             # the reference reflect-pads to a multiple of 8 pixels and then fails in window_partition unless the token
             # grid is a multiple of the window (model/swinir.py:834-839, :46): only multiples of 64 pixels ever work
             raise ValueError(f"H and W must be multiples of {sf * wsz} (got {H}x{W})")
-        ws = self._ws.setdefault((B, H, W), Workspace(self.device))
+        from .engine import stream_key
+
+        skey = (B, H, W, stream_key(self.device))
+        ws = self._ws.get(skey)
+        if ws is None:
+            ws = self._ws[skey] = Workspace(self.device)
+        ops.use_workspace((ws.uid, 0))
         sx = ws.get("in_x", (B, cfg["in_chans"], H, W), F32)
         out = ws.get("out_img", (B, cfg["in_chans"], H, W), F32)
         sx.copy_(x)
@@ -310,9 +316,9 @@ class SwinIREngine:
             self._mask(h, w_, wsj, shift)
         run = lambda: self._forward(ws, sx, out)
         if use_graph and x.is_cuda:
-            g = self._graphs.get((B, H, W))
+            g = self._graphs.get(skey)
             if g is None or not g.valid():
-                g = self._graphs[(B, H, W)] = _Graph(run, ws)
+                g = self._graphs[skey] = _Graph(run, ws)
             g.replay()
         else:
             run()
