@@ -99,6 +99,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 int prime_gemm_attributes();
 int prime_attention_attributes();
 int prime_gemm2_attributes();
+int prime_norm_attributes();
 size_t gemm2_workspace_size(int M, int N, int K);
 
 }  // namespace edtr
@@ -140,6 +141,8 @@ extern "C" int edtr_init(void) {
   rc = edtr::prime_attention_attributes();
   if (rc) return rc;
   rc = edtr::prime_gemm2_attributes();
+  if (rc) return rc;
+  rc = edtr::prime_norm_attributes();
   if (rc) return rc;
   if (edtr::get_encode_fn() == nullptr) return EDTR_ERR_CUDA;
   return EDTR_OK;

@@ -23,6 +23,29 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
+// SiLU for the normalisation kernels: y * sigmoid(y) with sigmoid(y) = 0.5 + 0.5 tanh(y / 2) — ONE MUFU op (tanh.approx,
+// relative error 2^-11, far below the bf16 resolution of the stored result) instead of the two (ex2 + rcp) of the exact
+// form.  The GroupNorm + SiLU launches are bound by instruction issue / MUFU, not by memory (profiles/r02q).
+__device__ __forceinline__ float silu_tanh(float y) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  return y * fmaf(0.5f, t, 0.5f);
+}
+// y = x * sc + sf (+ SiLU) on one 16-byte vector of 8 channels.
+__device__ __forceinline__ uint4 norm8(const uint4& u, const float (&sc)[8], const float (&sf)[8], bool silu) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  float f[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = fmaf(f[i], sc[i], sf[i]);
+  if (silu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = silu_tanh(f[i]);
+  }
+  uint4 o;
+  o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+  return o;
+}
+
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 u;
   u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
@@ -57,22 +80,32 @@ groupnorm_stats_kernel(const __nv_bfloat16* __restrict__ X, int ldx, int HW, int
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
   if (q < ppar) {
-    const __nv_bfloat16* base = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
-    for (int pidx = p0 + q; pidx < p1; pidx += U * ppar) {
+    const size_t xstep = static_cast<size_t>(ppar) * ldx;
+    const __nv_bfloat16* xp = X + (static_cast<size_t>(b) * HW + p0 + q) * ldx + c0 + v * 8;
+    int n = p1 - p0 - q;
+    n = n > 0 ? (n + ppar - 1) / ppar : 0;
+    auto acc8 = [&](const uint4& u) {
+      const float2 a = unpack_bf16(u.x), b2 = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      const float f[8] = {a.x, a.y, b2.x, b2.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] = fmaf(f[i], f[i], ss[i]); }
+    };
+    for (; n >= U; n -= U) {            // U independent 16-byte loads in flight, no bounds predicates
       uint4 u[U];
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        u[k] = make_uint4(0u, 0u, 0u, 0u);   // bf16 zeros add nothing to either sum
-        if (pidx + k * ppar < p1)
-          u[k] = __ldg(reinterpret_cast<const uint4*>(base + static_cast<size_t>(pidx + k * ppar) * ldx));
-      }
+      for (int k = 0; k < U; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xp + k * xstep));
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        float f[8];
-        unpack8(u[k], f);
+      for (int k = 0; k < U; ++k) acc8(u[k]);
+      xp += U * xstep;
+    }
+    if (n > 0) {                        // remainder: one more batch of (predicated) loads, not n round trips
+      uint4 u[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
-      }
+      for (int k = 0; k < U; ++k)
+        if (k < n) u[k] = __ldg(reinterpret_cast<const uint4*>(xp + k * xstep));
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+        if (k < n) acc8(u[k]);
     }
     float* row = sh + static_cast<size_t>(q) * 2 * cslab;
 #pragma unroll
@@ -194,27 +227,31 @@ groupnorm_apply_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
     }
     const int p0 = blockIdx.x * rows_per_cta;
     const int p1 = min(HW, p0 + rows_per_cta);
-    const __nv_bfloat16* xb = X + (static_cast<size_t>(b) * HW) * ldx + c0 + v * 8;
-    __nv_bfloat16* yb = Y + (static_cast<size_t>(b) * HW) * ldy + c0 + v * 8;
-    for (int pidx = p0 + q; pidx < p1; pidx += U * ppar) {
+    // pointer-stepped loop (no per-vector index arithmetic or bounds predicates in the main body): this thread owns
+    // vectors p0 + q, p0 + q + ppar, ... of its channel column
+    const size_t xstep = static_cast<size_t>(ppar) * ldx, ystep = static_cast<size_t>(ppar) * ldy;
+    const __nv_bfloat16* xp = X + (static_cast<size_t>(b) * HW + p0 + q) * ldx + c0 + v * 8;
+    __nv_bfloat16* yp = Y + (static_cast<size_t>(b) * HW + p0 + q) * ldy + c0 + v * 8;
+    int n = p1 - p0 - q;
+    n = n > 0 ? (n + ppar - 1) / ppar : 0;
+    const bool do_silu = silu != 0;
+    for (; n >= U; n -= U) {
+      uint4 u[U];
+#pragma unroll
+      for (int k = 0; k < U; ++k) u[k] = __ldg(reinterpret_cast<const uint4*>(xp + k * xstep));
+#pragma unroll
+      for (int k = 0; k < U; ++k) *reinterpret_cast<uint4*>(yp + k * ystep) = norm8(u[k], sc, sf, do_silu);
+      xp += U * xstep;
+      yp += U * ystep;
+    }
+    if (n > 0) {                        // remainder: one more batch of (predicated) loads, not n round trips
       uint4 u[U];
 #pragma unroll
       for (int k = 0; k < U; ++k)
-        if (pidx + k * ppar < p1)
-          u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+        if (k < n) u[k] = __ldg(reinterpret_cast<const uint4*>(xp + k * xstep));
 #pragma unroll
-      for (int k = 0; k < U; ++k) {
-        if (pidx + k * ppar < p1) {
-          float f[8];
-          unpack8(u[k], f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float y = f[i] * sc[i] + sf[i];
-            f[i] = silu ? silu_f(y) : y;
-          }
-          *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
-        }
-      }
+      for (int k = 0; k < U; ++k)
+        if (k < n) *reinterpret_cast<uint4*>(yp + k * ystep) = norm8(u[k], sc, sf, do_silu);
     }
   }
   pdl_launch_dependents();
@@ -357,8 +394,9 @@ __device__ __forceinline__ float ld_dsmem_f32(uint32_t cluster_addr) {
 __global__ void __launch_bounds__(512)
 groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat16* __restrict__ Y, int ldy,
                        int HW, int C, int groups, int cs, const float* __restrict__ gamma,
-                       const float* __restrict__ beta, float eps, int silu) {
-  extern __shared__ float sh[];            // [ppar][2][C] per-thread-row channel sums
+                       const float* __restrict__ beta, float eps, int silu, int smem_rows) {
+  extern __shared__ __align__(16) float sh[];   // [ppar][2][C] per-thread-row channel sums, then (smem_rows > 0) the CTA's
+                                                // slice of the image, [smem_rows][C] bf16, kept between the two passes
   __shared__ float part[128];              // this CTA's per-group (sum, sumsq)
   __shared__ float g_mean[64], g_rstd[64];
   const int vpr = C >> 3;
@@ -381,6 +419,10 @@ groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
   // passes, so the tensor is read once; larger slices fall back to re-reading their rows (L2 hits) in pass 2.
   constexpr int kIt = 2;
   const bool in_regs = rows <= kIt * 8 * ppar;
+  // Mid-size tensors (1 - 2.75 MB per image: the 64x64 and 32x32 levels): the slice does not fit the registers but it
+  // fits shared memory (<= 168 KB of the 227 KB), so it is still read from L2 exactly once.
+  const bool in_smem = !in_regs && smem_rows >= p1 - p0;
+  uint4* sdata = reinterpret_cast<uint4*>(sh + static_cast<size_t>(ppar) * 2 * C);
   uint4 keep[kIt][8];
   {
     float s[8], ss[8];
@@ -421,6 +463,7 @@ groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
           unpack8(u[k], f);
 #pragma unroll
           for (int i = 0; i < 8; ++i) { s[i] += f[i]; ss[i] += f[i] * f[i]; }
+          if (in_smem && pidx + k * ppar < p1) sdata[static_cast<size_t>(pidx + k * ppar - p0) * vpr + v] = u[k];
         }
       }
     }
@@ -474,22 +517,15 @@ groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
     }
   }
   __nv_bfloat16* yb = Y + (static_cast<size_t>(b) * HW) * ldy + v * 8;
+  const bool do_silu = silu != 0;
   if (in_regs) {
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
       const int pidx = p0 + q + it * 8 * ppar;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (pidx + k * ppar < p1) {
-          float f[8];
-          unpack8(keep[it][k], f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float y = f[i] * sc[i] + sf[i];
-            f[i] = silu ? silu_f(y) : y;
-          }
-          *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
-        }
+        if (pidx + k * ppar < p1)
+          *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = norm8(keep[it][k], sc, sf, do_silu);
       }
     }
   } else {
@@ -498,19 +534,12 @@ groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         if (pidx + k * ppar < p1)
-          u[k] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
+          u[k] = in_smem ? sdata[static_cast<size_t>(pidx + k * ppar - p0) * vpr + v]   // written by this same thread
+                         : __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(pidx + k * ppar) * ldx));
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (pidx + k * ppar < p1) {
-          float f[8];
-          unpack8(u[k], f);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float y = f[i] * sc[i] + sf[i];
-            f[i] = silu ? silu_f(y) : y;
-          }
-          *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = pack8(f);
-        }
+        if (pidx + k * ppar < p1)
+          *reinterpret_cast<uint4*>(yb + static_cast<size_t>(pidx + k * ppar) * ldy) = norm8(u[k], sc, sf, do_silu);
       }
     }
   }
@@ -522,9 +551,11 @@ groupnorm_fused_kernel(const __nv_bfloat16* __restrict__ X, int ldx, __nv_bfloat
 struct GnFusedGeom {
   int cs, threads;
   size_t smem;
+  int smem_rows;   // rows of the image slice kept in shared memory between the passes (0: registers / re-read)
 };
+constexpr size_t kGnFusedSmemMax = 220 * 1024;
 static GnFusedGeom gn_fused_geom(int B, int HW, int C, int groups) {
-  GnFusedGeom g{0, 0, 0};
+  GnFusedGeom g{0, 0, 0, 0};
   if (C % 8 != 0 || groups <= 0 || groups > 64 || C % groups != 0) return g;
   const int vpr = C / 8;
   if (vpr > 512) return g;
@@ -532,7 +563,16 @@ static GnFusedGeom gn_fused_geom(int B, int HW, int C, int groups) {
   // Small L2-resident tensors only: measured on B200 the single launch wins up to ~1 MB per image (8x8 / 16x16
   // levels); above that the 8 CTAs per image cannot pull enough bandwidth and the two-pass kernels are faster.
   // (16-CTA non-portable clusters for the 1 - 2.75 MB tensors were measured too: no gain, profiles/r01g.)
-  const size_t limit = 1u << 20;
+  static const bool smem_path = [] {
+    // Opt-in experiment (EDTR_GN_SMEM=1): 16-CTA clusters with the image slice resident in shared memory for the
+    // 1 - 2.75 MB tensors.  Measured on B200 (profiles/r02p_groupnorm_smem_cluster.txt): 41 us vs 33 us for the two
+    // launches of the two-pass kernels at 8 x 64 x 64 x 320 — eight 16-CTA clusters do not fill the GPU.  Off.
+    const char* e = getenv("EDTR_GN_SMEM");
+    return e != nullptr && e[0] == '1';
+  }();
+  // above 1 MB per image the slice of a CTA no longer fits the registers: a 16-CTA (non-portable) cluster per image
+  // keeps it in shared memory instead, up to 2.75 MB per image (16 x 168 KB)
+  const size_t limit = smem_path ? (2816u << 10) : (1u << 20);
   if (bytes_per_image > limit || static_cast<size_t>(B) * bytes_per_image > (64u << 20)) return g;
   const int ppar = 512 / vpr;
   g.threads = vpr * ppar;
@@ -544,6 +584,16 @@ static GnFusedGeom gn_fused_geom(int B, int HW, int C, int groups) {
   }
   g.smem = static_cast<size_t>(g.threads / vpr) * 2 * C * sizeof(float);
   g.cs = HW >= 64 ? 8 : (HW >= 8 ? 2 : 1);
+  if (bytes_per_image > (1u << 20)) {
+    const int pp = g.threads / vpr;
+    for (int cs = 8; cs <= 16; cs *= 2) {
+      const int rows = (HW + cs - 1) / cs;
+      if (rows <= 2 * 8 * pp) { g.cs = cs; break; }                       // fits the registers after all
+      const size_t need = g.smem + static_cast<size_t>(rows) * C * 2;
+      if (need <= kGnFusedSmemMax) { g.cs = cs; g.smem = need; g.smem_rows = rows; break; }
+      if (cs == 16) { g.cs = 0; return g; }
+    }
+  }
   return g;
 }
 
@@ -587,6 +637,17 @@ static GnGeom gn_geom(int B, int HW, int C) {
   g.rows = rows;
   g.nchunks = (HW + rows - 1) / rows;
   return g;
+}
+
+int prime_norm_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(groupnorm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kGnFusedSmemMax));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(groupnorm_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (e != cudaSuccess) {
+    set_error("cudaFuncSetAttribute(groupnorm_fused): %s", cudaGetErrorString(e));
+    return EDTR_ERR_CUDA;
+  }
+  return EDTR_OK;
 }
 
 }  // namespace edtr
@@ -715,7 +776,8 @@ extern "C" int edtr_groupnorm_fused(const void* X, int ldx, void* Y, int ldy, in
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
   (void)cudaLaunchKernelEx(&cfg, groupnorm_fused_kernel, reinterpret_cast<const __nv_bfloat16*>(X), ldx,
-                           reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups, g.cs, gamma, beta, eps, silu);
+                           reinterpret_cast<__nv_bfloat16*>(Y), ldy, HW, C, groups, g.cs, gamma, beta, eps, silu,
+                           g.smem_rows);
   return check_launch("groupnorm_fused_kernel");
 }
 
