@@ -750,7 +750,7 @@ class CldmEngine:
     @_on_device
     def sample(self, x_T, timesteps: Sequence[int], tables: Dict[str, torch.Tensor], c_img, c_txt,
                noise: Sequence[torch.Tensor], control_scales=None, use_graph: bool = True,
-               return_intermediates: bool = False, ctx_key=None):
+               return_intermediates: bool = False, ctx_key=None, stage_inputs: bool = True):
         """The loop of SpacedSampler.sample / manual_sample_with_timesteps (utils/sampler.py:304-323) with
         cfg_scale == 1: `timesteps` descending model timesteps, `tables` the five fp32 coefficient
         vectors of make_schedule, `noise[i]` the i-th torch.randn_like draw."""
@@ -771,17 +771,18 @@ class CldmEngine:
         xs = ws.get("out_xs", (n,) + tuple(x_T.shape), F32)
         x0s = ws.get("out_x0s", (n,) + tuple(x_T.shape), F32)
         eps = ws.get("out_eps", (B, self.out_c, H, W), F32)
-        sx.copy_(x_T)
-        si.copy_(c_img)
-        sc.copy_(c_txt)
-        for i in range(n):
-            sn[i].copy_(noise[i])
-        names = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
-                 "posterior_mean_coef2", "posterior_variance")
-        for r, k in enumerate(names):
-            tabs[r].copy_(tables[k])
-        ts.copy_(torch.tensor([[int(s)] * B for s in timesteps], dtype=torch.int64))
-        idx.copy_(torch.tensor([[n - i - 1] * B for i in range(n)], dtype=torch.int64))
+        if stage_inputs:
+            sx.copy_(x_T)
+            si.copy_(c_img)
+            sc.copy_(c_txt)
+            for i in range(n):
+                sn[i].copy_(noise[i])
+            names = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+                     "posterior_mean_coef2", "posterior_variance")
+            for r, k in enumerate(names):
+                tabs[r].copy_(tables[k])
+            ts.copy_(torch.tensor([[int(s)] * B for s in timesteps], dtype=torch.int64))
+            idx.copy_(torch.tensor([[n - i - 1] * B for i in range(n)], dtype=torch.int64))
 
         # K/V cache: valid while nothing else projected a context into this workspace and no buffer moved
         reuse_ctx = ctx_key is not None and getattr(ws, "ctx_key", None) == (ctx_key, ws.generation, c_txt.shape[1])
