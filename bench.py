@@ -410,12 +410,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("EDTR_NCCL_LOG", "0") == "1":     # keep the algorithm / channel lines of the communicator
-            # (opt-in: NCCL_DEBUG prints its version banner on stdout, which must carry the one JSON line only)
-            os.environ.setdefault("NCCL_DEBUG", "INFO")
-            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
-            os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", f"nccl_n{world}.%h.%p.log"))
-            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         dist.init_process_group("nccl", device_id=dev)
     if args.config == "c4":
         return run_c4(args, rank, world, dev)
@@ -964,6 +958,14 @@ def main():
     ap.add_argument("--sustain-seconds", type=float, default=5.0,
                     help="also report throughput over a region of at least this many seconds (0 = off)")
     args = ap.parse_args()
+    if os.environ.get("EDTR_NCCL_LOG", "0") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # keep the algorithm / channel lines of the communicator (opt-in: NCCL_DEBUG prints its version banner on stdout,
+        # which must carry the one JSON line only).  Must be in the environment before torch loads NCCL.
+        world = int(os.environ["WORLD_SIZE"])
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
+        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", f"nccl_n{world}.%h.%p.log"))
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "reference-gpu":
