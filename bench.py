@@ -569,6 +569,13 @@ def run_ours(args):
     img_dev = torch.rand(B, 3, 512, 512, device=dev)
     ms_enc, _, _ = timed(lambda j: model.vae_encode(img_dev * 2 - 1, sample=False), 5, 3)
     ms_fix, _, _ = timed(lambda j: wavelet_reconstruction(img_dev, img_dev), 5, 3)
+    swinir_ms = None
+    if world == 1:        # the pre-restoration network in front of the encoder (random init, s4 config)
+        from edtr_b200.swinir import SwinIR
+        swin = SwinIR(**S4_SWINIR).to(dev).eval()
+        ms_sw, _, _ = timed(lambda j: swin(img_dev), 5, 3)
+        swinir_ms = ms_sw / 5
+        del swin
 
     # kernel families, measured live and in situ (FamilyGraph): the restore captured with only that family's launches
     pk = peaks()
@@ -679,6 +686,7 @@ def run_ours(args):
         line["config"]["unet_step_ms"] = unet_step_ms
         line["config"]["vae_encode_ms"] = ms_enc / 5
         line["config"]["colorfix_ms"] = ms_fix / 5
+        line["config"]["swinir_ms"] = swinir_ms
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
