@@ -354,6 +354,163 @@ attention_ts_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 
+// ------------------------------------------------------------------------------------------------------------------
+// Cross-attention against a short key sequence (the 77 OpenCLIP tokens, model/attention.py:176-203 with context=c_txt).
+// The whole K / V of a (sample, head) is 2 x 77 x 64 bf16 = 20 KB, the arithmetic (3.2 GFLOP at 8 x 64 x 64 tokens) is
+// far below the size where the TMA / tcgen05 / TMEM pipeline of attention_ts_kernel pays (that kernel spends ~30 us,
+// one CTA set-up per 128 query rows for two key tiles), and the launch is bound by streaming Q in and O out.  So: one
+// CTA keeps K (row-major) and V (row-major, read through ldmatrix.trans) of its (sample, head) in shared memory and
+// walks `chunks` consecutive 128-row query chunks; each of the 8 warps owns 16 query rows per chunk, takes its Q
+// fragments straight from global memory (32 contiguous bytes per lane: the k index of Q K^T is permuted identically
+// on both operands so that a lane's 16 columns are its own k slots), S = Q K^T and O = P V run on mma.sync m16n8k16,
+// the soft-max lives in registers (a row = one quad), no online rescaling (all keys at once).
+constexpr int kXK = 80;            // keys held (>= Lk, multiple of 16)
+constexpr int kXKPitch = 68;       // K rows: 136 B pitch -> the 8-byte fragment loads of a half-warp hit 16 distinct bank pairs
+constexpr int kXVPitch = 72;       // V rows: 144 B pitch -> conflict-free ldmatrix (rows 16-byte aligned)
+constexpr int kXWarps = 8;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+__global__ void __launch_bounds__(kXWarps * 32, 2)
+cross_attention_small_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const __nv_bfloat16* __restrict__ K, int ldk,
+                             const __nv_bfloat16* __restrict__ V, int ldv, __nv_bfloat16* __restrict__ O, int ldo,
+                             int Lq, int Lk, int chunks, float scale_log2) {
+  __shared__ __align__(16) __nv_bfloat16 sK[kXK * kXKPitch];
+  __shared__ __align__(16) __nv_bfloat16 sV[kXK * kXVPitch];
+  const int head = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  pdl_wait();
+  {
+    const __nv_bfloat16* kb = K + static_cast<size_t>(b) * Lk * ldk + head * kD;
+    const __nv_bfloat16* vb = V + static_cast<size_t>(b) * Lk * ldv + head * kD;
+    for (int i = tid; i < kXK * 8; i += kXWarps * 32) {     // 80 rows x 8 vectors of 8 bf16
+      const int r = i >> 3, c = (i & 7) * 8;
+      uint4 uk = make_uint4(0u, 0u, 0u, 0u), uv = uk;        // keys >= Lk: zero rows (their probabilities are zero too)
+      if (r < Lk) {
+        uk = __ldg(reinterpret_cast<const uint4*>(kb + static_cast<size_t>(r) * ldk + c));
+        uv = __ldg(reinterpret_cast<const uint4*>(vb + static_cast<size_t>(r) * ldv + c));
+      }
+      uint2* dk = reinterpret_cast<uint2*>(&sK[r * kXKPitch + c]);   // 136 B pitch: 8-byte aligned only
+      dk[0] = make_uint2(uk.x, uk.y);
+      dk[1] = make_uint2(uk.z, uk.w);
+      *reinterpret_cast<uint4*>(&sV[r * kXVPitch + c]) = uv;
+    }
+  }
+  __syncthreads();
+  const uint32_t sV_u32 = smem_u32(sV);
+  // ldmatrix.x4.trans source row of this lane: matrix m = lane >> 3 -> keys 8 (m & 1) + (lane & 7), d block (m >> 1)
+  const uint32_t v_lane = sV_u32 + (((lane >> 3) & 1) * 8 + (lane & 7)) * (kXVPitch * 2) + (lane >> 4) * 16;
+  const int row_base = blockIdx.x * chunks * (kXWarps * 16);
+  for (int ch = 0; ch < chunks; ++ch) {
+    const int q0 = row_base + ch * (kXWarps * 16) + warp * 16;
+    if (q0 >= Lq) break;
+    const int r0 = q0 + g, r1 = q0 + g + 8;
+    // Q fragments: lane t owns columns [16 t, 16 t + 16) of rows g and g + 8
+    uint4 qa0 = make_uint4(0u, 0u, 0u, 0u), qa1 = qa0, qb0 = qa0, qb1 = qa0;
+    if (r0 < Lq) {
+      const uint4* src = reinterpret_cast<const uint4*>(Q + (static_cast<size_t>(b) * Lq + r0) * ldq + head * kD + 16 * t);
+      qa0 = __ldg(src);
+      qa1 = __ldg(src + 1);
+    }
+    if (r1 < Lq) {
+      const uint4* src = reinterpret_cast<const uint4*>(Q + (static_cast<size_t>(b) * Lq + r1) * ldq + head * kD + 16 * t);
+      qb0 = __ldg(src);
+      qb1 = __ldg(src + 1);
+    }
+    const uint32_t qa[8] = {qa0.x, qa0.y, qa0.z, qa0.w, qa1.x, qa1.y, qa1.z, qa1.w};
+    const uint32_t qb[8] = {qb0.x, qb0.y, qb0.z, qb0.w, qb1.x, qb1.y, qb1.z, qb1.w};
+    float s[kXK / 8][4];
+#pragma unroll
+    for (int j = 0; j < kXK / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      // k slots of step kk: this lane's columns 16 t + 4 kk + {0, 1} (fragment columns 2t, 2t+1) and + {2, 3} (8 + 2t, ...)
+      const uint32_t a[4] = {qa[2 * kk], qb[2 * kk], qa[2 * kk + 1], qb[2 * kk + 1]};
+#pragma unroll
+      for (int j = 0; j < kXK / 8; ++j) {
+        const uint2 kf = *reinterpret_cast<const uint2*>(&sK[(j * 8 + g) * kXKPitch + 16 * t + 4 * kk]);
+        mma_bf16_16816(s[j], a, kf.x, kf.y);
+      }
+    }
+    // soft-max over the Lk valid keys; columns 8 j + 2 t + {0, 1} of rows g (s[j][0..1]) and g + 8 (s[j][2..3])
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kXK / 8; ++j) {
+      const int col = j * 8 + 2 * t;
+      if (col >= Lk) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+      if (col + 1 >= Lk) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float m0 = mx0 * scale_log2, m1 = mx1 * scale_log2;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kXK / 8; ++j) {
+      s[j][0] = exp2f(fmaf(s[j][0], scale_log2, -m0));
+      s[j][1] = exp2f(fmaf(s[j][1], scale_log2, -m0));
+      s[j][2] = exp2f(fmaf(s[j][2], scale_log2, -m1));
+      s[j][3] = exp2f(fmaf(s[j][3], scale_log2, -m1));
+      l0 += s[j][0] + s[j][1];
+      l1 += s[j][2] + s[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // O[16 x 64] = P[16 x 80] V[80 x 64]: 5 key steps of 16, 8 d tiles of 8 (two per ldmatrix.x4.trans)
+    float o[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < kXK / 16; ++kk) {
+      const uint32_t a[4] = {pack_bf16(s[2 * kk][0], s[2 * kk][1]), pack_bf16(s[2 * kk][2], s[2 * kk][3]),
+                             pack_bf16(s[2 * kk + 1][0], s[2 * kk + 1][1]), pack_bf16(s[2 * kk + 1][2], s[2 * kk + 1][3])};
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t vf[4];
+        ldmatrix_x4_trans(vf, v_lane + kk * 16 * (kXVPitch * 2) + np * 32);
+        mma_bf16_16816(o[2 * np], a, vf[0], vf[1]);
+        mma_bf16_16816(o[2 * np + 1], a, vf[2], vf[3]);
+      }
+    }
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    if (r0 < Lq) {
+      __nv_bfloat16* dst = O + (static_cast<size_t>(b) * Lq + r0) * ldo + head * kD + 2 * t;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][0] * i0, o[n][1] * i0);
+    }
+    if (r1 < Lq) {
+      __nv_bfloat16* dst = O + (static_cast<size_t>(b) * Lq + r1) * ldo + head * kD + 2 * t;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) *reinterpret_cast<uint32_t*>(dst + n * 8) = pack_bf16(o[n][2] * i1, o[n][3] * i1);
+    }
+  }
+  pdl_launch_dependents();
+}
+
+// EDTR_XATTN_SMALL=0 sends the short-key launches to attention_ts_kernel again (A/B switch).
+static bool cross_attention_small_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("EDTR_XATTN_SMALL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return v;
+}
+
 int prime_attention_attributes() {
   cudaError_t e = cudaFuncSetAttribute(attention_ts_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmem);
   if (e == cudaSuccess)
@@ -399,6 +556,19 @@ extern "C" int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ld
   EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(K) | reinterpret_cast<uintptr_t>(V) |
                  reinterpret_cast<uintptr_t>(O)) & 15) == 0, "Q/K/V/O must be 16-byte aligned");
   EDTR_REQUIRE(heads <= 65535 && B <= 65535, "grid too large");
+  if (Lk <= kXK && cross_attention_small_enabled()) {
+    // chunks of 128 query rows per CTA: enough CTAs for two per SM, as few K / V reloads as that allows
+    const int nchunk = (Lq + kXWarps * 16 - 1) / (kXWarps * 16);
+    int chunks = static_cast<int>((static_cast<long long>(nchunk) * heads * B + 2 * 148 - 1) / (2 * 148));
+    if (chunks < 1) chunks = 1;
+    if (chunks > 8) chunks = 8;
+    dim3 grid((nchunk + chunks - 1) / chunks, heads, B);
+    EDTR_LAUNCH(cross_attention_small_kernel, grid, kXWarps * 32, 0, static_cast<cudaStream_t>(stream),
+                reinterpret_cast<const __nv_bfloat16*>(Q), ldq, reinterpret_cast<const __nv_bfloat16*>(K), ldk,
+                reinterpret_cast<const __nv_bfloat16*>(V), ldv, reinterpret_cast<__nv_bfloat16*>(O), ldo, Lq, Lk, chunks,
+                scale * 1.4426950408889634f);
+    return check_launch("cross_attention_small_kernel");
+  }
   CUtensorMap tmQ, tmK, tmV;
   int rc = make_head_tmap(&tmQ, Q, ldq, B, heads, Lq, kQT);
   if (rc) return rc;

@@ -68,7 +68,35 @@ struct Gemm2Params {
   int rows_per_group;
   float* nchw_out;         // != NULL: N <= 8 output channels stored straight to an fp32 [B, N, hw] tensor (the eps /
   int nchw_hw;             //          image / moments outputs of the path); one 64-column tile, bias only
+  float* gn_partial;       // != NULL: GroupNorm partial sums of the stored values, [image][gn_slabs][N/4][2] per
+  int gn_hw, gn_slabs, gn_slab0;   // (32-row slab, 4-column unit) — see EdtrEpilogue::gn_partial
 };
+
+// GroupNorm statistics in the epilogue: v[32] = one row x 32 consecutive stored columns of this lane.  Per 4-column unit
+// the lane forms (sum, sum of squares); the 16 values are then summed over the warp's 32 rows with a transposing
+// butterfly (at every step a lane keeps one half of its values and hands the other half to its partner), which costs
+// 16 shuffles instead of 16 x 5.  Afterwards lane L holds value L >> 1 (unit L >> 2, sum / sum of squares by bit 1) of the
+// whole 32-row slab; even lanes store 16 consecutive floats.  Fixed order: deterministic.
+__device__ __forceinline__ void gn_partial_store(const float (&v)[32], int lane, float* dst) {
+  float a[16];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    a[2 * q] = (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
+    a[2 * q + 1] = fmaf(v[4 * q], v[4 * q], fmaf(v[4 * q + 1], v[4 * q + 1], fmaf(v[4 * q + 2], v[4 * q + 2], v[4 * q + 3] * v[4 * q + 3])));
+  }
+#pragma unroll
+  for (int n = 8, bit = 16; n >= 1; n >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? a[i] : a[i + n];
+      const float keep = up ? a[i + n] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+  if ((lane & 1) == 0) dst[lane >> 1] = a[0];
+}
 
 __device__ __forceinline__ float gelu_fast(float x) {
   // x * Phi(x), erf form (model/attention.py:25-27 uses the exact erf GELU).  erf from Abramowitz-Stegun 7.1.27,
@@ -440,6 +468,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                     ? p.rowvec + static_cast<size_t>(row / p.rows_per_group) * p.rowvec_ld
                                     : nullptr;
       float rs1 = 0.f, rs2 = 0.f;   // producer side of the folded LayerNorm: this row's sums over the warp's chunks
+      float* gn_dst = nullptr;      // GroupNorm partial sums of this warp's 32-row slab (warp-uniform)
+      if (p.gn_partial != nullptr && m0 < p.M) {
+        const int img = m0 / p.gn_hw;
+        const int slab = img * p.gn_slabs + p.gn_slab0 + ((m0 - img * p.gn_hw) >> 5);
+        gn_dst = p.gn_partial + (static_cast<size_t>(slab) * (p.N >> 2) + (n_tile0 >> 2)) * 2;
+      }
 #pragma unroll 1
       for (int c = grp; c < nchunks; c += 2, ++g) {
         const int out_col0 = out_col_tile0 + c * 64;
@@ -563,6 +597,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 32; ++j) { rs1 += v[j]; rs2 = fmaf(v[j], v[j], rs2); }
           }
+          if (gn_dst != nullptr) gn_partial_store(v, lane, gn_dst + (cb >> 1));
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 o;
@@ -774,8 +809,21 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   // split-K scratch (fp32 partial tiles).  The folded LayerNorm and the row statistics live in the tile epilogue only,
   // so launches that use them do not split (they are N = C GEMMs with K <= 4C: the planner would not split them anyway)
   size_t ws_partial_bytes = 0;
-  if (ep->workspace != nullptr && !p.up2x && !nchw && ep->ln_stats == nullptr && ep->row_stats == nullptr)
+  if (ep->workspace != nullptr && !p.up2x && !nchw && ep->ln_stats == nullptr && ep->row_stats == nullptr &&
+      ep->gn_partial == nullptr)
     ws_partial_bytes = static_cast<size_t>(ep->workspace_bytes);
+  if (ep->gn_partial != nullptr) {
+    if (nchw || p.geglu || ep->gn_hw <= 0 || ep->gn_hw % 32 != 0 || M % ep->gn_hw != 0 || ep->gn_slab0 < 0 ||
+        ep->gn_slabs < ep->gn_slab0 + ep->gn_hw / 32 || (reinterpret_cast<uintptr_t>(ep->gn_partial) & 7) != 0) {
+      set_error("gn_partial needs a bf16 output, act != GEGLU, gn_hw %% 32 == 0, gn_hw | M, gn_slabs >= gn_slab0 + gn_hw/32 "
+                "(gn_hw %d, M %d, gn_slabs %d, gn_slab0 %d)", ep->gn_hw, M, ep->gn_slabs, ep->gn_slab0);
+      return EDTR_ERR_INVALID;
+    }
+    p.gn_partial = ep->gn_partial;
+    p.gn_hw = ep->gn_hw;
+    p.gn_slabs = ep->gn_slabs;
+    p.gn_slab0 = ep->gn_slab0;
+  }
   plan_tiles(M, N, p.num_kblocks, p.geglu, ws_partial_bytes, max_clusters, &p.tiles_n, &p.bn_base, &p.splits);
   if (nchw) {
     p.nchw_out = static_cast<float*>(ep->out);

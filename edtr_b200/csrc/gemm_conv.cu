@@ -418,6 +418,9 @@ static int check_epilogue(const EdtrEpilogue* ep, int M, int N) {
     EDTR_REQUIRE(ep->out_mode == EDTR_OUT_BF16 && ep->act != EDTR_ACT_GEGLU &&
                      (reinterpret_cast<uintptr_t>(ep->row_stats) & 7) == 0,
                  "row_stats needs a bf16 output, act != GEGLU and an 8-byte aligned buffer");
+  if (ep->gn_partial != nullptr)
+    EDTR_REQUIRE(gemm2_eligible(M, N, ep) && ep->out_mode == EDTR_OUT_BF16 && ep->act != EDTR_ACT_GEGLU,
+                 "gn_partial is written by the CTA-pair kernel only (M >= 256, N %% 64 == 0, bf16 output, act != GEGLU)");
   if (ep->rowvec != nullptr)
     EDTR_REQUIRE(ep->rows_per_group > 0 && ep->rowvec_ld >= n_out, "bad rowvec geometry");
   if (ep->bias != nullptr)
@@ -524,8 +527,15 @@ extern "C" int edtr_conv3x3_up2x_bf16(const void* X, int ldx, int B, int H, int 
   if (sh > H) { sn = sh / H; sh = H; }
   const int K = 4 * Cin;
   const size_t ldc = static_cast<size_t>(ep->ldc);
+  EdtrEpilogue ep_phase = *ep;   // GroupNorm partial sums: the four phases fill disjoint slab ranges of every image
+  if (ep->gn_partial != nullptr) {
+    EDTR_REQUIRE((H * W) % 32 == 0 && ep->gn_slabs >= 4 * (H * W / 32), "gn_partial of the up-sampling convolution needs "
+                 "H*W %% 32 == 0 and gn_slabs >= 4*H*W/32 (got %d)", ep->gn_slabs);
+    ep_phase.gn_hw = H * W;
+  }
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
+      ep_phase.gn_slab0 = ep->gn_partial != nullptr ? (py * 2 + px) * (H * W / 32) : 0;
       CUtensorMap tmD;
       __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(ep->out) + (static_cast<size_t>(py) * 2 * W + px) * ldc;
       uint64_t dims[4] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
@@ -536,8 +546,8 @@ extern "C" int edtr_conv3x3_up2x_bf16(const void* X, int ldx, int B, int H, int 
       rc = make_tmap_bf16(&tmD, base, 4, dims, strides, box);
       if (rc) return rc;
       const __nv_bfloat16* wp = reinterpret_cast<const __nv_bfloat16*>(Wt4) + static_cast<size_t>(py * 2 + px) * Cout * K;
-      rc = launch_gemm2(tmA, wp, K, K, M, Cout, 1, H, W, Cin / kBK, ep, static_cast<cudaStream_t>(stream), 2, py - 1,
-                        px - 1, &tmD);
+      rc = launch_gemm2(tmA, wp, K, K, M, Cout, 1, H, W, Cin / kBK, &ep_phase, static_cast<cudaStream_t>(stream), 2,
+                        py - 1, px - 1, &tmD);
       if (rc) return rc;
     }
   return EDTR_OK;

@@ -285,6 +285,66 @@ __global__ void groupnorm_pool_kernel(const float* __restrict__ partial, int B, 
   acc[2 * i + 1] += weight * var;
 }
 
+// ------------------------------------------------- GroupNorm statistics from GEMM-epilogue partial sums
+// partial = [B][slabs][C/4][2] (sum, sum of squares) per (32-row slab, 4-channel unit), written by the epilogue of the
+// convolution / GEMM that produced the tensor (gemm2.cu: gn_partial_store).  One CTA per (image, four consecutive units =
+// 32 contiguous bytes per slab): thread t sums slabs t, t + 512, ... (eight 2 x 16-byte loads in flight), then a fixed
+// shuffle tree + a fixed-order sum over the 16 warps; cpg / 4 units form a group (cpg in {4, 8, 16}, so a group never
+// leaves the CTA).  Writes (mean, biased variance) per (image, group): the input of groupnorm_apply_kernel's direct mode.
+__global__ void __launch_bounds__(512)
+groupnorm_fold_kernel(const float* __restrict__ partial, int slabs, int units, int groups, int cpg, float inv_n,
+                      float* __restrict__ mean_var) {
+  PdlScope pdl_scope;
+  __shared__ float red[16][8];
+  const int b = blockIdx.y, u0 = blockIdx.x * 4;
+  const float* src = partial + (static_cast<size_t>(b) * slabs * units + u0) * 2;
+  const size_t sstride = static_cast<size_t>(units) * 2;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int s0 = threadIdx.x; s0 < slabs; s0 += 8 * 512) {
+    float4 lo[8], hi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int s = s0 + k * 512;
+      lo[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      hi[k] = lo[k];
+      if (s < slabs) {
+        const float4* q = reinterpret_cast<const float4*>(src + static_cast<size_t>(s) * sstride);
+        lo[k] = __ldg(q);
+        hi[k] = __ldg(q + 1);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc[0] += lo[k].x; acc[1] += lo[k].y; acc[2] += lo[k].z; acc[3] += lo[k].w;
+      acc[4] += hi[k].x; acc[5] += hi[k].y; acc[6] += hi[k].z; acc[7] += hi[k].w;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][i] = acc[i];
+  }
+  __syncthreads();
+  const int upg = cpg >> 2;            // units per group: 1, 2 or 4
+  const int ng = 4 / upg;              // groups of this CTA
+  if (static_cast<int>(threadIdx.x) < ng) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int w = 0; w < 16; ++w)
+      for (int u = 0; u < upg; ++u) {
+        s1 += red[w][2 * (threadIdx.x * upg + u)];
+        s2 += red[w][2 * (threadIdx.x * upg + u) + 1];
+      }
+    const int g = u0 / upg + threadIdx.x;
+    const float mean = s1 * inv_n;
+    const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
+    reinterpret_cast<float2*>(mean_var)[static_cast<size_t>(b) * groups + g] = make_float2(mean, var);
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm
 // One warp per row, the row lives in registers (two exact passes).
 template <int MAXV>
@@ -744,6 +804,21 @@ extern "C" int edtr_groupnorm_pool(const float* stats, int B, int HW, int C, int
   EDTR_LAUNCH(groupnorm_pool_kernel, (n + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), stats, B, HW, C,
               groups, g.nchunks, g.nslab, g.vslab * 8, weight, acc);
   return check_launch("groupnorm_pool_kernel");
+}
+
+extern "C" int edtr_groupnorm_fold(const float* gn_partial, int B, int slabs, int C, int groups, float* mean_var,
+                                   void* stream) {
+  EDTR_REQUIRE(gn_partial && mean_var, "gn_partial/mean_var is NULL");
+  EDTR_REQUIRE(B > 0 && B <= 65535 && slabs > 0 && C > 0 && groups > 0 && C % groups == 0, "bad GroupNorm shape");
+  const int cpg = C / groups;
+  EDTR_REQUIRE(cpg == 4 || cpg == 8 || cpg == 16, "edtr_groupnorm_fold needs C / groups in {4, 8, 16} (got %d)", cpg);
+  EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(gn_partial) & 31) == 0) && ((reinterpret_cast<uintptr_t>(mean_var) & 7) == 0),
+               "gn_partial must be 32-byte aligned, mean_var 8-byte aligned");
+  const int units = C / 4;                       // C % 16 == 0 here, so the four-unit blocks tile the row
+  const float inv_n = 1.f / (static_cast<float>(cpg) * 32.f * static_cast<float>(slabs));
+  EDTR_LAUNCH(groupnorm_fold_kernel, dim3(units / 4, B), 512, 0, static_cast<cudaStream_t>(stream), gn_partial, slabs,
+              units, groups, cpg, inv_n, mean_var);
+  return check_launch("groupnorm_fold_kernel");
 }
 
 extern "C" int edtr_groupnorm_fused_supported(int B, int HW, int C, int groups) {

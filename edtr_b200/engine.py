@@ -862,30 +862,60 @@ class _VaeBlocks:
     """Leaf blocks shared by the VAE decoder and encoder engines (model/vae.py:64-124, :250-308); the kernels are
     reached through ``self.ops`` and the packed weights through ``self.w``."""
 
+    # GroupNorm statistics from the producing epilogue (untiled paths).  Every GroupNorm of the VAE reads a tensor that a
+    # convolution / GEMM of the same pass has just written, so the producer's epilogue delivers the per-(32-row slab,
+    # 4-channel unit) partial sums (EdtrEpilogue.gn_partial) and the GroupNorm becomes fold (tiny) + apply instead of a
+    # statistics pass over the tensor + apply: 4 instead of 6 bytes of HBM traffic per element.  `_gnp_request` is called
+    # by every producer of a tensor a GroupNorm may read: it registers the partial buffer under the tensor's address, or
+    # drops a stale registration when the shape is not eligible (small tensors keep the single-launch / two-pass kernels).
+    EPILOGUE_GN = os.environ.get("EDTR_EPILOGUE_GN", "1") != "0"
+
+    def _gnp_request(self, ws: Workspace, out: torch.Tensor, K: int, phases: int = 1) -> Optional[torch.Tensor]:
+        ops = self.ops
+        table = self.__dict__.setdefault("_gnp", {})
+        B, C = out.shape[0], out.shape[-1]
+        HW = out.numel() // (B * C)
+        key = out.data_ptr()
+        table.pop(key, None)
+        if not self.EPILOGUE_GN or out.dtype != BF16 or not hasattr(ops, "gn_partial_supported"):
+            return None
+        if HW % (32 * phases) or not ops.gn_partial_supported(B * HW, HW, C, K):
+            return None
+        part = ws.get(f"gnp_{key:x}", ops.gn_partial_shape(B, HW, C), F32)
+        table[key] = (part, B, HW, C)
+        return part
+
+    def _gn(self, ws: Workspace, x: torch.Tensor, key: str, silu: bool, out: torch.Tensor) -> torch.Tensor:
+        """GroupNorm (+SiLU) of `x` with the parameters `key`; uses the producer's epilogue statistics when registered."""
+        ops, w = self.ops, self.w
+        B, C = x.shape[0], x.shape[-1]
+        ent = self.__dict__.setdefault("_gnp", {}).pop(x.data_ptr(), None)
+        if ent is not None and ent[1:] == (B, x.numel() // (B * C), C):
+            mv = ops.groupnorm_fold(ent[0], 32, out=ws.get("gn_mv", (B, 32, 2), F32))
+            return ops.groupnorm_apply_stats(x, mv, w[key + "weight"], w[key + "bias"], 32, 1e-6, silu, out=out)
+        return ops.groupnorm(x, w[key + "weight"], w[key + "bias"], 32, 1e-6, silu, stats=ws.gn_scratch(ops, x), out=out)
+
     def _res(self, ws: Workspace, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
         """ResnetBlock.forward, temb=None (model/vae.py:103-124)."""
         ops, w = self.ops, self.w
         B, H, W, cin = x.shape
         cout = out.shape[-1]
-        y = ops.groupnorm(x, w[p + "norm1.weight"], w[p + "norm1.bias"], 32, 1e-6, True, stats=ws.gn_scratch(ops, x),
-                          out=ws.get("gn", (B, H, W, cin)))
-        h = self._conv_any(ws, y, p + "conv1.", out=ws.get("res_h", (B, H, W, cout)))
-        y2 = ops.groupnorm(h, w[p + "norm2.weight"], w[p + "norm2.bias"], 32, 1e-6, True, stats=ws.gn_scratch(ops, h),
-                           out=ws.get("gn", (B, H, W, cout)))
+        y = self._gn(ws, x, p + "norm1.", True, ws.get("gn", (B, H, W, cin)))
+        h = self._conv_any(ws, y, p + "conv1.", out=ws.get("res_h", (B, H, W, cout)), gn=True)
+        y2 = self._gn(ws, h, p + "norm2.", True, ws.get("gn", (B, H, W, cout)))
         if (p + "nin_shortcut.weight") in w:
             skip = ops.gemm(x, w[p + "nin_shortcut.weight"], bias=w[p + "nin_shortcut.bias"],
                             out=ws.get("res_skip", (B, H, W, cout)))
         else:
             skip = x
-        self._conv_any(ws, y2, p + "conv2.", residual=skip, out=out)
+        self._conv_any(ws, y2, p + "conv2.", residual=skip, out=out, gn=True)
 
     def _attn(self, ws: Workspace, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
         """SDPAttnBlock.forward: one head of width C (model/vae.py:279-308)."""
         ops, w = self.ops, self.w
         B, H, W, C = x.shape
         L = H * W
-        y = ops.groupnorm(x, w[p + "norm.weight"], w[p + "norm.bias"], 32, 1e-6, False, stats=ws.gn_scratch(ops, x),
-                          out=ws.get("gn", (B, L, C)))
+        y = self._gn(ws, x, p + "norm.", False, ws.get("gn", (B, L, C)))
         qk = ops.gemm(y, w[p + "qk.weight"], bias=w[p + "qk.bias"], out=ws.get("va_qk", (B, L, 2 * C)))
         # V^T per image ([C, L], keys contiguous) is the K-major B operand of P @ V
         vt = ops.gemm(y, w[p + "v.weight"], bias=w[p + "v.bias"], out_mode=ops.OUT_NCHW_BF16, hw=L,
@@ -897,18 +927,26 @@ class _VaeBlocks:
             ops.gemm(qk[b, :, :C], qk[b, :, C:], out_mode=ops.OUT_F32, out=s)
             ops.softmax_rows(s, float(C) ** -0.5, out=pm)
             ops.gemm(pm, vt[b], out=o[b])
-        ops.gemm(o, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out)
+        part = self._gnp_request(ws, out, C)
+        gkw = dict(gn_partial=part, gn_hw=L) if part is not None else {}
+        ops.gemm(o, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out, **gkw)
 
-    def _conv_any(self, ws: Workspace, x: torch.Tensor, wk: str, **kw) -> torch.Tensor:
+    def _conv_any(self, ws: Workspace, x: torch.Tensor, wk: str, gn: bool = False, **kw) -> torch.Tensor:
         """3x3/p1 convolution at any tile geometry: the TMA implicit-GEMM kernel when the tile fits its box
-        rules, else im2col + GEMM (tiled-VAE tiles are e.g. 86x86 latent pixels)."""
+        rules, else im2col + GEMM (tiled-VAE tiles are e.g. 86x86 latent pixels).  gn=True: the output feeds a
+        GroupNorm of the untiled path (`_gn`), ask the epilogue for its statistics."""
         ops, w = self.ops, self.w
         B, H, W, C = x.shape
+        part = self._gnp_request(ws, kw["out"], 9 * C) if gn else None
         if ops.conv3x3_supported(H, W, C):
+            if part is not None:
+                kw["gn_partial"] = part
             return ops.conv3x3(x, w[wk + "weight"], bias=w[wk + "bias"], **kw)
         col = ops.im2col(x, 3, 3, 1, 1, 1, H, W, out=ws.get("col", (B * H * W, 9 * C)))
         if kw.get("out_mode", ops.OUT_BF16) in (ops.OUT_NCHW_F32, ops.OUT_NCHW_BF16):
             kw["hw"] = H * W
+        if part is not None:
+            kw.update(gn_partial=part, gn_hw=H * W)
         return ops.gemm(col, w[wk + "weight"], bias=w[wk + "bias"], **kw)
 
 
@@ -1033,7 +1071,10 @@ class VaeDecoderEngine(_VaeBlocks):
         ping = lambda i, shape: ws.get(f"v_h{i % 2}", shape)
         n = 0
         h = ping(n, (B, H, W, self.top))
-        ops.conv3x3(zin, w["decoder.conv_in.weight"], bias=w["decoder.conv_in.bias"], out=h)
+        self.__dict__.setdefault("_gnp", {}).clear()
+        part = self._gnp_request(ws, h, 9 * 64)
+        ops.conv3x3(zin, w["decoder.conv_in.weight"], bias=w["decoder.conv_in.bias"], out=h,
+                    **(dict(gn_partial=part) if part is not None else {}))
         for name in ("block_1", "attn_1", "block_2"):
             n += 1
             o = ping(n, (B, H, W, self.top))
@@ -1053,15 +1094,17 @@ class VaeDecoderEngine(_VaeBlocks):
                 q = f"decoder.up.{level}.upsample.conv."
                 n += 1
                 o = ping(n, (B, 2 * H, 2 * W, c))
-                if ops.conv3x3_up2x_supported(B, H, W, c, c):
-                    ops.conv3x3_up2x(h, w[q + "weight_up2x"], bias=w[q + "bias"], out=o)
+                up2x = ops.conv3x3_up2x_supported(B, H, W, c, c)   # four phase launches: slabs of 32 low-resolution pixels
+                part = self._gnp_request(ws, o, 4 * c, 4) if up2x else self._gnp_request(ws, o, 9 * c)
+                gkw = dict(gn_partial=part) if part is not None else {}
+                if up2x:
+                    ops.conv3x3_up2x(h, w[q + "weight_up2x"], bias=w[q + "bias"], out=o, **gkw)
                 else:
                     u = ops.upsample2x(h, out=ws.get("up", (B, 2 * H, 2 * W, c)))
-                    ops.conv3x3(u, w[q + "weight"], bias=w[q + "bias"], out=o)
+                    ops.conv3x3(u, w[q + "weight"], bias=w[q + "bias"], out=o, **gkw)
                 H, W = 2 * H, 2 * W
                 h = o
-        y = ops.groupnorm(h, w["decoder.norm_out.weight"], w["decoder.norm_out.bias"], 32, 1e-6, True,
-                          stats=ws.gn_scratch(ops, h), out=ws.get("gn", (B, H, W, self.last)))
+        y = self._gn(ws, h, "decoder.norm_out.", True, ws.get("gn", (B, H, W, self.last)))
         ops.conv3x3(y, w["decoder.conv_out.weight"], bias=w["decoder.conv_out.bias"],
                     out=img_out.view(B, self.dd["out_ch"], H * W), out_mode=ops.OUT_NCHW_F32)
 
@@ -1231,7 +1274,8 @@ class VaeEncoderEngine(_VaeBlocks):
         ops.nchw_to_nhwc(image, xin, 0)
         ping = lambda i, shape: ws.get(f"e_h{i % 2}", shape)
         n = 0
-        h = self._conv_any(ws, xin, "encoder.conv_in.", out=ping(n, (B, H, W, self.dd["ch"])))
+        self.__dict__.setdefault("_gnp", {}).clear()
+        h = self._conv_any(ws, xin, "encoder.conv_in.", out=ping(n, (B, H, W, self.dd["ch"])), gn=True)
         for level, blocks, has_down in self.levels:
             for i, (ci, co) in enumerate(blocks):
                 n += 1
@@ -1244,7 +1288,10 @@ class VaeEncoderEngine(_VaeBlocks):
                 q = f"encoder.down.{level}.downsample.conv."
                 col = ops.im2col(h, 3, 3, 2, 0, 0, Ho, Wo, out=ws.get("col", (B * Ho * Wo, 9 * c)))
                 n += 1
-                h = ops.gemm(col, w[q + "weight"], bias=w[q + "bias"], out=ping(n, (B, Ho, Wo, c)))
+                o = ping(n, (B, Ho, Wo, c))
+                part = self._gnp_request(ws, o, 9 * c)
+                h = ops.gemm(col, w[q + "weight"], bias=w[q + "bias"], out=o,
+                             **(dict(gn_partial=part, gn_hw=Ho * Wo) if part is not None else {}))
                 H, W = Ho, Wo
         for name in ("block_1", "attn_1", "block_2"):
             n += 1
@@ -1254,8 +1301,7 @@ class VaeEncoderEngine(_VaeBlocks):
             else:
                 self._res(ws, f"encoder.mid.{name}.", h, o)
             h = o
-        y = ops.groupnorm(h, w["encoder.norm_out.weight"], w["encoder.norm_out.bias"], 32, 1e-6, True,
-                          stats=ws.gn_scratch(ops, h), out=ws.get("gn", (B, H, W, self.top)))
+        y = self._gn(ws, h, "encoder.norm_out.", True, ws.get("gn", (B, H, W, self.top)))
         self._conv_any(ws, y, "encoder.moments.", out=moments.view(B, 2 * self.embed_dim, H * W),
                        out_mode=ops.OUT_NCHW_F32)
 

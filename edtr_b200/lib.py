@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 EXPORTED = [
     "edtr_last_error", "edtr_version", "edtr_set_device", "edtr_init", "edtr_gemm_workspace_size", "edtr_gemm_row_stats_parts", "edtr_gemm_tile_n", "edtr_gemm_bf16",
     "edtr_conv3x3_bf16", "edtr_conv3x3_up2x_bf16", "edtr_attention_bf16", "edtr_groupnorm_partial_size", "edtr_groupnorm_stats", "edtr_groupnorm_apply",
-    "edtr_groupnorm_fused_supported", "edtr_groupnorm_fused", "edtr_groupnorm_pool", "edtr_groupnorm_apply_stats",
+    "edtr_groupnorm_fused_supported", "edtr_groupnorm_fused", "edtr_groupnorm_pool", "edtr_groupnorm_apply_stats", "edtr_groupnorm_fold",
     "edtr_layernorm_bf16", "edtr_layernorm_padded_bf16", "edtr_pixel_unshuffle_f32_to_nhwc_bf16",
     "edtr_window_attention_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
     "edtr_nchw_f32_to_nhwc_bf16", "edtr_pointwise_nchw_f32_to_nhwc_bf16", "edtr_nhwc_bf16_to_nchw", "edtr_cast_f32_to_bf16",
@@ -64,6 +64,10 @@ class EdtrEpilogue(Structure):
         ("ln_colsum", c_void_p),
         ("row_stats", c_void_p),
         ("row_stats_cap", c_int32),
+        ("gn_partial", c_void_p),
+        ("gn_hw", c_int32),
+        ("gn_slabs", c_int32),
+        ("gn_slab0", c_int32),
     ]
 
 
@@ -143,6 +147,8 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_wavelet_level.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
     lib.edtr_groupnorm_pool.restype = ci
     lib.edtr_groupnorm_pool.argtypes = [vp, ci, ci, ci, ci, c_float, vp, vp]
+    lib.edtr_groupnorm_fold.restype = ci
+    lib.edtr_groupnorm_fold.argtypes = [vp, ci, ci, ci, ci, vp, vp]
     lib.edtr_groupnorm_apply_stats.restype = ci
     lib.edtr_groupnorm_apply_stats.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, vp, vp, vp, c_float, ci, vp]
     lib.edtr_groupnorm_apply.restype = ci

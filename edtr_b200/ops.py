@@ -124,7 +124,7 @@ def _f32(t: Optional[torch.Tensor], n: int, name: str) -> Optional[int]:
 
 
 def _epilogue(M: int, n_out: int, out: torch.Tensor, *, bias, rowvec, rows_per_group, residual, act, out_mode, hw,
-              alpha, ln=None, row_stats=None) -> EdtrEpilogue:
+              alpha, ln=None, row_stats=None, gn_partial=None, gn_hw=0, gn_phases=1) -> EdtrEpilogue:
     ep = EdtrEpilogue()
     dev = out.device.index if out.device.index is not None else torch.cuda.current_device()
     _lib.device_lib(dev)
@@ -148,6 +148,19 @@ def _epilogue(M: int, n_out: int, out: torch.Tensor, *, bias, rowvec, rows_per_g
             raise ValueError(f"row_stats must be a contiguous fp32 [{M}, row_stats_parts(M, N, K), 2] tensor")
         ep.row_stats = row_stats.data_ptr()
         ep.row_stats_cap = row_stats.shape[1]
+    if gn_partial is not None:
+        # GroupNorm partial sums from the epilogue: fp32 [images, slabs, N/4, 2], slabs = gn_phases * gn_hw / 32
+        if act == ACT_GEGLU or out_mode != OUT_BF16:
+            raise ValueError("gn_partial needs a bf16 output and act != GEGLU")
+        if gn_hw <= 0 or gn_hw % 32 or (M // gn_phases) % gn_hw or n_out % 4:
+            raise ValueError(f"gn_partial needs gn_hw % 32 == 0 and gn_hw | M (gn_hw {gn_hw}, M {M})")
+        want = (M // gn_phases // gn_hw, gn_phases * gn_hw // 32, n_out // 4, 2)
+        if gn_partial.dtype != torch.float32 or tuple(gn_partial.shape) != want or not gn_partial.is_contiguous():
+            raise ValueError(f"gn_partial must be a contiguous fp32 {want} tensor, got {tuple(gn_partial.shape)}")
+        ep.gn_partial = gn_partial.data_ptr()
+        ep.gn_hw = gn_hw
+        ep.gn_slabs = want[1]
+        ep.gn_slab0 = 0
     ep.bias = _f32(bias, n_out if act != ACT_GEGLU else 2 * n_out, "bias")
     if rowvec is not None:
         if rowvec.dtype != torch.float32 or rowvec.dim() != 2 or rowvec.stride(1) != 1:
@@ -196,13 +209,16 @@ def _alloc_out(M: int, n_out: int, out_mode: int, hw: int, device) -> torch.Tens
 
 
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, rows_per_group=0, residual=None,
-         act=ACT_NONE, out=None, out_mode=OUT_BF16, hw=0, alpha=1.0, ln=None, row_stats=None) -> torch.Tensor:
+         act=ACT_NONE, out=None, out_mode=OUT_BF16, hw=0, alpha=1.0, ln=None, row_stats=None, gn_partial=None,
+         gn_hw=0) -> torch.Tensor:
     """``epilogue(a @ w.T)`` — a [..., K] rows view, w [N, K] (bf16).
 
     ln = (stats [M, parts, 2], C, eps, colsum [N]): LayerNorm over the K = C channels of `a` folded into the GEMM — `a`
     holds the un-normalised rows, `w` is pre-scaled by the LayerNorm gain, `bias` already contains W @ beta, `stats`
     are the (sum, sum of squares) partials a producer wrote through `row_stats` (engine.fold_layernorm packs these).
-    row_stats = fp32 [M, N/32, 2]: receives per-row partial (sum, sum of squares) of the stored matrix."""
+    row_stats = fp32 [M, N/32, 2]: receives per-row partial (sum, sum of squares) of the stored matrix.
+    gn_partial = fp32 [M/gn_hw, gn_hw/32, N/4, 2]: receives GroupNorm partial sums of the stored matrix (gn_hw rows per
+    image; see gn_partial_supported / groupnorm_from_partial)."""
     _require_cuda(a, w, bias, rowvec, residual, out)
     M, K, lda = rows_view(a)
     N, Kw, ldw = rows_view(w)
@@ -214,7 +230,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, rows_per_g
     if ln is not None and ln[1] != K:
         raise ValueError(f"folded LayerNorm width {ln[1]} != K {K}")
     ep = _epilogue(M, n_out, out, bias=bias, rowvec=rowvec, rows_per_group=rows_per_group, residual=residual,
-                   act=act, out_mode=out_mode, hw=hw, alpha=alpha, ln=ln, row_stats=row_stats)
+                   act=act, out_mode=out_mode, hw=hw, alpha=alpha, ln=ln, row_stats=row_stats, gn_partial=gn_partial,
+                   gn_hw=gn_hw)
     L = _lib.load()
     if row_stats is not None and row_stats.shape[1] != L.edtr_gemm_row_stats_parts(M, N, K, ctypes.byref(ep)):
         raise ValueError(f"row_stats must hold exactly row_stats_parts(M, N, K) = "
@@ -225,7 +242,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, rows_per_g
 
 
 def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, residual=None, act=ACT_NONE, out=None,
-            out_mode=OUT_BF16, alpha=1.0) -> torch.Tensor:
+            out_mode=OUT_BF16, alpha=1.0, gn_partial=None) -> torch.Tensor:
     """3x3/s1/p1 conv. x [B,H,W,Cin] channels-last rows view, w [Cout, 9*Cin] (tap-major)."""
     _require_cuda(x, w, bias, rowvec, residual, out)
     if x.dim() != 4:
@@ -239,7 +256,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, bias=None, rowvec=None, residua
     if out is None:
         out = _alloc_out(M, Cout, out_mode, hw, x.device)
     ep = _epilogue(M, Cout, out, bias=bias, rowvec=rowvec, rows_per_group=hw, residual=residual, act=act,
-                   out_mode=out_mode, hw=hw, alpha=alpha)
+                   out_mode=out_mode, hw=hw, alpha=alpha, gn_partial=gn_partial, gn_hw=hw)
     L = _lib.device_lib()
     _lib.check(L.edtr_conv3x3_bf16(x.data_ptr(), ldx, B, H, W, Cin, w.data_ptr(), Cout, ctypes.byref(ep), _stream()),
                "edtr_conv3x3_bf16")
@@ -254,7 +271,7 @@ def conv3x3_up2x_supported(B: int, H: int, W: int, Cin: int, Cout: int) -> bool:
     return H % rows == 0 if H >= rows else rows % H == 0
 
 
-def conv3x3_up2x(x: torch.Tensor, w4: torch.Tensor, *, bias=None, act=ACT_NONE, out=None) -> torch.Tensor:
+def conv3x3_up2x(x: torch.Tensor, w4: torch.Tensor, *, bias=None, act=ACT_NONE, out=None, gn_partial=None) -> torch.Tensor:
     """nearest-2x + 3x3/p1 conv as four 2x2-tap convs. x [B,H,W,Cin]; w4 [4, Cout, 4*Cin] phase filters
     (engine.pack_conv3x3_up2x); out [B,2H,2W,Cout] rows view."""
     _require_cuda(x, w4, bias, out)
@@ -272,7 +289,7 @@ def conv3x3_up2x(x: torch.Tensor, w4: torch.Tensor, *, bias=None, act=ACT_NONE, 
     if out is None:
         out = torch.empty((B, 2 * H, 2 * W, Cout), dtype=BF16, device=x.device)
     ep = _epilogue(4 * B * H * W, Cout, out, bias=bias, rowvec=None, rows_per_group=0, residual=None, act=act,
-                   out_mode=OUT_BF16, hw=0, alpha=1.0)
+                   out_mode=OUT_BF16, hw=0, alpha=1.0, gn_partial=gn_partial, gn_hw=H * W, gn_phases=4)
     if tuple(out.shape) != (B, 2 * H, 2 * W, Cout):
         raise ValueError(f"out must be [B, 2H, 2W, Cout], got {tuple(out.shape)}")
     L = _lib.device_lib()
@@ -384,6 +401,36 @@ def groupnorm_pool(x: torch.Tensor, groups: int, weight: float, acc: torch.Tenso
     _lib.check(L.edtr_groupnorm_pool(stats.data_ptr(), B, HW, C, groups, float(weight), acc.data_ptr(), st),
                "edtr_groupnorm_pool")
     return acc
+
+
+def gn_partial_supported(M: int, HW: int, N: int, K: int, groups: int = 32) -> bool:
+    """True when the GEMM / convolution that produces an [M, N] tensor (HW rows per image) can deliver the GroupNorm
+    partial sums from its epilogue: CTA-pair kernel, 32-row slabs inside one image, 4-channel units inside one group
+    (C / groups in {4, 8, 16}: the VAE widths), and a shape the planner would not split along K anyway."""
+    if M < 256 or N % 64 or HW % 32 or M % HW or N % groups or (N // groups) not in (4, 8, 16):
+        return False
+    return gemm_workspace_size(M, N, K) == 0
+
+
+def gn_partial_shape(B: int, HW: int, C: int) -> Tuple[int, int, int, int]:
+    return (B, HW // 32, C // 4, 2)
+
+
+def groupnorm_fold(gn_partial: torch.Tensor, groups: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(mean, biased variance) per (image, group), fp32 [B, groups, 2], from the partial sums an epilogue wrote
+    (gn_partial fp32 [B, slabs, C/4, 2]); feeds groupnorm_apply_stats."""
+    _require_cuda(gn_partial, out)
+    if gn_partial.dtype != torch.float32 or gn_partial.dim() != 4 or gn_partial.shape[3] != 2 or not gn_partial.is_contiguous():
+        raise ValueError("gn_partial must be a contiguous fp32 [B, slabs, C/4, 2] tensor")
+    B, slabs, units, _ = gn_partial.shape
+    C = 4 * units
+    if out is None:
+        out = torch.empty((B, groups, 2), dtype=torch.float32, device=gn_partial.device)
+    elif out.dtype != torch.float32 or tuple(out.shape) != (B, groups, 2) or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous fp32 [{B}, {groups}, 2] tensor")
+    _lib.check(_lib.device_lib().edtr_groupnorm_fold(gn_partial.data_ptr(), B, slabs, C, groups, out.data_ptr(), _stream()),
+               "edtr_groupnorm_fold")
+    return out
 
 
 def groupnorm_apply_stats(x: torch.Tensor, mean_var: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,

@@ -50,7 +50,7 @@ def device_guard(device):
 
 
 def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, out_mode, hw, alpha, geglu_bias=None,
-            ln=None, row_stats=None):
+            ln=None, row_stats=None, gn_partial=None, gn_hw=0):
     LAUNCHES[0] += 1
     if ln is not None:
         # folded LayerNorm (EdtrEpilogue.ln_*): acc' = rstd * (acc - mean * colsum[n]) from the producer's partial sums
@@ -86,6 +86,13 @@ def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, ou
         for j, vv in enumerate(torch.tensor_split(v, row_stats.shape[1], dim=1)):
             row_stats[:, j, 0] = vv.sum(-1)
             row_stats[:, j, 1] = (vv * vv).sum(-1)
+    if gn_partial is not None:
+        # EdtrEpilogue.gn_partial: (sum, sum of squares) per (32-row slab, 4-column unit) of the fp32 values
+        assert act != ACT_GEGLU and out_mode == OUT_BF16 and gn_hw % 32 == 0 and M % gn_hw == 0 and n_out % 4 == 0
+        assert gn_partial.dtype == torch.float32 and tuple(gn_partial.shape) == (M // gn_hw, gn_hw // 32, n_out // 4, 2)
+        u = v.view(M // gn_hw, gn_hw // 32, 32, n_out // 4, 4)
+        gn_partial[..., 0] = u.sum((2, 4))
+        gn_partial[..., 1] = (u * u).sum((2, 4))
     if out_mode in (OUT_BF16, OUT_F32):
         want = torch.bfloat16 if out_mode == OUT_BF16 else torch.float32
         if out is None:
@@ -102,7 +109,7 @@ def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, ou
 
 
 def gemm(a, w, *, bias=None, rowvec=None, rows_per_group=0, residual=None, act=ACT_NONE, out=None,
-         out_mode=OUT_BF16, hw=0, alpha=1.0, ln=None, row_stats=None):
+         out_mode=OUT_BF16, hw=0, alpha=1.0, ln=None, row_stats=None, gn_partial=None, gn_hw=0):
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     A = _rows(a)
     M, K = A.shape
@@ -111,10 +118,11 @@ def gemm(a, w, *, bias=None, rowvec=None, rows_per_group=0, residual=None, act=A
     n_out = N // 2 if act == ACT_GEGLU else N
     return _finish(A @ w.float().t(), M, n_out, bias=bias, rowvec=rowvec, rows_per_group=rows_per_group,
                    residual=residual, act=act, out=out, out_mode=out_mode, hw=hw, alpha=alpha, ln=ln,
-                   row_stats=row_stats)
+                   row_stats=row_stats, gn_partial=gn_partial, gn_hw=gn_hw)
 
 
-def conv3x3(x, w, *, bias=None, rowvec=None, residual=None, act=ACT_NONE, out=None, out_mode=OUT_BF16, alpha=1.0):
+def conv3x3(x, w, *, bias=None, rowvec=None, residual=None, act=ACT_NONE, out=None, out_mode=OUT_BF16, alpha=1.0,
+            gn_partial=None):
     assert x.dtype == torch.bfloat16 and x.dim() == 4
     B, H, W, Cin = x.shape
     assert Cin % 64 == 0
@@ -123,7 +131,7 @@ def conv3x3(x, w, *, bias=None, rowvec=None, residual=None, act=ACT_NONE, out=No
     wt = w.float().view(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
     y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, None, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
     return _finish(y, B * H * W, Cout, bias=bias, rowvec=rowvec, rows_per_group=H * W, residual=residual, act=act,
-                   out=out, out_mode=out_mode, hw=H * W, alpha=alpha)
+                   out=out, out_mode=out_mode, hw=H * W, alpha=alpha, gn_partial=gn_partial, gn_hw=H * W)
 
 
 def conv3x3_up2x_supported(B, H, W, Cin, Cout):
@@ -133,7 +141,7 @@ def conv3x3_up2x_supported(B, H, W, Cin, Cout):
     return H % rows == 0 if H >= rows else rows % H == 0
 
 
-def conv3x3_up2x(x, w4, *, bias=None, act=ACT_NONE, out=None):
+def conv3x3_up2x(x, w4, *, bias=None, act=ACT_NONE, out=None, gn_partial=None):
     """Four 2x2-tap phase convolutions, evaluated literally from the packed phase filters."""
     LAUNCHES[0] += 4
     B, H, W, Cin = x.shape
@@ -157,6 +165,15 @@ def conv3x3_up2x(x, w4, *, bias=None, act=ACT_NONE, out=None):
         y = F.silu(y)
     elif act == ACT_LRELU_02:
         y = F.leaky_relu(y, 0.2)
+    if gn_partial is not None:
+        # slabs of an image: phase-major (four launches), 32 consecutive low-resolution pixels each
+        assert (H * W) % 32 == 0 and tuple(gn_partial.shape) == (B, 4 * H * W // 32, Cout // 4, 2)
+        for py in (0, 1):
+            for px in (0, 1):
+                u = y[:, py::2, px::2, :].reshape(B, H * W // 32, 32, Cout // 4, 4)
+                sl = slice((py * 2 + px) * (H * W // 32), (py * 2 + px + 1) * (H * W // 32))
+                gn_partial[:, sl, :, 0] = u.sum((2, 4))
+                gn_partial[:, sl, :, 1] = (u * u).sum((2, 4))
     if out is None:
         out = torch.empty((B, 2 * H, 2 * W, Cout), dtype=torch.bfloat16)
     out.copy_(y)
@@ -198,6 +215,34 @@ def groupnorm_pool(x, groups, weight, acc, stats=None):
     acc[..., 0] += weight * mean
     acc[..., 1] += weight * var
     return acc
+
+
+GN_PARTIAL = True   # tests flip this to run the engines without epilogue GroupNorm statistics
+
+
+def gn_partial_supported(M, HW, N, K, groups=32):
+    return bool(GN_PARTIAL and M >= 256 and N % 64 == 0 and HW % 32 == 0 and M % HW == 0 and N % groups == 0
+                and (N // groups) in (4, 8, 16))
+
+
+def gn_partial_shape(B, HW, C):
+    return (B, HW // 32, C // 4, 2)
+
+
+def groupnorm_fold(gn_partial, groups, out=None):
+    LAUNCHES[0] += 1
+    B, slabs, units, _ = gn_partial.shape
+    cpg = 4 * units // groups
+    assert cpg in (4, 8, 16)
+    s = gn_partial.view(B, slabs, groups, cpg // 4, 2).sum((1, 3))
+    n = float(cpg * 32 * slabs)
+    mean = s[..., 0] / n
+    var = torch.clamp(s[..., 1] / n - mean * mean, min=0.0)
+    if out is None:
+        out = torch.empty((B, groups, 2), dtype=torch.float32)
+    out[..., 0] = mean
+    out[..., 1] = var
+    return out
 
 
 def groupnorm_apply_stats(x, mean_var, gamma, beta, groups, eps, silu, out=None):

@@ -678,3 +678,54 @@ def test_clip_text_tower_matches_reference():
     with torch.no_grad():
         a, b = ref.encode(["", "a photo of a cat"]), ours.encode(["", "a photo of a cat"])
     assert O.max_rel_err(b, a) < 1e-5
+
+
+# ----------------------------------------------------------------------------- GroupNorm statistics from the epilogue
+def test_vae_groupnorm_from_epilogue_partials_equals_statistics_pass():
+    """Untiled VAE decode / encode: every eligible GroupNorm takes its statistics from the producing convolution's
+    epilogue (EdtrEpilogue.gn_partial -> edtr_groupnorm_fold -> edtr_groupnorm_apply_stats).  On the stand-in kernels
+    (same contract: 32-row slabs x 4-channel units, phase-major slabs for the up-sampling convolution) the result
+    must equal the plain statistics-pass dataflow, and the fold must actually be used."""
+    from edtr_b200.engine import VaeDecoderEngine, VaeEncoderEngine
+
+    v = dict(O.TINY_VAE8, ch=128, ch_mult=(1, 2, 4, 4))           # the s4 VAE widths: C / 32 in {4, 8, 16}
+    sd = O.make_weights(O.vae_decoder_param_shapes(v), seed=5)
+    vd = VaeDecoderEngine(_dd(v), v["embed_dim"], sd, "cpu", ops=fake_ops)
+    z = torch.randn(2, 4, 16, 16, generator=torch.Generator().manual_seed(0))
+    folds = []
+    real_fold = fake_ops.groupnorm_fold
+    try:
+        fake_ops.groupnorm_fold = lambda *a, **k: (folds.append(1), real_fold(*a, **k))[1]
+        with_partials = vd.decode(z, 0.18215, use_graph=False)
+        n_dec = len(folds)
+        fake_ops.GN_PARTIAL = False
+        vd2 = VaeDecoderEngine(_dd(v), v["embed_dim"], sd, "cpu", ops=fake_ops)
+        plain = vd2.decode(z, 0.18215, use_graph=False)
+        assert len(folds) == n_dec
+    finally:
+        fake_ops.GN_PARTIAL = True
+        fake_ops.groupnorm_fold = real_fold
+    # mid block_1 (2) + attn (1) + block_2 (2) + 4 levels x 2 blocks x 2 + norm_out = 22 GroupNorms, all eligible here
+    assert n_dec == 22, n_dec
+    # two equally valid bf16 dataflows (statistics of the fp32 values vs of the bf16-rounded tensor): each is compared
+    # with the fp32 oracle, and the epilogue statistics must not be the worse one by more than noise
+    ref = O.vae_decode(sd, v, z, 0.18215)
+    err_p, err_s = O.max_rel_err(with_partials, ref), O.max_rel_err(plain, ref)
+    assert err_p < 2e-2 and err_p < 1.5 * err_s + 2e-3, (err_p, err_s)
+
+    sde = O.make_weights(O.vae_encoder_param_shapes(v), seed=6)
+    img = torch.rand(1, 3, 128, 128, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    folds.clear()
+    try:
+        fake_ops.groupnorm_fold = lambda *a, **k: (folds.append(1), real_fold(*a, **k))[1]
+        mo = VaeEncoderEngine(_dd(v), v["embed_dim"], sde, "cpu", ops=fake_ops).encode(img, use_graph=False)
+        n_enc = len(folds)
+        fake_ops.GN_PARTIAL = False
+        mo2 = VaeEncoderEngine(_dd(v), v["embed_dim"], sde, "cpu", ops=fake_ops).encode(img, use_graph=False)
+    finally:
+        fake_ops.GN_PARTIAL = True
+        fake_ops.groupnorm_fold = real_fold
+    assert n_enc >= 10, n_enc
+    ref = O.vae_encode_moments(sde, v, img)
+    err_p, err_s = O.max_rel_err(mo, ref), O.max_rel_err(mo2, ref)
+    assert err_p < 2e-2 and err_p < 1.5 * err_s + 2e-3, (err_p, err_s, n_enc)

@@ -199,7 +199,10 @@ def test_conv3x3_channel_slice_input(ops):
 
 @pytest.mark.parametrize("B,heads,Lq,Lk", [(2, 5, 256, 256), (1, 2, 4096, 4096), (2, 3, 128, 77), (1, 20, 64, 64),
                                             (1, 1, 200, 130), (2, 2, 1024, 77), (1, 2, 130, 192), (2, 1, 300, 290),
-                                            (1, 3, 64, 1), (1, 1, 128, 65)])
+                                            (1, 3, 64, 1), (1, 1, 128, 65),
+                                            # short key sequences run cross_attention_small_kernel (Lk <= 80)
+                                            (8, 5, 4096, 77), (3, 20, 200, 77), (1, 10, 37, 80), (2, 2, 1000, 33),
+                                            (1, 1, 16, 8), (2, 4, 129, 79), (1, 2, 300, 81)])
 def test_attention(ops, B, heads, Lq, Lk):
     C = heads * 64
     qkv = rnd(B, Lq, 3 * C, seed=1)
@@ -568,3 +571,92 @@ def test_conv3x3_split_k(ops):
     out = ops.conv3x3(x, wp, bias=bias, rowvec=emb)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + emb[:, :, None, None]
     assert relerr(out.view(B, H, W, Cout), ref.permute(0, 2, 3, 1)) < 1e-2
+
+
+# ------------------------------------------------- GroupNorm statistics from the GEMM / convolution epilogue
+def _gn_from_partial(ops, y_bf16, part, gamma, beta, eps, silu):
+    mv = ops.groupnorm_fold(part, 32)
+    return ops.groupnorm_apply_stats(y_bf16, mv, gamma, beta, 32, eps, silu), mv
+
+
+def _check_partial(part, ref_rows, B, HW, C):
+    """part [B, HW/32, C/4, 2] vs the fp32 reference rows [B*HW, C] in launch-row order."""
+    u = ref_rows.view(B, HW // 32, 32, C // 4, 4)
+    s1, s2 = u.sum((2, 4)), (u * u).sum((2, 4))
+    assert (part[..., 0] - s1).abs().max().item() < 2e-2 * s1.abs().max().item() + 1e-3
+    assert (part[..., 1] - s2).abs().max().item() < 2e-2 * s2.abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,res", [(2, 64, 64, 128, 128, True), (1, 128, 128, 256, 128, False),
+                                                 (4, 32, 32, 512, 512, True), (3, 64, 64, 64, 256, False),
+                                                 (8, 16, 16, 128, 192, True)])
+def test_conv3x3_groupnorm_partials_and_fold(ops, B, H, W, Cin, Cout, res):
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = torch.randn(Cout, device="cuda")
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    r = rnd(B, H, W, Cout, seed=3) if res else None
+    HW = H * W
+    part = torch.full(ops.gn_partial_shape(B, HW, Cout), float("nan"), device="cuda")
+    out = ops.conv3x3(x, wp, bias=bias, residual=None if r is None else r.view(-1, Cout), gn_partial=part)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    if r is not None:
+        ref = ref + r.view(-1, Cout).float()
+    assert relerr(out, ref) < 1e-2
+    assert not torch.isnan(part).any()          # every (slab, unit) entry is written exactly once
+    _check_partial(part, ref, B, HW, Cout)
+    if Cout // 32 in (4, 8, 16):
+        gamma, beta = torch.randn(Cout, device="cuda"), torch.randn(Cout, device="cuda")
+        y, mv = _gn_from_partial(ops, out.view(B, H, W, Cout), part, gamma, beta, 1e-6, True)
+        g = ref.view(B, HW, 32, Cout // 32)
+        assert (mv[..., 0] - g.mean((1, 3))).abs().max().item() < 1e-3
+        assert relerr(mv[..., 1], g.var((1, 3), unbiased=False)) < 1e-3
+        yref = F.silu(F.group_norm(ref.view(B, HW, Cout).permute(0, 2, 1), 32, gamma, beta, 1e-6)).permute(0, 2, 1)
+        assert relerr(y.view(B, HW, Cout), yref) < 2e-2
+        # and the same numbers as the statistics-pass GroupNorm of the stored tensor, up to bf16 rounding of its input
+        y2 = ops.groupnorm(out.view(B, H, W, Cout), gamma, beta, 32, 1e-6, True)
+        assert relerr(y, y2) < 2e-2
+
+
+def test_gemm_groupnorm_partials(ops):
+    B, HW, K, N = 4, 1024, 512, 512
+    a, w = rnd(B * HW, K, seed=1), rnd(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda")
+    r = rnd(B * HW, N, seed=3)
+    part = torch.full(ops.gn_partial_shape(B, HW, N), float("nan"), device="cuda")
+    out = ops.gemm(a, w, bias=bias, residual=r, gn_partial=part, gn_hw=HW)
+    ref = a.float() @ w.float().t() + bias + r.float()
+    assert relerr(out, ref) < 1e-2
+    assert not torch.isnan(part).any()
+    _check_partial(part, ref, B, HW, N)
+    assert ops.gn_partial_supported(B * HW, HW, N, K) in (True, False)
+    with pytest.raises(Exception):      # slabs must not straddle images
+        ops.gemm(a, w, gn_partial=part, gn_hw=1000)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 32, 32, 128, 128), (1, 64, 64, 256, 256), (8, 16, 16, 512, 512)])
+def test_conv3x3_up2x_groupnorm_partials(ops, B, H, W, Cin, Cout):
+    from edtr_b200.engine import pack_conv3x3_up2x
+
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = torch.randn(Cout, device="cuda")
+    w4 = pack_conv3x3_up2x(w.float(), "cuda")
+    HW = 4 * H * W
+    part = torch.full(ops.gn_partial_shape(B, HW, Cout), float("nan"), device="cuda")
+    out = ops.conv3x3_up2x(x, w4, bias=bias, gn_partial=part)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias, padding=1).permute(0, 2, 3, 1)      # [B, 2H, 2W, C]
+    assert relerr(out, ref) < 1.5e-2
+    assert not torch.isnan(part).any()
+    # slabs are phase-major, 32 consecutive low-resolution pixels each: the per-(image, group) totals are what matters
+    gamma, beta = torch.randn(Cout, device="cuda"), torch.randn(Cout, device="cuda")
+    y, mv = _gn_from_partial(ops, out, part, gamma, beta, 1e-6, False)
+    g = ref.reshape(B, HW, 32, Cout // 32)
+    assert (mv[..., 0] - g.mean((1, 3))).abs().max().item() < 1e-3
+    assert relerr(mv[..., 1], g.var((1, 3), unbiased=False)) < 1e-3
+    yref = F.group_norm(ref.reshape(B, HW, Cout).permute(0, 2, 1), 32, gamma, beta, 1e-6).permute(0, 2, 1)
+    assert relerr(y.view(B, HW, Cout), yref) < 2e-2
+    ph = ref[:, 1::2, 0::2, :].reshape(B, H * W // 32, 32, Cout // 4, 4)      # phase (py, px) = (1, 0) -> slab block 2
+    blk = part[:, 2 * (H * W // 32):3 * (H * W // 32)]
+    assert (blk[..., 0] - ph.sum((2, 4))).abs().max().item() < 2e-2 * ph.sum((2, 4)).abs().max().item() + 1e-3
