@@ -375,6 +375,11 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
@@ -390,45 +395,52 @@ cross_attention_small_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   pdl_wait();
+  const int row_base = blockIdx.x * chunks * (kXWarps * 16);
+  // Q fragments of one 16-row slab: lane t owns columns [16 t, 16 t + 16) of rows g and g + 8 (zeros past Lq)
+  auto load_q = [&](int q0, uint4 (&q)[4]) {
+    q[0] = q[1] = q[2] = q[3] = make_uint4(0u, 0u, 0u, 0u);
+    if (q0 + g < Lq) {
+      const uint4* src = reinterpret_cast<const uint4*>(Q + (static_cast<size_t>(b) * Lq + q0 + g) * ldq + head * kD + 16 * t);
+      q[0] = __ldg(src);
+      q[1] = __ldg(src + 1);
+    }
+    if (q0 + g + 8 < Lq) {
+      const uint4* src = reinterpret_cast<const uint4*>(Q + (static_cast<size_t>(b) * Lq + q0 + g + 8) * ldq + head * kD + 16 * t);
+      q[2] = __ldg(src);
+      q[3] = __ldg(src + 1);
+    }
+  };
+  uint4 qcur[4];
+  load_q(row_base + warp * 16, qcur);        // in flight while K / V are staged
   {
     const __nv_bfloat16* kb = K + static_cast<size_t>(b) * Lk * ldk + head * kD;
     const __nv_bfloat16* vb = V + static_cast<size_t>(b) * Lk * ldv + head * kD;
-    for (int i = tid; i < kXK * 8; i += kXWarps * 32) {     // 80 rows x 8 vectors of 8 bf16
+    const uint32_t sK_u32 = smem_u32(sK), sVd_u32 = smem_u32(sV);
+    for (int i = tid; i < kXK * 8; i += kXWarps * 32) {     // 80 rows x 8 vectors of 8 bf16, all copies in flight at once
       const int r = i >> 3, c = (i & 7) * 8;
-      uint4 uk = make_uint4(0u, 0u, 0u, 0u), uv = uk;        // keys >= Lk: zero rows (their probabilities are zero too)
-      if (r < Lk) {
-        uk = __ldg(reinterpret_cast<const uint4*>(kb + static_cast<size_t>(r) * ldk + c));
-        uv = __ldg(reinterpret_cast<const uint4*>(vb + static_cast<size_t>(r) * ldv + c));
-      }
-      uint2* dk = reinterpret_cast<uint2*>(&sK[r * kXKPitch + c]);   // 136 B pitch: 8-byte aligned only
-      dk[0] = make_uint2(uk.x, uk.y);
-      dk[1] = make_uint2(uk.z, uk.w);
-      *reinterpret_cast<uint4*>(&sV[r * kXVPitch + c]) = uv;
+      const int rs = r < Lk ? r : 0;
+      const uint32_t n16 = r < Lk ? 16u : 0u, n8 = r < Lk ? 8u : 0u;   // keys >= Lk: zero-filled rows (their probabilities are zero too)
+      const __nv_bfloat16* ks = kb + static_cast<size_t>(rs) * ldk + c;
+      const __nv_bfloat16* vs = vb + static_cast<size_t>(rs) * ldv + c;
+      const uint32_t dk = sK_u32 + (r * kXKPitch + c) * 2;             // 136 B pitch: 8-byte aligned only
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dk), "l"(ks), "r"(n8) : "memory");
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dk + 8), "l"(ks + 4), "r"(n8) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sVd_u32 + (r * kXVPitch + c) * 2), "l"(vs), "r"(n16) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
   const uint32_t sV_u32 = smem_u32(sV);
   // ldmatrix.x4.trans source row of this lane: matrix m = lane >> 3 -> keys 8 (m & 1) + (lane & 7), d block (m >> 1)
   const uint32_t v_lane = sV_u32 + (((lane >> 3) & 1) * 8 + (lane & 7)) * (kXVPitch * 2) + (lane >> 4) * 16;
-  const int row_base = blockIdx.x * chunks * (kXWarps * 16);
   for (int ch = 0; ch < chunks; ++ch) {
     const int q0 = row_base + ch * (kXWarps * 16) + warp * 16;
     if (q0 >= Lq) break;
     const int r0 = q0 + g, r1 = q0 + g + 8;
-    // Q fragments: lane t owns columns [16 t, 16 t + 16) of rows g and g + 8
-    uint4 qa0 = make_uint4(0u, 0u, 0u, 0u), qa1 = qa0, qb0 = qa0, qb1 = qa0;
-    if (r0 < Lq) {
-      const uint4* src = reinterpret_cast<const uint4*>(Q + (static_cast<size_t>(b) * Lq + r0) * ldq + head * kD + 16 * t);
-      qa0 = __ldg(src);
-      qa1 = __ldg(src + 1);
-    }
-    if (r1 < Lq) {
-      const uint4* src = reinterpret_cast<const uint4*>(Q + (static_cast<size_t>(b) * Lq + r1) * ldq + head * kD + 16 * t);
-      qb0 = __ldg(src);
-      qb1 = __ldg(src + 1);
-    }
-    const uint32_t qa[8] = {qa0.x, qa0.y, qa0.z, qa0.w, qa1.x, qa1.y, qa1.z, qa1.w};
-    const uint32_t qb[8] = {qb0.x, qb0.y, qb0.z, qb0.w, qb1.x, qb1.y, qb1.z, qb1.w};
+    const uint32_t qa[8] = {qcur[0].x, qcur[0].y, qcur[0].z, qcur[0].w, qcur[1].x, qcur[1].y, qcur[1].z, qcur[1].w};
+    const uint32_t qb[8] = {qcur[2].x, qcur[2].y, qcur[2].z, qcur[2].w, qcur[3].x, qcur[3].y, qcur[3].z, qcur[3].w};
+    if (ch + 1 < chunks) load_q(q0 + kXWarps * 16, qcur);   // next slab's Q streams in under this slab's arithmetic
     float s[kXK / 8][4];
 #pragma unroll
     for (int j = 0; j < kXK / 8; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
@@ -460,10 +472,10 @@ cross_attention_small_kernel(const __nv_bfloat16* __restrict__ Q, int ldq, const
     float l0 = 0.f, l1 = 0.f;
 #pragma unroll
     for (int j = 0; j < kXK / 8; ++j) {
-      s[j][0] = exp2f(fmaf(s[j][0], scale_log2, -m0));
-      s[j][1] = exp2f(fmaf(s[j][1], scale_log2, -m0));
-      s[j][2] = exp2f(fmaf(s[j][2], scale_log2, -m1));
-      s[j][3] = exp2f(fmaf(s[j][3], scale_log2, -m1));
+      s[j][0] = ex2_approx(fmaf(s[j][0], scale_log2, -m0));
+      s[j][1] = ex2_approx(fmaf(s[j][1], scale_log2, -m0));
+      s[j][2] = ex2_approx(fmaf(s[j][2], scale_log2, -m1));
+      s[j][3] = ex2_approx(fmaf(s[j][3], scale_log2, -m1));
       l0 += s[j][0] + s[j][1];
       l1 += s[j][2] + s[j][3];
     }

@@ -68,6 +68,14 @@ struct Gemm2Params {
   int rows_per_group;
   float* nchw_out;         // != NULL: N <= 8 output channels stored straight to an fp32 [B, N, hw] tensor (the eps /
   int nchw_hw;             //          image / moments outputs of the path); one 64-column tile, bias only
+  int halo;                // 1: 3x3 convolution with W % 128 == 0 in "halo" mode — one pipeline stage holds the 130-pixel
+                           //    row segment (x0-1 .. x0+128) of ONE input row and channel block plus the three weight
+                           //    k-blocks of that row's taps; the three dx taps read it through A descriptors whose start
+                           //    address is shifted by one pixel (128 B): a third of the operand traffic of nine boxes
+  int a_bytes;             // bytes reserved for A per stage (16 KB; 17 KB in halo mode)
+  int b_tile_bytes;        // one weight k-block of this CTA: b_box_rows * 128 B
+  int stage_tx;            // bytes the TMA loads of one stage deliver per CTA (expect_tx)
+  int halo_base_offset;    // experiment switch: 1 = put the pixel shift into the descriptor's matrix-base-offset field
   float* gn_partial;       // != NULL: GroupNorm partial sums of the stored values, [image][gn_slabs][N/4][2] per
   int gn_hw, gn_slabs, gn_slab0;   // (32-row slab, 4-column unit) — see EdtrEpilogue::gn_partial
 };
@@ -163,7 +171,7 @@ __device__ __forceinline__ void geglu_pair(float accx0, float accx1, float accg0
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmD,
-             const Gemm2Params p) {
+             const __grid_constant__ CUtensorMap tmH, const Gemm2Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sPipe = smem;                             // stage s: A at s*stage_bytes, B right after it
@@ -186,7 +194,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int num_work = p.tiles_m * p.tiles_n * p.splits;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(p.halo ? &tmH : &tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
     if (p.has_residual) tma_prefetch_desc(&tmC);
@@ -239,6 +247,27 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         cx += p.tap_dx0;
         cy += p.tap_dy0;
       }
+      if (p.halo) {
+        // one stage = (input row y + ty - 1, channel block cb): 130 pixels x 64 channels + the weights of taps (ty, 0..2)
+        const int hx = m0 % p.W - 1;
+        for (int it = 0; it < 3 * p.cblocks; ++it) {
+          mbar_wait_u32(empty_u32 + s * 8, ph ^ 1);
+          if (elect_one()) {
+            const uint32_t fb = full_leader + s * 8;
+            const uint32_t sa = pipe_u32 + s * p.stage_bytes;
+            mbar_arrive_expect_tx_cluster(fb, p.stage_tx);
+            tma_load_4d_pair_u32(sa, &tmH, fb, cb * k2BK, hx, cy + ty, cn);
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+              tma_load_2d_pair_u32(sa + p.a_bytes + dx * p.b_tile_bytes, &tmB, fb,
+                                   ((ty * 3 + dx) * p.cblocks + cb) * k2BK, nrow0);
+          }
+          __syncwarp();
+          if (++cb == p.cblocks) { cb = 0; ++ty; }
+          if (++s == static_cast<uint32_t>(nstages)) { s = 0; ph ^= 1; }
+        }
+        continue;
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait_u32(empty_u32 + s * 8, ph ^ 1);
         if (elect_one()) {
@@ -284,6 +313,31 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait_u32(tempty_u32 + a * 8, aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * k2MaxBN;
+        if (p.halo) {
+          for (int it = 0; it < 3 * p.cblocks; ++it) {
+            mbar_wait_u32(full_u32 + s * 8, ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t sa = pipe_u32 + s * p.stage_bytes;
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                // tap dx reads pixels dx .. dx + 127 of the 130-pixel row segment: same swizzled layout, start + dx * 128 B
+                uint64_t adesc = umma_smem_desc_sw128(sa + dx * 128);
+                if (p.halo_base_offset) adesc |= static_cast<uint64_t>(dx) << 49;
+                const uint64_t bdesc = umma_smem_desc_sw128(sa + p.a_bytes + dx * p.b_tile_bytes);
+#pragma unroll
+                for (int k = 0; k < k2BK / 16; ++k)
+                  umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (it | dx | k) != 0);
+              }
+              umma_commit_pair_u32(empty_u32 + s * 8, 0x3);
+            }
+            __syncwarp();
+            if (++s == static_cast<uint32_t>(nstages)) { s = 0; ph ^= 1; }
+          }
+          if (elect_one()) umma_commit_pair_u32(tfull_u32 + a * 8, 0x3);
+          __syncwarp();
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait_u32(full_u32 + s * 8, ph);
           tc_fence_after();
@@ -798,7 +852,7 @@ bool gemm2_disabled() {
 // A/B tensor maps are built by the caller (gemm or conv geometry); C/D maps are built here.
 int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, int N, int mode, int H, int W,
                  int cblocks, const EdtrEpilogue* ep, cudaStream_t stream, int taps_x, int tap_dy0, int tap_dx0,
-                 const CUtensorMap* tmD_up) {
+                 const CUtensorMap* tmD_up, const CUtensorMap* tmA_halo) {
   Gemm2Params p{};
   p.M = M; p.N = N; p.num_kblocks = K / k2BK; p.mode = mode; p.H = H; p.W = W; p.cblocks = cblocks;
   p.taps_x = taps_x; p.tap_dy0 = tap_dy0; p.tap_dx0 = tap_dx0; p.up2x = tmD_up != nullptr;
@@ -844,7 +898,25 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
     return EDTR_ERR_INVALID;
   }
   p.b_box_rows = p.bn_base / 2;
-  p.stage_bytes = k2ABytes + p.b_box_rows * k2BK * 2;
+  p.a_bytes = k2ABytes;
+  p.b_tile_bytes = p.b_box_rows * k2BK * 2;
+  p.stage_bytes = k2ABytes + p.b_tile_bytes;
+  p.stage_tx = p.stage_bytes;
+  // Halo mode (see Gemm2Params::halo): narrow convolutions at W % 128 == 0 are bound by the operand traffic of the nine
+  // tap boxes through L2 (measured 8 TB/s at 512 x 512 x 128 channels), not by the tensor pipe.  EDTR_CONV_HALO=0
+  // switches it off, =2 additionally writes the pixel shift into the descriptor's matrix-base-offset field.
+  static const int halo_mode = [] {
+    const char* e = getenv("EDTR_CONV_HALO");
+    return e == nullptr ? 1 : atoi(e);
+  }();
+  if (halo_mode > 0 && tmA_halo != nullptr && mode == 1 && taps_x == 3 && !p.up2x && W % (k2BM) == 0 && p.splits == 1 &&
+      p.bn_base <= 128 && p.num_kblocks == 9 * cblocks) {
+    p.halo = 1;
+    p.halo_base_offset = halo_mode == 2;
+    p.a_bytes = 17 * 1024;                       // 130 pixels x 128 B, rounded up to the 1024 B swizzle atom
+    p.stage_bytes = p.a_bytes + 3 * p.b_tile_bytes;
+    p.stage_tx = 130 * k2BK * 2 + 3 * p.b_tile_bytes;
+  }
   // two staging buffers per epilogue warp; a ring of four (residual requested two chunks ahead) was measured on
   // B200 and changes nothing: the short-K GEMMs are bound by launch / fill / drain latency, not by the residual
   p.ring = 2;
@@ -891,7 +963,8 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
     set_error("internal: split-K is not available for the up-sampling convolution");
     return EDTR_ERR_INVALID;
   }
-  EDTR_LAUNCH(gemm2_kernel, 2 * clusters, k2Threads, k2SmemBytes, stream, tmA, tmB, tmC, tmD, p);
+  EDTR_LAUNCH(gemm2_kernel, 2 * clusters, k2Threads, k2SmemBytes, stream, tmA, tmB, tmC, tmD,
+              p.halo ? *tmA_halo : tmA, p);
   rc = check_launch("gemm2_kernel");
   if (rc || p.splits == 1) return rc;
   const size_t nvec = static_cast<size_t>(M) * (N / 8);

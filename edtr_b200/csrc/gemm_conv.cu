@@ -384,7 +384,7 @@ int gemm2_row_stats_parts(int M, int N, int K, const EdtrEpilogue* ep);
 bool gemm2_disabled();
 int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, int N, int mode, int H, int W,
                  int cblocks, const EdtrEpilogue* ep, cudaStream_t stream, int taps_x = 3, int tap_dy0 = -1,
-                 int tap_dx0 = -1, const CUtensorMap* tmD_up = nullptr);
+                 int tap_dx0 = -1, const CUtensorMap* tmD_up = nullptr, const CUtensorMap* tmA_halo = nullptr);
 
 static int check_epilogue(const EdtrEpilogue* ep, int M, int N) {
   EDTR_REQUIRE(ep != nullptr && ep->out != nullptr, "epilogue/out is NULL");
@@ -593,8 +593,21 @@ extern "C" int edtr_conv3x3_bf16(const void* X, int ldx, int B, int H, int W, in
     if (rc) return rc;
   }
   const int K = 9 * Cin;
-  if (gemm2_eligible(M, Cout, ep))
-    return launch_gemm2(tmA, Wt, K, K, M, Cout, 1, H, W, Cin / kBK, ep, static_cast<cudaStream_t>(stream));
+  if (gemm2_eligible(M, Cout, ep)) {
+    CUtensorMap tmH;
+    const bool halo = W % kBM == 0;   // 130-pixel row segments (one halo pixel on either side) for the kernel's halo mode
+    if (halo) {
+      uint64_t dims[4] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                          static_cast<uint64_t>(B)};
+      uint64_t strides[3] = {static_cast<uint64_t>(ldx) * 2, static_cast<uint64_t>(ldx) * 2 * W,
+                             static_cast<uint64_t>(ldx) * 2 * W * H};
+      uint32_t box[4] = {kBK, static_cast<uint32_t>(kBM + 2), 1, 1};
+      rc = make_tmap_bf16(&tmH, X, 4, dims, strides, box);
+      if (rc) return rc;
+    }
+    return launch_gemm2(tmA, Wt, K, K, M, Cout, 1, H, W, Cin / kBK, ep, static_cast<cudaStream_t>(stream), 3, -1, -1,
+                        nullptr, halo ? &tmH : nullptr);
+  }
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(Cout)};
     uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};

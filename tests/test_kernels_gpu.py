@@ -660,3 +660,26 @@ def test_conv3x3_up2x_groupnorm_partials(ops, B, H, W, Cin, Cout):
     ph = ref[:, 1::2, 0::2, :].reshape(B, H * W // 32, 32, Cout // 4, 4)      # phase (py, px) = (1, 0) -> slab block 2
     blk = part[:, 2 * (H * W // 32):3 * (H * W // 32)]
     assert (blk[..., 0] - ph.sum((2, 4))).abs().max().item() < 2e-2 * ph.sum((2, 4)).abs().max().item() + 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,res", [(1, 128, 128, 128, 128, True), (2, 16, 256, 64, 128, False),
+                                                 (1, 8, 512, 128, 64, True), (3, 5, 128, 256, 128, False),
+                                                 (1, 64, 512, 128, 3, False), (1, 3, 384, 64, 64, True)])
+def test_conv3x3_halo_mode(ops, B, H, W, Cin, Cout, res):
+    """Narrow convolutions at W % 128 == 0 run the kernel's halo mode (one 130-pixel row segment per stage, the three
+    dx taps through shifted A descriptors): borders (x = -1, x = W, y = -1, y = H), several channel blocks, odd H."""
+    x = rnd(B, H, W, Cin, seed=1)
+    w = rnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = torch.randn(Cout, device="cuda")
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
+    if Cout % 64 == 0:
+        r = rnd(B, H, W, Cout, seed=3) if res else None
+        out = ops.conv3x3(x, wp, bias=bias, residual=None if r is None else r.view(-1, Cout))
+        ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+        if r is not None:
+            ref = ref + r.view(-1, Cout).float()
+        assert relerr(out, ref) < 1e-2
+    else:
+        out = ops.conv3x3(x, wp, bias=bias, out_mode=ops.OUT_NCHW_F32)
+        assert relerr(out.view(B, Cout, H, W), ref) < 1e-2
