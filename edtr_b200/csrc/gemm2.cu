@@ -75,7 +75,6 @@ struct Gemm2Params {
   int a_bytes;             // bytes reserved for A per stage (16 KB; 17 KB in halo mode)
   int b_tile_bytes;        // one weight k-block of this CTA: b_box_rows * 128 B
   int stage_tx;            // bytes the TMA loads of one stage deliver per CTA (expect_tx)
-  int halo_base_offset;    // experiment switch: 1 = put the pixel shift into the descriptor's matrix-base-offset field
   float* gn_partial;       // != NULL: GroupNorm partial sums of the stored values, [image][gn_slabs][N/4][2] per
   int gn_hw, gn_slabs, gn_slab0;   // (32-row slab, 4-column unit) — see EdtrEpilogue::gn_partial
 };
@@ -321,9 +320,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               const uint32_t sa = pipe_u32 + s * p.stage_bytes;
 #pragma unroll
               for (int dx = 0; dx < 3; ++dx) {
-                // tap dx reads pixels dx .. dx + 127 of the 130-pixel row segment: same swizzled layout, start + dx * 128 B
-                uint64_t adesc = umma_smem_desc_sw128(sa + dx * 128);
-                if (p.halo_base_offset) adesc |= static_cast<uint64_t>(dx) << 49;
+                // tap dx reads pixels dx .. dx + 127 of the 130-pixel row segment: start address + dx * 128 B.  The 128 B
+                // swizzle of TMA and UMMA is a function of the absolute shared-memory address bits, so the shifted start
+                // needs nothing else (the descriptor's matrix-base-offset field stays 0; setting it to dx was measured
+                // on B200 and gives wrong results).
+                const uint64_t adesc = umma_smem_desc_sw128(sa + dx * 128);
                 const uint64_t bdesc = umma_smem_desc_sw128(sa + p.a_bytes + dx * p.b_tile_bytes);
 #pragma unroll
                 for (int k = 0; k < k2BK / 16; ++k)
@@ -904,7 +905,7 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   p.stage_tx = p.stage_bytes;
   // Halo mode (see Gemm2Params::halo): narrow convolutions at W % 128 == 0 are bound by the operand traffic of the nine
   // tap boxes through L2 (measured 8 TB/s at 512 x 512 x 128 channels), not by the tensor pipe.  EDTR_CONV_HALO=0
-  // switches it off, =2 additionally writes the pixel shift into the descriptor's matrix-base-offset field.
+  // switches it off (A/B).
   static const int halo_mode = [] {
     const char* e = getenv("EDTR_CONV_HALO");
     return e == nullptr ? 1 : atoi(e);
@@ -912,7 +913,6 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
   if (halo_mode > 0 && tmA_halo != nullptr && mode == 1 && taps_x == 3 && !p.up2x && W % (k2BM) == 0 && p.splits == 1 &&
       p.bn_base <= 128 && p.num_kblocks == 9 * cblocks) {
     p.halo = 1;
-    p.halo_base_offset = halo_mode == 2;
     p.a_bytes = 17 * 1024;                       // 130 pixels x 128 B, rounded up to the 1024 B swizzle atom
     p.stage_bytes = p.a_bytes + 3 * p.b_tile_bytes;
     p.stage_tx = 130 * k2BK * 2 + 3 * p.b_tile_bytes;
