@@ -148,7 +148,7 @@ def main():
                     fl = 4.0 * q.shape[0] * q.shape[1] * k_.shape[1] * q.shape[2]
                 elif name == "groupnorm_fold":
                     pt = args[0]            # [B, slabs, C/4, 2]
-                    key = ("groupnorm", pt.shape[0] * pt.shape[1] * 32, pt.shape[2] * 4, 0, "epi")
+                    key = ("groupnorm_fold", pt.shape[0] * pt.shape[1] * 32, pt.shape[2] * 4, 0, "+apply")
                     fl = 4.0 * pt.shape[0] * pt.shape[1] * 32 * pt.shape[2] * 4
                 elif name in ("groupnorm", "layernorm"):
                     x = args[0]
@@ -211,7 +211,7 @@ def main():
                          f"{len(evs)} kernels, {len(seq)} ops, {bad} unmatched  (op, M, N, K|Lk, flag): count, ms, TFLOP/s "
                          f"(norms: GB/s), ms at the sustained bf16 peak")
             for key, (n, us, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
-                ideal = fl / 1382.9e12 * 1e3 if key[0] not in ("groupnorm", "layernorm") else fl / 6539.2e9 * 1e3
+                ideal = fl / 1382.9e12 * 1e3 if key[0] not in ("groupnorm", "groupnorm_fold", "layernorm") else fl / 6539.2e9 * 1e3
                 lines.append(f"{us / 1e3:8.3f} ms {100 * us / tot:5.1f}% x{n:<4d} avg {us / max(n, 1):7.1f} us "
                              f"{fl / max(us, 1e-9) / 1e6:8.1f}  ideal {ideal:7.3f} ms  {key}")
     if not a.no_profile:
