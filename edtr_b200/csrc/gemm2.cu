@@ -76,7 +76,8 @@ struct Gemm2Params {
   int b_tile_bytes;        // one weight k-block of this CTA: b_box_rows * 128 B
   int stage_tx;            // bytes the TMA loads of one stage deliver per CTA (expect_tx)
   float* gn_partial;       // != NULL: GroupNorm partial sums of the stored values, [image][gn_slabs][N/4][2] per
-  int gn_hw, gn_slabs, gn_slab0;   // (32-row slab, 4-column unit) — see EdtrEpilogue::gn_partial
+  int gn_hw, gn_slabs, gn_slab0;   // (32-row slab, gn_unit-column unit) — see EdtrEpilogue::gn_partial
+  int gn_unit;                     // 4 or 2 columns per unit
 };
 
 // GroupNorm statistics in the epilogue: v[32] = one row x 32 consecutive stored columns of this lane.  Per 4-column unit
@@ -103,6 +104,27 @@ __device__ __forceinline__ void gn_partial_store(const float (&v)[32], int lane,
   }
   a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
   if ((lane & 1) == 0) dst[lane >> 1] = a[0];
+}
+// Same with 2-column units (group widths that are not multiples of 4: 320 / 32 = 10, 960 / 32 = 30): 32 values, five
+// transposing steps, lane L ends up with value L (unit L >> 1, sum / sum of squares by bit 0); 32 consecutive floats.
+__device__ __forceinline__ void gn_partial_store2(const float (&v)[32], int lane, float* dst) {
+  float a[32];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    a[2 * q] = v[2 * q] + v[2 * q + 1];
+    a[2 * q + 1] = fmaf(v[2 * q], v[2 * q], v[2 * q + 1] * v[2 * q + 1]);
+  }
+#pragma unroll
+  for (int n = 16, bit = 16; n >= 1; n >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? a[i] : a[i + n];
+      const float keep = up ? a[i + n] : a[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  dst[lane] = a[0];
 }
 
 __device__ __forceinline__ float gelu_fast(float x) {
@@ -527,7 +549,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (p.gn_partial != nullptr && m0 < p.M) {
         const int img = m0 / p.gn_hw;
         const int slab = img * p.gn_slabs + p.gn_slab0 + ((m0 - img * p.gn_hw) >> 5);
-        gn_dst = p.gn_partial + (static_cast<size_t>(slab) * (p.N >> 2) + (n_tile0 >> 2)) * 2;
+        gn_dst = p.gn_unit == 2 ? p.gn_partial + static_cast<size_t>(slab) * p.N + n_tile0               // N/2 units x 2
+                                : p.gn_partial + (static_cast<size_t>(slab) * (p.N >> 2) + (n_tile0 >> 2)) * 2;
       }
 #pragma unroll 1
       for (int c = grp; c < nchunks; c += 2, ++g) {
@@ -652,7 +675,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int j = 0; j < 32; ++j) { rs1 += v[j]; rs2 = fmaf(v[j], v[j], rs2); }
           }
-          if (gn_dst != nullptr) gn_partial_store(v, lane, gn_dst + (cb >> 1));
+          if (gn_dst != nullptr) {
+            if (p.gn_unit == 2) gn_partial_store2(v, lane, gn_dst + cb);
+            else gn_partial_store(v, lane, gn_dst + (cb >> 1));
+          }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 o;
@@ -878,6 +904,11 @@ int launch_gemm2(const CUtensorMap& tmA, const void* Wt, int ldw, int K, int M, 
     p.gn_hw = ep->gn_hw;
     p.gn_slabs = ep->gn_slabs;
     p.gn_slab0 = ep->gn_slab0;
+    p.gn_unit = ep->gn_unit == 2 ? 2 : 4;
+    if (ep->gn_unit != 0 && ep->gn_unit != 2 && ep->gn_unit != 4) {
+      set_error("gn_unit must be 0 (= 4), 2 or 4 (got %d)", ep->gn_unit);
+      return EDTR_ERR_INVALID;
+    }
   }
   plan_tiles(M, N, p.num_kblocks, p.geglu, ws_partial_bytes, max_clusters, &p.tiles_n, &p.bn_base, &p.splits);
   if (nchw) {

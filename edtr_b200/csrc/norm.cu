@@ -345,6 +345,46 @@ groupnorm_fold_kernel(const float* __restrict__ partial, int slabs, int units, i
   }
 }
 
+// General form (any group width that is a multiple of the unit, few slabs: the UNet / ControlNet tensors): one CTA of
+// four warps per (image, group); thread t sums the group's (slab, unit) pairs t, t + 128, ... (a group's units are
+// contiguous: upg * 8 bytes per slab), fixed shuffle tree + fixed-order sum over the warps.
+__global__ void __launch_bounds__(128)
+groupnorm_fold_general_kernel(const float* __restrict__ partial, int slabs, int units, int groups, int upg, float inv_n,
+                              float* __restrict__ mean_var) {
+  PdlScope pdl_scope;
+  __shared__ float red[4][2];
+  const int g = blockIdx.x, b = blockIdx.y;
+  const float2* src = reinterpret_cast<const float2*>(partial) + static_cast<size_t>(b) * slabs * units + g * upg;
+  const int n = slabs * upg;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * 128) {
+    float2 t[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * 128;
+      t[k] = make_float2(0.f, 0.f);
+      if (i < n) {
+        const int sl = i / upg, u = i - sl * upg;
+        t[k] = __ldg(src + static_cast<size_t>(sl) * units + u);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s1 += t[k].x; s2 += t[k].y; }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { red[warp][0] = s1; red[warp][1] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float a = (red[0][0] + red[1][0]) + (red[2][0] + red[3][0]);
+    const float a2 = (red[0][1] + red[1][1]) + (red[2][1] + red[3][1]);
+    const float mean = a * inv_n;
+    const float var = fmaxf(a2 * inv_n - mean * mean, 0.f);
+    reinterpret_cast<float2*>(mean_var)[static_cast<size_t>(b) * groups + g] = make_float2(mean, var);
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm
 // One warp per row, the row lives in registers (two exact passes).
 template <int MAXV>
@@ -806,19 +846,27 @@ extern "C" int edtr_groupnorm_pool(const float* stats, int B, int HW, int C, int
   return check_launch("groupnorm_pool_kernel");
 }
 
-extern "C" int edtr_groupnorm_fold(const float* gn_partial, int B, int slabs, int C, int groups, float* mean_var,
-                                   void* stream) {
+extern "C" int edtr_groupnorm_fold(const float* gn_partial, int B, int slabs, int C, int groups, int unit,
+                                   float* mean_var, void* stream) {
   EDTR_REQUIRE(gn_partial && mean_var, "gn_partial/mean_var is NULL");
-  EDTR_REQUIRE(B > 0 && B <= 65535 && slabs > 0 && C > 0 && groups > 0 && C % groups == 0, "bad GroupNorm shape");
+  EDTR_REQUIRE(B > 0 && B <= 65535 && slabs > 0 && C > 0 && groups > 0 && groups <= 65535 && C % groups == 0,
+               "bad GroupNorm shape");
+  EDTR_REQUIRE(unit == 2 || unit == 4, "unit must be 2 or 4 (got %d)", unit);
   const int cpg = C / groups;
-  EDTR_REQUIRE(cpg == 4 || cpg == 8 || cpg == 16, "edtr_groupnorm_fold needs C / groups in {4, 8, 16} (got %d)", cpg);
+  EDTR_REQUIRE(cpg % unit == 0, "edtr_groupnorm_fold needs (C / groups) %% unit == 0 (C/groups %d, unit %d)", cpg, unit);
   EDTR_REQUIRE(((reinterpret_cast<uintptr_t>(gn_partial) & 31) == 0) && ((reinterpret_cast<uintptr_t>(mean_var) & 7) == 0),
                "gn_partial must be 32-byte aligned, mean_var 8-byte aligned");
-  const int units = C / 4;                       // C % 16 == 0 here, so the four-unit blocks tile the row
+  const int units = C / unit;
   const float inv_n = 1.f / (static_cast<float>(cpg) * 32.f * static_cast<float>(slabs));
-  EDTR_LAUNCH(groupnorm_fold_kernel, dim3(units / 4, B), 512, 0, static_cast<cudaStream_t>(stream), gn_partial, slabs,
-              units, groups, cpg, inv_n, mean_var);
-  return check_launch("groupnorm_fold_kernel");
+  const cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (unit == 4 && (cpg == 4 || cpg == 8 || cpg == 16) && slabs >= 256) {
+    // the streaming VAE tensors: four-unit blocks (C % 16 == 0 here), 32 contiguous bytes per slab and thread
+    EDTR_LAUNCH(groupnorm_fold_kernel, dim3(units / 4, B), 512, 0, st, gn_partial, slabs, units, groups, cpg, inv_n, mean_var);
+    return check_launch("groupnorm_fold_kernel");
+  }
+  EDTR_LAUNCH(groupnorm_fold_general_kernel, dim3(groups, B), 128, 0, st, gn_partial, slabs, units, groups, cpg / unit,
+              inv_n, mean_var);
+  return check_launch("groupnorm_fold_general_kernel");
 }
 
 extern "C" int edtr_groupnorm_fused_supported(int B, int HW, int C, int groups) {

@@ -218,6 +218,55 @@ class _ScopedWorkspace:
         return self.base.get(self.prefix + "gn_partial", (ops.groupnorm_partial_size(B, hw, C, groups),), F32)
 
 
+# ------------------------------------------------------------------ GroupNorm statistics from the producing epilogue
+class _EpilogueGN:
+    """Mixin of the engines' block runners.  Almost every GroupNorm of the path reads a tensor that a convolution / GEMM
+    of the same pass has just written, so the producer's epilogue delivers per-(32-row slab, 2- or 4-channel unit)
+    partial sums (EdtrEpilogue.gn_partial) and the GroupNorm becomes fold (tiny) + apply instead of a statistics pass
+    over the tensor + apply (4 instead of 6 bytes of HBM traffic per element on the streaming VAE tensors) or instead of
+    the latency-bound single-launch cluster kernel (UNet / ControlNet).  `_gnp_request` is called by every producer of a
+    tensor a GroupNorm may read: it registers the partial buffer under (address, channels) of the tensor, or drops a
+    stale registration when the shape is not eligible; `_gn_apply` consumes the registration or falls back to the
+    statistics-pass kernels (concatenated decoder inputs, tiled paths, small or odd shapes)."""
+
+    EPILOGUE_GN = os.environ.get("EDTR_EPILOGUE_GN", "1") != "0"
+    EPILOGUE_GN_MIN_BYTES = 0      # per-engine threshold on the tensor size (bytes) below which the plain kernels are kept
+
+    def _gnp_table(self) -> Dict:
+        return self.__dict__.setdefault("_gnp", {})
+
+    def _gnp_request(self, ws, out: torch.Tensor, K: int, phases: int = 1) -> Optional[torch.Tensor]:
+        ops = self.ops
+        table = self._gnp_table()
+        B, C = out.shape[0], out.shape[-1]
+        HW = out.numel() // (B * C)
+        key = (out.data_ptr(), C)
+        table.pop(key, None)
+        if not self.EPILOGUE_GN or out.dtype != BF16 or not hasattr(ops, "gn_partial_supported"):
+            return None
+        if out.numel() * 2 < self.EPILOGUE_GN_MIN_BYTES:
+            return None
+        if HW % (32 * phases) or not ops.gn_partial_supported(B * HW, HW, C, K):
+            return None
+        part = ws.get(f"gnp_{key[0]:x}_{C}", ops.gn_partial_shape(B, HW, C), F32)
+        table[key] = (part, B, HW)
+        return part
+
+    def _gnp_forget(self, t: torch.Tensor) -> None:
+        """`t` is about to be modified in place by a launch that does not produce statistics."""
+        self._gnp_table().pop((t.data_ptr(), t.shape[-1]), None)
+
+    def _gn_apply(self, ws, x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, silu: bool,
+                  out: torch.Tensor) -> torch.Tensor:
+        ops = self.ops
+        B, C = x.shape[0], x.shape[-1]
+        ent = self._gnp_table().pop((x.data_ptr(), C), None)
+        if ent is not None and ent[1:] == (B, x.numel() // (B * C)):
+            mv = ops.groupnorm_fold(ent[0], C, 32, out=ws.get("gn_mv", (B, 32, 2), F32))
+            return ops.groupnorm_apply_stats(x, mv, gamma, beta, 32, eps, silu, out=out)
+        return ops.groupnorm(x, gamma, beta, 32, eps, silu, stats=ws.gn_scratch(ops, x), out=out)
+
+
 # ------------------------------------------------------------------ UNet / ControlNet
 class _PackedNet:
     """bf16/fp32 device copies of one UNet-family state-dict, laid out for the kernels."""
@@ -329,7 +378,12 @@ class _PackedNet:
         return n
 
 
-class _NetRunner:
+class _NetRunner(_EpilogueGN):
+    # A/B switches: EDTR_EPILOGUE_GN_UNET=0 keeps the single-launch / two-pass GroupNorm kernels in the UNet / ControlNet,
+    # EDTR_EPILOGUE_GN_MIN_KB=<n> keeps them for tensors below n KB
+    EPILOGUE_GN = _EpilogueGN.EPILOGUE_GN and os.environ.get("EDTR_EPILOGUE_GN_UNET", "1") != "0"
+    EPILOGUE_GN_MIN_BYTES = int(os.environ.get("EDTR_EPILOGUE_GN_MIN_KB", "0")) * 1024
+
     """Launch sequences of the reference leaf blocks on one packed net."""
 
     def __init__(self, net: _PackedNet, ws: Workspace, ops, tag: str, fold_ln: bool = True):
@@ -363,19 +417,30 @@ class _NetRunner:
         ops, ws, w = self.ops, self.ws, self.net.w
         B, H, W, cin = x.shape
         cout = out.shape[-1]
-        y = ops.groupnorm(x, w[p + "in_layers.0.weight"], w[p + "in_layers.0.bias"], 32, 1e-5, True,
-                          stats=ws.gn_scratch(ops, x), out=ws.get("gn", (B, H, W, cin)))
+        y = self._gn_apply(ws, x, w[p + "in_layers.0.weight"], w[p + "in_layers.0.bias"], 1e-5, True,
+                           ws.get("gn", (B, H, W, cin)))
         eo, _ = self.net.emb_off[p]
-        h = ops.conv3x3(y, w[p + "in_layers.2.weight"], bias=w[p + "in_layers.2.bias"],
-                        rowvec=self.emb[:, eo:eo + cout], out=ws.get("res_h", (B, H, W, cout)))
-        y2 = ops.groupnorm(h, w[p + "out_layers.0.weight"], w[p + "out_layers.0.bias"], 32, 1e-5, True,
-                           stats=ws.gn_scratch(ops, h), out=ws.get("gn", (B, H, W, cout)))
+        h = ws.get("res_h", (B, H, W, cout))
+        ops.conv3x3(y, w[p + "in_layers.2.weight"], bias=w[p + "in_layers.2.bias"], rowvec=self.emb[:, eo:eo + cout],
+                    out=h, **self._gnp_kw(h, 9 * cin))
+        y2 = self._gn_apply(ws, h, w[p + "out_layers.0.weight"], w[p + "out_layers.0.bias"], 1e-5, True,
+                            ws.get("gn", (B, H, W, cout)))
         if (p + "skip_connection.weight") in w:
             skip = ops.gemm(x, w[p + "skip_connection.weight"], bias=w[p + "skip_connection.bias"],
                             out=ws.get("res_skip", (B, H, W, cout)))
         else:
             skip = x
-        ops.conv3x3(y2, w[p + "out_layers.3.weight"], bias=w[p + "out_layers.3.bias"], residual=skip, out=out)
+        ops.conv3x3(y2, w[p + "out_layers.3.weight"], bias=w[p + "out_layers.3.bias"], residual=skip, out=out,
+                    **self._gnp_kw(out, 9 * cout))
+
+    def _gnp_kw(self, out: torch.Tensor, K: int, gemm: bool = False, phases: int = 1) -> Dict:
+        """Epilogue keyword arguments of the launch that produces `out` ([B, H, W, C], possibly a channel slice)."""
+        part = self._gnp_request(self.ws, out, K, phases)
+        if part is None:
+            return {}
+        if gemm:
+            return dict(gn_partial=part, gn_hw=out.numel() // (out.shape[0] * out.shape[-1]))
+        return dict(gn_partial=part)
 
     # -- SpatialTransformer.forward + BasicTransformerBlock (model/attention.py:283-302,230-234)
     def st(self, p: str, x: torch.Tensor, out: torch.Tensor, heads: int) -> None:
@@ -383,8 +448,7 @@ class _NetRunner:
         B, H, W, C = x.shape
         L = H * W
         t = p + "transformer_blocks.0."
-        y = ops.groupnorm(x, w[p + "norm.weight"], w[p + "norm.bias"], 32, 1e-6, False,
-                          stats=ws.gn_scratch(ops, x), out=ws.get("gn", (B, L, C)))
+        y = self._gn_apply(ws, x, w[p + "norm.weight"], w[p + "norm.bias"], 1e-6, False, ws.get("gn", (B, L, C)))
         co, _ = self.net.ctx_off[p]
         if self.fold_ln:
             # LayerNorm never runs as a kernel: the GEMM that produces each residual-stream tensor emits per-row partial
@@ -409,7 +473,8 @@ class _NetRunner:
             g = ops.gemm(t2, wq, bias=bq, ln=(rs[2], C, 1e-5, cs), act=ops.ACT_GEGLU, out=ws.get("st_ff", (B, L, 4 * C)))
             t3 = ops.gemm(g, w[t + "ff.net.2.weight"], bias=w[t + "ff.net.2.bias"], residual=t2,
                           out=ws.get("st_t1", (B, L, C)))
-            ops.gemm(t3, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out)
+            ops.gemm(t3, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out,
+                     **self._gnp_kw(out, C, gemm=True))
             return
         t0 = ops.gemm(y, w[p + "proj_in.weight"], bias=w[p + "proj_in.bias"], out=ws.get("st_t0", (B, L, C)))
         # self-attention
@@ -432,10 +497,12 @@ class _NetRunner:
                      out=ws.get("st_ff", (B, L, 4 * C)))
         t3 = ops.gemm(g, w[t + "ff.net.2.weight"], bias=w[t + "ff.net.2.bias"], residual=t2,
                       out=ws.get("st_t1", (B, L, C)))
-        ops.gemm(t3, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out)
+        ops.gemm(t3, w[p + "proj_out.weight"], bias=w[p + "proj_out.bias"], residual=x, out=out,
+                 **self._gnp_kw(out, C, gemm=True))
 
     def conv(self, q: str, x: torch.Tensor, out: torch.Tensor, **kw) -> None:
-        self.ops.conv3x3(x, self.net.w[q + "weight"], bias=self.net.w[q + "bias"], out=out, **kw)
+        self.ops.conv3x3(x, self.net.w[q + "weight"], bias=self.net.w[q + "bias"], out=out,
+                         **self._gnp_kw(out, 9 * x.shape[-1]), **kw)
 
     # -- Downsample (model/unet.py:99-108): 3x3 stride 2 pad 1 ----------------------------
     def down(self, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
@@ -443,14 +510,15 @@ class _NetRunner:
         B, H, W, C = x.shape
         Ho, Wo = (H + 1) // 2, (W + 1) // 2
         col = ops.im2col(x, 3, 3, 2, 1, 1, Ho, Wo, out=ws.get("col", (B * Ho * Wo, 9 * C)))
-        ops.gemm(col, w[p + "op.weight"], bias=w[p + "op.bias"], out=out)
+        ops.gemm(col, w[p + "op.weight"], bias=w[p + "op.bias"], out=out, **self._gnp_kw(out, 9 * C, gemm=True))
 
     # -- Upsample (model/unet.py:69-79): nearest x2 then 3x3 ------------------------------
     def up(self, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
         B, H, W, C = x.shape
         w = self.net.w
         if self.ops.conv3x3_up2x_supported(B, H, W, C, out.shape[-1]):
-            self.ops.conv3x3_up2x(x, w[p + "conv.weight_up2x"], bias=w[p + "conv.bias"], out=out)
+            self.ops.conv3x3_up2x(x, w[p + "conv.weight_up2x"], bias=w[p + "conv.bias"], out=out,
+                                  **self._gnp_kw(out, 4 * C, phases=4))
             return
         u = self.ops.upsample2x(x, out=self.ws.get("up", (B, 2 * H, 2 * W, C)))
         self.conv(p + "conv.", u, out)
@@ -633,7 +701,9 @@ class CldmEngine:
         # zero-conv epilogues accumulate into the UNet tensors (model/controlnet.py:270-275,31,37).  (Running the shallow
         # ones on the side stream under the first decoder blocks was measured: no gain, profiles/r01g_overlap.txt.)
         for s in range(n_in):
+            un._gnp_forget(hs_view(s))      # modified in place below: the encoder's statistics no longer describe it
             self._zero_conv(w, f"zero_convs.{s}.0.", couts[s], hs_view(s), control_scales[s])
+        un._gnp_forget(mid)
         self._zero_conv(w, "middle_block_out.0.", couts[n_in], mid, control_scales[n_in])
 
         # UNet decoder (model/controlnet.py:33-38)
@@ -646,8 +716,7 @@ class CldmEngine:
             un.block(f"output_blocks.{j}.", blk, cats[j], out)
         # out: GroupNorm32 -> SiLU -> conv3x3 (model/unet.py:675-679), stored NCHW fp32
         uw = self.unet.w
-        y = ops.groupnorm(out, uw["out.0.weight"], uw["out.0.bias"], 32, 1e-5, True, stats=ws.gn_scratch(ops, out),
-                          out=ws.get("gn", (B, H, W, self.final_ch)))
+        y = un._gn_apply(un.ws, out, uw["out.0.weight"], uw["out.0.bias"], 1e-5, True, un.ws.get("gn", (B, H, W, self.final_ch)))
         ops.conv3x3(y, uw["out.2.weight"], bias=uw["out.2.bias"], out=eps_out.view(B, self.out_c, H * W),
                     out_mode=ops.OUT_NCHW_F32)
         return eps_out
@@ -858,42 +927,13 @@ class _Graph:
 
 
 # ------------------------------------------------------------------------ VAE decoder
-class _VaeBlocks:
+class _VaeBlocks(_EpilogueGN):
     """Leaf blocks shared by the VAE decoder and encoder engines (model/vae.py:64-124, :250-308); the kernels are
     reached through ``self.ops`` and the packed weights through ``self.w``."""
 
-    # GroupNorm statistics from the producing epilogue (untiled paths).  Every GroupNorm of the VAE reads a tensor that a
-    # convolution / GEMM of the same pass has just written, so the producer's epilogue delivers the per-(32-row slab,
-    # 4-channel unit) partial sums (EdtrEpilogue.gn_partial) and the GroupNorm becomes fold (tiny) + apply instead of a
-    # statistics pass over the tensor + apply: 4 instead of 6 bytes of HBM traffic per element.  `_gnp_request` is called
-    # by every producer of a tensor a GroupNorm may read: it registers the partial buffer under the tensor's address, or
-    # drops a stale registration when the shape is not eligible (small tensors keep the single-launch / two-pass kernels).
-    EPILOGUE_GN = os.environ.get("EDTR_EPILOGUE_GN", "1") != "0"
-
-    def _gnp_request(self, ws: Workspace, out: torch.Tensor, K: int, phases: int = 1) -> Optional[torch.Tensor]:
-        ops = self.ops
-        table = self.__dict__.setdefault("_gnp", {})
-        B, C = out.shape[0], out.shape[-1]
-        HW = out.numel() // (B * C)
-        key = out.data_ptr()
-        table.pop(key, None)
-        if not self.EPILOGUE_GN or out.dtype != BF16 or not hasattr(ops, "gn_partial_supported"):
-            return None
-        if HW % (32 * phases) or not ops.gn_partial_supported(B * HW, HW, C, K):
-            return None
-        part = ws.get(f"gnp_{key:x}", ops.gn_partial_shape(B, HW, C), F32)
-        table[key] = (part, B, HW, C)
-        return part
-
     def _gn(self, ws: Workspace, x: torch.Tensor, key: str, silu: bool, out: torch.Tensor) -> torch.Tensor:
         """GroupNorm (+SiLU) of `x` with the parameters `key`; uses the producer's epilogue statistics when registered."""
-        ops, w = self.ops, self.w
-        B, C = x.shape[0], x.shape[-1]
-        ent = self.__dict__.setdefault("_gnp", {}).pop(x.data_ptr(), None)
-        if ent is not None and ent[1:] == (B, x.numel() // (B * C), C):
-            mv = ops.groupnorm_fold(ent[0], 32, out=ws.get("gn_mv", (B, 32, 2), F32))
-            return ops.groupnorm_apply_stats(x, mv, w[key + "weight"], w[key + "bias"], 32, 1e-6, silu, out=out)
-        return ops.groupnorm(x, w[key + "weight"], w[key + "bias"], 32, 1e-6, silu, stats=ws.gn_scratch(ops, x), out=out)
+        return self._gn_apply(ws, x, self.w[key + "weight"], self.w[key + "bias"], 1e-6, silu, out)
 
     def _res(self, ws: Workspace, p: str, x: torch.Tensor, out: torch.Tensor) -> None:
         """ResnetBlock.forward, temb=None (model/vae.py:103-124)."""
@@ -1071,7 +1111,7 @@ class VaeDecoderEngine(_VaeBlocks):
         ping = lambda i, shape: ws.get(f"v_h{i % 2}", shape)
         n = 0
         h = ping(n, (B, H, W, self.top))
-        self.__dict__.setdefault("_gnp", {}).clear()
+        self._gnp_table().clear()
         part = self._gnp_request(ws, h, 9 * 64)
         ops.conv3x3(zin, w["decoder.conv_in.weight"], bias=w["decoder.conv_in.bias"], out=h,
                     **(dict(gn_partial=part) if part is not None else {}))
@@ -1274,7 +1314,7 @@ class VaeEncoderEngine(_VaeBlocks):
         ops.nchw_to_nhwc(image, xin, 0)
         ping = lambda i, shape: ws.get(f"e_h{i % 2}", shape)
         n = 0
-        self.__dict__.setdefault("_gnp", {}).clear()
+        self._gnp_table().clear()
         h = self._conv_any(ws, xin, "encoder.conv_in.", out=ping(n, (B, H, W, self.dd["ch"])), gn=True)
         for level, blocks, has_down in self.levels:
             for i, (ci, co) in enumerate(blocks):

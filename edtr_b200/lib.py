@@ -68,6 +68,7 @@ class EdtrEpilogue(Structure):
         ("gn_hw", c_int32),
         ("gn_slabs", c_int32),
         ("gn_slab0", c_int32),
+        ("gn_unit", c_int32),
     ]
 
 
@@ -148,7 +149,7 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_groupnorm_pool.restype = ci
     lib.edtr_groupnorm_pool.argtypes = [vp, ci, ci, ci, ci, c_float, vp, vp]
     lib.edtr_groupnorm_fold.restype = ci
-    lib.edtr_groupnorm_fold.argtypes = [vp, ci, ci, ci, ci, vp, vp]
+    lib.edtr_groupnorm_fold.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp]
     lib.edtr_groupnorm_apply_stats.restype = ci
     lib.edtr_groupnorm_apply_stats.argtypes = [vp, ci, vp, ci, ci, ci, ci, ci, vp, vp, vp, c_float, ci, vp]
     lib.edtr_groupnorm_apply.restype = ci

@@ -125,6 +125,7 @@ def _f32(t: Optional[torch.Tensor], n: int, name: str) -> Optional[int]:
 
 def _epilogue(M: int, n_out: int, out: torch.Tensor, *, bias, rowvec, rows_per_group, residual, act, out_mode, hw,
               alpha, ln=None, row_stats=None, gn_partial=None, gn_hw=0, gn_phases=1) -> EdtrEpilogue:
+    # (the unit width of gn_partial, 2 or 4 channels, is read off its shape: [images, slabs, N / unit, 2])
     ep = EdtrEpilogue()
     dev = out.device.index if out.device.index is not None else torch.cuda.current_device()
     _lib.device_lib(dev)
@@ -149,18 +150,22 @@ def _epilogue(M: int, n_out: int, out: torch.Tensor, *, bias, rowvec, rows_per_g
         ep.row_stats = row_stats.data_ptr()
         ep.row_stats_cap = row_stats.shape[1]
     if gn_partial is not None:
-        # GroupNorm partial sums from the epilogue: fp32 [images, slabs, N/4, 2], slabs = gn_phases * gn_hw / 32
+        # GroupNorm partial sums from the epilogue: fp32 [images, slabs, N/unit, 2], slabs = gn_phases * gn_hw / 32
         if act == ACT_GEGLU or out_mode != OUT_BF16:
             raise ValueError("gn_partial needs a bf16 output and act != GEGLU")
         if gn_hw <= 0 or gn_hw % 32 or (M // gn_phases) % gn_hw or n_out % 4:
             raise ValueError(f"gn_partial needs gn_hw % 32 == 0 and gn_hw | M (gn_hw {gn_hw}, M {M})")
-        want = (M // gn_phases // gn_hw, gn_phases * gn_hw // 32, n_out // 4, 2)
-        if gn_partial.dtype != torch.float32 or tuple(gn_partial.shape) != want or not gn_partial.is_contiguous():
-            raise ValueError(f"gn_partial must be a contiguous fp32 {want} tensor, got {tuple(gn_partial.shape)}")
+        unit = n_out // gn_partial.shape[2] if gn_partial.dim() == 4 and gn_partial.shape[2] > 0 else 0
+        want = (M // gn_phases // gn_hw, gn_phases * gn_hw // 32, n_out // max(unit, 1), 2)
+        if unit not in (2, 4) or gn_partial.dtype != torch.float32 or tuple(gn_partial.shape) != want \
+                or not gn_partial.is_contiguous():
+            raise ValueError(f"gn_partial must be a contiguous fp32 [images, slabs, N/unit (unit 2 or 4), 2] tensor "
+                             f"(e.g. {want}), got {tuple(gn_partial.shape)}")
         ep.gn_partial = gn_partial.data_ptr()
         ep.gn_hw = gn_hw
         ep.gn_slabs = want[1]
         ep.gn_slab0 = 0
+        ep.gn_unit = unit
     ep.bias = _f32(bias, n_out if act != ACT_GEGLU else 2 * n_out, "bias")
     if rowvec is not None:
         if rowvec.dtype != torch.float32 or rowvec.dim() != 2 or rowvec.stride(1) != 1:
@@ -403,33 +408,42 @@ def groupnorm_pool(x: torch.Tensor, groups: int, weight: float, acc: torch.Tenso
     return acc
 
 
+def gn_partial_unit(C: int, groups: int = 32) -> int:
+    """Channels per unit of the epilogue's GroupNorm partial sums: 4 when the group width allows it, else 2 (0: none)."""
+    if C % groups:
+        return 0
+    cpg = C // groups
+    return 4 if cpg % 4 == 0 else (2 if cpg % 2 == 0 else 0)
+
+
 def gn_partial_supported(M: int, HW: int, N: int, K: int, groups: int = 32) -> bool:
     """True when the GEMM / convolution that produces an [M, N] tensor (HW rows per image) can deliver the GroupNorm
-    partial sums from its epilogue: CTA-pair kernel, 32-row slabs inside one image, 4-channel units inside one group
-    (C / groups in {4, 8, 16}: the VAE widths), and a shape the planner would not split along K anyway."""
-    if M < 256 or N % 64 or HW % 32 or M % HW or N % groups or (N // groups) not in (4, 8, 16):
+    partial sums from its epilogue: CTA-pair kernel, 32-row slabs inside one image, 2- or 4-channel units inside one
+    group, and a shape the planner would not split along K anyway."""
+    if M < 256 or N % 64 or HW % 32 or M % HW or gn_partial_unit(N, groups) == 0:
         return False
     return gemm_workspace_size(M, N, K) == 0
 
 
-def gn_partial_shape(B: int, HW: int, C: int) -> Tuple[int, int, int, int]:
-    return (B, HW // 32, C // 4, 2)
+def gn_partial_shape(B: int, HW: int, C: int, groups: int = 32) -> Tuple[int, int, int, int]:
+    return (B, HW // 32, C // gn_partial_unit(C, groups), 2)
 
 
-def groupnorm_fold(gn_partial: torch.Tensor, groups: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def groupnorm_fold(gn_partial: torch.Tensor, C: int, groups: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """(mean, biased variance) per (image, group), fp32 [B, groups, 2], from the partial sums an epilogue wrote
-    (gn_partial fp32 [B, slabs, C/4, 2]); feeds groupnorm_apply_stats."""
+    (gn_partial fp32 [B, slabs, C/unit, 2], C channels); feeds groupnorm_apply_stats."""
     _require_cuda(gn_partial, out)
     if gn_partial.dtype != torch.float32 or gn_partial.dim() != 4 or gn_partial.shape[3] != 2 or not gn_partial.is_contiguous():
-        raise ValueError("gn_partial must be a contiguous fp32 [B, slabs, C/4, 2] tensor")
+        raise ValueError("gn_partial must be a contiguous fp32 [B, slabs, C/unit, 2] tensor")
     B, slabs, units, _ = gn_partial.shape
-    C = 4 * units
+    if C % units or C // units not in (2, 4):
+        raise ValueError(f"gn_partial has {units} units per row: not C / 2 or C / 4 of C = {C}")
     if out is None:
         out = torch.empty((B, groups, 2), dtype=torch.float32, device=gn_partial.device)
     elif out.dtype != torch.float32 or tuple(out.shape) != (B, groups, 2) or not out.is_contiguous():
         raise ValueError(f"out must be a contiguous fp32 [{B}, {groups}, 2] tensor")
-    _lib.check(_lib.device_lib().edtr_groupnorm_fold(gn_partial.data_ptr(), B, slabs, C, groups, out.data_ptr(), _stream()),
-               "edtr_groupnorm_fold")
+    _lib.check(_lib.device_lib().edtr_groupnorm_fold(gn_partial.data_ptr(), B, slabs, C, groups, C // units,
+                                                     out.data_ptr(), _stream()), "edtr_groupnorm_fold")
     return out
 
 

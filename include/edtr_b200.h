@@ -101,10 +101,11 @@ typedef struct EdtrEpilogue {
   int32_t row_stats_cap;
   /* ---- GroupNorm statistics of the STORED matrix, produced by the epilogue (replaces the statistics pass of the
    * GroupNorm that consumes this launch's output: model/vae.py:103-113 norm1 / norm2, :279-283, :553): gn_partial =
-   * fp32 [images][gn_slabs][N/4][2].  Output rows are grouped in 32-row slabs (one epilogue warp; gn_hw = output rows
-   * per image of THIS launch, gn_hw % 32 == 0, gn_hw | M) and columns in 4-channel units; the launch writes, for every
+   * fp32 [images][gn_slabs][N/u][2], u = gn_unit (4, or 2 for group widths that are not multiples of 4: 320 / 32 = 10).
+   * Output rows are grouped in 32-row slabs (one epilogue warp; gn_hw = output rows
+   * per image of THIS launch, gn_hw % 32 == 0, gn_hw | M) and columns in u-channel units; the launch writes, for every
    * (slab, unit) it covers, the (sum, sum of squares) of the fp32 values before bf16 rounding to
-   * gn_partial[((image * gn_slabs + gn_slab0 + slab_in_image) * (N/4) + unit) * 2] — every entry exactly once, no
+   * gn_partial[((image * gn_slabs + gn_slab0 + slab_in_image) * (N/u) + unit) * 2] — every entry exactly once, no
    * atomics, fixed summation order.  gn_slabs >= gn_slab0 + gn_hw / 32 is the slab count per image of the buffer
    * (edtr_conv3x3_up2x_bf16 fills 4 * H*W/32 slabs per image: the library offsets gn_slab0 per phase itself).
    * edtr_groupnorm_fold turns the buffer into (mean, variance) per (image, group) for edtr_groupnorm_apply_stats.
@@ -114,6 +115,7 @@ typedef struct EdtrEpilogue {
   int32_t gn_hw;
   int32_t gn_slabs;
   int32_t gn_slab0;
+  int32_t gn_unit; /* channels per unit: 0 (= 4), 2 or 4 */
 } EdtrEpilogue;
 
 
@@ -203,11 +205,13 @@ int edtr_groupnorm_apply_stats(const void* X, int ldx, void* Y, int ldy, int B, 
                                const float* mean_var, const float* gamma, const float* beta, float eps, int silu,
                                void* stream);
 /* Folds the partial sums a GEMM / convolution epilogue wrote through EdtrEpilogue.gn_partial (fp32
- * [B][slabs][C/4][2], every slab = 32 rows of the image) into mean_var[B][groups][2] = (mean, biased variance) per
- * (image, group), the input of edtr_groupnorm_apply_stats: the GroupNorm of a tensor that a convolution just produced
- * needs no pass over the tensor for its statistics.  C / groups in {4, 8, 16}; fixed reduction order (deterministic).
+ * [B][slabs][C/unit][2], every slab = 32 rows of the image, unit = 2 or 4 channels) into mean_var[B][groups][2] =
+ * (mean, biased variance) per (image, group), the input of edtr_groupnorm_apply_stats: the GroupNorm of a tensor that
+ * a convolution just produced needs no pass over the tensor for its statistics.  (C / groups) % unit == 0; fixed
+ * reduction order (deterministic).
  * replaces: the statistics half of GroupNorm — model/vae.py:26-28 (Normalize), model/util.py:161-163. */
-int edtr_groupnorm_fold(const float* gn_partial, int B, int slabs, int C, int groups, float* mean_var, void* stream);
+int edtr_groupnorm_fold(const float* gn_partial, int B, int slabs, int C, int groups, int unit, float* mean_var,
+                        void* stream);
 
 /* Single-launch GroupNorm (+SiLU) for small L2-resident tensors (<= 1 MB per image): a thread-block cluster per
  * image, statistics exchanged through distributed shared memory, deterministic.  Same arithmetic as

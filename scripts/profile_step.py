@@ -147,9 +147,9 @@ def main():
                     key = (name, q.shape[0] * q.shape[1], k_.shape[1], q.shape[2], "")
                     fl = 4.0 * q.shape[0] * q.shape[1] * k_.shape[1] * q.shape[2]
                 elif name == "groupnorm_fold":
-                    pt = args[0]            # [B, slabs, C/4, 2]
-                    key = ("groupnorm_fold", pt.shape[0] * pt.shape[1] * 32, pt.shape[2] * 4, 0, "+apply")
-                    fl = 4.0 * pt.shape[0] * pt.shape[1] * 32 * pt.shape[2] * 4
+                    pt = args[0]            # [B, slabs, C/unit, 2], C
+                    key = ("groupnorm_fold", pt.shape[0] * pt.shape[1] * 32, args[1], 0, "+apply")
+                    fl = 4.0 * pt.shape[0] * pt.shape[1] * 32 * args[1]
                 elif name in ("groupnorm", "layernorm"):
                     x = args[0]
                     key = (name, x.numel() // x.shape[-1], x.shape[-1], 0, "")

@@ -89,8 +89,10 @@ def _finish(v, M, n_out, *, bias, rowvec, rows_per_group, residual, act, out, ou
     if gn_partial is not None:
         # EdtrEpilogue.gn_partial: (sum, sum of squares) per (32-row slab, 4-column unit) of the fp32 values
         assert act != ACT_GEGLU and out_mode == OUT_BF16 and gn_hw % 32 == 0 and M % gn_hw == 0 and n_out % 4 == 0
-        assert gn_partial.dtype == torch.float32 and tuple(gn_partial.shape) == (M // gn_hw, gn_hw // 32, n_out // 4, 2)
-        u = v.view(M // gn_hw, gn_hw // 32, 32, n_out // 4, 4)
+        unit = n_out // gn_partial.shape[2]
+        assert unit in (2, 4) and gn_partial.dtype == torch.float32
+        assert tuple(gn_partial.shape) == (M // gn_hw, gn_hw // 32, n_out // unit, 2)
+        u = v.view(M // gn_hw, gn_hw // 32, 32, n_out // unit, unit)
         gn_partial[..., 0] = u.sum((2, 4))
         gn_partial[..., 1] = (u * u).sum((2, 4))
     if out_mode in (OUT_BF16, OUT_F32):
@@ -167,10 +169,11 @@ def conv3x3_up2x(x, w4, *, bias=None, act=ACT_NONE, out=None, gn_partial=None):
         y = F.leaky_relu(y, 0.2)
     if gn_partial is not None:
         # slabs of an image: phase-major (four launches), 32 consecutive low-resolution pixels each
-        assert (H * W) % 32 == 0 and tuple(gn_partial.shape) == (B, 4 * H * W // 32, Cout // 4, 2)
+        unit = Cout // gn_partial.shape[2]
+        assert (H * W) % 32 == 0 and unit in (2, 4) and tuple(gn_partial.shape) == (B, 4 * H * W // 32, Cout // unit, 2)
         for py in (0, 1):
             for px in (0, 1):
-                u = y[:, py::2, px::2, :].reshape(B, H * W // 32, 32, Cout // 4, 4)
+                u = y[:, py::2, px::2, :].reshape(B, H * W // 32, 32, Cout // unit, unit)
                 sl = slice((py * 2 + px) * (H * W // 32), (py * 2 + px + 1) * (H * W // 32))
                 gn_partial[:, sl, :, 0] = u.sum((2, 4))
                 gn_partial[:, sl, :, 1] = (u * u).sum((2, 4))
@@ -220,21 +223,28 @@ def groupnorm_pool(x, groups, weight, acc, stats=None):
 GN_PARTIAL = True   # tests flip this to run the engines without epilogue GroupNorm statistics
 
 
+def gn_partial_unit(C, groups=32):
+    if C % groups:
+        return 0
+    cpg = C // groups
+    return 4 if cpg % 4 == 0 else (2 if cpg % 2 == 0 else 0)
+
+
 def gn_partial_supported(M, HW, N, K, groups=32):
-    return bool(GN_PARTIAL and M >= 256 and N % 64 == 0 and HW % 32 == 0 and M % HW == 0 and N % groups == 0
-                and (N // groups) in (4, 8, 16))
+    return bool(GN_PARTIAL and M >= 256 and N % 64 == 0 and HW % 32 == 0 and M % HW == 0 and gn_partial_unit(N, groups))
 
 
-def gn_partial_shape(B, HW, C):
-    return (B, HW // 32, C // 4, 2)
+def gn_partial_shape(B, HW, C, groups=32):
+    return (B, HW // 32, C // gn_partial_unit(C, groups), 2)
 
 
-def groupnorm_fold(gn_partial, groups, out=None):
+def groupnorm_fold(gn_partial, C, groups, out=None):
     LAUNCHES[0] += 1
     B, slabs, units, _ = gn_partial.shape
-    cpg = 4 * units // groups
-    assert cpg in (4, 8, 16)
-    s = gn_partial.view(B, slabs, groups, cpg // 4, 2).sum((1, 3))
+    unit = C // units
+    cpg = C // groups
+    assert unit in (2, 4) and cpg % unit == 0
+    s = gn_partial.view(B, slabs, groups, cpg // unit, 2).sum((1, 3))
     n = float(cpg * 32 * slabs)
     mean = s[..., 0] / n
     var = torch.clamp(s[..., 1] / n - mean * mean, min=0.0)

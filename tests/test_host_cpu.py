@@ -729,3 +729,44 @@ def test_vae_groupnorm_from_epilogue_partials_equals_statistics_pass():
     ref = O.vae_encode_moments(sde, v, img)
     err_p, err_s = O.max_rel_err(mo, ref), O.max_rel_err(mo2, ref)
     assert err_p < 2e-2 and err_p < 1.5 * err_s + 2e-3, (err_p, err_s, n_enc)
+
+
+def test_unet_groupnorm_from_epilogue_partials_equals_statistics_pass():
+    """UNet / ControlNet: the GroupNorms whose input a convolution / GEMM of the same pass produced (ResBlock in / out
+    layers, SpatialTransformer norm, the output norm) take their statistics from that producer's epilogue — 2-channel
+    units at model_channels = 320-style group widths (C / 32 = 10) and 4-channel units elsewhere; the concatenated
+    decoder inputs and the small levels keep the statistics kernels.  Both dataflows are compared with the fp32 oracle."""
+    from edtr_b200.engine import CldmEngine
+
+    net = dict(in_channels=4, out_channels=4, model_channels=320, attention_resolutions=(1,), num_res_blocks=1,
+               channel_mult=(1, 2), num_head_channels=64, context_dim=128)
+    cfg = dict(O.TINY, unet=net, controlnet=dict(net, hint_channels=4))
+    cfg["controlnet"].pop("out_channels")
+    w = O.make_cldm_weights(cfg, seed=3)
+    x_T, cond, _ = O.make_inputs(cfg, 1, 32, seed=4)
+    t = torch.full((1,), 150, dtype=torch.long)
+    folds, units = [], set()
+    real_fold = fake_ops.groupnorm_fold
+
+    def counting_fold(part, C, groups, out=None):
+        folds.append(C)
+        units.add(C // part.shape[2])
+        return real_fold(part, C, groups, out=out)
+
+    try:
+        fake_ops.groupnorm_fold = counting_fold
+        eng = CldmEngine(cfg["unet"], cfg["controlnet"], w["unet"], w["controlnet"], "cpu", ops=fake_ops)
+        eps_p = eng.forward(x_T, t, cond["c_img"], cond["c_txt"], use_graph=False)
+        n_folds = len(folds)
+        fake_ops.GN_PARTIAL = False
+        eng2 = CldmEngine(cfg["unet"], cfg["controlnet"], w["unet"], w["controlnet"], "cpu", ops=fake_ops)
+        eps_s = eng2.forward(x_T, t, cond["c_img"], cond["c_txt"], use_graph=False)
+        assert len(folds) == n_folds
+    finally:
+        fake_ops.GN_PARTIAL = True
+        fake_ops.groupnorm_fold = real_fold
+    assert n_folds >= 10 and units == {2, 4}, (n_folds, units)
+    with torch.no_grad():
+        ref = O.cldm_forward(w, cfg, x_T, t, cond)
+    err_p, err_s = O.max_rel_err(eps_p, ref), O.max_rel_err(eps_s, ref)
+    assert err_p < 3e-2 and err_p < 1.5 * err_s + 3e-3, (err_p, err_s)
