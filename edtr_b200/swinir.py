@@ -9,8 +9,9 @@ Layout: tokens and feature maps share one channels-last bf16 buffer ``[B, h, w, 
 wide (30 + 2 zero columns), the MLP hidden width 360 as 384.  The cyclic shift, window partition / reverse and patch
 embed / unembed of the reference are index arithmetic inside ``edtr_window_attention_bf16`` — no permute passes.
 
-UNVERIFIED ON HARDWARE (branch swinir-wip): the dataflow is checked on CPU against the live-reference fixture
-through the torch stand-in for the kernels (tests/test_host_cpu.py); the CUDA kernels it calls are compile-checked only.
+Checked on CPU against the live-reference fixture through the torch stand-in for the kernels (tests/test_host_cpu.py)
+and on B200 against the fixture and the fp32 oracle at the EDTR widths (tests/test_engine_gpu.py, test_kernels_gpu.py);
+measured 10.6 ms per 8 images of 512x512 (profiles/r02z_profile_swinir.txt).
 """
 from __future__ import annotations
 

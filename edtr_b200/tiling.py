@@ -1,8 +1,10 @@
 """Tiling helpers: latent windows of the cldm-tiled path (utils/common.py:151-165, 351-427) and the tile
 split of the tiled VAE (utils/tilevae/tilevae.py:325-399).  Host-side index arithmetic only.
 
-Same numerics as the reference: overlapped windows, gaussian weights, ``out / count``; tiles are
-evaluated one by one exactly as the reference does (batching the tiles of a step is planned).
+Same numerics as the reference: overlapped windows, gaussian weights, ``out / count``.  The generic wrapper here
+evaluates the tiles one by one as the reference does; an ``edtr_b200.ControlLDM`` takes ``CldmEngine.forward_tiled``
+instead, which runs all windows of a step (this rank's share of them) as one batched forward and blends them on the
+device (``edtr_tile_blend``).
 """
 from __future__ import annotations
 
