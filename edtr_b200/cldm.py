@@ -49,6 +49,42 @@ class ControlLDM(nn.Module):
         self.tile_group_check = True   # verify (one tiny collective per call) that the ranks really hold the same input
         self._engine = None
         self._engine_version = None
+        # "bf16" (default): the tensor-core engine.  "fp32": every tensor and every accumulation in fp32 through the
+        # edtr_f32_* kernels (engine_f32.py) — BASELINE.json's fp32 tolerance (per-step latent max-rel error <= 1e-4)
+        self.precision = "bf16"
+        self._engine32 = None
+        self._engine32_version = None
+        self._vae32 = None
+        self._vae32_version = None
+
+    def set_precision(self, precision: str) -> "ControlLDM":
+        """"bf16": tensor-core kernels, CUDA graphs (throughput mode).  "fp32": fp32 storage and accumulation on the CUDA
+        cores (accuracy mode; forward / sampling / vae_decode, untiled)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        self.precision = precision
+        return self
+
+    def engine_f32(self):
+        from .engine_f32 import CldmEngineF32
+
+        dev = next(self.unet.parameters()).device
+        ver = (state_version(self.unet), state_version(self.controlnet), dev)
+        if self._engine32 is None or self._engine32_version != ver:
+            self._engine32 = CldmEngineF32(self.unet.cfg, self.controlnet.cfg, self.unet.state_dict(),
+                                           self.controlnet.state_dict(), dev)
+            self._engine32_version = ver
+        return self._engine32
+
+    def _vae_decoder_f32(self):
+        from .engine_f32 import VaeDecoderF32
+
+        dev = next(self.vae.parameters()).device
+        ver = (state_version(self.vae), dev)
+        if self._vae32 is None or self._vae32_version != ver:
+            self._vae32 = VaeDecoderF32(self.vae.ddconfig, self.vae.embed_dim, self.vae.state_dict(), dev)
+            self._vae32_version = ver
+        return self._vae32
 
     # ----------------------------------------------------------------- construction helpers
     @classmethod
@@ -118,6 +154,7 @@ class ControlLDM(nn.Module):
         (EMA updates, hand-written loaders) — such writes do not bump the version counters `engine()` watches."""
         self._engine = None
         self._engine_version = None
+        self._engine32 = self._engine32_version = self._vae32 = self._vae32_version = None
         self.vae.invalidate_engine()
 
     refresh_weights = invalidate_engine
@@ -167,6 +204,10 @@ class ControlLDM(nn.Module):
         """model/cldm.py:136-156.  Returns fp32 NCHW in [-1, 1].  tiled=True is the reference's VAEHook decode
         (utils/tilevae/tilevae.py:307-579, pooled GroupNorm statistics); with `self.tile_group` set (opt-in, same
         latent on every rank) its tiles are spread over the ranks of that group (config C4)."""
+        if self.precision == "fp32":
+            if tiled:
+                raise NotImplementedError("the tiled VAE decode runs in the bf16 mode only")
+            return self._vae_decoder_f32().decode(z.float().contiguous(), float(self.scale_factor))
         eng = self.vae._decoder_engine()
         if not tiled:
             return eng.decode(z.float().contiguous(), float(self.scale_factor))
@@ -195,6 +236,10 @@ class ControlLDM(nn.Module):
         if woSD:
             raise NotImplementedError("woSD=True (tail_block) is not on the EDTR path")
         c_txt, c_img = cond["c_txt"], cond["c_img"]
+        if self.precision == "fp32":
+            eps = self.engine_f32().forward(x_noisy.float().contiguous(), t.long().contiguous(), c_img.float().contiguous(),
+                                            c_txt.float().contiguous(), control_scales=self.control_scales)
+            return eps.to(x_noisy.dtype)
         eps = self.engine().forward(x_noisy.float().contiguous(), t.long().contiguous(), c_img.float().contiguous(),
                                     c_txt.float().contiguous(), control_scales=self.control_scales)
         return eps.to(x_noisy.dtype)

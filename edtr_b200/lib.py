@@ -18,7 +18,7 @@ _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 _REPO_DIR = os.path.dirname(_PKG_DIR)
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 LIB_PATH = os.path.join(_PKG_DIR, "libedtr_b200.so")
-SOURCES = ["api.cu", "gemm_conv.cu", "gemm2.cu", "attention.cu", "norm.cu", "elementwise.cu", "swin.cu"]
+SOURCES = ["api.cu", "gemm_conv.cu", "gemm2.cu", "attention.cu", "norm.cu", "elementwise.cu", "swin.cu", "f32.cu"]
 HEADER = os.path.join(_REPO_DIR, "include", "edtr_b200.h")
 
 NVCC_FLAGS = [
@@ -35,6 +35,8 @@ EXPORTED = [
     "edtr_window_attention_bf16", "edtr_softmax_rows", "edtr_upsample2x_bf16", "edtr_im2col_bf16",
     "edtr_nchw_f32_to_nhwc_bf16", "edtr_pointwise_nchw_f32_to_nhwc_bf16", "edtr_nhwc_bf16_to_nchw", "edtr_cast_f32_to_bf16",
     "edtr_tile_blend", "edtr_timestep_embedding", "edtr_sampler_update", "edtr_wavelet_level",
+    "edtr_f32_gemm", "edtr_f32_groupnorm_scratch_bytes", "edtr_f32_groupnorm", "edtr_f32_layernorm", "edtr_f32_softmax_rows",
+    "edtr_f32_geglu", "edtr_f32_silu", "edtr_f32_nchw_to_nhwc", "edtr_f32_timestep_embedding",
 ]
 
 
@@ -69,6 +71,24 @@ class EdtrEpilogue(Structure):
         ("gn_slabs", c_int32),
         ("gn_slab0", c_int32),
         ("gn_unit", c_int32),
+    ]
+
+
+class EdtrF32Gemm(Structure):
+    """Mirror of ``struct EdtrF32Gemm`` (include/edtr_b200.h): the generic fp32 implicit GEMM of the fp32 mode."""
+
+    _fields_ = [
+        ("A", c_void_p), ("W", c_void_p), ("C", c_void_p),
+        ("M", c_int32), ("N", c_int32), ("K", c_int32),
+        ("lda", c_int64), ("ldw", c_int64), ("ldc", c_int64),
+        ("w_kn", c_int32), ("batch1", c_int32), ("batch2", c_int32),
+        ("a_stride1", c_int64), ("a_stride2", c_int64), ("w_stride1", c_int64), ("w_stride2", c_int64),
+        ("c_stride1", c_int64), ("c_stride2", c_int64),
+        ("conv", c_int32), ("H", c_int32), ("W_in", c_int32), ("Cin", c_int32), ("Ho", c_int32), ("Wo", c_int32),
+        ("conv_stride", c_int32), ("pad_top", c_int32), ("pad_left", c_int32), ("up2x", c_int32),
+        ("alpha", c_float), ("bias", c_void_p), ("rowvec", c_void_p), ("rowvec_ld", c_int64),
+        ("rows_per_group", c_int32), ("residual", c_void_p), ("ldr", c_int64),
+        ("act", c_int32), ("out_nchw", c_int32), ("hw", c_int32),
     ]
 
 
@@ -148,6 +168,25 @@ def _bind(lib: ctypes.CDLL) -> None:
     lib.edtr_wavelet_level.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
     lib.edtr_groupnorm_pool.restype = ci
     lib.edtr_groupnorm_pool.argtypes = [vp, ci, ci, ci, ci, c_float, vp, vp]
+    cll = ctypes.c_longlong
+    lib.edtr_f32_gemm.restype = ci
+    lib.edtr_f32_gemm.argtypes = [POINTER(EdtrF32Gemm), vp]
+    lib.edtr_f32_groupnorm_scratch_bytes.restype = c_size_t
+    lib.edtr_f32_groupnorm_scratch_bytes.argtypes = [ci, ci, ci]
+    lib.edtr_f32_groupnorm.restype = ci
+    lib.edtr_f32_groupnorm.argtypes = [vp, cll, vp, cll, ci, ci, ci, ci, vp, vp, c_float, ci, vp, vp]
+    lib.edtr_f32_layernorm.restype = ci
+    lib.edtr_f32_layernorm.argtypes = [vp, cll, vp, cll, ci, ci, vp, vp, c_float, vp]
+    lib.edtr_f32_softmax_rows.restype = ci
+    lib.edtr_f32_softmax_rows.argtypes = [vp, cll, cll, ci, c_float, vp]
+    lib.edtr_f32_geglu.restype = ci
+    lib.edtr_f32_geglu.argtypes = [vp, cll, vp, cll, cll, ci, vp]
+    lib.edtr_f32_silu.restype = ci
+    lib.edtr_f32_silu.argtypes = [vp, vp, cll, vp]
+    lib.edtr_f32_nchw_to_nhwc.restype = ci
+    lib.edtr_f32_nchw_to_nhwc.argtypes = [vp, vp, cll, ci, ci, ci, ci, c_float, vp]
+    lib.edtr_f32_timestep_embedding.restype = ci
+    lib.edtr_f32_timestep_embedding.argtypes = [vp, vp, ci, ci, c_float, vp]
     lib.edtr_groupnorm_fold.restype = ci
     lib.edtr_groupnorm_fold.argtypes = [vp, ci, ci, ci, ci, ci, vp, vp]
     lib.edtr_groupnorm_apply_stats.restype = ci

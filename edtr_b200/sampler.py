@@ -140,7 +140,8 @@ class SpacedSampler(nn.Module):
 
         timesteps = np.flip(self.timesteps)
         total = len(self.timesteps)
-        fused = (isinstance(model, ControlLDM) and not tiled and (uncond is None or cfg_scale == 1.)
+        bf16 = getattr(model, "precision", "bf16") == "bf16"    # the fp32 mode steps through model(x, t, cond) + the fused update
+        fused = (isinstance(model, ControlLDM) and bf16 and not tiled and (uncond is None or cfg_scale == 1.)
                  and type(model).forward is ControlLDM.forward and "forward" not in model.__dict__)
         if fused:
             x = img.float().contiguous()
@@ -156,7 +157,8 @@ class SpacedSampler(nn.Module):
             if return_intermediates:
                 return out[0], out[1]
             return out
-        ours = isinstance(model, ControlLDM) and type(model).forward is ControlLDM.forward and "forward" not in model.__dict__
+        ours = (isinstance(model, ControlLDM) and bf16 and type(model).forward is ControlLDM.forward
+                and "forward" not in model.__dict__)
         if tiled and ours and (uncond is None or cfg_scale == 1.):
             # batched tiles + on-device blend instead of the per-tile Python loop
             intermediates = []

@@ -311,6 +311,61 @@ int edtr_sampler_update(const float* x, const float* eps, const float* noise,
 int edtr_wavelet_level(const float* in, float* out, float* high, int planes, int H, int W, int radius, int mode,
                        int first, void* stream);
 
+/* ---- fp32 mode (BASELINE.json: per-step latent max-rel error <= 1e-4) ------------------------------------------
+ * Every tensor stays fp32 in HBM and every contraction accumulates fp32 products on the CUDA cores: the accuracy mode
+ * of the path (the bf16 tensor-core kernels above are the throughput mode).  One generic implicit GEMM:
+ *   C = act(alpha * A * W^T + bias[col] + rowvec[(row / rows_per_group) * rowvec_ld + col] + residual[row * ldr + col])
+ * A [M, K] row-major (lda), or — conv = 1 — the 3x3 im2col view of an NHWC tensor [B, H, W_in, Cin] with pixel stride
+ * lda: K = 9 * Cin tap-major / channel-minor, rows = output pixels (b, yo, xo) of an Ho x Wo grid, input pixel
+ * (yo * conv_stride + ty - pad_top, xo * conv_stride + tx - pad_left), zero outside; up2x = 1: 3x3 / pad 1 on the
+ * nearest-2x up-sampled grid (Ho = 2H, Wo = 2W_in).  W [N, K] row-major (ldw), or [K, N] when w_kn = 1.  batch1 x
+ * batch2 problems with element strides *_stride1 / *_stride2 (attention: samples x heads).  out_nchw = 1 stores
+ * C[((row / hw) * N + col) * hw + row % hw].
+ * replaces (fp32 mode): every nn.Conv2d / nn.Linear / einsum call site listed for edtr_gemm_bf16 / edtr_conv3x3_bf16
+ * and the attention products of model/attention.py:176-203, model/vae.py:279-308. */
+typedef struct EdtrF32Gemm {
+  const float* A;
+  const float* W;
+  float* C;
+  int32_t M, N, K;
+  int64_t lda, ldw, ldc;
+  int32_t w_kn;
+  int32_t batch1, batch2;
+  int64_t a_stride1, a_stride2, w_stride1, w_stride2, c_stride1, c_stride2;
+  int32_t conv, H, W_in, Cin, Ho, Wo, conv_stride, pad_top, pad_left, up2x;
+  float alpha;
+  const float* bias;
+  const float* rowvec;
+  int64_t rowvec_ld;
+  int32_t rows_per_group;
+  const float* residual;
+  int64_t ldr;
+  int32_t act;      /* EDTR_ACT_NONE or EDTR_ACT_SILU */
+  int32_t out_nchw;
+  int32_t hw;
+} EdtrF32Gemm;
+int edtr_f32_gemm(const EdtrF32Gemm* g, void* stream);
+/* GroupNorm (+SiLU) on fp32 [B, HW, C] rows (row strides ldx / ldy), statistics accumulated in double precision;
+ * scratch >= edtr_f32_groupnorm_scratch_bytes(B, HW, C) bytes, 8-byte aligned.
+ * replaces (fp32 mode): GroupNorm32 / Normalize — model/util.py:146-163, model/attention.py:50-51, model/vae.py:26-28. */
+size_t edtr_f32_groupnorm_scratch_bytes(int B, int HW, int C);
+int edtr_f32_groupnorm(const float* X, long long ldx, float* Y, long long ldy, int B, int HW, int C, int groups,
+                       const float* gamma, const float* beta, float eps, int silu, void* scratch, void* stream);
+/* nn.LayerNorm over the last dimension (model/attention.py:222-224). */
+int edtr_f32_layernorm(const float* X, long long ldx, float* Y, long long ldy, int M, int C, const float* gamma,
+                       const float* beta, float eps, void* stream);
+/* In place: S[r, :N] = softmax(scale * S[r, :N]) (model/attention.py:196-199, model/vae.py:298-301). */
+int edtr_f32_softmax_rows(float* S, long long lds, long long rows, int N, float scale, void* stream);
+/* Y[m, n] = X[m, n] * gelu_erf(X[m, N + n]) (model/attention.py:20-27). */
+int edtr_f32_geglu(const float* X, long long ldx, float* Y, long long ldy, long long M, int N, void* stream);
+/* Y = X * sigmoid(X) (model/unet.py:166-172: the SiLU in front of the embedding projections). */
+int edtr_f32_silu(const float* X, float* Y, long long n, void* stream);
+/* X [B, C, HW] fp32 (NCHW) times `scale` -> channels [coff, coff + C) of Y [B, HW, ldy] fp32 (channels-last). */
+int edtr_f32_nchw_to_nhwc(const float* X, float* Y, long long ldy, int B, int C, int HW, int coff, float scale,
+                          void* stream);
+/* out[b] = [cos(t_b f_k) | sin(t_b f_k)], f_k = exp(-ln(max_period) k / (dim/2)), fp32 (model/util.py:98-118). */
+int edtr_f32_timestep_embedding(const long long* t, float* out, int B, int dim, float max_period, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -664,3 +664,128 @@ def test_c5_detection_pipeline_against_oracle():
         f_ref = detnet.backbone(res_ref.clamp(0, 1).to(dev))
         for k in f_ref:
             assert O.max_rel_err(f_new[k], f_ref[k]) < 5e-2, k
+
+
+# ----------------------------------------------------------------------------- fp32 mode (BASELINE.json: <= 1e-4 per step)
+FP32_TOL = 1e-4   # BASELINE.json north_star: per-step latent max relative error in the fp32 mode
+
+
+def test_fp32_mode_tiny_against_reference_fixture(tiny):
+    """CldmEngineF32 / VaeDecoderF32 on the edtr_f32_* kernels vs the fixture recorded from the live reference in fp32
+    (C1: fp32 on the CPU): eps of the first forward, every sampler step, the decoded image."""
+    from edtr_b200.engine_f32 import CldmEngineF32, VaeDecoderF32
+    from edtr_b200 import ops
+
+    w, x_T, cond, noise, g, _ = tiny
+    cfg = O.TINY
+    eng = CldmEngineF32(cfg["unet"], cfg["controlnet"], w["unet"], w["controlnet"], "cuda")
+    dev = torch.device("cuda")
+    c_img, c_txt = cond["c_img"].to(dev), cond["c_txt"].to(dev)
+    t = torch.full((2,), 200, dtype=torch.long, device=dev)
+    eps = eng.forward(x_T.to(dev), t, c_img, c_txt)
+    assert O.max_rel_err(eps.cpu(), torch.from_numpy(g["eps0"])) < FP32_TOL
+    sched = O.make_schedule(O.make_betas(**cfg["diffusion"]), 4, cfg["used_timesteps"])
+    tabs = [torch.from_numpy(sched[k]).to(dev) for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                                                         "posterior_mean_coef1", "posterior_mean_coef2",
+                                                         "posterior_variance")]
+    x = x_T.to(dev)
+    for i, step in enumerate([200, 150, 100, 50]):
+        ts = torch.full((2,), step, dtype=torch.long, device=dev)
+        e = eng.forward(x, ts, c_img, c_txt)
+        idx = torch.full((2,), 3 - i, dtype=torch.long, device=dev)
+        x, _ = ops.sampler_update(x, e, noise[i].to(dev), idx, tabs)
+        assert O.max_rel_err(x.cpu(), torch.from_numpy(g["xs"][i])) < FP32_TOL, i
+    vd = VaeDecoderF32(_dd(cfg["vae"]), cfg["vae"]["embed_dim"], w["vae"], "cuda")
+    img = vd.decode(x, cfg["latent_scale_factor"])
+    assert O.max_rel_err(img.cpu(), torch.from_numpy(g["img"])) < FP32_TOL
+    assert O.psnr((img.cpu() + 1) / 2, (torch.from_numpy(g["img"]) + 1) / 2) >= 80.0
+
+
+def test_fp32_mode_s4_against_reference_fixture():
+    """The real s4 widths (SD-2.1 UNet + ControlNet, 64x64 latent, 512x512 image), B = 1, through the drop-in:
+    ControlLDM.set_precision("fp32") + SpacedSampler.manual_sample_with_timesteps + vae_decode vs golden_s4.npz (the
+    live reference in fp32): every step within 1e-4."""
+    from edtr_b200.engine_f32 import CldmEngineF32, VaeDecoderF32
+    from edtr_b200 import ops
+
+    g = np.load(os.path.join(GOLD, "golden_s4.npz"))
+    cfg = O.S4
+    w = O.make_cldm_weights(cfg, seed=0)
+    dev = torch.device("cuda")
+    eng = CldmEngineF32(cfg["unet"], cfg["controlnet"], w["unet"], w["controlnet"], dev)
+    x_T, cond, noise = O.make_inputs(cfg, 1, 64, seed=1)
+    c_img, c_txt = cond["c_img"].to(dev), cond["c_txt"].to(dev)
+    sched = O.make_schedule(O.make_betas(**cfg["diffusion"]), 4, cfg["used_timesteps"])
+    tabs = [torch.from_numpy(sched[k]).to(dev) for k in ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+                                                         "posterior_mean_coef1", "posterior_mean_coef2",
+                                                         "posterior_variance")]
+    x = x_T.to(dev)
+    for i, step in enumerate([200, 150, 100, 50]):
+        ts = torch.full((1,), step, dtype=torch.long, device=dev)
+        e = eng.forward(x, ts, c_img, c_txt)
+        idx = torch.full((1,), 3 - i, dtype=torch.long, device=dev)
+        x, _ = ops.sampler_update(x, e, noise[i].to(dev), idx, tabs)
+        assert O.max_rel_err(x.cpu(), torch.from_numpy(g["xs"][i])) < FP32_TOL, i
+    del eng
+    torch.cuda.empty_cache()
+    vd = VaeDecoderF32(_dd(cfg["vae"]), cfg["vae"]["embed_dim"], w["vae"], dev)
+    img = vd.decode(x, cfg["latent_scale_factor"])
+    ref = torch.from_numpy(g["img"].astype(np.float32))      # the fixture stores the image as fp16 (2^-11 ~ 5e-4 per value)
+    assert O.max_rel_err(img.cpu(), ref) < 2e-3
+    assert O.psnr((img.cpu() + 1) / 2, (ref + 1) / 2) >= 60.0
+
+
+def test_fp32_mode_dropin_sampler_and_decode():
+    """ControlLDM.set_precision("fp32"): the reference call sequence (sampler + vae_decode) on the drop-in runs the
+    fp32 engines and stays within 1e-4 of the fp32 oracle; switching back to bf16 restores the tensor-core path."""
+    from edtr_b200.cldm import ControlLDM
+    from edtr_b200.diffusion import Diffusion
+    from edtr_b200.sampler import SpacedSampler
+
+    cfg = O.TINY
+
+    def kw(c, controlnet):
+        d = dict(image_size=32, in_channels=c["in_channels"], model_channels=c["model_channels"],
+                 attention_resolutions=list(c["attention_resolutions"]), num_res_blocks=c["num_res_blocks"],
+                 channel_mult=list(c["channel_mult"]), num_head_channels=c["num_head_channels"],
+                 use_spatial_transformer=True, use_linear_in_transformer=True, transformer_depth=1,
+                 context_dim=c["context_dim"], legacy=False, use_checkpoint=True)
+        d["hint_channels" if controlnet else "out_channels"] = c["hint_channels" if controlnet else "out_channels"]
+        return d
+
+    v = cfg["vae"]
+    model = ControlLDM(kw(cfg["unet"], False), dict(ddconfig=dict(_dd(v), double_z=True), embed_dim=v["embed_dim"]),
+                       None, kw(cfg["controlnet"], True), cfg["latent_scale_factor"])
+    w = O.make_cldm_weights(cfg, seed=0)
+    model.unet.load_state_dict(w["unet"], strict=True)
+    model.controlnet.load_state_dict(w["controlnet"], strict=True)
+    model.vae.load_state_dict({k: t for k, t in w["vae"].items()}, strict=False)
+    model = model.cuda().eval()
+    x_T, cond, noise = O.make_inputs(cfg, 2, 16, seed=1)
+    with torch.no_grad():
+        z_ref, xs_ref, _ = O.sample(w, cfg, x_T, cond, noise)
+        img_ref = O.vae_decode(w["vae"], v, z_ref, cfg["latent_scale_factor"])
+    dev = torch.device("cuda")
+    diffusion = Diffusion(timesteps=1000, beta_schedule="linear", linear_start=0.00085, linear_end=0.0120).to(dev)
+    sampler = SpacedSampler(diffusion.betas)
+    cond_d = {k: t.to(dev) for k, t in cond.items()}
+
+    def run():
+        draws = [n.to(dev) for n in noise]
+        real = torch.randn_like
+        torch.randn_like = lambda t, *a, **k: draws.pop(0)
+        try:
+            return sampler.manual_sample_with_timesteps(model, dev, x_T.to(dev), 4, list(cfg["used_timesteps"]), 2, cond_d,
+                                                        None, 1.0, progress=False)
+        finally:
+            torch.randn_like = real
+
+    model.set_precision("fp32")
+    z32 = run()
+    assert O.max_rel_err(z32.cpu(), z_ref) < FP32_TOL
+    img32 = model.vae_decode(z32)
+    assert O.max_rel_err(img32.cpu(), img_ref) < FP32_TOL
+    model.set_precision("bf16")
+    zb = run()
+    err_b = O.max_rel_err(zb.cpu(), z_ref)
+    assert 1e-5 < err_b < STEP_TOL          # the tensor-core path again (bf16 rounding is visible)

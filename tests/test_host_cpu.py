@@ -770,3 +770,61 @@ def test_unet_groupnorm_from_epilogue_partials_equals_statistics_pass():
         ref = O.cldm_forward(w, cfg, x_T, t, cond)
     err_p, err_s = O.max_rel_err(eps_p, ref), O.max_rel_err(eps_s, ref)
     assert err_p < 3e-2 and err_p < 1.5 * err_s + 3e-3, (err_p, err_s)
+
+
+# ----------------------------------------------------------------------------- fp32 mode (engine_f32.py)
+def test_fp32_engine_dataflow_matches_reference_fixture(tiny):
+    """The fp32-mode engines (CldmEngineF32 / VaeDecoderF32) on the torch stand-in for the edtr_f32_* kernels against
+    the fixture recorded from the live reference in fp32: the fp32 bar of BASELINE.json (per-step latent max-rel error
+    <= 1e-4), per sampler step, and the decoded image."""
+    import fake_ops32
+    from edtr_b200.engine_f32 import CldmEngineF32, VaeDecoderF32
+
+    cfg, w, _, _, g = tiny
+    eng = CldmEngineF32(cfg["unet"], cfg["controlnet"], w["unet"], w["controlnet"], "cpu", ops=fake_ops32)
+    x_T, cond, noise = O.make_inputs(cfg, 2, 16, seed=1)
+    t = torch.full((2,), 200, dtype=torch.long)
+    eps = eng.forward(x_T, t, cond["c_img"], cond["c_txt"])
+    assert O.max_rel_err(eps, torch.from_numpy(g["eps0"])) < 1e-4
+    sched = O.make_schedule(O.make_betas(**cfg["diffusion"]), 4, cfg["used_timesteps"])
+    x = x_T
+    for i, step in enumerate([200, 150, 100, 50]):
+        ts = torch.full((2,), step, dtype=torch.long)
+        e = eng.forward(x, ts, cond["c_img"], cond["c_txt"])
+        x, _ = O.p_sample_update(sched, x, e, 3 - i, noise[i])
+        assert O.max_rel_err(x, torch.from_numpy(g["xs"][i])) < 1e-4, i
+    vd = VaeDecoderF32(_dd(cfg["vae"]), cfg["vae"]["embed_dim"], w["vae"], "cpu", ops=fake_ops32)
+    img = vd.decode(x, cfg["latent_scale_factor"])
+    assert O.max_rel_err(img, torch.from_numpy(g["img"])) < 1e-4
+    # control scales and validation behave like the bf16 engine
+    n = len(eng.u_in) + 1
+    with torch.no_grad():
+        control = O.controlnet_forward(w["controlnet"], cfg["controlnet"], x_T, cond["c_img"], t, cond["c_txt"])
+        ref = O.unet_forward(w["unet"], cfg["unet"], x_T, t, cond["c_txt"], [c * 0.5 for c in control])
+    assert O.max_rel_err(eng.forward(x_T, t, cond["c_img"], cond["c_txt"], control_scales=[0.5] * n), ref) < 1e-4
+    with pytest.raises(ValueError):
+        eng.forward(x_T[:, :3], t, cond["c_img"], cond["c_txt"])
+
+
+def test_fp32_precision_switch_on_the_dropin():
+    from edtr_b200.cldm import ControlLDM
+
+    cfg = O.TINY
+
+    def kw(c, controlnet):
+        d = dict(image_size=32, in_channels=c["in_channels"], model_channels=c["model_channels"],
+                 attention_resolutions=list(c["attention_resolutions"]), num_res_blocks=c["num_res_blocks"],
+                 channel_mult=list(c["channel_mult"]), num_head_channels=c["num_head_channels"],
+                 use_spatial_transformer=True, use_linear_in_transformer=True, transformer_depth=1,
+                 context_dim=c["context_dim"], legacy=False, use_checkpoint=True)
+        d["hint_channels" if controlnet else "out_channels"] = c["hint_channels" if controlnet else "out_channels"]
+        return d
+
+    v = cfg["vae"]
+    m = ControlLDM(kw(cfg["unet"], False), dict(ddconfig=dict(_dd(v), double_z=True), embed_dim=v["embed_dim"]), None,
+                   kw(cfg["controlnet"], True), cfg["latent_scale_factor"])
+    assert m.precision == "bf16" and m.set_precision("fp32") is m and m.precision == "fp32"
+    with pytest.raises(ValueError):
+        m.set_precision("fp16")
+    with pytest.raises(NotImplementedError):
+        m.vae_decode(torch.zeros(1, 4, 8, 8), tiled=True, tile_size=8)

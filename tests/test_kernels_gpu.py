@@ -687,3 +687,118 @@ def test_conv3x3_halo_mode(ops, B, H, W, Cin, Cout, res):
     else:
         out = ops.conv3x3(x, wp, bias=bias, out_mode=ops.OUT_NCHW_F32)
         assert relerr(out.view(B, Cout, H, W), ref) < 1e-2
+
+
+# ------------------------------------------------- fp32 mode kernels (edtr_f32_*), against fp32 / fp64 PyTorch
+@pytest.fixture(scope="module")
+def ops32():
+    from edtr_b200 import ops32 as o
+
+    return o
+
+
+def frnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return torch.randn(*shape, generator=g, device="cuda") * scale
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    a, b = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = a, b
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (300, 320, 320), (8, 1280, 320), (4096, 77, 64), (1000, 4, 36), (130, 70, 50)])
+def test_f32_gemm_epilogue(ops32, M, N, K):
+    a, w = frnd(M, K, seed=1), frnd(N, K, scale=K ** -0.5, seed=2)
+    bias, res = frnd(N, seed=3), frnd(M, N, seed=4)
+    ref = (a.double() @ w.double().t()).float()
+    assert relerr(ops32.gemm(a, w), ref) < 2e-6
+    rpg = M // 2 if M % 2 == 0 else M
+    rowvec = frnd(M // rpg, N, seed=5)
+    out = ops32.gemm(a, w, bias=bias, residual=res, rowvec=rowvec, rows_per_group=rpg, act=ops32.ACT_SILU, alpha=0.5)
+    ref2 = F.silu(0.5 * ref + bias + res + rowvec.repeat_interleave(rpg, 0))
+    assert relerr(out, ref2) < 5e-6
+    # strided operand and destination (channel slices of wider buffers), in-place residual
+    wide = frnd(M, N + 40, seed=6)
+    before = wide.clone()
+    ops32.gemm(a, w, residual=wide[:, 8:8 + N], out=wide[:, 8:8 + N])
+    assert relerr(wide[:, 8:8 + N], ref + before[:, 8:8 + N]) < 5e-6
+    assert torch.equal(wide[:, :8], before[:, :8]) and torch.equal(wide[:, 8 + N:], before[:, 8 + N:])
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,mode", [(2, 16, 16, 4, 64, "same"), (1, 17, 9, 32, 48, "same"), (2, 16, 16, 64, 64, "s2"),
+                                                  (1, 15, 15, 32, 32, "s2"), (2, 16, 16, 32, 32, "vae_s2"), (2, 8, 8, 64, 32, "up"),
+                                                  (1, 32, 32, 128, 3, "nchw")])
+def test_f32_conv3x3_modes(ops32, B, H, W, Cin, Cout, mode):
+    x = frnd(B, H, W, Cin, seed=1)
+    w = frnd(Cout, Cin, 3, 3, scale=(9 * Cin) ** -0.5, seed=2)
+    bias = frnd(Cout, seed=3)
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous()
+    xi = x.double().permute(0, 3, 1, 2)
+    wd, bd = w.double(), bias.double()
+    if mode == "same":
+        emb = frnd(B, Cout, seed=4)
+        out = ops32.conv3x3(x, wp, bias=bias, rowvec=emb)
+        ref = (F.conv2d(xi, wd, bd, padding=1) + emb.double()[:, :, None, None]).permute(0, 2, 3, 1)
+    elif mode == "s2":        # UNet Downsample: stride 2, pad 1 (model/unet.py:99-101)
+        out = ops32.conv3x3(x, wp, bias=bias, stride=2, pad=(1, 1))
+        ref = F.conv2d(xi, wd, bd, stride=2, padding=1).permute(0, 2, 3, 1)
+    elif mode == "vae_s2":    # VAE Downsample: pad right / bottom only, stride 2 (model/vae.py:54-58)
+        out = ops32.conv3x3(x, wp, bias=bias, stride=2, pad=(0, 0), out_hw=(H // 2, W // 2))
+        ref = F.conv2d(F.pad(xi, (0, 1, 0, 1)), wd, bd, stride=2).permute(0, 2, 3, 1)
+    elif mode == "up":
+        out = ops32.conv3x3(x, wp, bias=bias, up2x=True)
+        ref = F.conv2d(F.interpolate(xi, scale_factor=2.0, mode="nearest"), wd, bd, padding=1).permute(0, 2, 3, 1)
+    else:
+        out = ops32.conv3x3(x, wp, bias=bias, nchw=True).view(B, Cout, H, W)
+        ref = F.conv2d(xi, wd, bd, padding=1)
+    assert out.shape == ref.shape
+    assert relerr(out, ref.float()) < 5e-6
+
+
+@pytest.mark.parametrize("B,heads,Lq,Lk,d", [(2, 5, 256, 256, 64), (1, 3, 130, 77, 64), (2, 1, 64, 64, 512), (3, 2, 33, 1, 64)])
+def test_f32_attention(ops32, B, heads, Lq, Lk, d):
+    C = heads * d
+    qkv = frnd(B, Lq, 3 * C, seed=1)
+    q = qkv[..., :C]
+    kv = frnd(B, Lk, 2 * C, seed=2)
+    k, v = kv[..., :C], kv[..., C:]
+    out = ops32.attention(q, k, v, heads, d ** -0.5)
+    sp = lambda t: t.double().reshape(B, -1, heads, d).permute(0, 2, 1, 3)
+    ref = (torch.softmax(sp(q) @ sp(k).transpose(-1, -2) * d ** -0.5, -1) @ sp(v)).permute(0, 2, 1, 3).reshape(B, Lq, C)
+    assert relerr(out, ref.float()) < 5e-6
+
+
+def test_f32_norms_and_elementwise(ops32):
+    x = frnd(3, 24, 24, 320, seed=1) * 3 + 5            # a large mean: the double-precision statistics matter
+    gamma, beta = frnd(320, seed=2), frnd(320, seed=3)
+    for silu in (False, True):
+        y = ops32.groupnorm(x, gamma, beta, 32, 1e-5, silu)
+        ref = F.group_norm(x.double().permute(0, 3, 1, 2), 32, gamma.double(), beta.double(), 1e-5)
+        ref = (F.silu(ref) if silu else ref).permute(0, 2, 3, 1)
+        assert relerr(y, ref.float()) < 5e-6
+    wide = frnd(2, 64, 640, seed=4)
+    ys = ops32.groupnorm(wide[..., 320:], gamma, beta, 32, 1e-6, False)      # a channel slice as input
+    refs = F.group_norm(wide[..., 320:].double().permute(0, 2, 1), 32, gamma.double(), beta.double(), 1e-6).permute(0, 2, 1)
+    assert relerr(ys, refs.float()) < 5e-6
+    t = frnd(100, 320, seed=5)
+    assert relerr(ops32.layernorm(t, gamma, beta, 1e-5), F.layer_norm(t.double(), (320,), gamma.double(), beta.double(), 1e-5).float()) < 5e-6
+    g = frnd(50, 2560, seed=6)
+    a, b = g.double().chunk(2, -1)
+    assert relerr(ops32.geglu(g), (a * F.gelu(b)).float()) < 5e-6
+    assert relerr(ops32.silu(t), F.silu(t.double()).float()) < 5e-6
+    nchw = frnd(2, 4, 8, 8, seed=7)
+    dst = torch.zeros(2, 8, 8, 8, device="cuda")
+    ops32.nchw_to_nhwc(nchw, dst, 4, 0.5)
+    assert torch.equal(dst[..., 4:], nchw.permute(0, 2, 3, 1) * 0.5) and dst[..., :4].abs().max().item() == 0
+    ts = torch.tensor([200, 50, 999], device="cuda")
+    half = 160
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float64, device="cuda") / half)
+    arg = ts.double()[:, None] * f[None]
+    assert relerr(ops32.timestep_embedding(ts, 320), torch.cat([arg.cos(), arg.sin()], -1).float()) < 2e-4
+    with pytest.raises(RuntimeError):
+        ops32.gemm(torch.zeros(4, 4), torch.zeros(4, 4))
