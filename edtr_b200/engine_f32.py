@@ -157,8 +157,8 @@ class CldmEngineF32:
             raise ValueError(f"x_noisy / c_img must be [B, {self.zc}, H, W]")
         n_in = len(self.u_in)
         scales = list(control_scales) if control_scales is not None else [1.0] * (n_in + 1)
-        if len(scales) != n_in + 1:
-            raise ValueError(f"control_scales must have {n_in + 1} entries")
+        if len(scales) < n_in + 1:     # (ControlLDM keeps the reference's 13 entries whatever the depth, model/cldm.py:34)
+            raise ValueError(f"control_scales must have at least {n_in + 1} entries")
         dev = x_noisy.device
         new = lambda *shape: torch.empty(shape, dtype=F32, device=dev)
         with ops.device_guard(dev):

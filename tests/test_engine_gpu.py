@@ -698,7 +698,7 @@ def test_fp32_mode_tiny_against_reference_fixture(tiny):
     vd = VaeDecoderF32(_dd(cfg["vae"]), cfg["vae"]["embed_dim"], w["vae"], "cuda")
     img = vd.decode(x, cfg["latent_scale_factor"])
     assert O.max_rel_err(img.cpu(), torch.from_numpy(g["img"])) < FP32_TOL
-    assert O.psnr((img.cpu() + 1) / 2, (torch.from_numpy(g["img"]) + 1) / 2) >= 80.0
+    assert O.psnr((img.cpu() + 1) / 2, (torch.from_numpy(g["img"]) + 1) / 2) >= 79.0     # the formula saturates at 80 dB (mse + 1e-8)
 
 
 def test_fp32_mode_s4_against_reference_fixture():
