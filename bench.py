@@ -1015,14 +1015,19 @@ def main():
     ap.add_argument("--sustain-seconds", type=float, default=5.0,
                     help="also report throughput over a region of at least this many seconds (0 = off)")
     args = ap.parse_args()
-    if os.environ.get("EDTR_NCCL_LOG", "0") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+    if os.environ.get("EDTR_NCCL_LOG", "0") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1 \
+            and "NCCL_DEBUG_FILE" not in os.environ:
         # keep the algorithm / channel lines of the communicator (opt-in: NCCL_DEBUG prints its version banner on stdout,
-        # which must carry the one JSON line only).  Must be in the environment before torch loads NCCL.
+        # which must carry the one JSON line only).  The variables must be in the process environment from the start
+        # (setting them through os.environ after start-up was measured not to reach NCCL's logger): re-exec once.
         world = int(os.environ["WORLD_SIZE"])
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
-        os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(ROOT, "gpurun_out", f"nccl_n{world}.%h.%p.log"))
+        env = dict(os.environ)
+        env.setdefault("NCCL_DEBUG", "INFO")
+        env.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
+        env["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", f"nccl_n{world}.%h.%p.log")
+        sys.stdout.flush()
+        os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env)
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "reference-gpu":

@@ -572,6 +572,11 @@ extern "C" int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ld
     // chunks of 128 query rows per CTA: enough CTAs for two per SM, as few K / V reloads as that allows
     const int nchunk = (Lq + kXWarps * 16 - 1) / (kXWarps * 16);
     int chunks = static_cast<int>((static_cast<long long>(nchunk) * heads * B + 2 * 148 - 1) / (2 * 148));
+    static const int chunks_override = [] {      // EDTR_XATTN_CHUNKS=<n>: A/B switch for the chunk count per CTA
+      const char* e = getenv("EDTR_XATTN_CHUNKS");
+      return e == nullptr ? 0 : atoi(e);
+    }();
+    if (chunks_override > 0) chunks = chunks_override;
     if (chunks < 1) chunks = 1;
     if (chunks > 8) chunks = 8;
     dim3 grid((nchunk + chunks - 1) / chunks, heads, B);
