@@ -569,9 +569,12 @@ extern "C" int edtr_attention_bf16(const void* Q, int ldq, const void* K, int ld
                  reinterpret_cast<uintptr_t>(O)) & 15) == 0, "Q/K/V/O must be 16-byte aligned");
   EDTR_REQUIRE(heads <= 65535 && B <= 65535, "grid too large");
   if (Lk <= kXK && cross_attention_small_enabled()) {
-    // chunks of 128 query rows per CTA: enough CTAs for two per SM, as few K / V reloads as that allows
+    // chunks of 128 query rows per CTA: at most two — measured on B200 inside the sample graph (profiles/r03h): 1 / 2 /
+    // one-wave (5, 3, 2 on the three levels) / 8 chunks per CTA give 47.8 / 47.2 / 47.6 / 48.0 ms per 4-step sample; a
+    // few waves of short CTAs hide the Q latency better than one wave of long ones, K / V reloads are L2 hits
     const int nchunk = (Lq + kXWarps * 16 - 1) / (kXWarps * 16);
     int chunks = static_cast<int>((static_cast<long long>(nchunk) * heads * B + 2 * 148 - 1) / (2 * 148));
+    if (chunks > 2) chunks = 2;
     static const int chunks_override = [] {      // EDTR_XATTN_CHUNKS=<n>: A/B switch for the chunk count per CTA
       const char* e = getenv("EDTR_XATTN_CHUNKS");
       return e == nullptr ? 0 : atoi(e);
