@@ -1023,8 +1023,8 @@ def main():
         world = int(os.environ["WORLD_SIZE"])
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         env = dict(os.environ)
-        env.setdefault("NCCL_DEBUG", "INFO")
-        env.setdefault("NCCL_DEBUG_SUBSYS", "INIT,COLL")
+        env["NCCL_DEBUG"] = "INFO"        # (the box environment may pin a lower level, e.g. VERSION: override it)
+        env["NCCL_DEBUG_SUBSYS"] = "INIT,COLL"
         env["NCCL_DEBUG_FILE"] = os.path.join(ROOT, "gpurun_out", f"nccl_n{world}.%h.%p.log")
         sys.stdout.flush()
         os.execve(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:], env)
