@@ -740,19 +740,31 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def nccl_log_tail(world, keep=6):
-    """A few algorithm / channel lines of the NCCL_DEBUG=INFO log of this run (kept in gpurun_out/)."""
+def nccl_log_tail(world, keep=12):
+    """A few topology / algorithm lines of the NCCL_DEBUG=INFO log of this run (files kept in gpurun_out/): communicator
+    size, NVLS availability, channel count, connection summary, and the first collective of every kind and size."""
     import glob
+    import re
 
-    out = []
-    for f in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"nccl_n{world}.*.log")))[:1]:
-        try:
-            for ln in open(f, errors="replace"):
-                if any(k in ln for k in ("NVLS", "Channel", "AllGather", "Connected all", "comm 0x", "nranks")):
-                    out.append(ln.strip()[:200])
-        except OSError:
-            pass
-    return out[:keep] + (["..."] + out[-keep:] if len(out) > 2 * keep else out[keep:])
+    files = sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"nccl_n{world}.*.log")), key=os.path.getmtime)
+    if not files:
+        return []
+    init, colls, seen = [], [], set()
+    try:
+        for ln in open(files[-1], errors="replace"):
+            ln = ln.strip()
+            m = re.search(r"NCCL INFO (AllGather|AllReduce|Broadcast|ReduceScatter): .* count (\d+) datatype (\d+)", ln)
+            if m:
+                if m.groups() not in seen and len(colls) < keep:
+                    seen.add(m.groups())
+                    colls.append(f"{m.group(1)} count {m.group(2)} datatype {m.group(3)} [nranks={world}]")
+                continue
+            if any(k in ln for k in ("NVLS", "nRanks", "Connected all", "Init COMPLETE", "Channel 00/", "P2P Chunksize",
+                                     "threadThresholds")) and len(init) < keep:
+                init.append(re.sub(r"^.*NCCL INFO ", "", ln)[:180])
+    except OSError:
+        pass
+    return init + colls
 
 
 def multi_gpu_output_check(model, eng, vae_eng, tables, ts, rank, world, dev):
@@ -1015,11 +1027,11 @@ def main():
     ap.add_argument("--sustain-seconds", type=float, default=5.0,
                     help="also report throughput over a region of at least this many seconds (0 = off)")
     args = ap.parse_args()
-    if os.environ.get("EDTR_NCCL_LOG", "0") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1 \
+    if os.environ.get("EDTR_NCCL_LOG", "1") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1 \
             and "NCCL_DEBUG_FILE" not in os.environ:
-        # keep the algorithm / channel lines of the communicator (opt-in: NCCL_DEBUG prints its version banner on stdout,
-        # which must carry the one JSON line only).  The variables must be in the process environment from the start
-        # (setting them through os.environ after start-up was measured not to reach NCCL's logger): re-exec once.
+        # keep the topology / algorithm lines of the communicator in a file (EDTR_NCCL_LOG=0 switches it off; stdout must
+        # carry the one JSON line only).  The box environment pins NCCL_DEBUG=VERSION and NCCL reads its variables from the
+        # process environment at start-up, so the process re-executes itself once with the logging variables in place.
         world = int(os.environ["WORLD_SIZE"])
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         env = dict(os.environ)
