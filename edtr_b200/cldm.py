@@ -86,6 +86,16 @@ class ControlLDM(nn.Module):
             self._vae32_version = ver
         return self._vae32
 
+    def _vae_encoder_f32(self):
+        from .engine_f32 import VaeEncoderF32
+
+        dev = next(self.vae.parameters()).device
+        ver = (state_version(self.vae), dev)
+        if getattr(self, "_vae32e", None) is None or self._vae32e_version != ver:
+            self._vae32e = VaeEncoderF32(self.vae.ddconfig, self.vae.embed_dim, self.vae.state_dict(), dev)
+            self._vae32e_version = ver
+        return self._vae32e
+
     # ----------------------------------------------------------------- construction helpers
     @classmethod
     def from_reference(cls, ref: nn.Module, unet_cfg: Dict, vae_cfg: Dict, controlnet_cfg: Dict) -> "ControlLDM":
@@ -155,6 +165,7 @@ class ControlLDM(nn.Module):
         self._engine = None
         self._engine_version = None
         self._engine32 = self._engine32_version = self._vae32 = self._vae32_version = None
+        self._vae32e = self._vae32e_version = None
         self.vae.invalidate_engine()
 
     refresh_weights = invalidate_engine
@@ -193,9 +204,16 @@ class ControlLDM(nn.Module):
     def vae_encode(self, image: torch.Tensor, sample: bool = True, tiled: bool = False, tile_size: int = -1):
         """model/cldm.py:107-134: posterior sample or mode, times the latent scale factor; tiled=True is the
         reference's VAEHook encode (pad 32, pooled GroupNorm statistics)."""
-        posterior = (self.vae.encode_tiled(image, tile_size, tile_group=self.tile_group,
-                                           tile_group_check=self.tile_group_check)
-                     if tiled else self.vae.encode(image))
+        if self.precision == "fp32":
+            if tiled:
+                raise NotImplementedError("the tiled VAE encode runs in the bf16 mode only")
+            from .nets import DiagonalGaussianDistribution
+
+            posterior = DiagonalGaussianDistribution(self._vae_encoder_f32().encode(image.float().contiguous()))
+        else:
+            posterior = (self.vae.encode_tiled(image, tile_size, tile_group=self.tile_group,
+                                               tile_group_check=self.tile_group_check)
+                         if tiled else self.vae.encode(image))
         z = posterior.sample() if sample else posterior.mode()
         return z * self.scale_factor
 

@@ -6,7 +6,8 @@ This is the accuracy mode, selected with ``ControlLDM.set_precision("fp32")``: e
 activations, no weight repacking beyond the tap-major convolution layout, the contractions on the CUDA cores.  The
 throughput mode is the bf16 tensor-core engine.  Covered: ``ControlLDM.forward`` (ControlNet + controlled UNet,
 model/cldm.py:166-194), the sampler loop on top of it (the generic ``SpacedSampler`` loop with the fused update
-kernel) and ``vae_decode`` (model/cldm.py:136-156); the tiled variants and the encoder stay bf16-only.
+kernel), ``vae_decode`` (model/cldm.py:136-156) and ``vae_encode`` (model/cldm.py:107-134); the tiled variants and
+SwinIR stay bf16-only.
 """
 from __future__ import annotations
 
@@ -295,3 +296,52 @@ class VaeDecoderF32:
             ops.conv3x3(y, w["decoder.conv_out.weight"], bias=w["decoder.conv_out.bias"], out=img.view(B, out_ch, Hh * Wh),
                         nchw=True)
         return img
+
+
+class VaeEncoderF32(VaeDecoderF32):
+    """ControlLDM.vae_encode in fp32: Encoder.forward + quant_conv -> posterior moments
+    (model/cldm.py:107-134, model/vae.py:326-446, 725-729; Downsample pads right / bottom only, model/vae.py:54-58)."""
+
+    def __init__(self, ddconfig: Dict, embed_dim: int, sd: Dict[str, torch.Tensor], device, ops=None):
+        if ops is None:
+            from . import ops32 as ops
+        self.ops = ops
+        self.device = torch.device(device)
+        self.dd = ddconfig
+        self.embed_dim = embed_dim
+        self.levels, self.top = T.vae_encoder_levels(ddconfig)
+        keep = {k: v for k, v in sd.items() if k.startswith("encoder.") or k.startswith("quant_conv.")}
+        self.w = _pack(keep, self.device)
+
+    @torch.no_grad()
+    def encode(self, image: torch.Tensor) -> torch.Tensor:
+        """image [B, in_channels, H, W] fp32 in [-1, 1] -> moments [B, 2 * embed_dim, H/f, W/f] fp32 (mean | logvar)."""
+        ops, w = self.ops, self.w
+        if getattr(ops, "REQUIRES_CUDA", True) and not image.is_cuda:
+            raise RuntimeError("edtr_b200 has no CPU path: image must be a CUDA tensor")
+        B, cin, H, W = image.shape
+        f = 2 ** (len(self.levels) - 1)
+        if cin != self.dd["in_channels"] or H % f or W % f:
+            raise ValueError(f"image must be [B, {self.dd['in_channels']}, H, W] with H, W multiples of {f}")
+        dev = image.device
+        with ops.device_guard(dev):
+            x = torch.empty((B, H, W, cin), dtype=F32, device=dev)
+            ops.nchw_to_nhwc(image.to(F32).contiguous(), x, 0)
+            h = ops.conv3x3(x, w["encoder.conv_in.weight"], bias=w["encoder.conv_in.bias"])
+            for level, blocks, has_down in self.levels:
+                for i in range(len(blocks)):
+                    h = self._res(f"encoder.down.{level}.block.{i}.", h)
+                if has_down:
+                    q = f"encoder.down.{level}.downsample.conv."
+                    Hc, Wc = h.shape[1], h.shape[2]
+                    h = ops.conv3x3(h, w[q + "weight"], bias=w[q + "bias"], stride=2, pad=(0, 0), out_hw=(Hc // 2, Wc // 2))
+            h = self._res("encoder.mid.block_1.", h)
+            h = self._attn("encoder.mid.attn_1.", h)
+            h = self._res("encoder.mid.block_2.", h)
+            y = ops.groupnorm(h, w["encoder.norm_out.weight"], w["encoder.norm_out.bias"], 32, 1e-6, True)
+            m = ops.conv3x3(y, w["encoder.conv_out.weight"], bias=w["encoder.conv_out.bias"])
+            Bh, Hh, Wh, _ = m.shape
+            mo = torch.empty((B, 2 * self.embed_dim, Hh, Wh), dtype=F32, device=dev)
+            ops.gemm(m, w["quant_conv.weight"], bias=w["quant_conv.bias"], out=mo.view(B, 2 * self.embed_dim, Hh * Wh),
+                     nchw_hw=Hh * Wh)
+        return mo

@@ -789,3 +789,17 @@ def test_fp32_mode_dropin_sampler_and_decode():
     zb = run()
     err_b = O.max_rel_err(zb.cpu(), z_ref)
     assert 1e-5 < err_b < STEP_TOL          # the tensor-core path again (bf16 rounding is visible)
+
+
+def test_fp32_mode_vae_encoder_against_reference_fixture():
+    """VaeEncoderF32 (stride-2 convolutions with right / bottom padding, d = C single-head attention, quant_conv) vs the
+    live-reference fixture: the latent mode within the fp32 tolerance."""
+    from edtr_b200.engine_f32 import VaeEncoderF32
+    from edtr_b200.nets import DiagonalGaussianDistribution
+
+    g = np.load(os.path.join(GOLD, "golden_vae_encode.npz"))
+    v = O.TINY["vae"]
+    sd = O.make_weights(O.vae_encoder_param_shapes(v), seed=3)
+    mo = VaeEncoderF32(_dd(v), v["embed_dim"], sd, "cuda").encode(torch.from_numpy(g["image"]).cuda())
+    post = DiagonalGaussianDistribution(mo.cpu())
+    assert O.max_rel_err(post.mode() * 0.18215, torch.from_numpy(g["z_mode"])) < FP32_TOL

@@ -806,6 +806,21 @@ def test_fp32_engine_dataflow_matches_reference_fixture(tiny):
         eng.forward(x_T[:, :3], t, cond["c_img"], cond["c_txt"])
 
 
+def test_fp32_vae_encoder_dataflow_matches_reference_fixture():
+    import fake_ops32
+    from edtr_b200.engine_f32 import VaeEncoderF32
+    from edtr_b200.nets import DiagonalGaussianDistribution
+
+    g = np.load(os.path.join(GOLD, "golden_vae_encode.npz"))
+    v = O.TINY["vae"]
+    sd = O.make_weights(O.vae_encoder_param_shapes(v), seed=3)
+    mo = VaeEncoderF32(_dd(v), v["embed_dim"], sd, "cpu", ops=fake_ops32).encode(torch.from_numpy(g["image"]))
+    post = DiagonalGaussianDistribution(mo)
+    assert O.max_rel_err(post.mode() * 0.18215, torch.from_numpy(g["z_mode"])) < 1e-4
+    z_s = (post.mean + post.std * torch.from_numpy(g["draw"])) * 0.18215
+    assert O.max_rel_err(z_s, torch.from_numpy(g["z_sample"])) < 1e-4
+
+
 def test_fp32_precision_switch_on_the_dropin():
     from edtr_b200.cldm import ControlLDM
 
