@@ -248,6 +248,8 @@ class _EpilogueGN:
             return None
         if HW % (32 * phases) or not ops.gn_partial_supported(B * HW, HW, C, K):
             return None
+        # one partial buffer per (tensor address, width): 1:1 with the tensor, so no two live tensors can share one.  (If
+        # the workspace re-allocates a tensor, its old partial buffer is orphaned: a few MB per growth, which is rare.)
         part = ws.get(f"gnp_{key[0]:x}_{C}", ops.gn_partial_shape(B, HW, C), F32)
         table[key] = (part, B, HW)
         return part
