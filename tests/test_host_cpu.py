@@ -843,3 +843,28 @@ def test_fp32_precision_switch_on_the_dropin():
         m.set_precision("fp16")
     with pytest.raises(NotImplementedError):
         m.vae_decode(torch.zeros(1, 4, 8, 8), tiled=True, tile_size=8)
+
+
+def test_bench_nccl_log_tail_keeps_topology_and_distinct_collectives(tmp_path, monkeypatch):
+    """bench.py keeps a few NCCL_DEBUG=INFO lines of a multi-GPU run in `comm.nccl_log`: communicator size, NVLS,
+    channels, the connection summary and one line per distinct collective (not hundreds of repeated AllReduce lines)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    out = tmp_path / "gpurun_out"
+    out.mkdir()
+    log = ["vm:1:1 [0] NCCL INFO NVLS multicast support is available on dev 0 (NVLS_NCHANNELS 24)",
+           "vm:1:1 [0] NCCL INFO comm 0x1 rank 0 nRanks 8 nNodes 1 localRanks 8 localRank 0 MNNVL 0",
+           "vm:1:1 [0] NCCL INFO Channel 00/32 : 0 1 2 3 4 5 6 7",
+           "vm:1:1 [0] NCCL INFO Channel 01/32 : 0 1 2 3 4 5 6 7",
+           "vm:1:1 [0] NCCL INFO Connected all rings, use ring PXN 0 GDR 1"]
+    log += ["vm:1:1 [0] NCCL INFO AllReduce: opCount 0 sendbuff 0x1 recvbuff 0x1 count 1 datatype 7 op 0 root 0 comm 0x1 [nranks=8] stream (nil)"] * 50
+    log += ["vm:1:1 [0] NCCL INFO AllGather: opCount 0 sendbuff 0x2 recvbuff 0x3 count 6291456 datatype 9 op 0 root 0 comm 0x1 [nranks=8] stream (nil)"] * 20
+    (out / "nccl_n8.vm.1.log").write_text("\n".join(log))
+    monkeypatch.setattr(b, "ROOT", str(tmp_path))
+    tail = b.nccl_log_tail(8)
+    assert any("NVLS" in t for t in tail) and any("nRanks 8" in t for t in tail) and any("Connected all rings" in t for t in tail)
+    assert sum("AllReduce" in t for t in tail) == 1 and sum("AllGather count 6291456" in t for t in tail) == 1
+    assert len(tail) <= 24 and b.nccl_log_tail(4) == []
