@@ -4,6 +4,8 @@
 // implicit-GEMM kernel (plain rows, 3x3 convolution gather with stride / asymmetric padding / nearest-2x up-sampling,
 // two-level batching for the attention products), GroupNorm with double-precision statistics, LayerNorm, row soft-max,
 // GEGLU and the small layout helpers.  Same C-ABI conventions as the rest of the library.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -121,6 +123,120 @@ f32_gemm_kernel(const F32Gemm p) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int row = m0 + ty * 4 + i;
+    if (row >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= p.N) continue;
+      float v = acc[i][j] * p.alpha;
+      if (p.bias != nullptr) v += p.bias[col];
+      if (p.rowvec != nullptr) v += p.rowvec[static_cast<long long>(row / p.rows_per_group) * p.rowvec_ld + col];
+      if (p.residual != nullptr) v += p.residual[static_cast<long long>(row) * p.ldr + col];
+      if (p.act == EDTR_ACT_SILU) v = f32_silu(v);
+      if (p.out_nchw) {
+        const int img = row / p.hw;
+        C[(static_cast<long long>(img) * p.N + col) * p.hw + (row - img * p.hw)] = v;
+      } else {
+        C[static_cast<long long>(row) * p.ldc + col] = v;
+      }
+    }
+  }
+}
+
+
+// Second form of the same contraction for the shapes that allow 16-byte operand loads (K % 4 == 0, strides % 4 == 0,
+// 16-byte aligned bases; convolution: Cin % 4 == 0; W as [N, K]): 128 x 64 x 16 tiles, 8 x 4 outputs per thread, the
+// next tile's global loads are issued into registers before the current tile's arithmetic (software pipelining), two
+// float4 of A and one of W per thread and tile.  Same epilogue, same summation order inside a tile row.
+constexpr int kGBM = 128;
+
+__device__ __forceinline__ float4 f32_load_a4(const F32Gemm& p, const float* A, int row, int k, int rb, int ry, int rx) {
+  // four consecutive k of one row; in convolution mode they lie inside one tap (Cin % 4 == 0, k % 4 == 0)
+  if (!p.conv) return __ldg(reinterpret_cast<const float4*>(A + static_cast<long long>(row) * p.lda + k));
+  const int tap = k / p.Cin, c = k - tap * p.Cin;
+  const int ty = tap / 3, tx = tap - ty * 3;
+  int y, x;
+  if (p.up2x) {
+    const int yu = ry + ty - 1, xu = rx + tx - 1;
+    if (yu < 0 || xu < 0 || yu >= 2 * p.H || xu >= 2 * p.W_) return make_float4(0.f, 0.f, 0.f, 0.f);
+    y = yu >> 1;
+    x = xu >> 1;
+  } else {
+    y = ry * p.stride + ty - p.pad_t;
+    x = rx * p.stride + tx - p.pad_l;
+    if (y < 0 || x < 0 || y >= p.H || x >= p.W_) return make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  return __ldg(reinterpret_cast<const float4*>(A + ((static_cast<long long>(rb) * p.H + y) * p.W_ + x) * p.lda + c));
+}
+
+__global__ void __launch_bounds__(256)
+f32_gemm_vec_kernel(const F32Gemm p) {
+  PdlScope pdl_scope;
+  __shared__ __align__(16) float As[kFBK][kGBM + 4];
+  __shared__ __align__(16) float Ws[kFBK][kFBN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * kGBM, n0 = blockIdx.x * kFBN;
+  const int b1 = blockIdx.z / p.nb2, b2 = blockIdx.z - b1 * p.nb2;
+  const float* A = p.A + b1 * p.a_s1 + b2 * p.a_s2;
+  const float* W = p.W + b1 * p.w_s1 + b2 * p.w_s2;
+  float* C = p.C + b1 * p.c_s1 + b2 * p.c_s2;
+  // loaders: A row = tid / 2, k offsets (tid & 1) * 8 + {0, 4}; W row (n) = tid / 4, k offset (tid & 3) * 4
+  const int ar = tid >> 1, ak = (tid & 1) * 8;
+  const int wr = tid >> 2, wk = (tid & 3) * 4;
+  const int arow = m0 + ar;
+  const bool a_ok = arow < p.M, w_ok = n0 + wr < p.N;
+  int rb = 0, ry = 0, rx = 0;
+  if (p.conv && a_ok) {
+    const int hw = p.Ho * p.Wo;
+    rb = arow / hw;
+    const int r = arow - rb * hw;
+    ry = r / p.Wo;
+    rx = r - ry * p.Wo;
+  }
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch = [&](int k0, float4& a0, float4& a1, float4& w0) {
+    a0 = (a_ok && k0 + ak < p.K) ? f32_load_a4(p, A, arow, k0 + ak, rb, ry, rx) : z4;
+    a1 = (a_ok && k0 + ak + 4 < p.K) ? f32_load_a4(p, A, arow, k0 + ak + 4, rb, ry, rx) : z4;
+    w0 = (w_ok && k0 + wk < p.K) ? __ldg(reinterpret_cast<const float4*>(W + static_cast<long long>(n0 + wr) * p.ldw + k0 + wk)) : z4;
+  };
+  auto stash = [&](const float4& a0, const float4& a1, const float4& w0) {
+    As[ak + 0][ar] = a0.x; As[ak + 1][ar] = a0.y; As[ak + 2][ar] = a0.z; As[ak + 3][ar] = a0.w;
+    As[ak + 4][ar] = a1.x; As[ak + 5][ar] = a1.y; As[ak + 6][ar] = a1.z; As[ak + 7][ar] = a1.w;
+    Ws[wk + 0][wr] = w0.x; Ws[wk + 1][wr] = w0.y; Ws[wk + 2][wr] = w0.z; Ws[wk + 3][wr] = w0.w;
+  };
+  const int ty = tid >> 4, tx = tid & 15;      // outputs: rows ty * 8 .. + 7, columns tx * 4 .. + 3
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float4 a0, a1, w0;
+  fetch(0, a0, a1, w0);
+  stash(a0, a1, w0);
+  __syncthreads();
+  for (int k0 = 0; k0 < p.K; k0 += kFBK) {
+    const bool more = k0 + kFBK < p.K;
+    if (more) fetch(k0 + kFBK, a0, a1, w0);      // in flight during the arithmetic below
+#pragma unroll
+    for (int k = 0; k < kFBK; ++k) {
+      const float4 x0 = *reinterpret_cast<const float4*>(&As[k][ty * 8]);
+      const float4 x1 = *reinterpret_cast<const float4*>(&As[k][ty * 8 + 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float av[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (more) {
+      stash(a0, a1, w0);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = m0 + ty * 8 + i;
     if (row >= p.M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -332,6 +448,21 @@ extern "C" int edtr_f32_gemm(const EdtrF32Gemm* g, void* stream) {
   p.rows_per_group = g->rows_per_group > 0 ? g->rows_per_group : 1;
   p.residual = g->residual; p.ldr = g->ldr; p.act = g->act; p.out_nchw = g->out_nchw; p.hw = g->hw;
   EDTR_REQUIRE(!g->out_nchw || (g->hw > 0 && g->M % g->hw == 0), "NCHW output needs hw | M");
+  // EDTR_F32_GEMM_VEC=1 routes the shapes that allow 16-byte operand loads to the 128 x 64 software-pipelined form
+  static const bool vec_enabled = [] {
+    const char* e = getenv("EDTR_F32_GEMM_VEC");
+    return e != nullptr && e[0] == '1';
+  }();
+  const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool strides_ok = g->a_stride1 % 4 == 0 && g->a_stride2 % 4 == 0 && g->w_stride1 % 4 == 0 && g->w_stride2 % 4 == 0;
+  const bool vec = vec_enabled && !g->w_kn && g->K % 4 == 0 && g->lda % 4 == 0 && g->ldw % 4 == 0 && al16(g->A) && al16(g->W) &&
+                   strides_ok && (!g->conv || g->Cin % 4 == 0) && g->M >= kGBM;
+  if (vec) {
+    dim3 grid((g->N + kFBN - 1) / kFBN, (g->M + kGBM - 1) / kGBM, g->batch1 * g->batch2);
+    EDTR_REQUIRE(grid.y <= 65535, "M too large for the fp32 GEMM grid");
+    EDTR_LAUNCH(f32_gemm_vec_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), p);
+    return check_launch("f32_gemm_vec_kernel");
+  }
   dim3 grid((g->N + kFBN - 1) / kFBN, (g->M + kFBM - 1) / kFBM, g->batch1 * g->batch2);
   EDTR_REQUIRE(grid.y <= 65535, "M too large for the fp32 GEMM grid");
   EDTR_LAUNCH(f32_gemm_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), p);
